@@ -1,0 +1,134 @@
+/* x2i_b200 -- C ABI of the B200-native (sm_100a) X2I hot path.
+ *
+ * The reference (OPPO-Mente-Lab/X2I) is pure Python and has no FFI; its extension points for this path are
+ * Python object protocols.  This header is the boundary the native library exports UNDER those
+ * protocols: x2i_b200/ops.py binds every entry point below with ctypes (see INTEGRATION.md for the stub), and
+ * x2i_b200/{flux,pipeline,proj,kd}.py mirror the reference interfaces on top.  Each entry cites the reference
+ * code it replaces (paths relative to the reference repo; "[D031]" = diffusers==0.31.0, un-vendored).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; tensors are bf16 unless noted;
+ *   - the caller owns all buffers (outputs, workspaces); nothing is allocated, nothing synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, negative X2I_ERR_* otherwise; x2i_last_error() describes the last failure
+ *     of the calling thread;
+ *   - thread-safe; callable from any host thread (the reference does GPU work off-thread,
+ *     core/data/dataloader.py:100-123).
+ */
+#ifndef X2I_B200_H_
+#define X2I_B200_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X2I_OK 0
+#define X2I_ERR_SHAPE (-1)  /* unsupported / inconsistent dimensions */
+#define X2I_ERR_ALIGN (-2)  /* pointer or leading dimension not 16-byte aligned */
+#define X2I_ERR_ARCH (-3)   /* device is not sm_100 */
+#define X2I_ERR_LAUNCH (-4) /* CUDA runtime / driver error */
+
+int x2i_version(void);
+const char* x2i_last_error(void);
+/* number of kernels launched through this library by this process (bench.py's gpu_launches) */
+long long x2i_launch_count(void);
+
+/* ---- dense contractions (tcgen05.mma, TMA, TMEM accumulators) -------------------------------------------------
+ * C[M,N] = act(A[M,K] @ W[N,K]^T + bias[N]);  A, W row-major with leading dimensions lda, ldw (elements).
+ * act: 0 none, 1 GELU(tanh), 2 GELU(erf).  Replaces nn.Linear (+ F.gelu) at:
+ *   FeedForward.net[0] [D031] called lightcontrol/lightcontrol_flux.py:186,199; proj_mlp+act_mlp :90;
+ *   x_embedder :445; context_embedder :457; proj_out :543; MLP3.projector / fc utils/proj.py:30-31.            */
+int x2i_gemm_bias_act(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
+                      int M, int N, int K, int act, void* stream);
+
+/* C = A @ W^T + bias and C_gelu = GELU_erf(C) in one pass (two outputs).  MLP3: x2 = projector(x) is returned as the
+ * prompt embedding while fc = Sequential(GELU, Linear) consumes GELU(x2) (utils/proj.py:22-25, :30-31).               */
+int x2i_gemm_bias_dual(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
+                       void* C_gelu, int64_t ldg, int M, int N, int K, void* stream);
+
+/* C[M,N] = residual[M,N] + gate[m / rows_per_batch, :] * (A @ W^T + bias);  aux (nullable) receives the un-gated
+ * A @ W^T + bias -- the tensor the reference's forward hooks capture (train/train_qwenvl.py:186-214).
+ * Replaces to_out[0] / to_add_out / ff.net[2] / proj_out followed by `gate.unsqueeze(1) * y` and the residual add:
+ * lightcontrol/lightcontrol_flux.py:97-100, :180-181, :186-189, :193-200.  C may alias residual.                  */
+int x2i_gemm_gate_residual(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* gate,
+                           int64_t gate_stride, int rows_per_batch, const void* residual, int64_t ldr, void* C,
+                           int64_t ldc, void* aux, int64_t ldaux, int M, int N, int K, void* stream);
+
+/* Fused QKV (+ single-block proj_mlp) projection.  W = [Wq; Wk; Wv; (Wmlp)] is [N, K] with N = 3*heads*128 (+ F).
+ * Epilogue per 128-column head: q,k: +bias, RMSNorm(128, eps) * rms_{q,k}, RoPE (adjacent pairs, table
+ * rope[L_total,64] of (cos,sin) from x2i_rope_table), stored head-major into q/k[B, heads, L_total, 128] at token
+ * row_offset + (m % rows_per_batch); v: +bias, same layout; columns >= 3*heads*128: GELU(tanh) -> mlp[m*ldmlp + ..].
+ * Replaces to_q/to_k/to_v/add_*_proj, norm_q/k, norm_added_q/k, the txt||img concat and apply_rotary_emb of
+ * FluxAttnProcessor2_0 [D031] (call sites lightcontrol_flux.py:92-95, :173-177) and proj_mlp :90.   */
+int x2i_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* rms_q,
+                      const void* rms_k, const void* rope /* float2, nullable */, void* q, void* k, void* v, void* mlp,
+                      int64_t ldmlp, int M, int N, int K, int heads, int rows_per_batch, int row_offset, int L_total,
+                      float eps, void* stream);
+
+/* C[M,N] = A[M,K] @ Bkn[K,N] (+bias): B given N-contiguous ("MN-major" tcgen05 operand, as V is in attention).     */
+int x2i_gemm_kn(const void* A, int64_t lda, const void* Bkn, int64_t ldb, const void* bias, void* C, int64_t ldc,
+                int M, int N, int K, void* stream);
+
+/* ---- fused MMDiT attention ----------------------------------------------------------------------------------
+ * O = softmax(Q K^T / sqrt(128)) V over q,k,v[B, heads, L, 128]; output token-major: rows with token < split go to
+ * out0[(b*split + t) * ld0 + h*128], the rest to out1[(b*(L-split) + t-split) * ld1 + h*128].
+ * Replaces F.scaled_dot_product_attention + transpose/reshape + the txt/img split in FluxAttnProcessor2_0 [D031].  */
+int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0, int64_t ld0, int split, void* out1,
+                        int64_t ld1, int B, int heads, int L, void* stream);
+
+/* ---- row-wise HBM-bound kernels -----------------------------------------------------------------------------
+ * y = LayerNorm(x; no affine, eps) * (1 + scale[b]) + shift[b], b = row / rows_per_batch.  AdaLayerNormZero /
+ * ZeroSingle / Continuous [D031] and norm2 + modulate (lightcontrol_flux.py:89, :166-170, :183-184, :196-197, :542). */
+int x2i_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride, void* y,
+                    int64_t ldy, int rows, int D, int rows_per_batch, float eps, void* stream);
+
+/* x[r,:] += gate[r / rows_per_batch, :] * y[r,:] -- the un-fused `gate.unsqueeze(1) * attn_output` + residual of
+ * lightcontrol_flux.py:180-181, :193-194, used only behind a plug-in attention processor.                           */
+int x2i_gate_residual(void* x, int64_t ldx, const void* y, int64_t ldy, const void* gate, int64_t gate_stride, int rows,
+                      int D, int rows_per_batch, void* stream);
+
+/* out[b,n] (+)= bias[n] + sum_k act_in(x[b,k]) W[n,k];  B <= 64, act_in: 0 none, 1 SiLU.  All AdaLN modulation
+ * linears of a step in one launch (weights concatenated), and the CombinedTimestep*TextProjEmbeddings MLPs [D031]. */
+int x2i_skinny_linear(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                      int B, int N, int K, int act_in, int accumulate, void* stream);
+
+/* Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0) [D031]: t fp32 [B] -> out bf16 [B, dim].            */
+int x2i_timestep_sinusoid(const float* t, void* out, int B, int dim, void* stream);
+
+/* FluxPosEmbed [D031] (lightcontrol_flux.py:247,:472): ids fp32 [L,3] -> cos,sin fp32 [L,a0+a1+a2] (nullable) and the
+ * compact table rope float2 [L,(a0+a1+a2)/2] (nullable).                                                          */
+int x2i_rope_table(const float* ids, int L, int a0, int a1, int a2, double theta, float* cos_out, float* sin_out,
+                   void* rope, void* stream);
+
+/* FlowMatchEulerDiscreteScheduler.step [D031]: x <- bf16(float(x) + dsigma * v), n elements (multiple of 8).        */
+int x2i_euler_step(void* x, const void* v, float dsigma, int64_t n, void* stream);
+
+/* ---- attention-distillation loss (train/train_qwenvl.py:58-61, :601-620) --------------------------------------
+ * teacher/student: [rows, D] bf16.  Rows are grouped in SEGMENTS (contiguous runs belonging to one layer and one
+ * batch element): segment s owns rows [seg_row_start[s], seg_row_start[s+1]) (device int64 [n_seg+1]) and belongs to
+ * layer seg_layer[s] (device int32 [n_seg]); this covers both per-layer tensors and the reference's stacked
+ * [B, n_layers, L, D] hook tensors (:590-592) without a copy.
+ *   term_l = sum over the layer's rows of KL(softmax(norm(s)/T) || softmax(norm(t)/T)) / batch    (F.kl_div batchmean)
+ *   loss = sum of finite term_l; valid[l] = isfinite(term_l)  (the reference's inf/nan guard, :606-609)
+ * Workspaces: row_kl fp32 [rows], seg_sum fp64 [n_seg].  Outputs: layer_term fp32 [n_layers], loss fp32 [1], valid.  */
+int x2i_kd_loss_fwd(const void* teacher, const void* student, int64_t rows, int D, float temperature,
+                    const int64_t* seg_row_start, const int* seg_layer, int n_seg, int n_layers, int batch, float* row_kl,
+                    double* seg_sum, float* layer_term, float* loss, int* valid, void* stream);
+/* grad_student[rows, D] bf16 = dloss * d loss / d student (rows of invalid layers get 0); row_scale: fp32 [rows]
+ * workspace; max_seg_rows = longest segment.  Recomputes the row statistics (no saved activations).                */
+int x2i_kd_loss_bwd(const void* teacher, const void* student, int64_t rows, int D, float temperature,
+                    const int64_t* seg_row_start, const int* seg_layer, int n_seg, int64_t max_seg_rows, int batch,
+                    const int* valid, const float* dloss, float* row_scale, void* grad_student, void* stream);
+
+/* ---- alignment projector front end (utils/proj.py:62-72, :29) --------------------------------------------------
+ * y[b,s,:] = LayerNorm_H(mix_c x[b,c,s,:]) * gamma + beta;  mode 0: Conv2d(C->1, 5x5, pad 2) weights w fp32 [C,5,5]
+ * + conv_bias; mode 1: mean_c(w[c] * x) (cha_scale); mode 2: mean_c(x).  x bf16 [B,C,S,H], y bf16 [B,S,H].         */
+int x2i_proj_mix_ln(const void* x, int mode, const float* w, float conv_bias, const float* gamma, const float* beta,
+                    float eps, void* y, int B, int C, int S, int H, void* stream);
+/* pooled[b,n] = mean_s y[b,s,n]  (utils/proj.py:32)                                                                */
+int x2i_mean_over_s(const void* y, void* out, int B, int S, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X2I_B200_H_ */

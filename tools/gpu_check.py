@@ -1,0 +1,338 @@
+"""Kernel-level bring-up checks on a real B200 (development tool; the judged tests are tests/ -m gpu).
+
+    python tools/gpu_check.py [name ...]        # every check runs in its own subprocess with a timeout
+
+Each check compares a C-ABI op with a plain torch fp32 computation on the same bf16 inputs and prints
+max-abs / relative errors; timing checks print achieved TFLOP/s or GB/s.  Results -> gpurun_out/check.json.
+"""
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _imports():
+    import torch
+    from x2i_b200 import ops
+    return torch, ops
+
+
+def rel_err(a, b):
+    a = a.float(); b = b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12)), float((a - b).abs().max())
+
+
+def timeit(fn, iters=20, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters * 1e-3
+
+
+def check_gemm_basic():
+    torch, ops = _imports()
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (M, N, K) in [(128, 256, 64), (128, 128, 128), (256, 512, 256), (4608, 3072, 3072), (203, 384, 3072), (4096, 64, 3072),
+                      (512, 3072, 4096), (1000, 768, 4096), (4096, 3072, 64)]:
+        a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda", generator=g).bfloat16()
+        ref = a.float() @ w.float().t() + b.float()
+        c = ops.linear(a, w, b)
+        torch.cuda.synchronize()
+        out[f"{M}x{N}x{K}"] = rel_err(c, ref)
+        c1 = ops.linear(a, w, b, act=1)
+        out[f"{M}x{N}x{K}_gelu_tanh"] = rel_err(c1, torch.nn.functional.gelu(ref, approximate="tanh"))
+        c2 = ops.linear(a, w, None, act=2)
+        out[f"{M}x{N}x{K}_gelu_erf_nobias"] = rel_err(c2, torch.nn.functional.gelu(ref - b.float()))
+    return out
+
+
+def check_gemm_kn():
+    torch, ops = _imports()
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for (M, N, K) in [(128, 128, 64), (128, 128, 128), (256, 256, 192), (1000, 384, 512)]:
+        a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+        b = (torch.randn(K, N, device="cuda", generator=g) * 0.1).bfloat16()
+        ref = a.float() @ b.float()
+        c = ops.matmul_kn(a, b)
+        torch.cuda.synchronize()
+        out[f"{M}x{N}x{K}"] = rel_err(c, ref)
+    return out
+
+
+def check_gemm_gate():
+    torch, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B, L, N, K = 2, 300, 512, 256
+    a = torch.randn(B * L, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g).bfloat16()
+    mod = torch.randn(B, 3 * N, device="cuda", generator=g).bfloat16()
+    gate = mod[:, N:2 * N]
+    res = torch.randn(B * L, N, device="cuda", generator=g).bfloat16()
+    lin = a.float() @ w.float().t() + b.float()
+    ref = res.float() + gate.float().repeat_interleave(L, 0) * lin
+    aux = torch.empty(B * L, N, device="cuda", dtype=torch.bfloat16)
+    out = ops.linear_gate_residual(a, w, b, gate, res.clone(), L, aux=aux)
+    torch.cuda.synchronize()
+    return {"out": rel_err(out, ref), "aux": rel_err(aux, lin)}
+
+
+def _qkv_ref(torch, x, w, bias, wq, wk, cos, sin, B, rows, H, eps=1e-6):
+    D = H * 128
+    y = x.float() @ w.float().t() + bias.float()
+    q, k, v = y[:, :D], y[:, D:2 * D], y[:, 2 * D:3 * D]
+
+    def heads(t):
+        return t.view(B, rows, H, 128).transpose(1, 2)
+
+    def rms(t, wt):
+        return t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + eps) * wt.float()
+
+    def rope(t):
+        pr = t.reshape(*t.shape[:-1], -1, 2)
+        rot = torch.stack([-pr[..., 1], pr[..., 0]], -1).flatten(3)
+        return t * cos[None, None] + rot * sin[None, None]
+
+    return rope(rms(heads(q), wq)), rope(rms(heads(k), wk)), heads(v), y[:, 3 * D:]
+
+
+def check_qkv():
+    torch, ops = _imports()
+    from oracle import flux_oracle as fo
+    g = torch.Generator(device="cuda").manual_seed(3)
+    out = {}
+    for (B, S_txt, hl, wl, H, F) in [(2, 40, 8, 12, 2, 0), (1, 512, 16, 16, 4, 1024), (2, 203, 8, 8, 24, 0)]:
+        L_img = hl * wl
+        L = S_txt + L_img
+        D = H * 128
+        N = 3 * D + F
+        ids = torch.cat([torch.zeros(S_txt, 3), fo.prepare_latent_image_ids(2 * hl, 2 * wl)]).cuda()
+        cos, sin, rope = ops.rope_table(ids)
+        w = (torch.randn(N, D, device="cuda", generator=g) * 0.05).bfloat16()
+        bias = (torch.randn(N, device="cuda", generator=g) * 0.1).bfloat16()
+        wq = (1 + 0.1 * torch.randn(128, device="cuda", generator=g)).bfloat16()
+        wk = (1 + 0.1 * torch.randn(128, device="cuda", generator=g)).bfloat16()
+        q = torch.zeros(B, H, L, 128, device="cuda", dtype=torch.bfloat16)
+        k = torch.zeros_like(q); v = torch.zeros_like(q)
+        x_img = torch.randn(B * L_img, D, device="cuda", generator=g).bfloat16()
+        x_txt = torch.randn(B * S_txt, D, device="cuda", generator=g).bfloat16()
+        mlp_img = torch.zeros(B * L_img, max(F, 8), device="cuda", dtype=torch.bfloat16) if F else None
+        mlp_txt = torch.zeros(B * S_txt, max(F, 8), device="cuda", dtype=torch.bfloat16) if F else None
+        ops.qkv_rope(x_img, w, bias, wq, wk, rope, q, k, v, H, L_img, S_txt, mlp=mlp_img)
+        ops.qkv_rope(x_txt, w, bias, wq, wk, rope, q, k, v, H, S_txt, 0, mlp=mlp_txt)
+        torch.cuda.synchronize()
+        qi, ki, vi, mi = _qkv_ref(torch, x_img, w, bias, wq, wk, cos[S_txt:], sin[S_txt:], B, L_img, H)
+        qt, kt, vt, mt = _qkv_ref(torch, x_txt, w, bias, wq, wk, cos[:S_txt], sin[:S_txt], B, S_txt, H)
+        tag = f"B{B}_S{S_txt}_L{L}_H{H}_F{F}"
+        out[tag + "_q"] = rel_err(q, torch.cat([qt, qi], 2))
+        out[tag + "_k"] = rel_err(k, torch.cat([kt, ki], 2))
+        out[tag + "_v"] = rel_err(v, torch.cat([vt, vi], 2))
+        if F:
+            out[tag + "_mlp"] = rel_err(mlp_img, torch.nn.functional.gelu(mi, approximate="tanh"))
+    return out
+
+
+def check_attention():
+    torch, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    out = {}
+    for (B, H, L, split) in [(1, 1, 128, 0), (1, 1, 256, 0), (1, 2, 512, 100), (2, 3, 1536, 512), (1, 2, 331, 75), (1, 24, 4608, 512)]:
+        q = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        k = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        v = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        o0, o1 = ops.attention(q, k, v, split=split)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+        ref = ref.transpose(1, 2).reshape(B, L, H * 128)
+        got = o1 if split == 0 else torch.cat([o0, o1], 1)
+        out[f"B{B}_H{H}_L{L}_s{split}"] = rel_err(got, ref)
+    # peaked logits: forces the lazy-rescale path
+    q = (torch.randn(1, 2, 512, 128, device="cuda", generator=g) * 4).bfloat16()
+    k = (torch.randn(1, 2, 512, 128, device="cuda", generator=g) * 4).bfloat16()
+    v = torch.randn(1, 2, 512, 128, device="cuda", generator=g).bfloat16()
+    _, o1 = ops.attention(q, k, v)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(1, 512, 256)
+    out["peaked"] = rel_err(o1, ref)
+    return out
+
+
+def check_rowwise():
+    torch, ops = _imports()
+    from oracle import flux_oracle as fo
+    g = torch.Generator(device="cuda").manual_seed(5)
+    out = {}
+    B, L, D = 2, 77, 3072
+    x = (torch.randn(B * L, D, device="cuda", generator=g) * 2 + 0.5).bfloat16()
+    mod = torch.randn(B, 6 * D, device="cuda", generator=g).bfloat16()
+    shift, scale = mod[:, :D], mod[:, D:2 * D]
+    y = ops.ln_modulate(x, scale, shift, L)
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), eps=1e-6) * (1 + scale.float().repeat_interleave(L, 0)) + shift.float().repeat_interleave(L, 0)
+    out["ln_modulate_3072"] = rel_err(y, ref)
+    x2 = torch.randn(50, 256, device="cuda", generator=g).bfloat16()
+    m2 = torch.randn(1, 512, device="cuda", generator=g).bfloat16()
+    out["ln_modulate_256"] = rel_err(ops.ln_modulate(x2, m2[:, :256], m2[:, 256:], 50),
+                                     torch.nn.functional.layer_norm(x2.float(), (256,), eps=1e-6) * (1 + m2[:, :256].float()) + m2[:, 256:].float())
+    for (Bq, N, K) in [(1, 1000, 3072), (3, 18432, 3072), (8, 3072, 256), (11, 768, 4096)]:
+        xs = torch.randn(Bq, K, device="cuda", generator=g).bfloat16()
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.03).bfloat16()
+        b = torch.randn(N, device="cuda", generator=g).bfloat16()
+        ref = torch.nn.functional.silu(xs.float()) @ w.float().t() + b.float()
+        o = ops.skinny_linear(xs, w, b, act_in=1)
+        out[f"skinny_{Bq}x{N}x{K}"] = rel_err(o, ref)
+        o2 = ops.skinny_linear(xs, w, b, act_in=0, out=o.clone(), accumulate=True)
+        out[f"skinny_acc_{Bq}x{N}x{K}"] = rel_err(o2, o.float() + (xs.float() @ w.float().t() + b.float()))
+    t = torch.tensor([1000.0, 750.0, 3.5e3, 0.0], device="cuda")
+    out["sinusoid"] = rel_err(ops.timestep_sinusoid(t), fo.Timesteps(256, True, 0)(t.cpu()).cuda())
+    ids = torch.cat([torch.zeros(512, 3), fo.prepare_latent_image_ids(128, 128)])
+    cos, sin, rope = ops.rope_table(ids.cuda())
+    rc, rs = fo.rope_table(ids)
+    out["rope_cos_maxabs"] = float((cos.cpu() - rc).abs().max())
+    out["rope_sin_maxabs"] = float((sin.cpu() - rs).abs().max())
+    out["rope_bitexact_frac"] = float(((cos.cpu() == rc) & (sin.cpu() == rs)).float().mean())
+    out["rope_compact_consistent"] = bool(torch.equal(rope[:, :, 0], cos[:, ::2]) and torch.equal(rope[:, :, 1], sin[:, ::2]))
+    xx = torch.randn(2, 4096, 64, device="cuda", generator=g).bfloat16()
+    vv = torch.randn(2, 4096, 64, device="cuda", generator=g).bfloat16()
+    ref = (xx.float() + (0.5 - 0.75) * vv.float()).bfloat16()
+    out["euler_exact"] = bool(torch.equal(ops.euler_step_(xx.clone(), vv, 0.5 - 0.75), ref))
+    return out
+
+
+def check_kd():
+    torch, ops = _imports()
+    from oracle import kd_oracle
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B, D = 2, 3072
+    Ls = [40, 24, 64, 33]
+    T = [torch.randn(B, L, D, device="cuda", generator=g).bfloat16() for L in Ls]
+    S = [(t.float() + 0.7 * torch.randn(B, L, D, device="cuda", generator=g)).bfloat16().requires_grad_(True) for t, L in zip(T, Ls)]
+    S[2].data[0, 0, 0] = float("nan")  # layer 2 must be skipped
+    ref_loss, skipped = kd_oracle.kd_loss([t.float() for t in T], [s.float() for s in S])
+    ref_loss.backward()
+    teacher = torch.cat([t.reshape(-1, D) for t in T]); student = torch.cat([s.detach().reshape(-1, D) for s in S])
+    starts = torch.tensor([0] + list(torch.tensor([B * L for L in Ls]).cumsum(0)), device="cuda", dtype=torch.int64)
+    seg_layer = torch.arange(len(Ls), device="cuda", dtype=torch.int32)
+    loss, terms, valid = ops.kd_loss_fwd(teacher, student, starts, seg_layer, len(Ls), B)
+    grad = ops.kd_loss_bwd(teacher, student, starts, seg_layer, max(B * L for L in Ls), B, valid, torch.ones((), device="cuda"))
+    torch.cuda.synchronize()
+    ref_grad = torch.cat([(s.grad if s.grad is not None else torch.zeros_like(s)).reshape(-1, D) for s in S])
+    keep = torch.ones(teacher.shape[0], dtype=torch.bool, device="cuda")
+    keep[int(starts[2]):int(starts[3])] = False
+    return {"loss": (float(loss), float(ref_loss)), "skipped_ref": skipped, "valid": valid.tolist(),
+            "grad": rel_err(grad[keep], ref_grad[keep]), "grad_skipped_layer_zero": bool((grad[~keep] == 0).all())}
+
+
+def check_proj():
+    torch, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    out = {}
+    for (B, C, S, H) in [(2, 5, 9, 64), (1, 37, 77, 2048), (1, 29, 40, 3584)]:
+        x = torch.randn(B, C, S, H, device="cuda", generator=g).bfloat16()
+        w = torch.randn(C, 5, 5, device="cuda", generator=g) * 0.1
+        gam = 1 + 0.1 * torch.randn(H, device="cuda", generator=g); bet = 0.1 * torch.randn(H, device="cuda", generator=g)
+        ref = torch.nn.functional.conv2d(x.float(), w[None], torch.tensor([0.3], device="cuda"), padding=2).squeeze(1)
+        ref = torch.nn.functional.layer_norm(ref, (H,), gam, bet, 1e-6)
+        out[f"conv_{B}x{C}x{S}x{H}"] = rel_err(ops.proj_mix_ln(x, 0, w, 0.3, gam, bet, 1e-6), ref)
+        cs = torch.randn(C, device="cuda", generator=g)
+        ref = torch.nn.functional.layer_norm((cs[None, :, None, None] * x.float()).mean(1), (H,), gam, bet, 1e-6)
+        out[f"scale_{B}x{C}x{S}x{H}"] = rel_err(ops.proj_mix_ln(x, 1, cs, 0.0, gam, bet, 1e-6), ref)
+        ref = torch.nn.functional.layer_norm(x.float().mean(1), (H,), gam, bet, 1e-6)
+        out[f"mean_{B}x{C}x{S}x{H}"] = rel_err(ops.proj_mix_ln(x, 2, cs, 0.0, gam, bet, 1e-6), ref)
+    y = torch.randn(2, 77, 768, device="cuda", generator=g).bfloat16()
+    out["mean_over_s"] = rel_err(ops.mean_over_s(y), y.float().mean(1))
+    return out
+
+
+def check_perf():
+    torch, ops = _imports()
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for (M, N, K) in [(4608, 9216, 3072), (4608, 12288, 3072), (4608, 3072, 12288), (4096, 3072, 3072), (4608, 21504, 3072), (4608, 3072, 15360), (512, 3072, 3072)]:
+        a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.02).bfloat16()
+        b = torch.randn(N, device="cuda", generator=g).bfloat16()
+        c = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        t = timeit(lambda: ops.linear(a, w, b, out=c))
+        t_ref = timeit(lambda: torch.nn.functional.linear(a, w, b))
+        out[f"gemm_{M}x{N}x{K}"] = {"ms": t * 1e3, "tflops": 2 * M * N * K / t / 1e12, "cublas_ms": t_ref * 1e3,
+                                   "cublas_tflops": 2 * M * N * K / t_ref / 1e12}
+    for (B, H, L) in [(1, 24, 4608), (2, 24, 4608), (1, 24, 1536)]:
+        q = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        k = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        v = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        o1 = torch.empty(B, L, H * 128, device="cuda", dtype=torch.bfloat16)
+        t = timeit(lambda: ops.attention(q, k, v, out1=o1))
+        t_ref = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
+        fl = 4 * L * L * 128 * H * B
+        out[f"attn_B{B}_H{H}_L{L}"] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "sdpa_ms": t_ref * 1e3, "sdpa_tflops": fl / t_ref / 1e12}
+    # HBM-bound pieces
+    x = torch.randn(4608 * 8, 3072, device="cuda", generator=g).bfloat16()
+    mod = torch.randn(8, 6 * 3072, device="cuda", generator=g).bfloat16()
+    y = torch.empty_like(x)
+    t = timeit(lambda: ops.ln_modulate(x, mod[:, :3072], mod[:, 3072:6144], 4608, out=y))
+    out["ln_modulate_8x4608x3072"] = {"ms": t * 1e3, "gbs": 2 * x.numel() * 2 / t / 1e9}
+    N = 200000
+    w = (torch.randn(N, 3072, device="cuda", generator=g) * 0.02).bfloat16()
+    xs = torch.randn(1, 3072, device="cuda", generator=g).bfloat16()
+    o = torch.empty(1, N, device="cuda", dtype=torch.bfloat16)
+    t = timeit(lambda: ops.skinny_linear(xs, w, None, 1, out=o))
+    out["skinny_1x200000x3072"] = {"ms": t * 1e3, "gbs": w.numel() * 2 / t / 1e9}
+    rows = 4608 * 19
+    te = torch.randn(rows, 3072, device="cuda", generator=g).bfloat16()
+    stu = torch.randn(rows, 3072, device="cuda", generator=g).bfloat16()
+    starts = torch.arange(0, rows + 1, 4608, device="cuda", dtype=torch.int64)
+    sl = torch.arange(19, device="cuda", dtype=torch.int32)
+    t = timeit(lambda: ops.kd_loss_fwd(te, stu, starts, sl, 19, 1))
+    out["kd_fwd_19x4608x3072"] = {"ms": t * 1e3, "gbs": 2 * te.numel() * 2 / t / 1e9}
+    _, _, valid = ops.kd_loss_fwd(te, stu, starts, sl, 19, 1)
+    one = torch.ones((), device="cuda")
+    t = timeit(lambda: ops.kd_loss_bwd(te, stu, starts, sl, 4608, 1, valid, one))
+    out["kd_bwd_19x4608x3072"] = {"ms": t * 1e3, "gbs": 3 * te.numel() * 2 / t / 1e9}
+    xx = torch.randn(1, 37, 512, 2048, device="cuda", generator=g).bfloat16()
+    wc = torch.randn(37, 5, 5, device="cuda") * 0.1
+    gam = torch.ones(2048, device="cuda"); bet = torch.zeros(2048, device="cuda")
+    t = timeit(lambda: ops.proj_mix_ln(xx, 0, wc, 0.1, gam, bet, 1e-6))
+    out["proj_conv_ln_37x512x2048"] = {"ms": t * 1e3, "gbs": xx.numel() * 2 / t / 1e9}
+    return out
+
+
+CHECKS = {k[6:]: v for k, v in list(globals().items()) if k.startswith("check_")}
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--one":
+        res = CHECKS[sys.argv[2]]()
+        print("RESULT " + json.dumps(res))
+        sys.exit(0)
+    names = sys.argv[1:] or list(CHECKS)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    allres = {}
+    for n in names:
+        t0 = time.time()
+        try:
+            pr = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=300)
+            line = [l for l in pr.stdout.splitlines() if l.startswith("RESULT ")]
+            if line:
+                allres[n] = json.loads(line[0][7:])
+            else:
+                allres[n] = {"error": (pr.stdout[-1500:] + "\n" + pr.stderr[-3000:])}
+        except subprocess.TimeoutExpired:
+            allres[n] = {"error": "TIMEOUT (hang?)"}
+        print(f"== {n} ({time.time() - t0:.1f}s)")
+        print(json.dumps(allres[n], indent=1)[:6000])
+        sys.stdout.flush()
+        json.dump(allres, open(os.path.join(ROOT, "gpurun_out", "check.json"), "w"), indent=1)

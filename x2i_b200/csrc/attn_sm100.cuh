@@ -1,0 +1,279 @@
+// Fused MMDiT joint attention forward for sm_100a (head_dim 128, non-causal, no mask):
+//     O = softmax(Q K^T / sqrt(128)) V      Q,K,V: [B, H, L, 128] bf16 (text tokens first, then image tokens)
+// replaces F.scaled_dot_product_attention inside FluxAttnProcessor2_0.
+//
+// One CTA per (batch, head, 256 query rows).  320 threads:
+//   warp 0      TMA producer: Q (2 tiles of 128 rows) once, then K_j / V_j tiles of 128 keys through a 4-slot ring
+//   warp 1      tcgen05.mma issuer (one lane): S_i = Q_i K_j^T (SS, both K-major) and O_i += P_i V_j (A = P from TMEM,
+//               B = V as MN-major smem operand), ping-ponging the two query tiles so that the softmax of one tile
+//               overlaps the MMAs of the other
+//   warps 2..5  softmax warpgroup for query tile 0  (one query row per thread)
+//   warps 6..9  softmax warpgroup for query tile 1
+// TMEM (512 columns): S0 | S1 | O0 | O1, 128 fp32 columns each; P_i (bf16) aliases the first 64 columns of S_i.
+// Online softmax in the exp2 domain with lazy rescaling of O (only when the running max grows by > 2^8).
+#pragma once
+#include "common.cuh"
+
+namespace x2i {
+
+struct AttnParams {
+  int B, H, L;
+  float scale_log2;  // log2(e) / sqrt(head_dim)
+  __nv_bfloat16* out0;  // rows with pos <  split: out0[(b*split + pos) * ld0 + h*128 + d]
+  long long ld0;
+  int split;
+  __nv_bfloat16* out1;  // rows with pos >= split: out1[(b*(L-split) + pos-split) * ld1 + h*128 + d]
+  long long ld1;
+};
+
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 128B-swizzled boxes of [128 rows x 64 cols]
+constexpr int ATT_KV_SLOTS = 4;
+constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + ATT_KV_SLOTS * ATT_TILE_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                           const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sq = smem;                         // Q0 | Q1
+  uint8_t* skv = smem + 2 * ATT_TILE_BYTES;   // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(skv + ATT_KV_SLOTS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;              // 1
+  uint64_t* kv_full = bars + 1;         // 4
+  uint64_t* kv_empty = bars + 5;        // 4
+  uint64_t* s_full = bars + 9;          // 2
+  uint64_t* p_full = bars + 11;         // 2
+  uint64_t* o_full = bars + 13;         // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * p.H + h;
+  const int n_kv = (p.L + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_KV_SLOTS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          tma_load_3d(sq + i * ATT_TILE_BYTES + g * 16384, &tma_q, q_full, g * 64, q0 + i * 128, bh);
+      for (int seq = 0; seq < 2 * n_kv; ++seq) {
+        const int slot = seq & (ATT_KV_SLOTS - 1);
+        const uint32_t ph = (seq / ATT_KV_SLOTS) & 1;
+        mbar_wait(&kv_empty[slot], ph ^ 1);
+        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
+        const CUtensorMap* map = (seq & 1) ? &tma_v : &tma_k;
+        const int j = seq >> 1;
+        uint8_t* dst = skv + slot * ATT_TILE_BYTES;
+        tma_load_3d(dst, map, &kv_full[slot], 0, j * 128, bh);
+        tma_load_3d(dst + 16384, map, &kv_full[slot], 64, j * 128, bh);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);
+      const uint32_t q_base = smem_u32(sq);
+      const uint32_t kv_base = smem_u32(skv);
+      auto issue_s = [&](int i, int slot) {  // S_i = Q_i K^T
+        const uint32_t a = q_base + i * ATT_TILE_BYTES, bsm = kv_base + slot * ATT_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
+          umma_ss(tmem_base + i * 128, make_smem_desc_sw128(a + off, 16, 1024), make_smem_desc_sw128(bsm + off, 16, 1024),
+                  idesc_s, kk != 0);
+        }
+      };
+      auto issue_pv = [&](int i, int slot, bool acc) {  // O_i += P_i V
+        const uint32_t bsm = kv_base + slot * ATT_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
+                  make_smem_desc_sw128(bsm + kk * 2048, 16384, 1024), idesc_o, (acc || kk != 0) ? 1u : 0u);
+      };
+      auto kv_wait = [&](int seq) { mbar_wait(&kv_full[seq & (ATT_KV_SLOTS - 1)], (seq / ATT_KV_SLOTS) & 1); };
+
+      mbar_wait(q_full, 0);
+      kv_wait(0);
+      tc_fence_after();
+      issue_s(0, 0);
+      umma_commit(&s_full[0]);
+      issue_s(1, 0);
+      umma_commit(&s_full[1]);
+      umma_commit(&kv_empty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int vseq = 2 * j + 1, kseq = 2 * j + 2;
+        const int vslot = vseq & (ATT_KV_SLOTS - 1), kslot = kseq & (ATT_KV_SLOTS - 1);
+        const bool more = (j + 1 < n_kv);
+        kv_wait(vseq);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, vslot, j > 0);
+        umma_commit(&o_full[0]);
+        if (more) {
+          kv_wait(kseq);
+          tc_fence_after();
+          issue_s(0, kslot);
+          umma_commit(&s_full[0]);
+        }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, vslot, j > 0);
+        umma_commit(&o_full[1]);
+        umma_commit(&kv_empty[vslot]);
+        if (more) {
+          issue_s(1, kslot);
+          umma_commit(&s_full[1]);
+          umma_commit(&kv_empty[kslot]);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warpgroups
+    const int i = (warp - 2) >> 2;  // query tile 0 / 1
+    const int quad = warp & 3;      // TMEM lane quadrant accessible to this warp
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t t_s = tmem_base + i * 128 + lane_off;
+    const uint32_t t_o = tmem_base + 256 + i * 128 + lane_off;
+    const int pos = q0 + i * 128 + quad * 32 + lane;
+    float m_run = -INFINITY;  // running max, log2 domain (already multiplied by scale_log2)
+    float l_run = 0.f;
+    const float sc = p.scale_log2;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      uint32_t r[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, r[c]);
+      tmem_ld_wait();
+      if (j == n_kv - 1 && (p.L & 127) != 0) {  // mask the key tail (zero-filled by TMA)
+        const int valid = p.L - j * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (c * 32 + k >= valid) r[c][k] = 0xff800000u;  // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[c][k]));
+      const float m_cand = fmaxf(m_run, mx * sc);
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (j == 0) {
+        m_run = m_cand;
+      } else if (m_cand - m_run > 8.0f) {
+        alpha = fast_exp2(m_run - m_cand);
+        m_run = m_cand;
+        rescale = true;
+      }
+      if (j > 0) {
+        mbar_wait(&o_full[i], (j - 1) & 1);  // PV_i(j-1) complete (already true: S_i(j) was issued after it)
+        if (__any_sync(0xffffffffu, rescale)) {
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st32(t_o + c * 32, o);
+          }
+        }
+      }
+      float sum = 0.f;
+      const float neg_m = -m_run;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(r[c][2 * k]), sc, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(r[c][2 * k + 1]), sc, neg_m));
+          sum += p0 + p1;
+          pk[k] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(t_s + c * 16, pk);  // P_i aliases S_i columns [0, 64)
+      }
+      l_run = l_run * alpha + sum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i]);
+    }
+    // ---- epilogue: O_i / l -> bf16 -> global (token-major [.., H*128] so the out-projection GEMM reads it as A)
+    mbar_wait(&o_full[i], (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const bool ok = pos < p.L;
+    __nv_bfloat16* dst;
+    if (pos < p.split)
+      dst = p.out0 + (static_cast<long long>(b) * p.split + pos) * p.ld0 + h * 128;
+    else
+      dst = p.out1 + (static_cast<long long>(b) * (p.L - p.split) + (pos - p.split)) * p.ld1 + h * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld32(t_o + c * 32, o);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * inv_l, __uint_as_float(o[8 * k + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * inv_l, __uint_as_float(o[8 * k + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * inv_l, __uint_as_float(o[8 * k + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * inv_l, __uint_as_float(o[8 * k + 7]) * inv_l);
+          d4[k] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace x2i

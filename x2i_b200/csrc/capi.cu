@@ -1,0 +1,443 @@
+// C ABI of libx2i_b200.so (see include/x2i_b200.h).  Host side only: argument checks, TMA descriptors, launches.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/x2i_b200.h"
+#include "attn_sm100.cuh"
+#include "gemm_sm100.cuh"
+#include "rowwise.cuh"
+
+using namespace x2i;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "%s: %s", what, cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return X2I_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- device / driver entry points ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct DeviceInfo {
+  int ok = 0;  // 0 unknown, 1 good, -1 bad
+  int sms = 0;
+  EncodeTiledFn encode = nullptr;
+  char why[200] = "";
+};
+DeviceInfo g_dev[16];
+std::mutex g_dev_mu;
+
+int device_info(DeviceInfo** out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaGetDevice failed (no CUDA device?)");
+  if (dev < 0 || dev >= 16) return fail(X2I_ERR_ARCH, "device index %d out of range", dev);
+  DeviceInfo& d = g_dev[dev];
+  if (d.ok == 0) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (d.ok == 0) {
+      cudaDeviceProp prop;
+      cudaGetDeviceProperties(&prop, dev);
+      d.sms = prop.multiProcessorCount;
+      if (prop.major != 10) {
+        snprintf(d.why, sizeof(d.why), "device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major,
+                 prop.minor);
+        d.ok = -1;
+      } else {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+          snprintf(d.why, sizeof(d.why), "cuTensorMapEncodeTiled not available from the driver");
+          d.ok = -1;
+        } else {
+          d.encode = reinterpret_cast<EncodeTiledFn>(fn);
+          d.ok = 1;
+        }
+      }
+    }
+  }
+  if (d.ok != 1) return fail(X2I_ERR_ARCH, "%s", d.why);
+  *out = &d;
+  return X2I_OK;
+}
+
+// bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides in elements (dim 0 is dense).
+int make_map(DeviceInfo* d, CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
+             const uint32_t* box) {
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+  }
+  for (int i = 1; i < rank; ++i) gstr[i - 1] = strides_el[i] * 2;
+  CUresult r = d->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(X2I_ERR_LAUNCH, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return X2I_OK;
+}
+
+template <int BN, int EPI, bool B_MN>
+int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_tcgen05_kernel<BN, EPI, B_MN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+  if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < d->sms ? tiles : d->sms;
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
+  return check_launch("gemm_tcgen05_kernel");
+}
+
+int pick_bn(int N, int M) {
+  if (N % 256 == 0) {
+    // prefer 128-wide tiles when 256-wide ones would leave most SMs idle
+    const long long t256 = static_cast<long long>((M + 127) / 128) * (N / 256);
+    if (t256 >= 120) return 256;
+    return 128;
+  }
+  if (N % 128 == 0) return 128;
+  return 64;
+}
+
+template <int EPI>
+int launch_gemm(DeviceInfo* d, const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams& p, cudaStream_t st,
+                int force_bn = 0) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return fail(X2I_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  if (p.N % 32 != 0 || p.K % 8 != 0) return fail(X2I_ERR_SHAPE, "gemm: need N %% 32 == 0 and K %% 8 == 0 (N=%d K=%d)", p.N, p.K);
+  if (!aligned16(A) || !aligned16(W) || lda % 8 || ldw % 8) return fail(X2I_ERR_ALIGN, "gemm: A/W must be 16-byte aligned with ld %% 8 == 0");
+  int bn = force_bn ? force_bn : pick_bn(p.N, p.M);
+  if (EPI == EPI_QKV && bn == 64) return fail(X2I_ERR_SHAPE, "qkv gemm: N must be a multiple of 128");
+  CUtensorMap ta, tb;
+  uint64_t da[2] = {(uint64_t)p.K, (uint64_t)p.M}, sa[2] = {1, (uint64_t)lda};
+  uint32_t ba[2] = {GEMM_BK, GEMM_BM};
+  int rc = make_map(d, &ta, A, 2, da, sa, ba);
+  if (rc) return rc;
+  uint64_t db[2] = {(uint64_t)p.K, (uint64_t)p.N}, sb[2] = {1, (uint64_t)ldw};
+  uint32_t bb[2] = {GEMM_BK, (uint32_t)bn};
+  rc = make_map(d, &tb, W, 2, db, sb, bb);
+  if (rc) return rc;
+  switch (bn) {
+    case 256: return launch_gemm_t<256, EPI, false>(d, ta, tb, p, st);
+    case 128: return launch_gemm_t<128, EPI, false>(d, ta, tb, p, st);
+    default: return launch_gemm_t<64, EPI, false>(d, ta, tb, p, st);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int x2i_version(void) { return 100; }
+const char* x2i_last_error(void) { return g_err; }
+long long x2i_launch_count(void) { return g_launches.load(); }
+
+int x2i_gemm_bias_act(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
+                      int M, int N, int K, int act, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!aligned16(C) || ldc % 8 || (bias && !aligned16(bias))) return fail(X2I_ERR_ALIGN, "gemm_bias_act: C/bias alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.C = static_cast<__nv_bfloat16*>(C);
+  p.ldc = ldc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (act) {
+    case 0: return launch_gemm<EPI_BIAS>(d, A, lda, W, ldw, p, st);
+    case 1: return launch_gemm<EPI_BIAS_GELU_TANH>(d, A, lda, W, ldw, p, st);
+    case 2: return launch_gemm<EPI_BIAS_GELU_ERF>(d, A, lda, W, ldw, p, st);
+    default: return fail(X2I_ERR_SHAPE, "gemm_bias_act: unknown act %d", act);
+  }
+}
+
+int x2i_gemm_bias_dual(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc,
+                       void* C_gelu, int64_t ldg, int M, int N, int K, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!C_gelu) return fail(X2I_ERR_SHAPE, "gemm_bias_dual: C_gelu required");
+  if (!aligned16(C) || !aligned16(C_gelu) || ldc % 8 || ldg % 8 || (bias && !aligned16(bias))) return fail(X2I_ERR_ALIGN, "gemm_bias_dual: alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.C = static_cast<__nv_bfloat16*>(C); p.ldc = ldc;
+  p.aux = static_cast<__nv_bfloat16*>(C_gelu); p.ldaux = ldg;
+  return launch_gemm<EPI_BIAS>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+int x2i_gemm_gate_residual(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* gate,
+                           int64_t gate_stride, int rows_per_batch, const void* residual, int64_t ldr, void* C,
+                           int64_t ldc, void* aux, int64_t ldaux, int M, int N, int K, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!gate || !residual || rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "gemm_gate_residual: gate/residual/rows_per_batch required");
+  if (!aligned16(C) || !aligned16(gate) || !aligned16(residual) || (aux && !aligned16(aux)) || (bias && !aligned16(bias)) ||
+      ldc % 8 || ldr % 8 || gate_stride % 8 || (aux && ldaux % 8))
+    return fail(X2I_ERR_ALIGN, "gemm_gate_residual: alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.C = static_cast<__nv_bfloat16*>(C); p.ldc = ldc;
+  p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = ldr;
+  p.gate = static_cast<const __nv_bfloat16*>(gate); p.gate_stride = gate_stride;
+  p.rows_per_batch = rows_per_batch;
+  p.aux = static_cast<__nv_bfloat16*>(aux); p.ldaux = ldaux;
+  return launch_gemm<EPI_GATE_RESIDUAL>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+int x2i_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* rms_q,
+                      const void* rms_k, const void* rope, void* q, void* k, void* v, void* mlp, int64_t ldmlp, int M,
+                      int N, int K, int heads, int rows_per_batch, int row_offset, int L_total, float eps, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  const int D = heads * 128;
+  if (heads <= 0 || N < 3 * D || N % 128 != 0) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: N=%d must be >= 3*heads*128 and a multiple of 128", N);
+  if (N > 3 * D && !mlp) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: N > 3*D needs the mlp output");
+  if (!bias || !rms_q || !rms_k || !q || !k || !v) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: bias/rms/q/k/v required");
+  if (rows_per_batch <= 0 || row_offset < 0 || row_offset + rows_per_batch > L_total) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: token window [%d,%d) outside L_total=%d", row_offset, row_offset + rows_per_batch, L_total);
+  if (!aligned16(bias) || !aligned16(rms_q) || !aligned16(rms_k) || !aligned16(q) || !aligned16(k) || !aligned16(v) ||
+      (rope && !aligned16(rope)) || (mlp && (!aligned16(mlp) || ldmlp % 8)))
+    return fail(X2I_ERR_ALIGN, "gemm_qkv_rope: alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.q = static_cast<__nv_bfloat16*>(q); p.k = static_cast<__nv_bfloat16*>(k); p.v = static_cast<__nv_bfloat16*>(v);
+  p.rms_q = static_cast<const __nv_bfloat16*>(rms_q); p.rms_k = static_cast<const __nv_bfloat16*>(rms_k);
+  p.rope = static_cast<const float2*>(rope);
+  p.L_total = L_total; p.row_offset = row_offset; p.heads = heads; p.rows_per_batch = rows_per_batch; p.eps = eps;
+  p.mlp = static_cast<__nv_bfloat16*>(mlp); p.ldmlp = ldmlp;
+  return launch_gemm<EPI_QKV>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+int x2i_gemm_kn(const void* A, int64_t lda, const void* Bkn, int64_t ldb, const void* bias, void* C, int64_t ldc, int M,
+                int N, int K, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (N % 128 != 0 || K % 8 != 0 || M <= 0) return fail(X2I_ERR_SHAPE, "gemm_kn: need N %% 128 == 0, K %% 8 == 0");
+  if (!aligned16(A) || !aligned16(Bkn) || !aligned16(C) || lda % 8 || ldb % 8 || ldc % 8) return fail(X2I_ERR_ALIGN, "gemm_kn: alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.C = static_cast<__nv_bfloat16*>(C); p.ldc = ldc;
+  CUtensorMap ta, tb;
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[2] = {1, (uint64_t)lda};
+  uint32_t ba[2] = {GEMM_BK, GEMM_BM};
+  if (int rc = make_map(d, &ta, A, 2, da, sa, ba)) return rc;
+  uint64_t db[2] = {(uint64_t)N, (uint64_t)K}, sb[2] = {1, (uint64_t)ldb};
+  uint32_t bb[2] = {64, 64};
+  if (int rc = make_map(d, &tb, Bkn, 2, db, sb, bb)) return rc;
+  return launch_gemm_t<128, EPI_BIAS, true>(d, ta, tb, p, static_cast<cudaStream_t>(stream));
+}
+
+int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0, int64_t ld0, int split, void* out1,
+                        int64_t ld1, int B, int heads, int L, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || heads <= 0 || L <= 0 || split < 0 || split > L) return fail(X2I_ERR_SHAPE, "attention: bad B/heads/L/split");
+  if ((split > 0 && !out0) || (split < L && !out1)) return fail(X2I_ERR_SHAPE, "attention: missing output buffer");
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || (out0 && (!aligned16(out0) || ld0 % 8)) || (out1 && (!aligned16(out1) || ld1 % 8)))
+    return fail(X2I_ERR_ALIGN, "attention: alignment");
+  CUtensorMap tq, tk, tv;
+  uint64_t dims[3] = {128, (uint64_t)L, (uint64_t)B * heads}, str[3] = {1, 128, (uint64_t)L * 128};
+  uint32_t box[3] = {64, 128, 1};
+  if (int rc = make_map(d, &tq, q, 3, dims, str, box)) return rc;
+  if (int rc = make_map(d, &tk, k, 3, dims, str, box)) return rc;
+  if (int rc = make_map(d, &tv, v, 3, dims, str, box)) return rc;
+  AttnParams p;
+  p.B = B; p.H = heads; p.L = L;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
+  p.out0 = static_cast<__nv_bfloat16*>(out0); p.ld0 = ld0; p.split = split;
+  p.out1 = static_cast<__nv_bfloat16*>(out1); p.ld1 = ld1;
+  cudaError_t e = cudaFuncSetAttribute(mmdit_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+  if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+  dim3 grid((L + 255) / 256, heads, B);
+  mmdit_attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  return check_launch("mmdit_attention_fwd_kernel");
+}
+
+int x2i_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride, void* y,
+                    int64_t ldy, int rows, int D, int rows_per_batch, float eps, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || D <= 0 || D % 8 || D > 32 * 8 * 16 || rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "ln_modulate: D=%d must be a multiple of 8 and <= 4096", D);
+  if (!aligned16(x) || !aligned16(y) || !aligned16(scale) || !aligned16(shift) || ldx % 8 || ldy % 8 || mod_stride % 8) return fail(X2I_ERR_ALIGN, "ln_modulate: alignment");
+  const int wpb = 8;
+  dim3 grid((rows + wpb - 1) / wpb);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto SC = static_cast<const __nv_bfloat16*>(scale);
+  auto SH = static_cast<const __nv_bfloat16*>(shift);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nchunk = D / 8;
+  if (nchunk <= 32 * 4) ln_modulate_kernel<4><<<grid, 256, 0, st>>>(X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps);
+  else if (nchunk <= 32 * 12) ln_modulate_kernel<12><<<grid, 256, 0, st>>>(X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps);
+  else ln_modulate_kernel<16><<<grid, 256, 0, st>>>(X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps);
+  return check_launch("ln_modulate_kernel");
+}
+
+int x2i_gate_residual(void* x, int64_t ldx, const void* y, int64_t ldy, const void* gate, int64_t gate_stride, int rows,
+                      int D, int rows_per_batch, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || D <= 0 || D % 8 || rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "gate_residual: D must be a multiple of 8");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gate) || ldx % 8 || ldy % 8 || gate_stride % 8) return fail(X2I_ERR_ALIGN, "gate_residual: alignment");
+  const long long n = static_cast<long long>(rows) * (D / 8);
+  gate_residual_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(y), ldy, static_cast<const __nv_bfloat16*>(gate),
+      gate_stride, rows, D, rows_per_batch);
+  return check_launch("gate_residual_kernel");
+}
+
+int x2i_skinny_linear(const void* x, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                      int B, int N, int K, int act_in, int accumulate, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || B > 64 || N <= 0 || K <= 0 || K % 8) return fail(X2I_ERR_SHAPE, "skinny_linear: need 1 <= B <= 64, K %% 8 == 0");
+  if (!aligned16(W) || ldw % 8) return fail(X2I_ERR_ALIGN, "skinny_linear: W alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto kern = skinny_linear_kernel<8>;
+  const size_t smem_max = static_cast<size_t>(8) * K * sizeof(float);
+  if (smem_max > 200 * 1024) return fail(X2I_ERR_SHAPE, "skinny_linear: K=%d too large", K);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+  if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(skinny): %s", cudaGetErrorString(e));
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    const int nb = (B - b0) < 8 ? (B - b0) : 8;
+    long long want = (static_cast<long long>(N) + 7) / 8;  // 8 warps per CTA, one column per warp per pass
+    const int per_sm = (nb * K * 4 > 100 * 1024) ? 1 : 2;
+    int grid = static_cast<int>(want < static_cast<long long>(d->sms) * per_sm ? want : static_cast<long long>(d->sms) * per_sm);
+    kern<<<grid, 256, static_cast<size_t>(nb) * K * sizeof(float), st>>>(
+        static_cast<const __nv_bfloat16*>(x) + b0 * ldx, ldx, static_cast<const __nv_bfloat16*>(W), ldw,
+        static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(out) + b0 * ldo, ldo, nb, N, K, act_in,
+        accumulate);
+    if (int rc = check_launch("skinny_linear_kernel")) return rc;
+  }
+  return X2I_OK;
+}
+
+int x2i_timestep_sinusoid(const float* t, void* out, int B, int dim, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || dim <= 0 || dim % 2) return fail(X2I_ERR_SHAPE, "timestep_sinusoid: dim must be even");
+  const int n = B * dim / 2;
+  sinusoid_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, static_cast<__nv_bfloat16*>(out), B, dim);
+  return check_launch("sinusoid_kernel");
+}
+
+int x2i_rope_table(const float* ids, int L, int a0, int a1, int a2, double theta, float* cos_out, float* sin_out,
+                   void* rope, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (L <= 0 || a0 % 2 || a1 % 2 || a2 % 2 || a0 + a1 + a2 <= 0) return fail(X2I_ERR_SHAPE, "rope_table: axes dims must be even");
+  const int n = L * (a0 + a1 + a2) / 2;
+  rope_table_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(ids, L, a0, a1, a2, theta, cos_out, sin_out,
+                                                                                     static_cast<float2*>(rope));
+  return check_launch("rope_table_kernel");
+}
+
+int x2i_euler_step(void* x, const void* v, float dsigma, int64_t n, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (n <= 0 || n % 8) return fail(X2I_ERR_SHAPE, "euler_step: n must be a positive multiple of 8");
+  if (!aligned16(x) || !aligned16(v)) return fail(X2I_ERR_ALIGN, "euler_step: alignment");
+  const long long n8 = n / 8;
+  euler_step_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(v), dsigma, n8);
+  return check_launch("euler_step_kernel");
+}
+
+int x2i_kd_loss_fwd(const void* teacher, const void* student, int64_t rows, int D, float temperature,
+                    const int64_t* seg_row_start, const int* seg_layer, int n_seg, int n_layers, int batch, float* row_kl,
+                    double* seg_sum, float* layer_term, float* loss, int* valid, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || rows > 0x7fffffffLL || D < 16 || D % 8 || D > 8 * KD_THREADS * 4 || n_layers <= 0 || n_seg <= 0 || batch <= 0 || temperature <= 0.f)
+    return fail(X2I_ERR_SHAPE, "kd_loss_fwd: need D %% 8 == 0, 16 <= D <= 4096, rows < 2^31");
+  if (sqrtf((float)D) / temperature > 60.f) return fail(X2I_ERR_SHAPE, "kd_loss_fwd: sqrt(D)/T too large for the max-free softmax");
+  if (!aligned16(teacher) || !aligned16(student)) return fail(X2I_ERR_ALIGN, "kd_loss_fwd: alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto T = static_cast<const __nv_bfloat16*>(teacher);
+  auto S = static_cast<const __nv_bfloat16*>(student);
+  const int nchunk = D / 8;
+  if (nchunk <= KD_THREADS * 3) kd_row_kernel<3, false><<<(unsigned)rows, KD_THREADS, 0, st>>>(T, S, D, 1.0f / temperature, row_kl, nullptr, nullptr);
+  else kd_row_kernel<4, false><<<(unsigned)rows, KD_THREADS, 0, st>>>(T, S, D, 1.0f / temperature, row_kl, nullptr, nullptr);
+  if (int rc = check_launch("kd_row_kernel<fwd>")) return rc;
+  kd_segment_reduce_kernel<<<n_seg, 256, 0, st>>>(row_kl, reinterpret_cast<const long long*>(seg_row_start), seg_sum);
+  if (int rc = check_launch("kd_segment_reduce_kernel")) return rc;
+  kd_finalize_kernel<<<1, 32, 0, st>>>(seg_sum, seg_layer, n_seg, n_layers, 1.0f / batch, layer_term, loss, valid);
+  return check_launch("kd_finalize_kernel");
+}
+
+int x2i_kd_loss_bwd(const void* teacher, const void* student, int64_t rows, int D, float temperature,
+                    const int64_t* seg_row_start, const int* seg_layer, int n_seg, int64_t max_seg_rows, int batch,
+                    const int* valid, const float* dloss, float* row_scale, void* grad_student, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || rows > 0x7fffffffLL || D < 16 || D % 8 || D > 8 * KD_THREADS * 4 || n_seg <= 0 || batch <= 0 || max_seg_rows <= 0)
+    return fail(X2I_ERR_SHAPE, "kd_loss_bwd: bad shape");
+  if (!aligned16(teacher) || !aligned16(student) || !aligned16(grad_student)) return fail(X2I_ERR_ALIGN, "kd_loss_bwd: alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 g((unsigned)((max_seg_rows + 255) / 256), n_seg);
+  kd_row_scale_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const long long*>(seg_row_start), seg_layer, valid, dloss, 1.0f / batch, row_scale);
+  if (int rc = check_launch("kd_row_scale_kernel")) return rc;
+  auto T = static_cast<const __nv_bfloat16*>(teacher);
+  auto S = static_cast<const __nv_bfloat16*>(student);
+  auto G = static_cast<__nv_bfloat16*>(grad_student);
+  const int nchunk = D / 8;
+  if (nchunk <= KD_THREADS * 3) kd_row_kernel<3, true><<<(unsigned)rows, KD_THREADS, 0, st>>>(T, S, D, 1.0f / temperature, nullptr, row_scale, G);
+  else kd_row_kernel<4, true><<<(unsigned)rows, KD_THREADS, 0, st>>>(T, S, D, 1.0f / temperature, nullptr, row_scale, G);
+  return check_launch("kd_row_kernel<bwd>");
+}
+
+int x2i_proj_mix_ln(const void* x, int mode, const float* w, float conv_bias, const float* gamma, const float* beta,
+                    float eps, void* y, int B, int C, int S, int H, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || C <= 0 || S <= 0 || H <= 0 || H % 8 || H > 8 * PROJ_THREADS * 2 || mode < 0 || mode > 2) return fail(X2I_ERR_SHAPE, "proj_mix_ln: H must be a multiple of 8, <= 4096; mode in 0..2");
+  if (mode != 2 && !w) return fail(X2I_ERR_SHAPE, "proj_mix_ln: weights required for mode %d", mode);
+  if (!aligned16(x) || !aligned16(y)) return fail(X2I_ERR_ALIGN, "proj_mix_ln: alignment");
+  const size_t smem = (((static_cast<size_t>(C) * 25 + 3) & ~size_t(3)) + H + 8 + 2 * (PROJ_THREADS / 32)) * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+  const int nchunk = H / 8;
+  if (nchunk <= PROJ_THREADS) proj_mix_ln_kernel<1><<<B * S, PROJ_THREADS, smem, st>>>(X, mode, w, conv_bias, gamma, beta, eps, Y, B, C, S, H);
+  else proj_mix_ln_kernel<2><<<B * S, PROJ_THREADS, smem, st>>>(X, mode, w, conv_bias, gamma, beta, eps, Y, B, C, S, H);
+  return check_launch("proj_mix_ln_kernel");
+}
+
+int x2i_mean_over_s(const void* y, void* out, int B, int S, int N, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || S <= 0 || N <= 0) return fail(X2I_ERR_SHAPE, "mean_over_s: bad shape");
+  const int n = B * N;
+  mean_over_s_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(y),
+                                                                                    static_cast<__nv_bfloat16*>(out), B, S, N);
+  return check_launch("mean_over_s_kernel");
+}
+
+}  // extern "C"

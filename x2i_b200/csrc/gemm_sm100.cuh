@@ -1,0 +1,340 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   acc[M,N] = A[M,K] (bf16, K contiguous) x W[N,K]^T (bf16, K contiguous -- torch Linear layout)
+//
+// One CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one lane),
+// warps 2..5 = epilogue (TMEM -> registers -> fused math -> global).  A/B tiles are staged by TMA
+// into a multi-stage 128B-swizzled shared-memory ring; the fp32 accumulator lives in TMEM and is
+// double-buffered (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Epilogues (the reference ops they replace are cited in include/x2i_b200.h):
+//   EPI_BIAS            C = acc + bias; optional second output aux = gelu_erf(C)
+//   EPI_BIAS_GELU_TANH  C = gelu_tanh(acc + bias)                        FeedForward net.0 / proj_mlp
+//   EPI_BIAS_GELU_ERF   C = gelu_erf(acc + bias)                         projector MLP3
+//   EPI_GATE_RESIDUAL   C = residual + gate[b,:] * (acc + bias); aux = acc + bias (optional, KD hook tensor)
+//   EPI_QKV             per 128-column head tile: q,k -> +bias, RMSNorm(128)*w, RoPE, head-major store;
+//                       v -> +bias, head-major store; columns >= 3D -> gelu_tanh -> mlp buffer (single block)
+#pragma once
+#include "common.cuh"
+
+namespace x2i {
+
+enum { EPI_BIAS = 0, EPI_BIAS_GELU_TANH = 1, EPI_BIAS_GELU_ERF = 2, EPI_GATE_RESIDUAL = 3, EPI_QKV = 4 };
+
+struct GemmParams {
+  int M, N, K;
+  const __nv_bfloat16* bias;  // [N] or null
+  __nv_bfloat16* C;           // [M, ldc]
+  long long ldc;
+  // EPI_GATE_RESIDUAL
+  const __nv_bfloat16* residual;  // [M, ldr] (may alias C)
+  long long ldr;
+  const __nv_bfloat16* gate;  // gate[(m / rows_per_batch) * gate_stride + n]
+  long long gate_stride;
+  int rows_per_batch;
+  __nv_bfloat16* aux;  // optional un-gated output [M, ldaux]
+  long long ldaux;
+  // EPI_QKV
+  __nv_bfloat16 *q, *k, *v;           // [B, H, L_total, 128]
+  const __nv_bfloat16 *rms_q, *rms_k;  // [128]
+  const float2* rope;                  // [L_total, 64] (cos, sin) per rotated pair, or null
+  int L_total, row_offset, heads;
+  float eps;
+  __nv_bfloat16* mlp;  // [M, ldmlp]
+  long long ldmlp;
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 2 accumulator stages (power of two for BN in {64,128,256})
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float (&out)[32]) {
+  const uint4* p4 = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u = __ldg(p4 + i);
+    out[8 * i + 0] = bf16_lo(u.x); out[8 * i + 1] = bf16_hi(u.x);
+    out[8 * i + 2] = bf16_lo(u.y); out[8 * i + 3] = bf16_hi(u.y);
+    out[8 * i + 4] = bf16_lo(u.z); out[8 * i + 5] = bf16_hi(u.z);
+    out[8 * i + 6] = bf16_lo(u.w); out[8 * i + 7] = bf16_hi(u.w);
+  }
+}
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float (&v)[32]) {
+  uint4* p4 = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+    p4[i] = u;
+  }
+}
+
+template <int BN, int EPI, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int NS = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tfull_bar = empty_bar + NS;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g)  // B stored [K, N]: boxes of 64 (n) x 64 (k rows)
+              tma_load_2d(sb + g * 8192, &tma_b, &full_bar[stage], n_blk * BN + g * 64, kb * GEMM_BK);
+          }
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, 8192, 1024)
+                                        : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + as * BN + lane_off;
+      const int m = m_blk * GEMM_BM + quad * 32 + lane;
+      const bool row_ok = m < p.M;
+      const int n_tile0 = n_blk * BN;
+
+      if constexpr (EPI == EPI_QKV) {
+        const int D = p.heads * 128;
+        const int b = row_ok ? m / p.rows_per_batch : 0;
+        const int tok = row_ok ? m - b * p.rows_per_batch : 0;
+        const int pos = p.row_offset + tok;
+#pragma unroll 1
+        for (int hh = 0; hh < BN / 128; ++hh) {
+          const int n_h = n_tile0 + hh * 128;
+          if (n_h >= p.N) break;
+          const int sec = n_h / D;  // 0 q, 1 k, 2 v, >=3 mlp
+          uint32_t r[32];
+          float x[32], bb[32];
+          if (sec < 2) {
+            float ss = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld32(t_acc + hh * 128 + c * 32, r);
+              load_bf16x32(p.bias + n_h + c * 32, bb);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float t = __uint_as_float(r[j]) + bb[j];
+                ss += t * t;
+              }
+            }
+            const float rinv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+            const int h = (n_h - sec * D) >> 7;
+            __nv_bfloat16* dst = (sec == 0 ? p.q : p.k) +
+                                 ((static_cast<long long>(b) * p.heads + h) * p.L_total + pos) * 128;
+            const __nv_bfloat16* w = sec == 0 ? p.rms_q : p.rms_k;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld32(t_acc + hh * 128 + c * 32, r);
+              load_bf16x32(p.bias + n_h + c * 32, bb);
+              float ww[32];
+              load_bf16x32(w + c * 32, ww);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(r[j]) + bb[j]) * rinv * ww[j];
+              if (p.rope != nullptr && row_ok) {
+                const float4* rp = reinterpret_cast<const float4*>(p.rope + static_cast<long long>(pos) * 64 + c * 16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 cs = __ldg(rp + j);  // (cos0, sin0, cos1, sin1)
+                  const float a0 = x[4 * j + 0], a1 = x[4 * j + 1], a2 = x[4 * j + 2], a3 = x[4 * j + 3];
+                  x[4 * j + 0] = a0 * cs.x - a1 * cs.y;
+                  x[4 * j + 1] = a1 * cs.x + a0 * cs.y;
+                  x[4 * j + 2] = a2 * cs.z - a3 * cs.w;
+                  x[4 * j + 3] = a3 * cs.z + a2 * cs.w;
+                }
+              }
+              if (row_ok) store_bf16x32(dst + c * 32, x);
+            }
+          } else if (sec == 2) {
+            const int h = (n_h - 2 * D) >> 7;
+            __nv_bfloat16* dst = p.v + ((static_cast<long long>(b) * p.heads + h) * p.L_total + pos) * 128;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld32(t_acc + hh * 128 + c * 32, r);
+              load_bf16x32(p.bias + n_h + c * 32, bb);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) + bb[j];
+              if (row_ok) store_bf16x32(dst + c * 32, x);
+            }
+          } else {
+            __nv_bfloat16* dst = p.mlp + static_cast<long long>(m) * p.ldmlp + (n_h - 3 * D);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld32(t_acc + hh * 128 + c * 32, r);
+              load_bf16x32(p.bias + n_h + c * 32, bb);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(__uint_as_float(r[j]) + bb[j]);
+              if (row_ok) store_bf16x32(dst + c * 32, x);
+            }
+          }
+        }
+      } else {
+        const __nv_bfloat16* gate_row = nullptr;
+        if constexpr (EPI == EPI_GATE_RESIDUAL) {
+          const int b = row_ok ? m / p.rows_per_batch : 0;
+          gate_row = p.gate + static_cast<long long>(b) * p.gate_stride;
+        }
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_tile0 + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t r[32];
+          float x[32];
+          tmem_ld32(t_acc + c * 32, r);
+          if (p.bias != nullptr) {
+            load_bf16x32(p.bias + n0, x);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = 0.f;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(r[j]);
+          if constexpr (EPI == EPI_BIAS_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
+          } else if constexpr (EPI == EPI_BIAS_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
+          }
+          if (row_ok) {
+            if constexpr (EPI == EPI_BIAS) {
+              if (p.aux != nullptr) {  // second output: gelu_erf(C) (projector: MLP3.fc consumes GELU(x2), utils/proj.py:31)
+                float g[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) g[j] = gelu_erf_f(x[j]);
+                store_bf16x32(p.aux + static_cast<long long>(m) * p.ldaux + n0, g);
+              }
+            }
+            if constexpr (EPI == EPI_GATE_RESIDUAL) {
+              if (p.aux != nullptr) store_bf16x32(p.aux + static_cast<long long>(m) * p.ldaux + n0, x);
+              float g[32], res[32];
+              load_bf16x32(gate_row + n0, g);
+              load_bf16x32(p.residual + static_cast<long long>(m) * p.ldr + n0, res);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = res[j] + g[j] * x[j];
+            }
+            store_bf16x32(p.C + static_cast<long long>(m) * p.ldc + n0, x);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace x2i

@@ -1,0 +1,603 @@
+"""Drop-in ``FluxTransformer2DModel`` (the X2I MMDiT denoiser) on hand-written sm_100a kernels.
+
+Mirrors the interface the reference consumes:
+  * class / attribute / state-dict names of diffusers' FLUX transformer, as used by
+    ``/root/reference/lightcontrol/lightcontrol_flux.py:208-553`` and loaded by
+    ``train/train_qwenvl.py:417-429`` / ``infer/inference_qwenvl.py:72-75``;
+  * ``forward(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+    joint_attention_kwargs, return_dict)`` -> 1-tuple / object with ``.sample``;
+  * ``blk.attn`` is a real ``nn.Module`` invoked through ``__call__`` so ``register_forward_hook`` works and sees
+    ``(img_out, txt_out)`` for double blocks and the raw attention output for single blocks
+    (``train/train_qwenvl.py:186-214``);
+  * the attention-processor plugin protocol: ``attn_processors`` / ``set_attn_processor`` /
+    ``Attention.set_processor`` with ``proc(attn, hidden_states, encoder_hidden_states, attention_mask,
+    image_rotary_emb)`` (``lightcontrol_flux.py:286-384``).
+
+Every FLOP of the forward runs in libx2i_b200.so (tcgen05 GEMMs with fused epilogues, the fused attention kernel and
+the row-wise kernels); PyTorch only owns the buffers.  Forward only (inference / teacher): the backward kernels for
+distillation training are a later scope row.  There is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import X2IError
+
+BF16 = torch.bfloat16
+
+
+def _no_grad_needed(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise X2IError("x2i_b200.flux: autograd through the MMDiT is not implemented yet (forward-only kernels); "
+                       "call under torch.no_grad() with inputs that do not require grad")
+
+
+# ------------------------------------------------------------------------------------------------ leaves
+class _Holder(nn.Module):
+    """Parameter holders are never called; the owning block launches the fused kernels."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise X2IError(f"{type(self).__name__} is a parameter holder inside a fused x2i_b200 block")
+
+
+class RMSNorm(_Holder):
+    def __init__(self, dim, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class AdaLayerNormZero(_Holder):
+    def __init__(self, dim):
+        super().__init__()
+        self.linear = nn.Linear(dim, 6 * dim)
+
+
+class AdaLayerNormZeroSingle(_Holder):
+    def __init__(self, dim):
+        super().__init__()
+        self.linear = nn.Linear(dim, 3 * dim)
+
+
+class AdaLayerNormContinuous(_Holder):
+    def __init__(self, dim, cond_dim, elementwise_affine=False, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+        self.linear = nn.Linear(cond_dim, 2 * dim)
+
+
+class GELU(_Holder):
+    def __init__(self, dim_in, dim_out, approximate="tanh"):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out)
+        self.approximate = approximate
+
+
+class FeedForward(nn.Module):
+    """Linear -> GELU(tanh) -> Linear; callable stand-alone (un-gated) through the same kernels."""
+
+    def __init__(self, dim, dim_out=None, mult=4, activation_fn="gelu-approximate"):
+        super().__init__()
+        if activation_fn != "gelu-approximate":
+            raise X2IError("FeedForward: only activation_fn='gelu-approximate' (FLUX) is implemented")
+        self.net = nn.ModuleList([GELU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim_out or dim)])
+
+    def forward(self, x):
+        _no_grad_needed(x)
+        h = ops.linear(x, self.net[0].proj.weight, self.net[0].proj.bias, act=1)
+        return ops.linear(h, self.net[2].weight, self.net[2].bias)
+
+
+class TimestepEmbedding(_Holder):
+    def __init__(self, in_channels, time_embed_dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+
+
+class PixArtAlphaTextProjection(_Holder):
+    def __init__(self, in_features, hidden_size):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_features, hidden_size)
+        self.linear_2 = nn.Linear(hidden_size, hidden_size)
+
+
+class CombinedTimestepTextProjEmbeddings(nn.Module):
+    """temb = MLP(sinusoid(t)) [+ MLP(sinusoid(guidance))] + MLP(pooled)   (SURVEY.md A.6)."""
+
+    has_guidance = False
+
+    def __init__(self, embedding_dim, pooled_projection_dim):
+        super().__init__()
+        self.timestep_embedder = TimestepEmbedding(256, embedding_dim)
+        if self.has_guidance:
+            self.guidance_embedder = TimestepEmbedding(256, embedding_dim)
+        self.text_embedder = PixArtAlphaTextProjection(pooled_projection_dim, embedding_dim)
+
+    @staticmethod
+    def _mlp(mod, x, out=None, accumulate=False):
+        h = ops.skinny_linear(x, mod.linear_1.weight, mod.linear_1.bias)
+        return ops.skinny_linear(h, mod.linear_2.weight, mod.linear_2.bias, act_in=1, out=out, accumulate=accumulate)
+
+    def forward(self, timestep, *rest):
+        if self.has_guidance:
+            guidance, pooled = rest
+        else:
+            (pooled,) = rest
+            guidance = None
+        temb = self._mlp(self.timestep_embedder, ops.timestep_sinusoid(timestep.float().contiguous()))
+        if guidance is not None:
+            self._mlp(self.guidance_embedder, ops.timestep_sinusoid(guidance.float().contiguous()), out=temb, accumulate=True)
+        self._mlp(self.text_embedder, pooled.to(BF16).contiguous(), out=temb, accumulate=True)
+        return temb
+
+
+class CombinedTimestepGuidanceTextProjEmbeddings(CombinedTimestepTextProjEmbeddings):
+    has_guidance = True
+
+
+class FluxPosEmbed(nn.Module):
+    def __init__(self, theta=10000, axes_dim=(16, 56, 56)):
+        super().__init__()
+        self.theta = theta
+        self.axes_dim = tuple(axes_dim)
+
+    def forward(self, ids):
+        cos, sin, _ = ops.rope_table(ids.float(), self.axes_dim, float(self.theta))
+        return cos, sin
+
+
+def compact_rope(image_rotary_emb):
+    """(cos[L,128], sin[L,128]) pair-repeated tables -> the [L,64,2] table the QKV epilogue reads."""
+    cos, sin = image_rotary_emb
+    return torch.stack([cos[:, ::2], sin[:, ::2]], dim=-1).float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ attention
+class FusedCtx:
+    """Private side-channel from a block to the default processor: lets the out-projection GEMM apply the AdaLN
+    gate and the residual in its epilogue while the module still returns the un-gated tensors to forward hooks."""
+
+    __slots__ = ("rope", "gate_img", "res_img", "gate_txt", "res_txt", "want_aux", "cat_buf", "ws")
+
+    def __init__(self, **kw):
+        for k in self.__slots__:
+            setattr(self, k, kw.get(k))
+
+
+class FluxAttnProcessor2_0:
+    """Default processor: fused QKV GEMM (bias + per-head RMSNorm + RoPE epilogue, head-major, txt rows first),
+    the fused tcgen05 attention kernel, and the out-projections."""
+
+    def __call__(self, attn: "Attention", hidden_states, encoder_hidden_states=None, attention_mask=None,
+                 image_rotary_emb=None, x2i_fused: Optional[FusedCtx] = None):
+        if attention_mask is not None:
+            raise X2IError("FluxAttnProcessor2_0: attention_mask is not supported (FLUX never passes one)")
+        _no_grad_needed(hidden_states, encoder_hidden_states)
+        B, L_img, D = hidden_states.shape
+        H = attn.heads
+        S = 0 if encoder_hidden_states is None else encoder_hidden_states.shape[1]
+        L = S + L_img
+        dev = hidden_states.device
+        ctx = x2i_fused
+        if ctx is not None:
+            rope = ctx.rope
+        else:
+            rope = compact_rope(image_rotary_emb) if image_rotary_emb is not None else None
+        ws = ctx.ws if ctx is not None else {}
+        q = ws.get("q"); k = ws.get("k"); v = ws.get("v")
+        if q is None or q.shape != (B, H, L, 128):
+            q = torch.empty(B, H, L, 128, device=dev, dtype=BF16)
+            k = torch.empty_like(q); v = torch.empty_like(q)
+        attn._pack()
+        x2 = hidden_states.reshape(B * L_img, D)
+        if encoder_hidden_states is None:
+            # single block: W = [q;k;v;(proj_mlp)], attention output straight into the [.., D+F] concat buffer
+            cat_buf = ctx.cat_buf if ctx is not None else None
+            w, b = (attn._w_qkv_mlp, attn._b_qkv_mlp) if cat_buf is not None else (attn._w_qkv, attn._b_qkv)
+            ops.qkv_rope(x2, w, b, attn.norm_q.weight, attn.norm_k.weight, rope, q, k, v, H, L_img, 0, attn.norm_q.eps,
+                         mlp=None if cat_buf is None else cat_buf[:, D:])
+            if cat_buf is not None:
+                out = cat_buf.view(B, L, -1)[:, :, :D]
+                ops.attention(q, k, v, split=0, out1=out)
+            else:
+                _, out = ops.attention(q, k, v, split=0)
+            return out
+        c2 = encoder_hidden_states.reshape(B * S, D)
+        ops.qkv_rope(x2, attn._w_qkv, attn._b_qkv, attn.norm_q.weight, attn.norm_k.weight, rope, q, k, v, H, L_img, S,
+                     attn.norm_q.eps)
+        ops.qkv_rope(c2, attn._w_add_qkv, attn._b_add_qkv, attn.norm_added_q.weight, attn.norm_added_k.weight, rope, q, k, v,
+                     H, S, 0, attn.norm_added_q.eps)
+        a_txt = ws.get("a_txt"); a_img = ws.get("a_img")
+        if a_txt is None or a_txt.shape != (B, S, D) or a_img.shape != (B, L_img, D):
+            a_txt = torch.empty(B, S, D, device=dev, dtype=BF16)
+            a_img = torch.empty(B, L_img, D, device=dev, dtype=BF16)
+        ops.attention(q, k, v, split=S, out0=a_txt, out1=a_img)
+        wo, wa = attn.to_out[0], attn.to_add_out
+        if ctx is None or ctx.gate_img is None:
+            img = ops.linear(a_img, wo.weight, wo.bias)
+            txt = ops.linear(a_txt, wa.weight, wa.bias)
+            return img, txt
+        aux_img = torch.empty(B, L_img, D, device=dev, dtype=BF16) if ctx.want_aux else None
+        aux_txt = torch.empty(B, S, D, device=dev, dtype=BF16) if ctx.want_aux else None
+        ops.linear_gate_residual(a_img.view(B * L_img, D), wo.weight, wo.bias, ctx.gate_img, ctx.res_img, L_img, aux=aux_img)
+        ops.linear_gate_residual(a_txt.view(B * S, D), wa.weight, wa.bias, ctx.gate_txt, ctx.res_txt, S, aux=aux_txt)
+        return aux_img, aux_txt
+
+
+FusedFluxAttnProcessor2_0 = FluxAttnProcessor2_0
+AttentionProcessor = FluxAttnProcessor2_0
+
+
+class Attention(nn.Module):
+    """Parameter layout of diffusers' ``Attention`` as configured by FLUX."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, added_kv_proj_dim=None, dim_head=128, heads=24, out_dim=None,
+                 context_pre_only=None, bias=True, processor=None, qk_norm="rms_norm", eps=1e-6, pre_only=False):
+        super().__init__()
+        if dim_head != 128:
+            raise X2IError("Attention: the sm_100a attention kernel is specialised for head_dim 128 (FLUX)")
+        inner = out_dim if out_dim is not None else dim_head * heads
+        self.heads = inner // dim_head
+        self.inner_dim = inner
+        self.pre_only = pre_only
+        self.to_q = nn.Linear(query_dim, inner, bias=bias)
+        self.to_k = nn.Linear(query_dim, inner, bias=bias)
+        self.to_v = nn.Linear(query_dim, inner, bias=bias)
+        self.norm_q = RMSNorm(dim_head, eps)
+        self.norm_k = RMSNorm(dim_head, eps)
+        self.has_added = added_kv_proj_dim is not None
+        if self.has_added:
+            self.add_q_proj = nn.Linear(added_kv_proj_dim, inner)
+            self.add_k_proj = nn.Linear(added_kv_proj_dim, inner)
+            self.add_v_proj = nn.Linear(added_kv_proj_dim, inner)
+            self.norm_added_q = RMSNorm(dim_head, eps)
+            self.norm_added_k = RMSNorm(dim_head, eps)
+            self.to_add_out = nn.Linear(inner, query_dim)
+        if not pre_only:
+            self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+        self.processor = processor if processor is not None else FluxAttnProcessor2_0()
+        self._extra_w = None  # (weight, bias) of the owning single block's proj_mlp, fused behind q;k;v
+        self._w_qkv = None
+
+    def set_processor(self, processor):
+        self.processor = processor
+
+    def get_processor(self):
+        return self.processor
+
+    # -- fused weight storage: q;k;v (;proj_mlp) rows concatenated once, the original Parameters re-pointed at
+    #    views of it (no extra memory, state_dict keys unchanged).  Re-done automatically after .to()/.cuda().
+    @staticmethod
+    def _fuse(linears):
+        w = torch.cat([l.weight.data for l in linears], 0)
+        b = torch.cat([l.bias.data for l in linears], 0)
+        o = 0
+        for l in linears:
+            n = l.weight.shape[0]
+            l.weight.data = w[o:o + n]
+            l.bias.data = b[o:o + n]
+            o += n
+        return w, b
+
+    def _pack(self):
+        if self._w_qkv is not None and self._w_qkv.data_ptr() == self.to_q.weight.data_ptr():
+            return
+        if self.to_q.weight.dtype != BF16 or not self.to_q.weight.is_cuda:
+            raise X2IError("x2i_b200 modules run in bf16 on a CUDA device: call .to('cuda', torch.bfloat16) first")
+        lin = [self.to_q, self.to_k, self.to_v]
+        if self._extra_w is not None:
+            w, b = self._fuse(lin + [self._extra_w])
+            D3 = 3 * self.inner_dim
+            self._w_qkv_mlp, self._b_qkv_mlp = w, b
+            self._w_qkv, self._b_qkv = w[:D3], b[:D3]
+        else:
+            self._w_qkv, self._b_qkv = self._fuse(lin)
+        if self.has_added:
+            self._w_add_qkv, self._b_add_qkv = self._fuse([self.add_q_proj, self.add_k_proj, self.add_v_proj])
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kwargs):
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask, **kwargs)
+
+
+def _default_proc(attn: Attention) -> bool:
+    return type(attn.processor) is FluxAttnProcessor2_0
+
+
+# ------------------------------------------------------------------------------------------------ blocks
+class FluxTransformerBlock(nn.Module):
+    """Double-stream block (lightcontrol_flux.py:108-204)."""
+
+    def __init__(self, dim, num_attention_heads, attention_head_dim, qk_norm="rms_norm", eps=1e-6):
+        super().__init__()
+        self.dim = dim
+        self.norm1 = AdaLayerNormZero(dim)
+        self.norm1_context = AdaLayerNormZero(dim)
+        self.attn = Attention(query_dim=dim, added_kv_proj_dim=dim, dim_head=attention_head_dim, heads=num_attention_heads,
+                              out_dim=dim, context_pre_only=False, bias=True, qk_norm=qk_norm, eps=eps)
+        self.norm2 = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+        self.ff = FeedForward(dim=dim, dim_out=dim)
+        self.norm2_context = nn.LayerNorm(dim, elementwise_affine=False, eps=1e-6)
+        self.ff_context = FeedForward(dim=dim, dim_out=dim)
+
+    def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb=None, _mod=None, _rope=None, _ws=None):
+        """hidden_states [B,L_img,D] and encoder_hidden_states [B,S,D] are updated IN PLACE and returned (c, x)."""
+        _no_grad_needed(hidden_states, encoder_hidden_states, temb)
+        x, c = hidden_states, encoder_hidden_states
+        B, L_img, D = x.shape
+        S = c.shape[1]
+        ws = _ws if _ws is not None else {}
+        if _mod is None:  # stand-alone use: compute this block's modulation from temb
+            _mod = torch.cat([ops.skinny_linear(temb, self.norm1.linear.weight, self.norm1.linear.bias, act_in=1),
+                              ops.skinny_linear(temb, self.norm1_context.linear.weight, self.norm1_context.linear.bias, act_in=1)], 1)
+        mi = [_mod[:, i * D:(i + 1) * D] for i in range(6)]           # shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+        mc = [_mod[:, (6 + i) * D:(7 + i) * D] for i in range(6)]
+        if _rope is None and image_rotary_emb is not None:
+            _rope = compact_rope(image_rotary_emb)
+        x2, c2 = x.view(B * L_img, D), c.view(B * S, D)
+        nx = ops.ln_modulate(x2, mi[1], mi[0], L_img, out=ws.get("nx")).view(B, L_img, D)
+        nc = ops.ln_modulate(c2, mc[1], mc[0], S, out=ws.get("nc")).view(B, S, D)
+        if _default_proc(self.attn):
+            ctx = FusedCtx(rope=_rope, gate_img=mi[2], res_img=x2, gate_txt=mc[2], res_txt=c2,
+                           want_aux=len(self.attn._forward_hooks) > 0, ws=ws)
+            self.attn(hidden_states=nx, encoder_hidden_states=nc, x2i_fused=ctx)
+        else:  # plug-in processor: plain protocol, gate + residual applied afterwards
+            a_img, a_txt = self.attn(hidden_states=nx, encoder_hidden_states=nc, image_rotary_emb=image_rotary_emb)
+            ops.gate_residual_(x2, a_img.reshape(B * L_img, D), mi[2], L_img)
+            ops.gate_residual_(c2, a_txt.reshape(B * S, D), mc[2], S)
+        for (t2, m, ff, rows, key) in ((x2, mi, self.ff, L_img, "ffx"), (c2, mc, self.ff_context, S, "ffc")):
+            n2 = ops.ln_modulate(t2, m[4], m[3], rows, out=ws.get("nx" if rows == L_img else "nc"))
+            h = ops.linear(n2, ff.net[0].proj.weight, ff.net[0].proj.bias, act=1, out=ws.get(key))
+            ops.linear_gate_residual(h, ff.net[2].weight, ff.net[2].bias, m[5], t2, rows)
+        return c, x
+
+
+class FluxSingleTransformerBlock(nn.Module):
+    """Single-stream block (lightcontrol_flux.py:45-104)."""
+
+    def __init__(self, dim, num_attention_heads, attention_head_dim, mlp_ratio=4.0):
+        super().__init__()
+        self.dim = dim
+        self.mlp_hidden_dim = int(dim * mlp_ratio)
+        self.norm = AdaLayerNormZeroSingle(dim)
+        self.proj_mlp = nn.Linear(dim, self.mlp_hidden_dim)
+        self.act_mlp = nn.GELU(approximate="tanh")
+        self.proj_out = nn.Linear(dim + self.mlp_hidden_dim, dim)
+        self.attn = Attention(query_dim=dim, dim_head=attention_head_dim, heads=num_attention_heads, out_dim=dim, bias=True,
+                              qk_norm="rms_norm", eps=1e-6, pre_only=True)
+        object.__setattr__(self.attn, "_extra_w", self.proj_mlp)  # fused behind q;k;v (not a registered child)
+
+    def forward(self, hidden_states, temb, image_rotary_emb=None, _mod=None, _rope=None, _ws=None):
+        """hidden_states [B,L,D] is updated IN PLACE and returned."""
+        _no_grad_needed(hidden_states, temb)
+        h = hidden_states
+        B, L, D = h.shape
+        F = self.mlp_hidden_dim
+        ws = _ws if _ws is not None else {}
+        if _mod is None:
+            _mod = ops.skinny_linear(temb, self.norm.linear.weight, self.norm.linear.bias, act_in=1)
+        shift, scale, gate = (_mod[:, i * D:(i + 1) * D] for i in range(3))
+        if _rope is None and image_rotary_emb is not None:
+            _rope = compact_rope(image_rotary_emb)
+        h2 = h.view(B * L, D)
+        n = ops.ln_modulate(h2, scale, shift, L, out=ws.get("n")).view(B, L, D)
+        cat_buf = ws.get("cat")
+        if cat_buf is None or cat_buf.shape != (B * L, D + F):
+            cat_buf = torch.empty(B * L, D + F, device=h.device, dtype=BF16)
+        if _default_proc(self.attn):
+            self.attn(hidden_states=n, x2i_fused=FusedCtx(rope=_rope, cat_buf=cat_buf, ws=ws))
+        else:
+            a = self.attn(hidden_states=n, image_rotary_emb=image_rotary_emb)
+            cat_buf.view(B, L, D + F)[:, :, :D].copy_(a)
+            ops.linear(n.view(B * L, D), self.proj_mlp.weight, self.proj_mlp.bias, act=1, out=cat_buf[:, D:])
+        ops.linear_gate_residual(cat_buf, self.proj_out.weight, self.proj_out.bias, gate, h2, L)
+        return h
+
+
+# ------------------------------------------------------------------------------------------------ transformer
+class FluxTransformer2DModel(nn.Module):
+    """The FLUX MMDiT denoiser (lightcontrol_flux.py:208-553; diffusers 0.31.0 transformer_flux.py [D031])."""
+
+    _supports_gradient_checkpointing = True
+
+    def __init__(self, patch_size=1, in_channels=64, num_layers=19, num_single_layers=38, attention_head_dim=128,
+                 num_attention_heads=24, joint_attention_dim=4096, pooled_projection_dim=768, guidance_embeds=False,
+                 axes_dims_rope=(16, 56, 56)):
+        super().__init__()
+        self.config = SimpleNamespace(patch_size=patch_size, in_channels=in_channels, num_layers=num_layers,
+                                      num_single_layers=num_single_layers, attention_head_dim=attention_head_dim,
+                                      num_attention_heads=num_attention_heads, joint_attention_dim=joint_attention_dim,
+                                      pooled_projection_dim=pooled_projection_dim, guidance_embeds=guidance_embeds,
+                                      axes_dims_rope=tuple(axes_dims_rope))
+        self.out_channels = in_channels
+        self.inner_dim = num_attention_heads * attention_head_dim
+        D = self.inner_dim
+        self.pos_embed = FluxPosEmbed(theta=10000, axes_dim=axes_dims_rope)
+        cls = CombinedTimestepGuidanceTextProjEmbeddings if guidance_embeds else CombinedTimestepTextProjEmbeddings
+        self.time_text_embed = cls(embedding_dim=D, pooled_projection_dim=pooled_projection_dim)
+        self.context_embedder = nn.Linear(joint_attention_dim, D)
+        self.x_embedder = nn.Linear(in_channels, D)
+        self.transformer_blocks = nn.ModuleList(
+            [FluxTransformerBlock(D, num_attention_heads, attention_head_dim) for _ in range(num_layers)])
+        self.single_transformer_blocks = nn.ModuleList(
+            [FluxSingleTransformerBlock(D, num_attention_heads, attention_head_dim) for _ in range(num_single_layers)])
+        self.norm_out = AdaLayerNormContinuous(D, D, elementwise_affine=False, eps=1e-6)
+        self.proj_out = nn.Linear(D, patch_size * patch_size * self.out_channels, bias=True)
+        self.gradient_checkpointing = False
+        self._w_mod = None
+        self._ws: Dict = {}
+        self._rope_cache = None
+
+    # -- reference API surface ------------------------------------------------------------------------------
+    @property
+    def dtype(self):
+        return self.x_embedder.weight.dtype
+
+    @property
+    def device(self):
+        return self.x_embedder.weight.device
+
+    @classmethod
+    def from_config(cls, config):
+        cfg = dict(config) if isinstance(config, dict) else vars(config)
+        return cls(**{k: v for k, v in cfg.items() if not k.startswith("_")})
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, torch_dtype=None, **kw):
+        """Load a diffusers FLUX transformer directory (config.json + *.safetensors / *.bin)."""
+        import glob
+        import json
+        import os
+        root = os.path.join(path, subfolder) if subfolder else path
+        with open(os.path.join(root, "config.json")) as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        model = cls(**cfg)
+        sd = {}
+        files = sorted(glob.glob(os.path.join(root, "*.safetensors")))
+        if files:
+            from safetensors.torch import load_file
+            for fn in files:
+                sd.update(load_file(fn))
+        else:
+            for fn in sorted(glob.glob(os.path.join(root, "*.bin"))):
+                sd.update(torch.load(fn, map_location="cpu"))
+        model.load_state_dict(sd)
+        return model.to(torch_dtype) if torch_dtype is not None else model
+
+    @property
+    def attn_processors(self):
+        procs = {}
+        for name, m in self.named_modules():
+            if isinstance(m, Attention):
+                procs[f"{name}.processor"] = m.get_processor()
+        return procs
+
+    def set_attn_processor(self, processor):
+        mods = [(n, m) for n, m in self.named_modules() if isinstance(m, Attention)]
+        if isinstance(processor, dict):
+            if len(processor) != len(mods):
+                raise ValueError(f"A dict of processors was passed, but the number of processors {len(processor)} does not "
+                                 f"match the number of attention layers: {len(mods)}.")
+            for n, m in mods:
+                m.set_processor(processor[f"{n}.processor"])
+        else:
+            for _, m in mods:
+                m.set_processor(processor)
+
+    def fuse_qkv_projections(self):  # the QKV projections are always fused in this implementation
+        return None
+
+    def unfuse_qkv_projections(self):
+        return None
+
+    def enable_gradient_checkpointing(self):
+        self.gradient_checkpointing = True
+
+    # -- packing of every AdaLN modulation linear into one [N_total, D] matrix (one GEMV launch per step) ----
+    def _mod_linears(self):
+        lins = []
+        for b in self.transformer_blocks:
+            lins += [b.norm1.linear, b.norm1_context.linear]
+        lins += [b.norm.linear for b in self.single_transformer_blocks]
+        lins.append(self.norm_out.linear)
+        return lins
+
+    def _pack(self):
+        first = self._mod_linears()[0]
+        if self._w_mod is not None and self._w_mod.data_ptr() == first.weight.data_ptr():
+            return
+        if self.dtype != BF16 or not first.weight.is_cuda:
+            raise X2IError("FluxTransformer2DModel runs in bf16 on a CUDA device: call .to('cuda', torch.bfloat16) first "
+                           "(x2i_b200 has no CPU or fp32 path)")
+        self._w_mod, self._b_mod = Attention._fuse(self._mod_linears())
+        for m in self.modules():
+            if isinstance(m, Attention):
+                m._pack()
+        self._ws = {}
+
+    def _workspace(self, B, S, L_img):
+        key = (B, S, L_img, str(self.device))
+        if self._ws.get("key") != key:
+            D, H, dev = self.inner_dim, self.config.num_attention_heads, self.device
+            F = self.single_transformer_blocks[0].mlp_hidden_dim if len(self.single_transformer_blocks) else 4 * D
+            L = S + L_img
+            e = lambda *s: torch.empty(*s, device=dev, dtype=BF16)  # noqa: E731
+            self._ws = dict(key=key, q=e(B, H, L, 128), k=e(B, H, L, 128), v=e(B, H, L, 128), a_txt=e(B, S, D),
+                            a_img=e(B, L_img, D), nx=e(B * L_img, D), nc=e(B * S, D), ffx=e(B * L_img, 4 * D),
+                            ffc=e(B * S, 4 * D), n=e(B * L, D), cat=e(B * L, D + F), x=e(B, L_img, D), c=e(B, S, D),
+                            h=e(B, L, D))
+        return self._ws
+
+    def _rope(self, txt_ids, img_ids):
+        key = (txt_ids.shape[0], img_ids.shape[0], txt_ids.data_ptr(), img_ids.data_ptr(), img_ids._version)
+        if self._rope_cache is None or self._rope_cache[0] != key:
+            ids = torch.cat((txt_ids.float(), img_ids.float()), dim=0).to(self.device)
+            cos, sin, rope = ops.rope_table(ids, self.config.axes_dims_rope, 10000.0)
+            self._rope_cache = (key, (cos, sin), rope)
+        return self._rope_cache[1], self._rope_cache[2]
+
+    # -- forward --------------------------------------------------------------------------------------------
+    def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
+                txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=True):
+        _no_grad_needed(hidden_states, encoder_hidden_states, pooled_projections)
+        self._pack()
+        B, L_img, _ = hidden_states.shape
+        S = encoder_hidden_states.shape[1]
+        D = self.inner_dim
+        ws = self._workspace(B, S, L_img)
+        if txt_ids.ndim == 3:
+            txt_ids = txt_ids[0]
+        if img_ids.ndim == 3:
+            img_ids = img_ids[0]
+        rope_full, rope = self._rope(txt_ids, img_ids)
+
+        x = ops.linear(hidden_states.to(BF16).contiguous(), self.x_embedder.weight, self.x_embedder.bias, out=ws["x"])
+        # timestep / guidance arrive as t/1000; the reference scales them IN bf16 (lightcontrol_flux.py:447-449)
+        t1000 = timestep.to(BF16) * 1000
+        if guidance is not None and self.config.guidance_embeds:
+            temb = self.time_text_embed(t1000, guidance.to(BF16) * 1000, pooled_projections)
+        else:
+            temb = self.time_text_embed(t1000, pooled_projections)
+        c = ops.linear(encoder_hidden_states.to(BF16).contiguous(), self.context_embedder.weight, self.context_embedder.bias,
+                       out=ws["c"])
+        mod = ops.skinny_linear(temb, self._w_mod, self._b_mod, act_in=1)  # every AdaLN modulation of this step
+
+        off = 0
+        for blk in self.transformer_blocks:
+            c, x = blk(hidden_states=x, encoder_hidden_states=c, temb=temb, image_rotary_emb=rope_full,
+                       _mod=mod[:, off:off + 12 * D], _rope=rope, _ws=ws)
+            off += 12 * D
+        h = ws["h"]
+        h[:, :S].copy_(c)
+        h[:, S:].copy_(x)
+        for blk in self.single_transformer_blocks:
+            h = blk(hidden_states=h, temb=temb, image_rotary_emb=rope_full, _mod=mod[:, off:off + 3 * D], _rope=rope, _ws=ws)
+            off += 3 * D
+        # norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out over all rows; text rows dropped after
+        n = ops.ln_modulate(h.view(B * (S + L_img), D), mod[:, off:off + D], mod[:, off + D:off + 2 * D], S + L_img,
+                            out=ws["n"])
+        out = ops.linear(n, self.proj_out.weight, self.proj_out.bias).view(B, S + L_img, -1)[:, S:].contiguous()
+        if not return_dict:
+            return (out,)
+        return SimpleNamespace(sample=out)
+
+
+def init_synthetic_(model: nn.Module, seed: int = 0, std: float = 0.02) -> nn.Module:
+    """Synthetic weights for benchmarks (no checkpoints are reachable): W ~ N(0, std^2), small biases, RMSNorm ~ 1.
+    Generated on the parameter's own device."""
+    with torch.no_grad():
+        for i, (name, p) in enumerate(model.named_parameters()):
+            g = torch.Generator(device=p.device).manual_seed(seed * 100003 + i)
+            if p.ndim >= 2:
+                p.copy_((torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32) * std).to(p.dtype))
+            elif "norm" in name and name.endswith("weight"):
+                p.copy_((1.0 + 0.1 * torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32)).to(p.dtype))
+            else:
+                p.copy_((torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32) * std).to(p.dtype))
+    return model

@@ -1,0 +1,226 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch is plumbing here (device memory + streams): every op below
+enqueues hand-written sm_100a kernels from libx2i_b200.so on torch's current stream.  No fallbacks."""
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name, dtype=BF16):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.X2IError(f"{name} must be a CUDA tensor (x2i_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.X2IError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() > 0 and t.stride(-1) != 1:
+        raise _lib.X2IError(f"{name} must be contiguous in its last dimension")
+
+
+def _rows(t):
+    """View [.., K] tensor as (rows, ld); requires a uniform row stride."""
+    if t.dim() == 2:
+        return t.shape[0], t.stride(0)
+    if not t.is_contiguous():
+        raise _lib.X2IError("expected a contiguous tensor or a 2-D row-strided view")
+    return t.numel() // t.shape[-1], t.shape[-1]
+
+
+def linear(x, weight, bias=None, act=0, out=None):
+    """act(x @ weight.T + bias); act: 0 none, 1 gelu-tanh, 2 gelu-erf.  x: [..., K] -> [..., N]."""
+    _chk(x, "x"); _chk(weight, "weight"); _chk(bias, "bias")
+    M, lda = _rows(x)
+    N, K = weight.shape
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=BF16)
+    _, ldc = _rows(out)
+    _lib.call("x2i_gemm_bias_act", _p(x), lda, _p(weight), weight.stride(0), _p(bias), _p(out), ldc, M, N, K, act, _stream())
+    return out
+
+
+def linear_dual_gelu(x, weight, bias=None):
+    """(y, gelu_erf(y)) with y = x @ weight.T + bias, one GEMM pass."""
+    _chk(x, "x"); _chk(weight, "weight"); _chk(bias, "bias")
+    M, lda = _rows(x)
+    N, K = weight.shape
+    y = torch.empty(*x.shape[:-1], N, device=x.device, dtype=BF16)
+    g = torch.empty_like(y)
+    _lib.call("x2i_gemm_bias_dual", _p(x), lda, _p(weight), weight.stride(0), _p(bias), _p(y), N, _p(g), N, M, N, K, _stream())
+    return y, g
+
+
+def linear_gate_residual(x, weight, bias, gate, residual, rows_per_batch, out=None, aux=None):
+    """residual + gate[b] * (x @ weight.T + bias); gate: [B, N] view (row-strided ok); aux receives the un-gated value."""
+    _chk(x, "x"); _chk(weight, "weight"); _chk(bias, "bias"); _chk(gate, "gate"); _chk(residual, "residual"); _chk(aux, "aux")
+    M, lda = _rows(x)
+    N, K = weight.shape
+    if out is None:
+        out = residual
+    _, ldr = _rows(residual)
+    _, ldc = _rows(out)
+    ldaux = _rows(aux)[1] if aux is not None else 0
+    _lib.call("x2i_gemm_gate_residual", _p(x), lda, _p(weight), weight.stride(0), _p(bias), _p(gate), gate.stride(0),
+              rows_per_batch, _p(residual), ldr, _p(out), ldc, _p(aux), ldaux, M, N, K, _stream())
+    return out
+
+
+def qkv_rope(x, weight, bias, rms_q, rms_k, rope, q, k, v, heads, rows_per_batch, row_offset, eps=1e-6, mlp=None):
+    """Fused QKV(+MLP) projection with RMSNorm + RoPE epilogue writing head-major q/k/v[B, heads, L, 128]."""
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (rms_q, "rms_q"), (rms_k, "rms_k"), (q, "q"), (k, "k"), (v, "v"), (mlp, "mlp")):
+        _chk(t, n)
+    if rope is not None and (rope.dtype != torch.float32 or not rope.is_contiguous()):
+        raise _lib.X2IError("rope must be the contiguous fp32 [L, 64, 2] table from rope_table()")
+    M, lda = _rows(x)
+    N, K = weight.shape
+    L_total = q.shape[2]
+    ldmlp = _rows(mlp)[1] if mlp is not None else 0
+    _lib.call("x2i_gemm_qkv_rope", _p(x), lda, _p(weight), weight.stride(0), _p(bias), _p(rms_q), _p(rms_k), _p(rope), _p(q),
+              _p(k), _p(v), _p(mlp), ldmlp, M, N, K, heads, rows_per_batch, row_offset, L_total, eps, _stream())
+
+
+def matmul_kn(a, b_kn, bias=None):
+    """a[M,K] @ b_kn[K,N] with b N-contiguous (exercises the MN-major tcgen05 operand path used for V)."""
+    _chk(a, "a"); _chk(b_kn, "b"); _chk(bias, "bias")
+    M, K = a.shape
+    N = b_kn.shape[1]
+    out = torch.empty(M, N, device=a.device, dtype=BF16)
+    _lib.call("x2i_gemm_kn", _p(a), a.stride(0), _p(b_kn), b_kn.stride(0), _p(bias), _p(out), N, M, N, K, _stream())
+    return out
+
+
+def attention(q, k, v, split=0, out0=None, out1=None):
+    """softmax(q k^T / sqrt(128)) v for q,k,v [B, H, L, 128] -> token-major outputs.
+    Rows t < split -> out0[B, split, H*128]; rows t >= split -> out1[B, L-split, >= H*128] (row-strided view ok)."""
+    _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
+    B, H, L, d = q.shape
+    if d != 128 or not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        raise _lib.X2IError("attention: q,k,v must be contiguous [B,H,L,128]")
+    if split > 0 and out0 is None:
+        out0 = torch.empty(B, split, H * 128, device=q.device, dtype=BF16)
+    if split < L and out1 is None:
+        out1 = torch.empty(B, L - split, H * 128, device=q.device, dtype=BF16)
+    _chk(out0, "out0"); _chk(out1, "out1")
+    ld0 = out0.stride(-2) if out0 is not None else 0
+    ld1 = out1.stride(-2) if out1 is not None else 0
+    _lib.call("x2i_mmdit_attention", _p(q), _p(k), _p(v), _p(out0), ld0, split, _p(out1), ld1, B, H, L, _stream())
+    return out0, out1
+
+
+def ln_modulate(x, scale, shift, rows_per_batch, eps=1e-6, out=None):
+    """LayerNorm(x) * (1 + scale[b]) + shift[b]; scale/shift: [B, D] views sharing one row stride."""
+    _chk(x, "x"); _chk(scale, "scale"); _chk(shift, "shift")
+    rows, ldx = _rows(x)
+    D = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _, ldy = _rows(out)
+    if scale.stride(0) != shift.stride(0):
+        raise _lib.X2IError("ln_modulate: scale and shift must share a row stride")
+    _lib.call("x2i_ln_modulate", _p(x), ldx, _p(scale), _p(shift), scale.stride(0), _p(out), ldy, rows, D, rows_per_batch, eps, _stream())
+    return out
+
+
+def gate_residual_(x, y, gate, rows_per_batch):
+    """x += gate[b] * y, in place; x, y: 2-D row-strided [rows, D]."""
+    _chk(x, "x"); _chk(y, "y"); _chk(gate, "gate")
+    rows, ldx = _rows(x)
+    _, ldy = _rows(y)
+    _lib.call("x2i_gate_residual", _p(x), ldx, _p(y), ldy, _p(gate), gate.stride(0), rows, x.shape[-1], rows_per_batch, _stream())
+    return x
+
+
+def skinny_linear(x, weight, bias=None, act_in=0, out=None, accumulate=False):
+    """out[b] (+)= act_in(x[b]) @ weight.T + bias for a handful of rows (B <= 64); weights streamed once."""
+    _chk(x, "x"); _chk(weight, "weight"); _chk(bias, "bias")
+    B, K = x.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty(B, N, device=x.device, dtype=BF16)
+    _lib.call("x2i_skinny_linear", _p(x), x.stride(0), _p(weight), weight.stride(0), _p(bias), _p(out), out.stride(0), B, N, K,
+              act_in, 1 if accumulate else 0, _stream())
+    return out
+
+
+def timestep_sinusoid(t, dim=256):
+    _chk(t, "t", torch.float32)
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=BF16)
+    _lib.call("x2i_timestep_sinusoid", _p(t), _p(out), t.shape[0], dim, _stream())
+    return out
+
+
+def rope_table(ids, axes_dim=(16, 56, 56), theta=10000.0, full=True):
+    """ids fp32 [L,3] -> (cos[L,128], sin[L,128], rope[L,64,2]) fp32."""
+    _chk(ids, "ids", torch.float32)
+    ids = ids.contiguous()
+    L = ids.shape[0]
+    D = sum(axes_dim)
+    cos = torch.empty(L, D, device=ids.device, dtype=torch.float32) if full else None
+    sin = torch.empty(L, D, device=ids.device, dtype=torch.float32) if full else None
+    rope = torch.empty(L, D // 2, 2, device=ids.device, dtype=torch.float32)
+    _lib.call("x2i_rope_table", _p(ids), L, axes_dim[0], axes_dim[1], axes_dim[2], float(theta), _p(cos), _p(sin), _p(rope), _stream())
+    return cos, sin, rope
+
+
+def euler_step_(x, v, dsigma):
+    _chk(x, "x"); _chk(v, "v")
+    if not (x.is_contiguous() and v.is_contiguous()):
+        raise _lib.X2IError("euler_step_: contiguous tensors required")
+    _lib.call("x2i_euler_step", _p(x), _p(v), float(dsigma), x.numel(), _stream())
+    return x
+
+
+def proj_mix_ln(x, mode, w, conv_bias, gamma, beta, eps):
+    """Projector front end: x bf16 [B,C,S,H] -> LayerNorm(mix(x)) bf16 [B,S,H]."""
+    _chk(x, "x"); _chk(w, "w", torch.float32); _chk(gamma, "gamma", torch.float32); _chk(beta, "beta", torch.float32)
+    x = x.contiguous()
+    B, C, S, H = x.shape
+    y = torch.empty(B, S, H, device=x.device, dtype=BF16)
+    _lib.call("x2i_proj_mix_ln", _p(x), mode, _p(w), float(conv_bias), _p(gamma), _p(beta), float(eps), _p(y), B, C, S, H, _stream())
+    return y
+
+
+def mean_over_s(y):
+    _chk(y, "y")
+    B, S, N = y.shape
+    out = torch.empty(B, N, device=y.device, dtype=BF16)
+    _lib.call("x2i_mean_over_s", _p(y.contiguous()), _p(out), B, S, N, _stream())
+    return out
+
+
+def kd_loss_fwd(teacher, student, seg_row_start, seg_layer, n_layers, batch, temperature=3.0):
+    """teacher/student: bf16 [rows, D]; seg_row_start int64 [n_seg+1], seg_layer int32 [n_seg] (device tensors).
+    Returns (loss fp32 scalar tensor, layer_term[n_layers], valid[n_layers] int32)."""
+    _chk(teacher, "teacher"); _chk(student, "student")
+    _chk(seg_row_start, "seg_row_start", torch.int64); _chk(seg_layer, "seg_layer", torch.int32)
+    rows, D = teacher.shape
+    if not (teacher.is_contiguous() and student.is_contiguous()) or student.shape != teacher.shape:
+        raise _lib.X2IError("kd_loss: teacher/student must be contiguous [rows, D] of equal shape")
+    n_seg = seg_layer.numel()
+    dev = teacher.device
+    row_kl = torch.empty(rows, device=dev, dtype=torch.float32)
+    seg_sum = torch.empty(n_seg, device=dev, dtype=torch.float64)
+    layer_term = torch.empty(n_layers, device=dev, dtype=torch.float32)
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    valid = torch.empty(n_layers, device=dev, dtype=torch.int32)
+    _lib.call("x2i_kd_loss_fwd", _p(teacher), _p(student), rows, D, float(temperature), _p(seg_row_start), _p(seg_layer),
+              n_seg, n_layers, batch, _p(row_kl), _p(seg_sum), _p(layer_term), _p(loss), _p(valid), _stream())
+    return loss, layer_term, valid
+
+
+def kd_loss_bwd(teacher, student, seg_row_start, seg_layer, max_seg_rows, batch, valid, dloss, temperature=3.0):
+    rows, D = teacher.shape
+    row_scale = torch.empty(rows, device=teacher.device, dtype=torch.float32)
+    grad = torch.empty_like(student)
+    _chk(dloss, "dloss", torch.float32); _chk(valid, "valid", torch.int32)
+    _lib.call("x2i_kd_loss_bwd", _p(teacher), _p(student), rows, D, float(temperature), _p(seg_row_start), _p(seg_layer),
+              seg_layer.numel(), int(max_seg_rows), batch, _p(valid), _p(dloss), _p(row_scale), _p(grad), _stream())
+    return grad
