@@ -1,0 +1,309 @@
+"""Benchmark of the X2I hot path on B200:  python bench.py --gpus N --steps K --warmup W  [--impl reference]
+
+Metric (BASELINE.json): denoise-steps/sec at 1024x1024 (4096 latent + 512 text tokens), bf16, FLUX-schnell
+architecture with random-init weights and synthetic embeddings; one "step" = one MMDiT denoise step (transformer
+forward + Euler update) over the per-GPU batch.  Prints ONE JSON line (rank 0).  Keys follow the driver contract:
+value (device-timed, inputs resident in HBM), e2e (through the FluxPipeline drop-in with HOST buffers: pinned H2D of the
+prompt embeddings and D2H of the latents inside the timed region), roofline (fused MMDiT attention kernel, timed live
+with CUDA events), cpu_baseline (oracle on the host cores, bounded sample), clocks, gpu_launches.
+
+--impl reference times the reference's own CPU path for the same config: the PyTorch oracle restatement of the
+diffusers FLUX transformer the reference calls (diffusers itself is not installable here), with all host
+threads, on a bounded sample of the step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLUX_SCHNELL = dict(patch_size=1, in_channels=64, num_layers=19, num_single_layers=38, attention_head_dim=128,
+                    num_attention_heads=24, joint_attention_dim=4096, pooled_projection_dim=768, guidance_embeds=False,
+                    axes_dims_rope=(16, 56, 56))
+HEIGHT = WIDTH = 1024
+S_TXT = 512
+PIPE_STEPS = 4  # FLUX-schnell sampling steps (README.md:93 of the reference)
+D, HEADS, FF = 3072, 24, 12288
+
+
+def step_flops(L_img=4096, S=S_TXT):
+    L = L_img + S
+    blocks = 57 * (2 * L * D * 3 * D + 2 * L * D * D + 4 * L * D * FF) + 57 * 4 * L * L * D
+    emb = 2 * L_img * 64 * D * 2 + 2 * S * 4096 * D
+    return blocks + emb
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(bf16=j["bf16_tflops"], bf16_sustained=j.get("bf16_tflops_sustained"), hbm=j["hbm_gbs"], source="measured")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(threads, n_double=1, n_single=2, repeat=1):
+    """Bounded sample of the 1024^2 step on the host: n_double double + n_single single oracle blocks at
+    L = 512 + 4096, bf16, extrapolated to the 19 + 38 blocks of a step.  Returns (seconds per full step, description)."""
+    import torch
+    from oracle import flux_oracle as fo
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    dbl = [fo.FluxTransformerBlock(D, HEADS, 128).to(torch.bfloat16).eval() for _ in range(n_double)]
+    sgl = [fo.FluxSingleTransformerBlock(D, HEADS, 128).to(torch.bfloat16).eval() for _ in range(n_single)]
+    x = torch.randn(1, 4096, D, generator=g).bfloat16()
+    c = torch.randn(1, S_TXT, D, generator=g).bfloat16()
+    temb = torch.randn(1, D, generator=g).bfloat16()
+    ids = torch.cat([torch.zeros(S_TXT, 3), fo.prepare_latent_image_ids(128, 128)])
+    rope = fo.rope_table(ids)
+    best_d = best_s = 1e30
+    with torch.no_grad():
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            for b in dbl:
+                c, x = b(x, c, temb, rope)
+            t1 = time.perf_counter()
+            h = torch.cat([c, x], 1)
+            for b in sgl:
+                h = b(h, temb, rope)
+            t2 = time.perf_counter()
+            best_d = min(best_d, (t1 - t0) / n_double)
+            best_s = min(best_s, (t2 - t1) / n_single)
+    per_step = 19 * best_d + 38 * best_s
+    desc = (f"oracle (PyTorch restatement of the diffusers FLUX blocks the reference calls) on CPU, bf16, B=1, L=512+4096: "
+            f"{n_double} double + {n_single} single block(s) timed, extrapolated x19/x38 to one denoise step")
+    return per_step, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    times = []
+    desc = ""
+    for i in range(args.warmup + args.steps):
+        if i < args.warmup and i > 0:
+            continue  # one warm-up pass is enough for a CPU arm measured in seconds
+        t, desc = cpu_sample(threads, 1, 2)
+        if i >= args.warmup:
+            times.append(t)
+        if sum(times) > 150:  # keep the whole run within a few minutes of host time
+            break
+    t_step = sum(times) / len(times)
+    v = 1.0 / t_step
+    print(json.dumps({
+        "impl": "reference", "metric": "denoise-steps/sec 1024px bf16", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "FLUX-schnell MMDiT denoise step 1024x1024 (4096 latent + 512 text tokens), batch 1, CPU"},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1, help="images per GPU")
+    ap.add_argument("--impl", default="x2i_b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    from x2i_b200 import _lib, dist as xdist, ops
+    from x2i_b200.flux import FluxTransformer2DModel
+    from x2i_b200.pipeline import FlowMatchEulerDiscreteScheduler, FluxPipeline
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the x2i_b200 arm has no CPU fallback; use --impl reference for the CPU arm)")
+    rank, local_rank, world = xdist.init()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    pk = peaks()
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU is loaded
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t_cpu, desc = cpu_sample(threads, 1, 2)
+        cpu_base = {"value": 1.0 / t_cpu, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc}
+
+    model = FluxTransformer2DModel.synthetic(FLUX_SCHNELL, device=dev, seed=0)
+    pipe = FluxPipeline(scheduler=FlowMatchEulerDiscreteScheduler(shift=1.0), transformer=model)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    L_img = (HEIGHT // 16) * (WIDTH // 16)
+    prompt = torch.randn(B, S_TXT, 4096, device=dev, generator=g).bfloat16()
+    pooled = torch.randn(B, 768, device=dev, generator=g).bfloat16()
+    latents = torch.randn(B, L_img, 64, device=dev, generator=g).bfloat16()
+    img_ids = FluxPipeline._prepare_latent_image_ids(B, 128, 128, dev, torch.bfloat16)
+    txt_ids = torch.zeros(S_TXT, 3, device=dev, dtype=torch.bfloat16)
+    sched = pipe.scheduler
+    sched.set_timesteps(PIPE_STEPS, device=dev)
+    ts = (sched.timesteps / 1000).to(torch.bfloat16)
+
+    def one_step(i):
+        t = ts[i % PIPE_STEPS].expand(B)
+        v = model(hidden_states=latents, timestep=t, pooled_projections=pooled, encoder_hidden_states=prompt, txt_ids=txt_ids,
+                  img_ids=img_ids, return_dict=False)[0]
+        ops.euler_step_(latents, v, -1.0 / PIPE_STEPS)
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            one_step(i)
+        torch.cuda.synchronize()
+        xdist.barrier()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        launches0 = _lib.launch_count()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            one_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        xdist.barrier()
+        launches = _lib.launch_count() - launches0
+        t_local = e0.elapsed_time(e1) * 1e-3
+        t = xdist.max_over_ranks(t_local, dev)
+        clk = clocks.stop() if rank == 0 else None
+
+        # ---- e2e: the public API (FluxPipeline.__call__) with HOST buffers, per call: H2D embeds, 4 steps, D2H latents
+        h_prompt = prompt.cpu().pin_memory(); h_pooled = pooled.cpu().pin_memory()
+        h_lat = torch.empty(B, L_img, 64, dtype=torch.bfloat16).pin_memory()
+        n_calls = max(1, args.steps // PIPE_STEPS)
+
+        def e2e_call(seed):
+            pe = h_prompt.to(dev, non_blocking=True); po = h_pooled.to(dev, non_blocking=True)
+            gen = torch.Generator(device=dev).manual_seed(seed)
+            out = pipe(prompt_embeds=pe, pooled_prompt_embeds=po, num_inference_steps=PIPE_STEPS, guidance_scale=3.5,
+                       height=HEIGHT, width=WIDTH, output_type="latent", generator=gen).images
+            h_lat.copy_(out, non_blocking=True)
+
+        e2e_call(0)
+        torch.cuda.synchronize()
+        xdist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for c in range(n_calls):
+            e2e_call(c + 1)
+        s1.record()
+        torch.cuda.synchronize()
+        xdist.barrier()
+        t_e2e = xdist.max_over_ranks(s0.elapsed_time(s1) * 1e-3, dev)
+        h2d = (h_prompt.numel() + h_pooled.numel()) * 2 / PIPE_STEPS
+        d2h = h_lat.numel() * 2 / PIPE_STEPS
+
+        # ---- roofline of the named kernel (fused MMDiT attention), timed alone with CUDA events on the launch stream.
+        # q,k,v of one call are 85 MB x B: rotate 4 sets (> 126 MB L2) so every launch streams its operands from HBM.
+        roof = None
+        if rank == 0:
+            L = S_TXT + L_img
+            sets = [[torch.randn(B, HEADS, L, 128, device=dev, generator=g).bfloat16() for _ in range(3)] for _ in range(4)]
+            o1 = torch.empty(B, L, D, device=dev, dtype=torch.bfloat16)
+            for s in sets:
+                ops.attention(*s, out1=o1)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_att = 40
+            a0.record()
+            for i in range(n_att):
+                ops.attention(*sets[i % 4], out1=o1)
+            a1.record()
+            torch.cuda.synchronize()
+            t_att = a0.elapsed_time(a1) * 1e-3 / n_att
+            fl = 4.0 * L * L * 128 * HEADS * B
+            ach = fl / t_att / 1e12
+            roof = {"kernel": "mmdit_attention_fwd_kernel", "bound": "tensor", "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16"], "frac_of_sustained": ach / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
+                    "peak_source": pk["source"] + " (burst cuBLAS bf16; kernel timed alone)", "ms_per_launch": t_att * 1e3,
+                    "algorithmic_flops_per_launch": fl, "traffic": None,
+                    "step_share_attention": 57 * t_att / (t_local / args.steps)}
+
+    if rank == 0:
+        total_steps = world * B * args.steps
+        value = total_steps / t
+        e2e_v = world * B * n_calls * PIPE_STEPS / t_e2e
+        fl = step_flops()
+        out = {
+            "metric": "denoise-steps/sec 1024px bf16", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init FLUX-schnell weights, N(0,1) embeddings/latents)",
+            "config": {"workload": "FLUX-schnell MMDiT denoise step, 1024x1024 (4096 latent + 512 text tokens), 19 double + 38 single blocks",
+                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world} (replicas, no collective)",
+                       "l2_policy": "per-step working set (24 GB weights) >> 126 MB L2; no flush needed"},
+            "tflops_per_gpu": fl * B * args.steps / t_local / 1e12,
+            "step_roofline_frac_bf16": fl * B * args.steps / t_local / 1e12 / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
+            "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
+                    "api": "x2i_b200.pipeline.FluxPipeline.__call__ (4-step schnell sampling per call, pinned host buffers)"},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clk,
+        }
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

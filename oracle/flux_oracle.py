@@ -470,8 +470,12 @@ def euler_step(x: torch.Tensor, v: torch.Tensor, sigma: float, sigma_next: float
 
 @torch.no_grad()
 def denoise(model: FluxTransformer2DModel, latents, prompt_embeds, pooled, height_lat, width_lat, num_steps,
-            guidance_scale: float = 3.5, dynamic_shift: bool = False):
-    """The FluxPipeline hot loop with vae=None, output_type='latent' (A.7)."""
+            guidance_scale: float = 3.5, dynamic_shift: bool = False, emulate_bf16_time: bool = False):
+    """The FluxPipeline hot loop with vae=None, output_type='latent' (A.7).
+
+    emulate_bf16_time: when this fp32 oracle stands in for the reference's bf16 run, feed it the timestep / guidance
+    values the bf16 run effectively uses (t.to(bf16) / 1000 in bf16, then * 1000 in bf16 inside the transformer,
+    lightcontrol_flux.py:447-449) -- e.g. sigma 0.75 -> 752 instead of 750."""
     B, L_img, _ = latents.shape
     img_ids = prepare_latent_image_ids(height_lat, width_lat).to(latents.device, latents.dtype)
     txt_ids = torch.zeros(prompt_embeds.shape[1], 3, device=latents.device, dtype=latents.dtype)
@@ -480,8 +484,12 @@ def denoise(model: FluxTransformer2DModel, latents, prompt_embeds, pooled, heigh
     g = None
     if model.config.guidance_embeds:
         g = torch.full((B,), guidance_scale, device=latents.device, dtype=torch.float32)
+        if emulate_bf16_time:
+            g = (g.to(torch.bfloat16) * 1000).float() / 1000
     for i in range(num_steps):
         t = (sig[i] * 1000).expand(B).to(latents.dtype)
+        if emulate_bf16_time:
+            t = (((sig[i] * 1000).expand(B).to(torch.bfloat16) / 1000) * 1000).float().to(latents.device)
         v = model(hidden_states=latents, timestep=t / 1000, guidance=g, pooled_projections=pooled,
                   encoder_hidden_states=prompt_embeds, txt_ids=txt_ids, img_ids=img_ids, return_dict=False)[0]
         latents = euler_step(latents, v, float(sig[i]), float(sig[i + 1]))

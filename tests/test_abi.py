@@ -1,0 +1,66 @@
+"""CPU: the C-ABI library builds, loads and exports exactly what include/x2i_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "x2i_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(?:int|long long|const char\*)\s+(x2i_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        decls[m.group(1)] = 0 if args == "void" else len([a for a in args.split(",") if a.strip()])
+    return decls
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from x2i_b200 import _lib
+    return _lib
+
+
+def test_every_declared_symbol_is_exported(built):
+    decls = _declared()
+    assert len(decls) >= 18
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for name in decls:
+        assert hasattr(lib, name), f"{name} declared in include/x2i_b200.h but not exported"
+
+
+def test_bindings_match_header(built):
+    decls = _declared()
+    for name, argtypes in built.SIGNATURES.items():
+        assert name in decls, f"{name} bound in _lib.py but not declared in the header"
+        assert len(argtypes) == decls[name], f"{name}: {len(argtypes)} bound args vs {decls[name]} declared"
+    unbound = set(decls) - set(built.SIGNATURES) - {"x2i_version", "x2i_last_error", "x2i_launch_count"}
+    assert not unbound, f"declared but unbound: {unbound}"
+
+
+def test_version_and_no_gpu_error_path(built):
+    lib = built.lib()
+    assert lib.x2i_version() >= 100
+    import torch
+    if not torch.cuda.is_available():
+        # without a device every entry point must fail loudly (no CPU fallback)
+        with pytest.raises(built.X2IError):
+            built.call("x2i_euler_step", 0, 0, 0.0, 8, 0)
+
+
+def test_library_has_blackwell_sass(built):
+    """tcgen05 / TMA evidence in the shipped SASS (B200_PROFILING.md): UTCHMMA, LDTM, UTMALDG."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", built.LIB_PATH], capture_output=True, text=True).stdout
+    for op in ("UTCHMMA", "LDTM", "UTMALDG", "STTM"):
+        assert op in sass, f"{op} missing from SASS"
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path found"

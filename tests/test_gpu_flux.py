@@ -1,0 +1,200 @@
+"""-m gpu: the drop-in FLUX MMDiT / pipeline / projector / KD loss against the fp32 CPU oracle on seeded inputs.
+
+Tolerance: BASELINE.md's 1e-2 relative (Frobenius) for bf16 paths.  The reference's own eager-bf16 path deviates from the
+fp32 oracle by a comparable amount (measured below as the yardstick).
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import __graft_entry__ as g
+    g.build()
+    from x2i_b200 import smoke
+    return smoke
+
+
+def _hooks(model):
+    from x2i_b200.kd import cast_hook_list
+    lists = []
+    cast_hook_list(model, lists)
+    return lists
+
+
+@pytest.mark.parametrize("guidance", [False, True])
+def test_transformer_step_matches_oracle(env, guidance):
+    cfg = env.tiny_config(guidance)
+    model, oracle = env.make_pair(cfg, seed=3 + guidance)
+    inp = env.make_inputs(cfg, B=2, hl=8, wl=12, S=40, seed=5)
+    with torch.no_grad():
+        ref = oracle(**env.oracle_inputs(inp), return_dict=False)[0]
+        out = model(**env.to_device(inp), return_dict=False)[0]
+        # yardstick: the reference's eager bf16 path (oracle modules run in bf16 on the GPU)
+        ob = oracle.to("cuda", torch.bfloat16)
+        eager = ob(**env.to_device(inp), return_dict=False)[0]
+    assert out.shape == ref.shape == (2, 96, 64)
+    e_mine, e_eager = env.rel(out, ref), env.rel(eager, ref)
+    print(f"rel err vs fp32 oracle: x2i_b200 {e_mine:.4f}, eager-bf16 reference path {e_eager:.4f}")
+    assert e_mine < TOL
+    assert env.rel(out, eager) < 2 * TOL
+
+
+def test_forward_hooks_see_reference_tensors(env):
+    """B3 contract (train_qwenvl.py:186-214): hooks on blk.attn get (img, txt) / single-attn outputs."""
+    cfg = env.tiny_config(True)
+    model, oracle = env.make_pair(cfg, seed=7)
+    inp = env.make_inputs(cfg, B=2, hl=8, wl=8, S=24, seed=8)
+    hm, ho = _hooks(model), _hooks(oracle)
+    with torch.no_grad():
+        ref = oracle(**env.oracle_inputs(inp), return_dict=False)[0]
+        out = model(**env.to_device(inp), return_dict=False)[0]
+    assert env.rel(out, ref) < TOL
+    assert [len(x) for x in hm] == [2, 2, 3]
+    for gm, go in zip(hm, ho):
+        for a, b in zip(gm, go):
+            assert a.shape == b.shape
+            assert env.rel(a, b) < TOL
+
+
+def test_plugin_processor_path_matches_fused_path(env):
+    """B4 contract: a user processor invoked with the diffusers protocol; result must equal the fused default."""
+    from x2i_b200.flux import FluxAttnProcessor2_0
+
+    class Wrapped:  # a plug-in that simply defers to the stock maths through the public protocol
+        calls = 0
+
+        def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, image_rotary_emb=None):
+            Wrapped.calls += 1
+            return FluxAttnProcessor2_0()(attn, hidden_states, encoder_hidden_states, attention_mask, image_rotary_emb)
+
+    cfg = env.tiny_config(False)
+    model, oracle = env.make_pair(cfg, seed=9)
+    inp = env.to_device(env.make_inputs(cfg, B=1, hl=8, wl=8, S=16, seed=10))
+    with torch.no_grad():
+        a = model(**inp, return_dict=False)[0].clone()
+        model.set_attn_processor(Wrapped())
+        b = model(**inp, return_dict=False)[0]
+    assert Wrapped.calls == 5
+    assert env.rel(b, a) < 5e-3
+
+
+def test_pipeline_four_step_sampling_matches_oracle(env):
+    from oracle import flux_oracle as fo
+    from x2i_b200.pipeline import FlowMatchEulerDiscreteScheduler, FluxPipeline
+    cfg = env.tiny_config(False)
+    model, oracle = env.make_pair(cfg, seed=11)
+    pipe = FluxPipeline(scheduler=FlowMatchEulerDiscreteScheduler(shift=1.0), transformer=model)
+    g = torch.Generator().manual_seed(12)
+    bf = lambda t: t.to(torch.bfloat16)  # noqa: E731
+    prompt, pooled = bf(torch.randn(2, 24, 64, generator=g)), bf(torch.randn(2, 32, generator=g))
+    lat = bf(torch.randn(2, 16, 16, 16, generator=g))  # [B,16,h,w] -> packed [B,64,64]
+    packed = fo.pack_latents(lat)
+    out = pipe(prompt_embeds=prompt.cuda(), pooled_prompt_embeds=pooled.cuda(), num_inference_steps=4, guidance_scale=3.5,
+               height=128, width=128, output_type="latent", latents=packed.cuda()).images
+    ref = fo.denoise(oracle, packed.float(), prompt.float(), pooled.float(), 16, 16, 4, emulate_bf16_time=True)
+    assert out.shape == (2, 64, 64)
+    assert env.rel(out, ref) < TOL
+    # generator path: shapes and determinism
+    a = pipe(prompt_embeds=prompt.cuda(), pooled_prompt_embeds=pooled.cuda(), num_inference_steps=2, height=128, width=128,
+             output_type="latent", generator=torch.Generator("cpu").manual_seed(3)).images
+    b = pipe(prompt_embeds=prompt.cuda(), pooled_prompt_embeds=pooled.cuda(), num_inference_steps=2, height=128, width=128,
+             output_type="latent", generator=torch.Generator("cpu").manual_seed(3)).images
+    assert torch.equal(a, b)
+    assert FluxPipeline._unpack_latents(a, 128, 128, 16).shape == (2, 16, 16, 16)
+
+
+def test_full_width_blocks_match_oracle(env):
+    """One double + one single block at the real width (D=3072, 24 heads) and a ragged sequence (S_txt=203)."""
+    from oracle import flux_oracle as fo
+    from x2i_b200 import flux as xf
+    torch.manual_seed(0)
+    D, H, B, S, hl, wl = 3072, 24, 1, 203, 16, 24
+    L_img = hl * wl
+    od = fo.FluxTransformerBlock(D, H, 128).eval()
+    os_ = fo.FluxSingleTransformerBlock(D, H, 128).eval()
+    for m in (od, os_):
+        fo.init_synthetic_(m, seed=21, std=0.02)
+        with torch.no_grad():
+            for p in m.parameters():
+                p.copy_(p.bfloat16().float())
+    md = xf.FluxTransformerBlock(D, H, 128); md.load_state_dict(od.state_dict()); md = md.to("cuda", torch.bfloat16)
+    ms = xf.FluxSingleTransformerBlock(D, H, 128); ms.load_state_dict(os_.state_dict()); ms = ms.to("cuda", torch.bfloat16)
+    g = torch.Generator().manual_seed(22)
+    bf = lambda t: t.bfloat16().float()  # noqa: E731
+    x, c, temb = bf(torch.randn(B, L_img, D, generator=g)), bf(torch.randn(B, S, D, generator=g)), bf(torch.randn(B, D, generator=g))
+    ids = torch.cat([torch.zeros(S, 3), fo.prepare_latent_image_ids(2 * hl, 2 * wl)])
+    rope = fo.rope_table(ids)
+    dev = lambda t: t.to("cuda", torch.bfloat16)  # noqa: E731
+    rope_dev = (rope[0].cuda(), rope[1].cuda())
+    with torch.no_grad():
+        od, os_ = od.cuda(), os_.cuda()  # fp32 oracle on the GPU (size)
+        rc, rx = od(x.cuda(), c.cuda(), temb.cuda(), rope_dev)
+        rh = os_(torch.cat([rc, rx], 1), temb.cuda(), rope_dev)
+        c2, x2 = md(dev(x), dev(c), dev(temb), image_rotary_emb=rope_dev)
+        h2 = ms(torch.cat([c2, x2], 1).contiguous(), dev(temb), image_rotary_emb=rope_dev)
+    assert env.rel(x2, rx) < TOL and env.rel(c2, rc) < TOL
+    assert env.rel(h2, rh) < TOL
+
+
+def test_projector_matches_oracle_and_reference_golden(env, golden_dir):
+    from oracle import proj_oracle
+    from oracle.make_golden import synth_state
+    from x2i_b200 import proj as xproj
+    # small, all three branches, weights and inputs of the fixture minted from the reference's utils/proj.py
+    gsmall = torch.load(os.path.join(golden_dir, "proj_small.pt"), weights_only=False)
+    # (H=64 fixture is below the kernels' GEMM granularity for N=24; use config-1 instead for the reference pin)
+    g1 = torch.load(os.path.join(golden_dir, "proj_c1.pt"), weights_only=False)
+    p = xproj.create_proj3_qwen3b(37, use_t5=False, use_scale=False, use_cnn=True)
+    sd = synth_state(p, 21, std=0.02)
+    p.load_state_dict(sd)
+    p = p.to("cuda", torch.bfloat16)
+    x = torch.randn(1, 37, 77, 2048, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        pooled, seq = p(x.cuda())
+    assert pooled.shape == (1, 768) and seq.shape == (1, 77, 4096)
+    assert env.rel(pooled, g1["pooled"]) < 2e-2           # reference fp32 weights vs bf16 weights + bf16 activations
+    assert env.rel(seq[:, ::7, ::13], g1["seq_sub"]) < 2e-2
+    # same bf16-rounded weights in the fp32 oracle -> tight comparison, all branches, 7B shape with ragged S
+    for kind, C, kw in (("qwen7b", 29, dict(use_scale=False, use_cnn=True)), ("internvl1b", 25, dict(use_scale=True, use_cnn=True)),
+                        ("qwen3b", 37, dict(use_scale=False, use_cnn=False))):
+        o = proj_oracle.create_proj(kind, C, **kw)
+        sd = {k: v.bfloat16().float() for k, v in synth_state(o, 5, std=0.03).items()}
+        o.load_state_dict(sd)
+        m = getattr(xproj, {"qwen7b": "create_proj3_qwen7b", "internvl1b": "create_proj_internvl1b", "qwen3b": "create_proj3_qwen3b"}[kind])(
+            C, use_t5=False, **kw)
+        m.load_state_dict(sd)
+        m = m.to("cuda", torch.bfloat16)
+        H = o.mlp.layernorm.normalized_shape[0]
+        x = torch.randn(2, C, 45, H, generator=torch.Generator().manual_seed(6)).bfloat16()
+        with torch.no_grad():
+            rp, rs = o(x.float())
+            mp_, ms_ = m(x.cuda())
+        assert env.rel(ms_, rs) < TOL and env.rel(mp_, rp) < TOL, kind
+
+
+def test_kd_loss_module_matches_oracle_stacked(env):
+    from oracle import kd_oracle
+    from x2i_b200.kd import attention_distillation_loss
+    g = torch.Generator().manual_seed(31)
+    B, D = 2, 3072
+    shapes = [(B, 3, 64, D), (B, 3, 24, D), (B, 4, 88, D)]
+    T = [torch.randn(s, generator=g).bfloat16() for s in shapes]
+    S = [(t.float() + 0.5 * torch.randn(s, generator=g)).bfloat16() for t, s in zip(T, shapes)]
+    S_ref = [s.float().requires_grad_(True) for s in S]
+    ref = kd_oracle.kd_loss_stacked(*[t.float() for t in T], *S_ref)
+    ref.backward()
+    S_dev = [s.cuda().requires_grad_(True) for s in S]
+    loss = attention_distillation_loss([t.cuda() for t in T], S_dev, temperature=3.0, verbose=False)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) / float(ref) < 2e-3
+    for a, b in zip(S_dev, S_ref):
+        assert a.grad.shape == b.grad.shape
+        assert env.rel(a.grad, b.grad) < TOL

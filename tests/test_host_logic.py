@@ -1,0 +1,116 @@
+"""CPU: host-side mirror of the reference interfaces (no kernels are launched here)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flux_oracle as fo
+from x2i_b200 import dist as xdist
+from x2i_b200._lib import X2IError
+from x2i_b200.flux import FluxTransformer2DModel
+from x2i_b200.pipeline import FlowMatchEulerDiscreteScheduler, FluxPipeline, calculate_shift
+from x2i_b200 import proj as xproj
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_pipeline_static_helpers_bit_exact(golden_dir):
+    g = _load(golden_dir, "helpers.pt")
+    assert torch.equal(FluxPipeline._prepare_latent_image_ids(2, 8, 12, "cpu", torch.float32), g["ids_8x12"])
+    assert torch.equal(FluxPipeline._prepare_latent_image_ids(1, 128, 128, "cpu", torch.float32), g["ids_128"])
+    assert torch.equal(FluxPipeline._pack_latents(g["pack_in"], 2, 16, 8, 12), g["pack_out"])
+    assert torch.equal(FluxPipeline._unpack_latents(g["pack_out"], 8 * 8, 12 * 8, 16), g["pack_in"])
+    assert calculate_shift(4096) == g["shift_4096"] and calculate_shift(1024) == g["shift_1024"]
+    assert calculate_shift(4096, 256, 4096, 0.5, 1.15) == g["shift_dev_4096"]
+
+
+@pytest.mark.parametrize("dyn", [False, True])
+def test_scheduler_matches_oracle(dyn):
+    s = FlowMatchEulerDiscreteScheduler(shift=1.0, use_dynamic_shifting=dyn)
+    mu = calculate_shift(4096, 256, 4096, 0.5, 1.15)
+    for n in (1, 4, 20, 28):
+        s.set_timesteps(sigmas=np.linspace(1.0, 1 / n, n), mu=mu if dyn else None)
+        ref = fo.flow_match_sigmas(n, mu if dyn else None, 1.0, dyn)
+        assert torch.equal(s.sigmas, ref)
+        assert torch.equal(s.timesteps, ref[:-1] * 1000)
+    s.set_timesteps(sigmas=[1.0], mu=mu if dyn else None)  # distillation: one step at t = 1000 (train_qwenvl.py:753-771)
+    assert float(s.timesteps[0]) == 1000.0
+
+
+def test_state_dict_keys_are_diffusers_names():
+    cfg = dict(num_layers=1, num_single_layers=1, attention_head_dim=128, num_attention_heads=1, joint_attention_dim=16,
+               pooled_projection_dim=8, in_channels=8, guidance_embeds=True)
+    with torch.device("meta"):
+        mine = FluxTransformer2DModel(**cfg)
+        ref = fo.FluxTransformer2DModel(**cfg)
+    a, b = mine.state_dict(), ref.state_dict()
+    assert set(a) == set(b)
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+    for k in ("transformer_blocks.0.attn.to_out.0.weight", "transformer_blocks.0.ff.net.0.proj.weight",
+              "single_transformer_blocks.0.proj_out.weight", "time_text_embed.guidance_embedder.linear_1.weight",
+              "transformer_blocks.0.attn.norm_added_k.weight", "norm_out.linear.bias"):
+        assert k in a
+
+
+def test_attn_processor_plugin_surface():
+    with torch.device("meta"):
+        m = FluxTransformer2DModel(num_layers=2, num_single_layers=3, num_attention_heads=1, joint_attention_dim=16,
+                                   pooled_projection_dim=8, in_channels=8)
+    procs = m.attn_processors
+    assert len(procs) == 5 and "transformer_blocks.0.attn.processor" in procs
+    sentinel = object()
+    m.set_attn_processor(sentinel)
+    assert all(p is sentinel for p in m.attn_processors.values())
+    with pytest.raises(ValueError):
+        m.set_attn_processor({"x": sentinel})
+    m.set_attn_processor({k: i for i, k in enumerate(procs)})
+    assert m.single_transformer_blocks[2].attn.get_processor() == 4
+    # hooks attach to a real nn.Module (train_qwenvl.py:206-214)
+    h = m.transformer_blocks[0].attn.register_forward_hook(lambda mod, i, o: None)
+    h.remove()
+
+
+def test_no_cpu_fallback():
+    m = FluxTransformer2DModel(num_layers=1, num_single_layers=1, num_attention_heads=1, joint_attention_dim=16,
+                               pooled_projection_dim=8, in_channels=8)
+    with torch.no_grad(), pytest.raises(X2IError):
+        m(hidden_states=torch.randn(1, 4, 8), encoder_hidden_states=torch.randn(1, 2, 16), pooled_projections=torch.randn(1, 8),
+          timestep=torch.ones(1), img_ids=torch.zeros(4, 3), txt_ids=torch.zeros(2, 3))
+    p = xproj.create_proj_internvl4b(5, use_t5=False, use_scale=False, use_cnn=True)
+    with torch.no_grad(), pytest.raises(X2IError):
+        p(torch.randn(1, 5, 4, 2048))
+
+
+def test_projector_factories_match_reference_shapes(golden_dir):
+    g = _load(golden_dir, "proj_c1.pt")
+    with torch.device("meta"):
+        p = xproj.create_proj3_qwen3b(37, use_t5=False, use_scale=False, use_cnn=True)
+        assert sum(x.numel() for x in p.parameters()) == g["n_params"]
+        assert set(p.state_dict()) == {"conv.weight", "conv.bias", "mlp.layernorm.weight", "mlp.layernorm.bias",
+                                       "mlp.projector.0.weight", "mlp.projector.2.weight", "mlp.fc.1.weight", "mlp.fc.1.bias"}
+        q = xproj.create_proj3_qwen7b(29, use_t5=False, use_scale=True, use_cnn=True)
+        assert "cha_scale" in q.state_dict() and not q.use_cnn  # use_scale wins (utils/proj.py:80)
+        assert xproj.create_proj_internvl1b(25, use_t5=False).mlp.layernorm.normalized_shape == (896,)
+    with pytest.raises(NameError):
+        xproj.create_proj_minicpm(29)  # use_t5=True default: dead branch of the reference (NameError there too)
+
+
+def test_projector_checkpoint_prefix_stripping():
+    p = xproj.Proj7Exp(in_channels=3, input_dim=16, output_dim0=8, output_dim1=16, use_t5=False, use_scale=False, use_cnn=True)
+    sd = {"module." + k: torch.randn_like(v) for k, v in p.state_dict().items()}
+    xproj.load_projector_state(p, sd)
+    assert torch.equal(p.conv.weight, sd["module.conv.weight"])
+
+
+def test_shard_range_covers_batch():
+    for n in (1, 7, 8, 16, 33):
+        for w in (1, 2, 4, 8):
+            spans = [xdist.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1

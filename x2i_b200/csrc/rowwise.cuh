@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(KD_THREADS) kd_row_kernel(const __nv_bfloat16*
     block_sum<2, KD_THREADS / 32>(r, red);
     const float up = row_scale[row];
     const float gmean = r[0] / D;
+    const bool dead = (up == 0.f);  // layer skipped by the inf/nan guard: exactly zero gradient, never 0 * NaN
     // du_j/ds_k = ks (delta_jk - 1/D) - (s_j-mean)(s_k-mean) * inv_T / ((eps+sd)^2 (D-1) sd)
     const float c2 = r[1] * inv_T / ((1e-7f + sd_s) * (1e-7f + sd_s) * (D - 1) * fmaxf(sd_s, 1e-30f));
     uint4* gr = reinterpret_cast<uint4*>(grad + row * D);
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(KD_THREADS) kd_row_kernel(const __nv_bfloat16*
       if (c < nchunk) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = up * (ks * (t[i][j] - gmean) - c2 * s[i][j]);
+        for (int j = 0; j < 8; ++j) o[j] = dead ? 0.f : up * (ks * (t[i][j] - gmean) - c2 * s[i][j]);
         gr[c] = pack8(o);
       }
     }

@@ -205,6 +205,8 @@ class FluxAttnProcessor2_0:
             if cat_buf is not None:
                 out = cat_buf.view(B, L, -1)[:, :, :D]
                 ops.attention(q, k, v, split=0, out1=out)
+                if len(attn._forward_hooks) > 0:
+                    out = out.clone()  # the concat buffer is reused by the next block; hooks keep their own copy
             else:
                 _, out = ops.attention(q, k, v, split=0)
             return out
@@ -447,6 +449,14 @@ class FluxTransformer2DModel(nn.Module):
     def from_config(cls, config):
         cfg = dict(config) if isinstance(config, dict) else vars(config)
         return cls(**{k: v for k, v in cfg.items() if not k.startswith("_")})
+
+    @classmethod
+    def synthetic(cls, config: dict, device="cuda", seed: int = 0, std: float = 0.02):
+        """Random-weight model built directly on `device` in bf16 (benchmarks: no checkpoints are reachable)."""
+        with torch.device("meta"):
+            m = cls(**config)
+        m = m.to(BF16).to_empty(device=device)
+        return init_synthetic_(m, seed=seed, std=std).eval()
 
     @classmethod
     def from_pretrained(cls, path, subfolder=None, torch_dtype=None, **kw):

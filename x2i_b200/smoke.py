@@ -43,6 +43,17 @@ def make_inputs(cfg, B=2, hl=8, wl=8, S=24, seed=1):
     return inp
 
 
+def oracle_inputs(inp):
+    """Inputs for the fp32 oracle that reproduce the reference's bf16 quirk: it forms `timestep.to(bf16) * 1000` and
+    `guidance.to(bf16) * 1000` IN bf16 (lightcontrol_flux.py:447-449), e.g. 0.75 -> 752 and 3.5 -> 3504.  The product
+    path does the same; a pure-fp32 oracle must be told the rounded values or the time embedding differs by ~25%."""
+    out = dict(inp)
+    for k in ("timestep", "guidance"):
+        if k in out and out[k] is not None:
+            out[k] = (out[k].to(torch.bfloat16) * 1000).float() / 1000
+    return out
+
+
 def to_device(inp, device="cuda"):
     out = {}
     for k, v in inp.items():
@@ -65,7 +76,7 @@ def run_smoke():
     model, oracle = make_pair(cfg)
     inp = make_inputs(cfg)
     with torch.no_grad():
-        ref = oracle(**inp, return_dict=False)[0]
+        ref = oracle(**oracle_inputs(inp), return_dict=False)[0]
         out = model(**to_device(inp), return_dict=False)[0]
     torch.cuda.synchronize()
     err = rel(out, ref)
