@@ -220,12 +220,17 @@ def main():
             clocks.start()
         launches0 = _lib.launch_count()
         torch.cuda.synchronize()
+        profiling = os.environ.get("X2I_NCU") == "1"  # ncu --profile-from-start off: capture only the timed region
+        if profiling:
+            torch.cuda.cudart().cudaProfilerStart()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
             one_step(i)
         e1.record()
         torch.cuda.synchronize()
+        if profiling:
+            torch.cuda.cudart().cudaProfilerStop()
         xdist.barrier()
         launches = _lib.launch_count() - launches0
         t_local = e0.elapsed_time(e1) * 1e-3

@@ -311,6 +311,23 @@ def check_perf():
     return out
 
 
+def check_attn_variants():
+    """Times the attention kernel for the POLY8 variant selected by the X2I_ATTN_POLY8 env var of this process."""
+    torch, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    out = {"poly8": os.environ.get("X2I_ATTN_POLY8", "0")}
+    for (B, H, L) in [(1, 24, 4608), (2, 24, 4608), (1, 24, 1536)]:
+        q = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        k = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        v = torch.randn(B, H, L, 128, device="cuda", generator=g).bfloat16()
+        o1 = torch.empty(B, L, H * 128, device="cuda", dtype=torch.bfloat16)
+        t = timeit(lambda: ops.attention(q, k, v, out1=o1), iters=30)
+        ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, L, H * 128)
+        fl = 4 * L * L * 128 * H * B
+        out[f"B{B}_L{L}"] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "rel": rel_err(o1, ref)[0]}
+    return out
+
+
 CHECKS = {k[6:]: v for k, v in list(globals().items()) if k.startswith("check_")}
 
 if __name__ == "__main__":

@@ -1,0 +1,79 @@
+"""Turn the raw ncu artefacts in gpurun_out/ into the committed summaries under profiles/ (run here, no GPU needed).
+
+    python tools/summarize_profiles.py r01
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+GP = os.path.join(ROOT, "gpurun_out")
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "sm__cycles_elapsed.max",
+        "sm__cycles_active.avg", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__cycles_elapsed.max.per_second",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+
+
+def launches(tag, steps=2):
+    src = os.path.join(GP, "launches.csv")
+    if not os.path.exists(src):
+        return
+    lines = [l for l in open(src) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    tot = 0.0
+    n = 0
+    for row in csv.DictReader(lines):
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except (ValueError, KeyError):
+            continue
+        u = row["Metric Unit"]
+        v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+        name = re.sub(r"^void ", "", row["Kernel Name"])
+        name = re.sub(r"\(.*", "", name)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+        tot += v
+        n += 1
+    with open(os.path.join(OUT, f"{tag}_launch_list_summary.md"), "w") as f:
+        f.write(f"# {tag}: kernels of the timed region of `python bench.py --steps {steps} --warmup 3` under ncu\n\n"
+                "`ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised, no power cap:\n"
+                "compare SHARES, not absolutes).  Raw list: gpurun_out/launches.csv (scratch).\n\n"
+                f"{n} launches, {tot / 1e3:.2f} ms kernel time over {steps} steps = {tot / steps / 1e3:.2f} ms/step\n\n"
+                "| share | us/step | launches/step | avg us | kernel |\n|---|---|---|---|---|\n")
+        for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"| {t / tot * 100:.2f}% | {t / steps:.1f} | {c / steps:.1f} | {t / c:.1f} | `{k[:120]}` |\n")
+    print("wrote launch summary:", n, "launches")
+
+
+def raw(tag, rep):
+    src = os.path.join(GP, rep + ".ncu-rep")
+    if not os.path.exists(src):
+        return
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    cols = [i for i, h in enumerate(hdr) if h in KEYS or h == "Kernel Name"]
+    with open(os.path.join(OUT, f"{tag}_{rep}_ncu_full.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] for i in cols])
+        w.writerow([units[i] for i in cols])
+        for r in data:
+            w.writerow([re.sub(r"\(CUtensorMap.*", "", r[i]) if hdr[i] == "Kernel Name" else r[i] for i in cols])
+    print("wrote", rep, len(data), "kernel instances")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(OUT, exist_ok=True)
+    launches(tag)
+    for rep in ("prof_attn", "prof_gemm", "prof_rowwise"):
+        raw(tag, rep)

@@ -62,5 +62,14 @@ def call(name, *args):
         raise X2IError(f"{name} failed ({rc}): {lib().x2i_last_error().decode()}")
 
 
+_graph_replayed = 0  # kernels executed through CUDA-graph replays (each replay re-runs the captured launches)
+
+
+def note_graph_replay(n_kernels: int) -> None:
+    global _graph_replayed
+    _graph_replayed += n_kernels
+
+
 def launch_count() -> int:
-    return int(lib().x2i_launch_count())
+    """Kernels of libx2i_b200.so executed so far: direct launches + launches re-run by graph replays."""
+    return int(lib().x2i_launch_count()) + _graph_replayed

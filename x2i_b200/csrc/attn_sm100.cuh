@@ -31,6 +31,8 @@ constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 128B-swizzled boxes
 constexpr int ATT_KV_SLOTS = 4;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + ATT_KV_SLOTS * ATT_TILE_BYTES + 1024 + 256;
 
+// POLY8: how many of every 8 softmax exponentials are evaluated with poly_exp2 instead of MUFU.EX2.
+template <int POLY8>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                            const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -188,11 +190,12 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
           for (int k = 0; k < 32; ++k)
             if (c * 32 + k >= valid) r[c][k] = 0xff800000u;  // -inf
       }
-      float mx = -INFINITY;
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains (ILP)
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[c][k]));
+        for (int k = 0; k < 32; ++k) mx4[k & 3] = fmaxf(mx4[k & 3], __uint_as_float(r[c][k]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_cand = fmaxf(m_run, mx * sc);
       float alpha = 1.0f;
       bool rescale = false;
@@ -218,20 +221,23 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
           }
         }
       }
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_run;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(r[c][2 * k]), sc, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(r[c][2 * k + 1]), sc, neg_m));
-          sum += p0 + p1;
+          const float a0 = fmaf(__uint_as_float(r[c][2 * k]), sc, neg_m);
+          const float a1 = fmaf(__uint_as_float(r[c][2 * k + 1]), sc, neg_m);
+          const float p0 = (((2 * k) & 7) < POLY8) ? poly_exp2(a0) : fast_exp2(a0);
+          const float p1 = (((2 * k + 1) & 7) < POLY8) ? poly_exp2(a1) : fast_exp2(a1);
+          sum4[k & 3] += p0 + p1;
           pk[k] = pack_bf16x2(p0, p1);
         }
         tmem_st16(t_s + c * 16, pk);  // P_i aliases S_i columns [0, 64)
       }
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       l_run = l_run * alpha + sum;
       tmem_st_wait();
       tc_fence_before();

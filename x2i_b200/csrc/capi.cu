@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -41,6 +42,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct DeviceInfo {
   int ok = 0;  // 0 unknown, 1 good, -1 bad
   int sms = 0;
+  int index = 0;
   EncodeTiledFn encode = nullptr;
   char why[200] = "";
 };
@@ -58,6 +60,7 @@ int device_info(DeviceInfo** out) {
       cudaDeviceProp prop;
       cudaGetDeviceProperties(&prop, dev);
       d.sms = prop.multiProcessorCount;
+      d.index = dev;
       if (prop.major != 10) {
         snprintf(d.why, sizeof(d.why), "device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major,
                  prop.minor);
@@ -101,8 +104,12 @@ int make_map(DeviceInfo* d, CUtensorMap* m, const void* ptr, int rank, const uin
 template <int BN, int EPI, bool B_MN>
 int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   auto kern = gemm_tcgen05_kernel<BN, EPI, B_MN>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
-  if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+  static std::atomic<bool> configured[16];  // per device, per instantiation (keeps the call out of graph captures)
+  if (!configured[d->index].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+    configured[d->index].store(true, std::memory_order_release);
+  }
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < d->sms ? tiles : d->sms;
   kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
@@ -273,10 +280,23 @@ int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0,
   p.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.ld0 = ld0; p.split = split;
   p.out1 = static_cast<__nv_bfloat16*>(out1); p.ld1 = ld1;
-  cudaError_t e = cudaFuncSetAttribute(mmdit_attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
-  if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+  static const int poly8 = []() { const char* e = getenv("X2I_ATTN_POLY8"); return e ? atoi(e) : 0; }();
+  auto kern = mmdit_attention_fwd_kernel<0>;
+  switch (poly8) {
+    case 1: kern = mmdit_attention_fwd_kernel<1>; break;
+    case 2: kern = mmdit_attention_fwd_kernel<2>; break;
+    case 3: kern = mmdit_attention_fwd_kernel<3>; break;
+    case 4: kern = mmdit_attention_fwd_kernel<4>; break;
+    default: break;
+  }
+  static std::atomic<bool> att_configured[16];
+  if (!att_configured[d->index].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+    att_configured[d->index].store(true, std::memory_order_release);
+  }
   dim3 grid((L + 255) / 256, heads, B);
-  mmdit_attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   return check_launch("mmdit_attention_fwd_kernel");
 }
 
@@ -323,12 +343,18 @@ int x2i_skinny_linear(const void* x, int64_t ldx, const void* W, int64_t ldw, co
   auto kern = skinny_linear_kernel<8>;
   const size_t smem_max = static_cast<size_t>(8) * K * sizeof(float);
   if (smem_max > 200 * 1024) return fail(X2I_ERR_SHAPE, "skinny_linear: K=%d too large", K);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-  if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(skinny): %s", cudaGetErrorString(e));
+  static std::atomic<int> skinny_smem[16];  // largest opt-in size configured so far on this device
+  if (skinny_smem[d->index].load(std::memory_order_acquire) < (int)smem_max) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(skinny): %s", cudaGetErrorString(e));
+    skinny_smem[d->index].store((int)smem_max, std::memory_order_release);
+  }
   for (int b0 = 0; b0 < B; b0 += 8) {
     const int nb = (B - b0) < 8 ? (B - b0) : 8;
     long long want = (static_cast<long long>(N) + 7) / 8;  // 8 warps per CTA, one column per warp per pass
-    const int per_sm = (nb * K * 4 > 100 * 1024) ? 1 : 2;
+    const size_t smem_cta = static_cast<size_t>(nb) * K * sizeof(float) + 1024;
+    int per_sm = static_cast<int>((220 * 1024) / smem_cta);  // as many resident CTAs as shared memory allows (<= 8)
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     int grid = static_cast<int>(want < static_cast<long long>(d->sms) * per_sm ? want : static_cast<long long>(d->sms) * per_sm);
     kern<<<grid, 256, static_cast<size_t>(nb) * K * sizeof(float), st>>>(
         static_cast<const __nv_bfloat16*>(x) + b0 * ldx, ldx, static_cast<const __nv_bfloat16*>(W), ldw,

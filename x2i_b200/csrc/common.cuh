@@ -178,6 +178,17 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, |rel err| < 1.2e-4 -- below bf16
+// resolution).  Used for a fraction of the softmax exponentials so the MUFU pipe is not the only bottleneck.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: low mantissa bits of t = round(x)
+  const float f = x - (t - 12582912.0f);    // f in [-0.5, 0.5]
+  float p = fmaf(0.0555054f, f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float gelu_tanh_f(float x) {
   // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

@@ -25,7 +25,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from ._lib import X2IError
 
 BF16 = torch.bfloat16
@@ -435,6 +435,7 @@ class FluxTransformer2DModel(nn.Module):
         self._w_mod = None
         self._ws: Dict = {}
         self._rope_cache = None
+        self._graphs: Dict = {}
 
     # -- reference API surface ------------------------------------------------------------------------------
     @property
@@ -530,10 +531,12 @@ class FluxTransformer2DModel(nn.Module):
             if isinstance(m, Attention):
                 m._pack()
         self._ws = {}
+        self._graphs = {}
 
     def _workspace(self, B, S, L_img):
         key = (B, S, L_img, str(self.device))
         if self._ws.get("key") != key:
+            self._graphs = {}  # captured graphs point into the old workspace
             D, H, dev = self.inner_dim, self.config.num_attention_heads, self.device
             F = self.single_transformer_blocks[0].mlp_hidden_dim if len(self.single_transformer_blocks) else 4 * D
             L = S + L_img
@@ -545,32 +548,105 @@ class FluxTransformer2DModel(nn.Module):
         return self._ws
 
     def _rope(self, txt_ids, img_ids):
-        key = (txt_ids.shape[0], img_ids.shape[0], txt_ids.data_ptr(), img_ids.data_ptr(), img_ids._version)
-        if self._rope_cache is None or self._rope_cache[0] != key:
+        """(cos, sin) full tables and the compact table for the concatenated ids, cached.  A pointer miss with identical
+        content (callers that rebuild their id tensors every call) keeps the cached table so captured graphs stay valid."""
+        key = (txt_ids.shape[0], img_ids.shape[0], txt_ids.data_ptr(), img_ids.data_ptr(), txt_ids._version, img_ids._version)
+        rc = self._rope_cache
+        if rc is not None and rc[0] != key and rc[0][:2] == key[:2]:
+            ids = torch.cat((txt_ids.float(), img_ids.float()), dim=0).to(self.device)
+            if torch.equal(ids, rc[3]):
+                self._rope_cache = rc = (key,) + rc[1:]
+        if rc is None or rc[0] != key:
             ids = torch.cat((txt_ids.float(), img_ids.float()), dim=0).to(self.device)
             cos, sin, rope = ops.rope_table(ids, self.config.axes_dims_rope, 10000.0)
-            self._rope_cache = (key, (cos, sin), rope)
-        return self._rope_cache[1], self._rope_cache[2]
+            self._rope_cache = rc = (key, (cos, sin), rope, ids)
+        return rc[1], rc[2]
 
     # -- forward --------------------------------------------------------------------------------------------
+    use_cuda_graph = True  # replay one captured graph per step instead of ~410 launches (inference, default processors)
+
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
                 txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=True):
         _no_grad_needed(hidden_states, encoder_hidden_states, pooled_projections)
         self._pack()
-        B, L_img, _ = hidden_states.shape
-        S = encoder_hidden_states.shape[1]
-        D = self.inner_dim
-        ws = self._workspace(B, S, L_img)
         if txt_ids.ndim == 3:
             txt_ids = txt_ids[0]
         if img_ids.ndim == 3:
             img_ids = img_ids[0]
+        if guidance is not None and not self.config.guidance_embeds:
+            guidance = None
+        if self._graphable():
+            out = self._forward_graphed(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
+                                        guidance)
+        else:
+            out = self._forward_eager(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
+                                      guidance)
+        if not return_dict:
+            return (out,)
+        return SimpleNamespace(sample=out)
+
+    def _graphable(self):
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+            return False
+        for m in self.modules():
+            if isinstance(m, Attention) and (len(m._forward_hooks) > 0 or not _default_proc(m)):
+                return False  # hooks / plug-in processors run Python per block: eager path
+        return True
+
+    def _forward_graphed(self, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance):
+        B, L_img, _ = hidden_states.shape
+        S = encoder_hidden_states.shape[1]
+        _, rope = self._rope(txt_ids, img_ids)
+        key = (B, S, L_img, guidance is not None, rope.data_ptr(), self._w_mod.data_ptr())
+        st = self._graphs.get(key) if hasattr(self, "_graphs") else None
+        if st is None:
+            if not hasattr(self, "_graphs"):
+                self._graphs = {}
+            dev = self.device
+            sin = dict(h=torch.empty(B, L_img, hidden_states.shape[2], device=dev, dtype=BF16),
+                       e=torch.empty(B, S, encoder_hidden_states.shape[2], device=dev, dtype=BF16),
+                       p=torch.empty(B, pooled.shape[1], device=dev, dtype=BF16),
+                       t=torch.empty(B, device=dev, dtype=torch.float32),
+                       g=torch.empty(B, device=dev, dtype=torch.float32) if guidance is not None else None)
+            self._copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up outside the capture: packing, workspaces, function attributes
+                self._forward_eager(sin["h"], sin["e"], sin["p"], sin["t"], img_ids, txt_ids, sin["g"])
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                out = self._forward_eager(sin["h"], sin["e"], sin["p"], sin["t"], img_ids, txt_ids, sin["g"])
+            st = (graph, sin, out, _lib.launch_count() - n0)
+            self._graphs = {key: st}  # keep one shape resident (24 GB of weights leave room, but workspaces are per shape)
+        graph, sin, out, n_kernels = st
+        self._copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance)
+        graph.replay()
+        _lib.note_graph_replay(n_kernels)
+        return out.clone()
+
+    @staticmethod
+    def _copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance):
+        sin["h"].copy_(hidden_states, non_blocking=True)
+        sin["e"].copy_(encoder_hidden_states, non_blocking=True)
+        sin["p"].copy_(pooled, non_blocking=True)
+        sin["t"].copy_(timestep.expand(sin["t"].shape[0]) if timestep.dim() > 0 else timestep, non_blocking=True)
+        if sin["g"] is not None:
+            sin["g"].copy_(guidance.expand(sin["g"].shape[0]) if guidance.dim() > 0 else guidance, non_blocking=True)
+
+    def _forward_eager(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance):
+        B, L_img, _ = hidden_states.shape
+        S = encoder_hidden_states.shape[1]
+        D = self.inner_dim
+        ws = self._workspace(B, S, L_img)
         rope_full, rope = self._rope(txt_ids, img_ids)
 
         x = ops.linear(hidden_states.to(BF16).contiguous(), self.x_embedder.weight, self.x_embedder.bias, out=ws["x"])
         # timestep / guidance arrive as t/1000; the reference scales them IN bf16 (lightcontrol_flux.py:447-449)
         t1000 = timestep.to(BF16) * 1000
-        if guidance is not None and self.config.guidance_embeds:
+        if guidance is not None:
             temb = self.time_text_embed(t1000, guidance.to(BF16) * 1000, pooled_projections)
         else:
             temb = self.time_text_embed(t1000, pooled_projections)
@@ -592,10 +668,7 @@ class FluxTransformer2DModel(nn.Module):
         # norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out over all rows; text rows dropped after
         n = ops.ln_modulate(h.view(B * (S + L_img), D), mod[:, off:off + D], mod[:, off + D:off + 2 * D], S + L_img,
                             out=ws["n"])
-        out = ops.linear(n, self.proj_out.weight, self.proj_out.bias).view(B, S + L_img, -1)[:, S:].contiguous()
-        if not return_dict:
-            return (out,)
-        return SimpleNamespace(sample=out)
+        return ops.linear(n, self.proj_out.weight, self.proj_out.bias).view(B, S + L_img, -1)[:, S:].contiguous()
 
 
 def init_synthetic_(model: nn.Module, seed: int = 0, std: float = 0.02) -> nn.Module:

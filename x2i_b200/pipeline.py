@@ -130,6 +130,7 @@ class FluxPipeline:
         self.vae_scale_factor = 16  # diffusers 0.31.0 value when vae is None
         self.default_sample_size = 64
         self._device = transformer.device if transformer is not None else torch.device("cpu")
+        self._ids_cache = {}
 
     @classmethod
     def from_pretrained(cls, path, text_encoder=None, text_encoder_2=None, tokenizer=None, tokenizer_2=None, vae=None,
@@ -180,10 +181,19 @@ class FluxPipeline:
         latents = latents.permute(0, 3, 1, 4, 2, 5)
         return latents.reshape(batch_size, channels // (2 * 2), height * 2, width * 2)
 
+    def _cached_text_ids(self, S, device, dtype):
+        ck = ("txt", S, str(device), dtype)
+        if ck not in self._ids_cache:
+            self._ids_cache[ck] = torch.zeros(S, 3, device=device, dtype=dtype)
+        return self._ids_cache[ck]
+
     def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
         height = 2 * (int(height) // self.vae_scale_factor)
         width = 2 * (int(width) // self.vae_scale_factor)
-        ids = self._prepare_latent_image_ids(batch_size, height, width, device, dtype)
+        ck = ("img", height, width, str(device), dtype)
+        if ck not in self._ids_cache:  # stable id tensors across calls keep the transformer's RoPE table and graph cached
+            self._ids_cache[ck] = self._prepare_latent_image_ids(batch_size, height, width, device, dtype)
+        ids = self._ids_cache[ck]
         if latents is not None:
             return latents.to(device=device, dtype=dtype), ids
         latents = randn_tensor((batch_size, num_channels_latents, height, width), generator, device, dtype)
@@ -209,7 +219,7 @@ class FluxPipeline:
             pooled_prompt_embeds = pooled_prompt_embeds.repeat_interleave(num_images_per_prompt, 0)
         prompt_embeds = prompt_embeds.to(device)
         pooled_prompt_embeds = pooled_prompt_embeds.to(device)
-        text_ids = torch.zeros(prompt_embeds.shape[1], 3, device=device, dtype=dtype)
+        text_ids = self._cached_text_ids(prompt_embeds.shape[1], device, dtype)
         latents, latent_image_ids = self.prepare_latents(B, self.transformer.config.in_channels // 4, height, width, dtype,
                                                          device, generator, latents)
         latents = latents.contiguous()
