@@ -31,7 +31,85 @@ constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 128B-swizzled boxes
 constexpr int ATT_KV_SLOTS = 4;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + ATT_KV_SLOTS * ATT_TILE_BYTES + 1024 + 256;
 
-// POLY8: how many of every 8 softmax exponentials are evaluated with poly_exp2 instead of MUFU.EX2.
+// One online-softmax step of one query row over a 128-key tile (executed by the 128 threads of a softmax warpgroup).
+// MASKED is instantiated only for the last, ragged key tile so the common path carries no masking instructions.
+template <int POLY8, bool MASKED>
+__device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, int j, int valid,
+                                             float sc, float& m_run, float& l_run, int lane) {
+  mbar_wait(s_full_i, j & 1);
+  tc_fence_after();
+  uint32_t r[4][32];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, r[c]);
+  tmem_ld_wait();
+  if constexpr (MASKED) {  // keys >= valid were zero-filled by TMA: exclude them
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (c * 32 + k >= valid) r[c][k] = 0xff800000u;  // -inf
+  }
+  float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent FMNMX3 chains
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 32; k += 2)
+      mx4[(k >> 1) & 3] = max3f(mx4[(k >> 1) & 3], __uint_as_float(r[c][k]), __uint_as_float(r[c][k + 1]));
+  const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+  const float m_cand = fmaxf(m_run, mx * sc);
+  float alpha = 1.0f;
+  bool rescale = false;
+  if (j == 0) {
+    m_run = m_cand;
+  } else if (m_cand - m_run > 8.0f) {  // lazy rescaling: tolerate a stale max up to 2^8
+    alpha = fast_exp2(m_run - m_cand);
+    m_run = m_cand;
+    rescale = true;
+  }
+  // O_i may be touched here without waiting on a barrier: S_i(j) was issued after PV_i(j-1) and tcgen05.commit
+  // tracks completion of ALL earlier MMAs of the issuing thread, so s_full(j) implies PV_i(j-1) has retired.
+  if (j > 0 && __any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld32(t_o + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+      tmem_st32(t_o + c * 32, o);
+    }
+  }
+  const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_run, -m_run);
+  uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};  // packed (FADD2) partial row sums, 4 independent chains
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint64_t a2 = fma_f32x2(pack_f32x2(__uint_as_float(r[c][2 * k]), __uint_as_float(r[c][2 * k + 1])), sc2, nm2);
+      float a0, a1, p0, p1;
+      unpack_f32x2(a2, a0, a1);
+      if ((k & 3) < POLY8) {  // POLY8 of every 4 pairs: exp2 on the FMA pipe instead of MUFU
+        poly_exp2_x2(a0, a1, p0, p1);
+      } else {
+        p0 = fast_exp2(a0);
+        p1 = fast_exp2(a1);
+      }
+      sum2[k & 3] = add_f32x2(sum2[k & 3], pack_f32x2(p0, p1));
+      pk[k] = pack_bf16x2(p0, p1);
+    }
+    tmem_st16(t_s + c * 16, pk);  // P_i aliases S_i columns [0, 64)
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&p_full_i[c]);  // this quarter of P is ready for its two PV MMAs
+  }
+  float s0, s1;
+  unpack_f32x2(add_f32x2(add_f32x2(sum2[0], sum2[1]), add_f32x2(sum2[2], sum2[3])), s0, s1);
+  l_run = l_run * alpha + (s0 + s1);
+}
+
+// POLY8: how many of every 4 element PAIRS of the softmax use the FMA-pipe poly_exp2_x2 instead of MUFU.EX2.
 template <int POLY8>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -45,9 +123,9 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
   uint64_t* kv_full = bars + 1;         // 4
   uint64_t* kv_empty = bars + 5;        // 4
   uint64_t* s_full = bars + 9;          // 2
-  uint64_t* p_full = bars + 11;         // 2
-  uint64_t* o_full = bars + 13;         // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_full = bars + 11;         // 2 tiles x 4 quarters (32 keys each): PV MMAs start as soon as a quarter of P lands
+  uint64_t* o_full = bars + 19;         // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,7 +146,7 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      for (int c = 0; c < 4; ++c) mbar_init(&p_full[i * 4 + c], 4);
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -119,12 +197,17 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
                   idesc_s, kk != 0);
         }
       };
-      auto issue_pv = [&](int i, int slot, bool acc) {  // O_i += P_i V
+      auto issue_pv = [&](int i, int slot, bool acc, uint32_t ph) {  // O_i += P_i V, quarter by quarter as P lands
         const uint32_t bsm = kv_base + slot * ATT_TILE_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
-                  make_smem_desc_sw128(bsm + kk * 2048, 16384, 1024), idesc_o, (acc || kk != 0) ? 1u : 0u);
+        for (int c = 0; c < 4; ++c) {
+          mbar_wait(&p_full[i * 4 + c], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 2 * c; kk < 2 * c + 2; ++kk)
+            umma_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
+                    make_smem_desc_sw128(bsm + kk * 2048, 16384, 1024), idesc_o, (acc || kk != 0) ? 1u : 0u);
+        }
       };
       auto kv_wait = [&](int seq) { mbar_wait(&kv_full[seq & (ATT_KV_SLOTS - 1)], (seq / ATT_KV_SLOTS) & 1); };
 
@@ -141,20 +224,16 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
         const int vslot = vseq & (ATT_KV_SLOTS - 1), kslot = kseq & (ATT_KV_SLOTS - 1);
         const bool more = (j + 1 < n_kv);
         kv_wait(vseq);
-        mbar_wait(&p_full[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, vslot, j > 0);
-        umma_commit(&o_full[0]);
+        issue_pv(0, vslot, j > 0, j & 1);
+        if (!more) umma_commit(&o_full[0]);
         if (more) {
           kv_wait(kseq);
           tc_fence_after();
           issue_s(0, kslot);
           umma_commit(&s_full[0]);
         }
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, vslot, j > 0);
-        umma_commit(&o_full[1]);
+        issue_pv(1, vslot, j > 0, j & 1);
+        if (!more) umma_commit(&o_full[1]);
         umma_commit(&kv_empty[vslot]);
         if (more) {
           issue_s(1, kslot);
@@ -175,77 +254,14 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
     float l_run = 0.f;
     const float sc = p.scale_log2;
 
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[i], j & 1);
-      tc_fence_after();
-      uint32_t r[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, r[c]);
-      tmem_ld_wait();
-      if (j == n_kv - 1 && (p.L & 127) != 0) {  // mask the key tail (zero-filled by TMA)
-        const int valid = p.L - j * 128;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (c * 32 + k >= valid) r[c][k] = 0xff800000u;  // -inf
-      }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains (ILP)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int k = 0; k < 32; ++k) mx4[k & 3] = fmaxf(mx4[k & 3], __uint_as_float(r[c][k]));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_cand = fmaxf(m_run, mx * sc);
-      float alpha = 1.0f;
-      bool rescale = false;
-      if (j == 0) {
-        m_run = m_cand;
-      } else if (m_cand - m_run > 8.0f) {
-        alpha = fast_exp2(m_run - m_cand);
-        m_run = m_cand;
-        rescale = true;
-      }
-      if (j > 0) {
-        mbar_wait(&o_full[i], (j - 1) & 1);  // PV_i(j-1) complete (already true: S_i(j) was issued after it)
-        if (__any_sync(0xffffffffu, rescale)) {
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld32(t_o + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-            tmem_st32(t_o + c * 32, o);
-          }
-        }
-      }
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-      const float neg_m = -m_run;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float a0 = fmaf(__uint_as_float(r[c][2 * k]), sc, neg_m);
-          const float a1 = fmaf(__uint_as_float(r[c][2 * k + 1]), sc, neg_m);
-          const float p0 = (((2 * k) & 7) < POLY8) ? poly_exp2(a0) : fast_exp2(a0);
-          const float p1 = (((2 * k + 1) & 7) < POLY8) ? poly_exp2(a1) : fast_exp2(a1);
-          sum4[k & 3] += p0 + p1;
-          pk[k] = pack_bf16x2(p0, p1);
-        }
-        tmem_st16(t_s + c * 16, pk);  // P_i aliases S_i columns [0, 64)
-      }
-      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      l_run = l_run * alpha + sum;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
-    }
+    const bool ragged = (p.L & 127) != 0;
+    const int n_full = ragged ? n_kv - 1 : n_kv;
+    for (int j = 0; j < n_full; ++j)
+      softmax_step<POLY8, false>(t_s, t_o, &s_full[i], &p_full[i * 4], j, 128, sc, m_run, l_run, lane);
+    if (ragged)
+      softmax_step<POLY8, true>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, p.L - (n_kv - 1) * 128, sc, m_run, l_run, lane);
     // ---- epilogue: O_i / l -> bf16 -> global (token-major [.., H*128] so the out-projection GEMM reads it as A)
-    mbar_wait(&o_full[i], (n_kv - 1) & 1);
+    mbar_wait(&o_full[i], 0);  // committed once, after the last PV MMA of this tile
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const bool ok = pos < p.L;

@@ -178,6 +178,48 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ------------------------------------------------------------------ packed fp32x2 math (FFMA2 / FADD2, sm_100+) and FMNMX3
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// two exp2 at once on the FMA/ALU pipes (same polynomial as poly_exp2 below)
+__device__ __forceinline__ void poly_exp2_x2(float x0, float x1, float& y0, float& y1) {
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  const uint64_t x = pack_f32x2(x0, x1);
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f), nmagic = pack_f32x2(-12582912.0f, -12582912.0f);
+  const uint64_t t = add_f32x2(x, magic);
+  const uint64_t rr = add_f32x2(t, nmagic);
+  const uint64_t f = fma_f32x2(rr, pack_f32x2(-1.0f, -1.0f), x);
+  uint64_t pp = fma_f32x2(pack_f32x2(0.0555054f, 0.0555054f), f, pack_f32x2(0.2402265f, 0.2402265f));
+  pp = fma_f32x2(pp, f, pack_f32x2(0.6931472f, 0.6931472f));
+  pp = fma_f32x2(pp, f, pack_f32x2(1.0f, 1.0f));
+  float t0, t1, p0, p1;
+  unpack_f32x2(t, t0, t1);
+  unpack_f32x2(pp, p0, p1);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
 // exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, |rel err| < 1.2e-4 -- below bf16
 // resolution).  Used for a fraction of the softmax exponentials so the MUFU pipe is not the only bottleneck.
 __device__ __forceinline__ float poly_exp2(float x) {

@@ -97,6 +97,9 @@ def matmul_kn(a, b_kn, bias=None):
     return out
 
 
+ATTN_EVENTS = None  # set to a list to collect (start, end) CUDA events around every attention launch (bench.py)
+
+
 def attention(q, k, v, split=0, out0=None, out1=None):
     """softmax(q k^T / sqrt(128)) v for q,k,v [B, H, L, 128] -> token-major outputs.
     Rows t < split -> out0[B, split, H*128]; rows t >= split -> out1[B, L-split, >= H*128] (row-strided view ok)."""
@@ -111,7 +114,13 @@ def attention(q, k, v, split=0, out0=None, out1=None):
     _chk(out0, "out0"); _chk(out1, "out1")
     ld0 = out0.stride(-2) if out0 is not None else 0
     ld1 = out1.stride(-2) if out1 is not None else 0
+    if ATTN_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.call("x2i_mmdit_attention", _p(q), _p(k), _p(v), _p(out0), ld0, split, _p(out1), ld1, B, H, L, _stream())
+    if ATTN_EVENTS is not None:
+        e1.record()
+        ATTN_EVENTS.append((e0, e1))
     return out0, out1
 
 
