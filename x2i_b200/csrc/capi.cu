@@ -8,6 +8,7 @@
 
 #include "../../include/x2i_b200.h"
 #include "attn_sm100.cuh"
+#include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "rowwise.cuh"
 
@@ -116,6 +117,28 @@ int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, c
   return check_launch("gemm_tcgen05_kernel");
 }
 
+template <int EPI>
+int launch_gemm2_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm2_tcgen05_kernel<EPI>;
+  static std::atomic<bool> configured[16];
+  if (!configured[d->index].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e));
+    configured[d->index].store(true, std::memory_order_release);
+  }
+  const int tiles = ((p.M + 255) / 256) * (p.N / 256);
+  const int pairs = d->sms / 2;
+  const int grid = 2 * (tiles < pairs ? tiles : pairs);
+  kern<<<grid, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, p);
+  return check_launch("gemm2_tcgen05_kernel");
+}
+
+// 0: single-CTA kernel only; 1 (default): CTA-pair kernel whenever N % 256 == 0 and M > 128
+int use_pair_kernel() {
+  static const int v = []() { const char* e = getenv("X2I_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 int pick_bn(int N, int M) {
   if (N % 256 == 0) {
     // prefer 128-wide tiles when 256-wide ones would leave most SMs idle
@@ -135,12 +158,19 @@ int launch_gemm(DeviceInfo* d, const void* A, int64_t lda, const void* W, int64_
   if (!aligned16(A) || !aligned16(W) || lda % 8 || ldw % 8) return fail(X2I_ERR_ALIGN, "gemm: A/W must be 16-byte aligned with ld %% 8 == 0");
   int bn = force_bn ? force_bn : pick_bn(p.N, p.M);
   if (EPI == EPI_QKV && bn == 64) return fail(X2I_ERR_SHAPE, "qkv gemm: N must be a multiple of 128");
+  const bool pair = !force_bn && use_pair_kernel() && p.N % 256 == 0 && p.M > 128;
   CUtensorMap ta, tb;
   uint64_t da[2] = {(uint64_t)p.K, (uint64_t)p.M}, sa[2] = {1, (uint64_t)lda};
   uint32_t ba[2] = {GEMM_BK, GEMM_BM};
   int rc = make_map(d, &ta, A, 2, da, sa, ba);
   if (rc) return rc;
   uint64_t db[2] = {(uint64_t)p.K, (uint64_t)p.N}, sb[2] = {1, (uint64_t)ldw};
+  if (pair) {  // each CTA of the pair loads a 128-row half of the 256-row W tile
+    uint32_t bb2[2] = {GEMM_BK, 128};
+    rc = make_map(d, &tb, W, 2, db, sb, bb2);
+    if (rc) return rc;
+    return launch_gemm2_t<EPI>(d, ta, tb, p, st);
+  }
   uint32_t bb[2] = {GEMM_BK, (uint32_t)bn};
   rc = make_map(d, &tb, W, 2, db, sb, bb);
   if (rc) return rc;

@@ -1,0 +1,187 @@
+// CTA-pair (cta_group::2) variant of the tcgen05 GEMM: two CTAs on the SMs of one TPC cooperate on a 256 x 256 tile.
+//
+// Each CTA stages ITS 128 rows of A and ITS 128-row half of the W tile (the pair's tensor cores read both halves), so per
+// SM the TMA write traffic into shared memory and the UMMA operand reads are both 2/3 of the single-CTA 128x256 kernel
+// -- the single-CTA kernel asks ~192 B/clk of a 128 B/clk shared-memory port.  The leader CTA (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 (M=256, N=256, K=16); accumulators live in both CTAs' TMEM (128 lanes x 256 columns each,
+// double-buffered); each CTA's epilogue warps drain their own 128 rows with the same fused epilogues as gemm_sm100.cuh.
+//
+// Synchronisation (per CTA pair):
+//   full_bar[s]   (leader CTA): armed by the leader's producer with the bytes of BOTH CTAs; both CTAs' TMA loads signal it
+//   empty_bar[s]  (each CTA)  : tcgen05.commit.cta_group::2 ... multicast -> both producers may refill stage s
+//   tfull_bar[a]  (each CTA)  : multicast commit after the last k-block -> both epilogues start
+//   tempty_bar[a] (leader CTA): 8 arrivals (4 epilogue warps x 2 CTAs; the peer arrives remotely via mapa)
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace x2i {
+
+constexpr int GEMM2_STAGES = 6;
+constexpr int GEMM2_STAGE_BYTES = 2 * 128 * GEMM_BK * 2;  // A half (16 KB) + W half (16 KB) per CTA
+constexpr int GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared-window address -> the pair's even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* leader_bar_local, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(leader_bar_local) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar_local) {  // arrive on the leader CTA's copy of `bar`
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar_local))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  constexpr int NS = GEMM2_STAGES;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * GEMM2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tfull_bar = empty_bar + NS;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m2 = (p.M + 255) / 256;
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m2 * num_n;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one per CTA)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m2 = tile % num_m2, n_blk = tile / num_m2;
+        const int row_a = m2 * 256 + rank * 128, row_b = n_blk * BN + rank * 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * GEMM2_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * GEMM2_STAGE_BYTES);
+          tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, row_a);
+          tma_load_2d_pair(sa + 16384, &tma_b, &full_bar[stage], kb * GEMM_BK, row_b);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * GEMM2_STAGE_BYTES);
+          const uint32_t b_base = a_base + 16384;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_ss_pair(d_tmem, make_smem_desc_sw128(a_base + k * 32, 16, 1024), make_smem_desc_sw128(b_base + k * 32, 16, 1024),
+                         idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..5) of each CTA: own 128 rows
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int m2 = tile % num_m2, n_blk = tile / num_m2;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + as * BN + lane_off;
+      const int m = m2 * 256 + rank * 128 + quad * 32 + lane;
+      gemm_epilogue_tile<BN, EPI>(p, t_acc, m, n_blk * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs done with TMEM / no more remote arrivals in flight
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+}  // namespace x2i

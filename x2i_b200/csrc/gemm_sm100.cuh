@@ -82,6 +82,142 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float (&v)
   }
 }
 
+// Fused epilogue of one 128 x BN accumulator tile: thread `m` owns output row m; t_acc is the TMEM address of the tile
+// (lane quadrant of the calling warp already applied).
+template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const uint32_t t_acc, const int m, const int n_tile0) {
+  const bool row_ok = m < p.M;
+
+  if constexpr (EPI == EPI_QKV) {
+    const int D = p.heads * 128;
+    const int b = row_ok ? m / p.rows_per_batch : 0;
+    const int tok = row_ok ? m - b * p.rows_per_batch : 0;
+    const int pos = p.row_offset + tok;
+#pragma unroll 1
+    for (int hh = 0; hh < BN / 128; ++hh) {
+      const int n_h = n_tile0 + hh * 128;
+      if (n_h >= p.N) break;
+      const int sec = n_h / D;  // 0 q, 1 k, 2 v, >=3 mlp
+      uint32_t r[32];
+      float x[32], bb[32];
+      if (sec < 2) {
+        float ss = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(t_acc + hh * 128 + c * 32, r);
+          load_bf16x32(p.bias + n_h + c * 32, bb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = __uint_as_float(r[j]) + bb[j];
+            ss += t * t;
+          }
+        }
+        const float rinv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+        const int h = (n_h - sec * D) >> 7;
+        __nv_bfloat16* dst = (sec == 0 ? p.q : p.k) +
+                             ((static_cast<long long>(b) * p.heads + h) * p.L_total + pos) * 128;
+        const __nv_bfloat16* w = sec == 0 ? p.rms_q : p.rms_k;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(t_acc + hh * 128 + c * 32, r);
+          load_bf16x32(p.bias + n_h + c * 32, bb);
+          float ww[32];
+          load_bf16x32(w + c * 32, ww);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(r[j]) + bb[j]) * rinv * ww[j];
+          if (p.rope != nullptr && row_ok) {
+            const float4* rp = reinterpret_cast<const float4*>(p.rope + static_cast<long long>(pos) * 64 + c * 16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 cs = __ldg(rp + j);  // (cos0, sin0, cos1, sin1)
+              const float a0 = x[4 * j + 0], a1 = x[4 * j + 1], a2 = x[4 * j + 2], a3 = x[4 * j + 3];
+              x[4 * j + 0] = a0 * cs.x - a1 * cs.y;
+              x[4 * j + 1] = a1 * cs.x + a0 * cs.y;
+              x[4 * j + 2] = a2 * cs.z - a3 * cs.w;
+              x[4 * j + 3] = a3 * cs.z + a2 * cs.w;
+            }
+          }
+          if (row_ok) store_bf16x32(dst + c * 32, x);
+        }
+      } else if (sec == 2) {
+        const int h = (n_h - 2 * D) >> 7;
+        __nv_bfloat16* dst = p.v + ((static_cast<long long>(b) * p.heads + h) * p.L_total + pos) * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(t_acc + hh * 128 + c * 32, r);
+          load_bf16x32(p.bias + n_h + c * 32, bb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) + bb[j];
+          if (row_ok) store_bf16x32(dst + c * 32, x);
+        }
+      } else {
+        __nv_bfloat16* dst = p.mlp + static_cast<long long>(m) * p.ldmlp + (n_h - 3 * D);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(t_acc + hh * 128 + c * 32, r);
+          load_bf16x32(p.bias + n_h + c * 32, bb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(__uint_as_float(r[j]) + bb[j]);
+          if (row_ok) store_bf16x32(dst + c * 32, x);
+        }
+      }
+    }
+  } else {
+    const __nv_bfloat16* gate_row = nullptr;
+    if constexpr (EPI == EPI_GATE_RESIDUAL) {
+      const int b = row_ok ? m / p.rows_per_batch : 0;
+      gate_row = p.gate + static_cast<long long>(b) * p.gate_stride;
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int n0 = n_tile0 + c * 32;
+      if (n0 >= p.N) break;
+      uint32_t r[32];
+      float x[32];
+      tmem_ld32(t_acc + c * 32, r);
+      if (p.bias != nullptr) {
+        load_bf16x32(p.bias + n0, x);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = 0.f;
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(r[j]);
+      if constexpr (EPI == EPI_BIAS_GELU_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
+      } else if constexpr (EPI == EPI_BIAS_GELU_ERF) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
+      }
+      if (row_ok) {
+        if constexpr (EPI == EPI_BIAS) {
+          if (p.aux != nullptr) {  // second output: gelu_erf(C) (projector: MLP3.fc consumes GELU(x2), utils/proj.py:31)
+            float g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g[j] = gelu_erf_f(x[j]);
+            store_bf16x32(p.aux + static_cast<long long>(m) * p.ldaux + n0, g);
+          }
+        }
+        if constexpr (EPI == EPI_GATE_RESIDUAL) {
+          if (p.aux != nullptr) store_bf16x32(p.aux + static_cast<long long>(m) * p.ldaux + n0, x);
+          float g[32], res[32];
+          load_bf16x32(gate_row + n0, g);
+          load_bf16x32(p.residual + static_cast<long long>(m) * p.ldr + n0, res);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = res[j] + g[j] * x[j];
+        }
+        store_bf16x32(p.C + static_cast<long long>(m) * p.ldc + n0, x);
+      }
+    }
+  }
+}
+
 template <int BN, int EPI, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
@@ -192,137 +328,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * BN + lane_off;
       const int m = m_blk * GEMM_BM + quad * 32 + lane;
-      const bool row_ok = m < p.M;
-      const int n_tile0 = n_blk * BN;
-
-      if constexpr (EPI == EPI_QKV) {
-        const int D = p.heads * 128;
-        const int b = row_ok ? m / p.rows_per_batch : 0;
-        const int tok = row_ok ? m - b * p.rows_per_batch : 0;
-        const int pos = p.row_offset + tok;
-#pragma unroll 1
-        for (int hh = 0; hh < BN / 128; ++hh) {
-          const int n_h = n_tile0 + hh * 128;
-          if (n_h >= p.N) break;
-          const int sec = n_h / D;  // 0 q, 1 k, 2 v, >=3 mlp
-          uint32_t r[32];
-          float x[32], bb[32];
-          if (sec < 2) {
-            float ss = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              tmem_ld32(t_acc + hh * 128 + c * 32, r);
-              load_bf16x32(p.bias + n_h + c * 32, bb);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float t = __uint_as_float(r[j]) + bb[j];
-                ss += t * t;
-              }
-            }
-            const float rinv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
-            const int h = (n_h - sec * D) >> 7;
-            __nv_bfloat16* dst = (sec == 0 ? p.q : p.k) +
-                                 ((static_cast<long long>(b) * p.heads + h) * p.L_total + pos) * 128;
-            const __nv_bfloat16* w = sec == 0 ? p.rms_q : p.rms_k;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              tmem_ld32(t_acc + hh * 128 + c * 32, r);
-              load_bf16x32(p.bias + n_h + c * 32, bb);
-              float ww[32];
-              load_bf16x32(w + c * 32, ww);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(r[j]) + bb[j]) * rinv * ww[j];
-              if (p.rope != nullptr && row_ok) {
-                const float4* rp = reinterpret_cast<const float4*>(p.rope + static_cast<long long>(pos) * 64 + c * 16);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 cs = __ldg(rp + j);  // (cos0, sin0, cos1, sin1)
-                  const float a0 = x[4 * j + 0], a1 = x[4 * j + 1], a2 = x[4 * j + 2], a3 = x[4 * j + 3];
-                  x[4 * j + 0] = a0 * cs.x - a1 * cs.y;
-                  x[4 * j + 1] = a1 * cs.x + a0 * cs.y;
-                  x[4 * j + 2] = a2 * cs.z - a3 * cs.w;
-                  x[4 * j + 3] = a3 * cs.z + a2 * cs.w;
-                }
-              }
-              if (row_ok) store_bf16x32(dst + c * 32, x);
-            }
-          } else if (sec == 2) {
-            const int h = (n_h - 2 * D) >> 7;
-            __nv_bfloat16* dst = p.v + ((static_cast<long long>(b) * p.heads + h) * p.L_total + pos) * 128;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              tmem_ld32(t_acc + hh * 128 + c * 32, r);
-              load_bf16x32(p.bias + n_h + c * 32, bb);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) + bb[j];
-              if (row_ok) store_bf16x32(dst + c * 32, x);
-            }
-          } else {
-            __nv_bfloat16* dst = p.mlp + static_cast<long long>(m) * p.ldmlp + (n_h - 3 * D);
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              tmem_ld32(t_acc + hh * 128 + c * 32, r);
-              load_bf16x32(p.bias + n_h + c * 32, bb);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(__uint_as_float(r[j]) + bb[j]);
-              if (row_ok) store_bf16x32(dst + c * 32, x);
-            }
-          }
-        }
-      } else {
-        const __nv_bfloat16* gate_row = nullptr;
-        if constexpr (EPI == EPI_GATE_RESIDUAL) {
-          const int b = row_ok ? m / p.rows_per_batch : 0;
-          gate_row = p.gate + static_cast<long long>(b) * p.gate_stride;
-        }
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n0 = n_tile0 + c * 32;
-          if (n0 >= p.N) break;
-          uint32_t r[32];
-          float x[32];
-          tmem_ld32(t_acc + c * 32, r);
-          if (p.bias != nullptr) {
-            load_bf16x32(p.bias + n0, x);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = 0.f;
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(r[j]);
-          if constexpr (EPI == EPI_BIAS_GELU_TANH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
-          } else if constexpr (EPI == EPI_BIAS_GELU_ERF) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = gelu_erf_f(x[j]);
-          }
-          if (row_ok) {
-            if constexpr (EPI == EPI_BIAS) {
-              if (p.aux != nullptr) {  // second output: gelu_erf(C) (projector: MLP3.fc consumes GELU(x2), utils/proj.py:31)
-                float g[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) g[j] = gelu_erf_f(x[j]);
-                store_bf16x32(p.aux + static_cast<long long>(m) * p.ldaux + n0, g);
-              }
-            }
-            if constexpr (EPI == EPI_GATE_RESIDUAL) {
-              if (p.aux != nullptr) store_bf16x32(p.aux + static_cast<long long>(m) * p.ldaux + n0, x);
-              float g[32], res[32];
-              load_bf16x32(gate_row + n0, g);
-              load_bf16x32(p.residual + static_cast<long long>(m) * p.ldr + n0, res);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = res[j] + g[j] * x[j];
-            }
-            store_bf16x32(p.C + static_cast<long long>(m) * p.ldc + n0, x);
-          }
-        }
-      }
+      gemm_epilogue_tile<BN, EPI>(p, t_acc, m, n_blk * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
