@@ -65,6 +65,33 @@ int x2i_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       int64_t ldmlp, int M, int N, int K, int heads, int rows_per_batch, int row_offset, int L_total,
                       float eps, void* stream);
 
+/* Grouped launch: up to two GEMMs of the SAME kind / N-tile shape in ONE persistent kernel (e.g. the image and the text
+ * stream of a FluxTransformerBlock -- different weights, M = B*4096 and B*512 -- lightcontrol_flux.py:166-200), so the
+ * small text problem fills the partial wave of the image problem instead of occupying the GPU alone.  Fields have the
+ * meaning of the same-named arguments of x2i_gemm_bias_act / x2i_gemm_gate_residual / x2i_gemm_qkv_rope; unused ones
+ * are zero.  Falls back to independent launches when a problem does not fit the CTA-pair kernel (N % 256, M <= 128).  */
+#define X2I_GEMM_BIAS_ACT 0
+#define X2I_GEMM_GATE_RESIDUAL 1
+#define X2I_GEMM_QKV_ROPE 2
+typedef struct x2i_gemm_desc {
+  int kind, act;
+  int M, N, K;
+  int rows_per_batch, heads, row_offset, L_total;
+  float eps;
+  const void *A, *W, *bias;
+  int64_t lda, ldw;
+  void* C;
+  int64_t ldc;
+  const void *gate, *residual;
+  int64_t gate_stride, ldr;
+  void* aux;
+  int64_t ldaux;
+  const void *rms_q, *rms_k, *rope;
+  void *q, *k, *v, *mlp;
+  int64_t ldmlp;
+} x2i_gemm_desc;
+int x2i_gemm_grouped(const x2i_gemm_desc* descs, int n, void* stream);
+
 /* C[M,N] = A[M,K] @ Bkn[K,N] (+bias): B given N-contiguous ("MN-major" tcgen05 operand, as V is in attention).     */
 int x2i_gemm_kn(const void* A, int64_t lda, const void* Bkn, int64_t ldb, const void* bias, void* C, int64_t ldc,
                 int M, int N, int K, void* stream);

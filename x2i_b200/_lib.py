@@ -10,12 +10,25 @@ LIB_PATH = os.path.join(_HERE, "libx2i_b200.so")
 
 _vp, _i64, _i, _f, _d = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_double
 
+class GemmDesc(ctypes.Structure):
+    """struct x2i_gemm_desc (include/x2i_b200.h), field for field."""
+    _fields_ = [("kind", _i), ("act", _i), ("M", _i), ("N", _i), ("K", _i), ("rows_per_batch", _i), ("heads", _i),
+                ("row_offset", _i), ("L_total", _i), ("eps", _f),
+                ("A", _vp), ("W", _vp), ("bias", _vp), ("lda", _i64), ("ldw", _i64), ("C", _vp), ("ldc", _i64),
+                ("gate", _vp), ("residual", _vp), ("gate_stride", _i64), ("ldr", _i64), ("aux", _vp), ("ldaux", _i64),
+                ("rms_q", _vp), ("rms_k", _vp), ("rope", _vp), ("q", _vp), ("k", _vp), ("v", _vp), ("mlp", _vp),
+                ("ldmlp", _i64)]
+
+
+GEMM_BIAS_ACT, GEMM_GATE_RESIDUAL, GEMM_QKV_ROPE = 0, 1, 2
+
 # name -> argtypes; mirrors include/x2i_b200.h one to one (tests/test_abi.py checks both directions)
 SIGNATURES = {
     "x2i_gemm_bias_act": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
     "x2i_gemm_bias_dual": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _vp],
     "x2i_gemm_gate_residual": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _vp],
     "x2i_gemm_qkv_rope": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "x2i_gemm_grouped": [ctypes.POINTER(GemmDesc), _i, _vp],
     "x2i_gemm_kn": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp],
     "x2i_mmdit_attention": [_vp, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _vp],
     "x2i_ln_modulate": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp],
@@ -29,6 +42,8 @@ SIGNATURES = {
     "x2i_proj_mix_ln": [_vp, _i, _vp, _f, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],
     "x2i_mean_over_s": [_vp, _vp, _i, _i, _i, _vp],
 }
+
+
 
 _lib = None
 

@@ -118,7 +118,7 @@ int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, c
 }
 
 template <int EPI>
-int launch_gemm2_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch_gemm2_t(DeviceInfo* d, const CUtensorMap* maps /* a0,b0,a1,b1 */, const GemmParams* ps, int n_prob, cudaStream_t st) {
   auto kern = gemm2_tcgen05_kernel<EPI>;
   static std::atomic<bool> configured[16];
   if (!configured[d->index].load(std::memory_order_acquire)) {
@@ -126,10 +126,18 @@ int launch_gemm2_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, 
     if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e));
     configured[d->index].store(true, std::memory_order_release);
   }
-  const int tiles = ((p.M + 255) / 256) * (p.N / 256);
+  GemmGroup g;
+  memset(&g, 0, sizeof(g));
+  g.p[0] = ps[0];
+  g.tiles0 = ((ps[0].M + 255) / 256) * (ps[0].N / 256);
+  g.num_tiles = g.tiles0;
+  if (n_prob > 1) {
+    g.p[1] = ps[1];
+    g.num_tiles += ((ps[1].M + 255) / 256) * (ps[1].N / 256);
+  }
   const int pairs = d->sms / 2;
-  const int grid = 2 * (tiles < pairs ? tiles : pairs);
-  kern<<<grid, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, p);
+  const int grid = 2 * (g.num_tiles < pairs ? g.num_tiles : pairs);
+  kern<<<grid, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(maps[0], maps[1], maps[n_prob > 1 ? 2 : 0], maps[n_prob > 1 ? 3 : 1], g);
   return check_launch("gemm2_tcgen05_kernel");
 }
 
@@ -169,7 +177,8 @@ int launch_gemm(DeviceInfo* d, const void* A, int64_t lda, const void* W, int64_
     uint32_t bb2[2] = {GEMM_BK, 128};
     rc = make_map(d, &tb, W, 2, db, sb, bb2);
     if (rc) return rc;
-    return launch_gemm2_t<EPI>(d, ta, tb, p, st);
+    CUtensorMap maps[2] = {ta, tb};
+    return launch_gemm2_t<EPI>(d, maps, &p, 1, st);
   }
   uint32_t bb[2] = {GEMM_BK, (uint32_t)bn};
   rc = make_map(d, &tb, W, 2, db, sb, bb);
@@ -268,6 +277,93 @@ int x2i_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, co
   p.L_total = L_total; p.row_offset = row_offset; p.heads = heads; p.rows_per_batch = rows_per_batch; p.eps = eps;
   p.mlp = static_cast<__nv_bfloat16*>(mlp); p.ldmlp = ldmlp;
   return launch_gemm<EPI_QKV>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+int desc_to_params(const x2i_gemm_desc& ds, GemmParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.M = ds.M; p.N = ds.N; p.K = ds.K;
+  p.bias = static_cast<const __nv_bfloat16*>(ds.bias);
+  p.C = static_cast<__nv_bfloat16*>(ds.C); p.ldc = ds.ldc;
+  p.residual = static_cast<const __nv_bfloat16*>(ds.residual); p.ldr = ds.ldr;
+  p.gate = static_cast<const __nv_bfloat16*>(ds.gate); p.gate_stride = ds.gate_stride;
+  p.rows_per_batch = ds.rows_per_batch;
+  p.aux = static_cast<__nv_bfloat16*>(ds.aux); p.ldaux = ds.ldaux;
+  p.q = static_cast<__nv_bfloat16*>(ds.q); p.k = static_cast<__nv_bfloat16*>(ds.k); p.v = static_cast<__nv_bfloat16*>(ds.v);
+  p.rms_q = static_cast<const __nv_bfloat16*>(ds.rms_q); p.rms_k = static_cast<const __nv_bfloat16*>(ds.rms_k);
+  p.rope = static_cast<const float2*>(ds.rope);
+  p.L_total = ds.L_total; p.row_offset = ds.row_offset; p.heads = ds.heads; p.eps = ds.eps;
+  p.mlp = static_cast<__nv_bfloat16*>(ds.mlp); p.ldmlp = ds.ldmlp;
+  return X2I_OK;
+}
+}  // namespace
+
+int x2i_gemm_grouped(const x2i_gemm_desc* descs, int n, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!descs || n < 1 || n > 2) return fail(X2I_ERR_SHAPE, "gemm_grouped: 1 or 2 problems");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int kind = descs[0].kind;
+  bool pair_ok = use_pair_kernel() != 0;
+  for (int i = 0; i < n; ++i) {
+    const x2i_gemm_desc& ds = descs[i];
+    if (ds.kind != kind) return fail(X2I_ERR_SHAPE, "gemm_grouped: all problems must share one epilogue kind");
+    if (ds.M <= 0 || ds.N <= 0 || ds.K <= 0 || ds.N % 32 || ds.K % 8) return fail(X2I_ERR_SHAPE, "gemm_grouped: bad M/N/K");
+    if (!aligned16(ds.A) || !aligned16(ds.W) || ds.lda % 8 || ds.ldw % 8) return fail(X2I_ERR_ALIGN, "gemm_grouped: A/W alignment");
+    pair_ok = pair_ok && ds.N % 256 == 0 && ds.M > 128;
+  }
+  if (!pair_ok || n == 1) {  // fall back to independent launches through the single-problem entry points
+    for (int i = 0; i < n; ++i) {
+      const x2i_gemm_desc& ds = descs[i];
+      int rc;
+      if (kind == X2I_GEMM_BIAS_ACT)
+        rc = x2i_gemm_bias_act(ds.A, ds.lda, ds.W, ds.ldw, ds.bias, ds.C, ds.ldc, ds.M, ds.N, ds.K, ds.act, stream);
+      else if (kind == X2I_GEMM_GATE_RESIDUAL)
+        rc = x2i_gemm_gate_residual(ds.A, ds.lda, ds.W, ds.ldw, ds.bias, ds.gate, ds.gate_stride, ds.rows_per_batch, ds.residual,
+                                    ds.ldr, ds.C, ds.ldc, ds.aux, ds.ldaux, ds.M, ds.N, ds.K, stream);
+      else if (kind == X2I_GEMM_QKV_ROPE)
+        rc = x2i_gemm_qkv_rope(ds.A, ds.lda, ds.W, ds.ldw, ds.bias, ds.rms_q, ds.rms_k, ds.rope, ds.q, ds.k, ds.v, ds.mlp, ds.ldmlp,
+                               ds.M, ds.N, ds.K, ds.heads, ds.rows_per_batch, ds.row_offset, ds.L_total, ds.eps, stream);
+      else
+        return fail(X2I_ERR_SHAPE, "gemm_grouped: unknown kind %d", kind);
+      if (rc) return rc;
+    }
+    return X2I_OK;
+  }
+  GemmParams ps[2];
+  CUtensorMap maps[4];
+  for (int i = 0; i < n; ++i) {
+    const x2i_gemm_desc& ds = descs[i];
+    desc_to_params(ds, ps[i]);
+    if (kind == X2I_GEMM_QKV_ROPE) {
+      const int D = ds.heads * 128;
+      if (ds.heads <= 0 || ds.N < 3 * D || !ds.bias || !ds.rms_q || !ds.rms_k || !ds.q || !ds.k || !ds.v || (ds.N > 3 * D && !ds.mlp) ||
+          ds.rows_per_batch <= 0 || ds.row_offset < 0 || ds.row_offset + ds.rows_per_batch > ds.L_total)
+        return fail(X2I_ERR_SHAPE, "gemm_grouped(qkv): inconsistent descriptor %d", i);
+    } else if (kind == X2I_GEMM_GATE_RESIDUAL) {
+      if (!ds.gate || !ds.residual || !ds.C || ds.rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "gemm_grouped(gate): descriptor %d", i);
+    } else if (!ds.C) {
+      return fail(X2I_ERR_SHAPE, "gemm_grouped: C missing in descriptor %d", i);
+    }
+    uint64_t da[2] = {(uint64_t)ds.K, (uint64_t)ds.M}, sa[2] = {1, (uint64_t)ds.lda};
+    uint32_t ba[2] = {GEMM_BK, 128};
+    if (int rc = make_map(d, &maps[2 * i], ds.A, 2, da, sa, ba)) return rc;
+    uint64_t db[2] = {(uint64_t)ds.K, (uint64_t)ds.N}, sb[2] = {1, (uint64_t)ds.ldw};
+    if (int rc = make_map(d, &maps[2 * i + 1], ds.W, 2, db, sb, ba)) return rc;
+  }
+  if (kind == X2I_GEMM_BIAS_ACT) {
+    for (int i = 1; i < n; ++i)
+      if (descs[i].act != descs[0].act) return fail(X2I_ERR_SHAPE, "gemm_grouped: problems must share the activation");
+    switch (descs[0].act) {
+      case 0: return launch_gemm2_t<EPI_BIAS>(d, maps, ps, n, st);
+      case 1: return launch_gemm2_t<EPI_BIAS_GELU_TANH>(d, maps, ps, n, st);
+      case 2: return launch_gemm2_t<EPI_BIAS_GELU_ERF>(d, maps, ps, n, st);
+      default: return fail(X2I_ERR_SHAPE, "gemm_grouped: unknown act");
+    }
+  }
+  if (kind == X2I_GEMM_GATE_RESIDUAL) return launch_gemm2_t<EPI_GATE_RESIDUAL>(d, maps, ps, n, st);
+  if (kind == X2I_GEMM_QKV_ROPE) return launch_gemm2_t<EPI_QKV>(d, maps, ps, n, st);
+  return fail(X2I_ERR_SHAPE, "gemm_grouped: unknown kind %d", kind);
 }
 
 int x2i_gemm_kn(const void* A, int64_t lda, const void* Bkn, int64_t ldb, const void* bias, void* C, int64_t ldc, int M,

@@ -66,9 +66,33 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// Up to two problems (same epilogue kind; e.g. the image and text streams of a double block, which have different
+// weights and M) share one persistent launch: tiles [0, tiles0) belong to problem 0, the rest to problem 1.  This fills
+// the partial waves a 512-row text GEMM (24-96 pair tiles on 74 SM pairs) would otherwise leave idle.
+struct GemmGroup {
+  GemmParams p[2];
+  int tiles0;     // pair tiles of problem 0
+  int num_tiles;  // pair tiles of both problems
+};
+
+struct TileRef {
+  int prob, m2, n_blk;
+};
+__device__ __forceinline__ TileRef locate_tile(const GemmGroup& g, int tile) {
+  TileRef t;
+  t.prob = tile >= g.tiles0 ? 1 : 0;
+  const int local = tile - (t.prob ? g.tiles0 : 0);
+  const int num_m2 = (g.p[t.prob].M + 255) / 256;
+  t.m2 = local % num_m2;
+  t.n_blk = local / num_m2;
+  return t;
+}
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_constant__ CUtensorMap tma_b0,
+                     const __grid_constant__ CUtensorMap tma_a1, const __grid_constant__ CUtensorMap tma_b1,
+                     const __grid_constant__ GemmGroup g) {
   constexpr int NS = GEMM2_STAGES;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -83,14 +107,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int num_m2 = (p.M + 255) / 256;
-  const int num_n = p.N / BN;
-  const int num_tiles = num_m2 * num_n;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_tiles = g.num_tiles;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_a0);
+    tma_prefetch_desc(&tma_b0);
+    if (g.num_tiles > g.tiles0) {
+      tma_prefetch_desc(&tma_a1);
+      tma_prefetch_desc(&tma_b1);
+    }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -116,14 +141,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m2 = tile % num_m2, n_blk = tile / num_m2;
-        const int row_a = m2 * 256 + rank * 128, row_b = n_blk * BN + rank * 128;
+        const TileRef t = locate_tile(g, tile);
+        const CUtensorMap* ma = t.prob ? &tma_a1 : &tma_a0;
+        const CUtensorMap* mb = t.prob ? &tma_b1 : &tma_b0;
+        const int num_kb = (g.p[t.prob].K + GEMM_BK - 1) / GEMM_BK;
+        const int row_a = t.m2 * 256 + rank * 128, row_b = t.n_blk * BN + rank * 128;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * GEMM2_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * GEMM2_STAGE_BYTES);
-          tma_load_2d_pair(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, row_a);
-          tma_load_2d_pair(sa + 16384, &tma_b, &full_bar[stage], kb * GEMM_BK, row_b);
+          tma_load_2d_pair(sa, ma, &full_bar[stage], kb * GEMM_BK, row_a);
+          tma_load_2d_pair(sa + 16384, mb, &full_bar[stage], kb * GEMM_BK, row_b);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
@@ -138,6 +166,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const int num_kb = (g.p[tile >= g.tiles0 ? 1 : 0].K + GEMM_BK - 1) / GEMM_BK;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -162,14 +191,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-      const int m2 = tile % num_m2, n_blk = tile / num_m2;
+      const TileRef t = locate_tile(g, tile);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * BN + lane_off;
-      const int m = m2 * 256 + rank * 128 + quad * 32 + lane;
-      gemm_epilogue_tile<BN, EPI>(p, t_acc, m, n_blk * BN);
+      const int m = t.m2 * 256 + rank * 128 + quad * 32 + lane;
+      gemm_epilogue_tile<BN, EPI>(g.p[t.prob], t_acc, m, t.n_blk * BN);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);

@@ -211,10 +211,11 @@ class FluxAttnProcessor2_0:
                 _, out = ops.attention(q, k, v, split=0)
             return out
         c2 = encoder_hidden_states.reshape(B * S, D)
-        ops.qkv_rope(x2, attn._w_qkv, attn._b_qkv, attn.norm_q.weight, attn.norm_k.weight, rope, q, k, v, H, L_img, S,
-                     attn.norm_q.eps)
-        ops.qkv_rope(c2, attn._w_add_qkv, attn._b_add_qkv, attn.norm_added_q.weight, attn.norm_added_k.weight, rope, q, k, v,
-                     H, S, 0, attn.norm_added_q.eps)
+        ops.gemm_grouped(  # image + text QKV projections in one launch
+            ops.desc_qkv_rope(x2, attn._w_qkv, attn._b_qkv, attn.norm_q.weight, attn.norm_k.weight, rope, q, k, v, H, L_img, S,
+                              attn.norm_q.eps),
+            ops.desc_qkv_rope(c2, attn._w_add_qkv, attn._b_add_qkv, attn.norm_added_q.weight, attn.norm_added_k.weight, rope,
+                              q, k, v, H, S, 0, attn.norm_added_q.eps))
         a_txt = ws.get("a_txt"); a_img = ws.get("a_img")
         if a_txt is None or a_txt.shape != (B, S, D) or a_img.shape != (B, L_img, D):
             a_txt = torch.empty(B, S, D, device=dev, dtype=BF16)
@@ -227,8 +228,9 @@ class FluxAttnProcessor2_0:
             return img, txt
         aux_img = torch.empty(B, L_img, D, device=dev, dtype=BF16) if ctx.want_aux else None
         aux_txt = torch.empty(B, S, D, device=dev, dtype=BF16) if ctx.want_aux else None
-        ops.linear_gate_residual(a_img.view(B * L_img, D), wo.weight, wo.bias, ctx.gate_img, ctx.res_img, L_img, aux=aux_img)
-        ops.linear_gate_residual(a_txt.view(B * S, D), wa.weight, wa.bias, ctx.gate_txt, ctx.res_txt, S, aux=aux_txt)
+        ops.gemm_grouped(  # both out-projections with gate + residual epilogues in one launch
+            ops.desc_gate_residual(a_img.view(B * L_img, D), wo.weight, wo.bias, ctx.gate_img, ctx.res_img, L_img, aux=aux_img),
+            ops.desc_gate_residual(a_txt.view(B * S, D), wa.weight, wa.bias, ctx.gate_txt, ctx.res_txt, S, aux=aux_txt))
         return aux_img, aux_txt
 
 
@@ -353,10 +355,17 @@ class FluxTransformerBlock(nn.Module):
             a_img, a_txt = self.attn(hidden_states=nx, encoder_hidden_states=nc, image_rotary_emb=image_rotary_emb)
             ops.gate_residual_(x2, a_img.reshape(B * L_img, D), mi[2], L_img)
             ops.gate_residual_(c2, a_txt.reshape(B * S, D), mc[2], S)
-        for (t2, m, ff, rows, key) in ((x2, mi, self.ff, L_img, "ffx"), (c2, mc, self.ff_context, S, "ffc")):
-            n2 = ops.ln_modulate(t2, m[4], m[3], rows, out=ws.get("nx" if rows == L_img else "nc"))
-            h = ops.linear(n2, ff.net[0].proj.weight, ff.net[0].proj.bias, act=1, out=ws.get(key))
-            ops.linear_gate_residual(h, ff.net[2].weight, ff.net[2].bias, m[5], t2, rows)
+        nx2 = ops.ln_modulate(x2, mi[4], mi[3], L_img, out=ws.get("nx"))
+        nc2 = ops.ln_modulate(c2, mc[4], mc[3], S, out=ws.get("nc"))
+        F = self.ff.net[0].proj.weight.shape[0]
+        hx, hc = ws.get("ffx"), ws.get("ffc")
+        if hx is None or hx.shape != (B * L_img, F) or hc.shape != (B * S, F):
+            hx = torch.empty(B * L_img, F, device=x.device, dtype=BF16)
+            hc = torch.empty(B * S, F, device=x.device, dtype=BF16)
+        f0, f2, g0, g2 = self.ff.net[0].proj, self.ff.net[2], self.ff_context.net[0].proj, self.ff_context.net[2]
+        ops.gemm_grouped(ops.desc_linear(nx2, f0.weight, f0.bias, hx, act=1), ops.desc_linear(nc2, g0.weight, g0.bias, hc, act=1))
+        ops.gemm_grouped(ops.desc_gate_residual(hx, f2.weight, f2.bias, mi[5], x2, L_img),
+                         ops.desc_gate_residual(hc, g2.weight, g2.bias, mc[5], c2, S))
         return c, x
 
 

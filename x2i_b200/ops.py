@@ -87,6 +87,45 @@ def qkv_rope(x, weight, bias, rms_q, rms_k, rope, q, k, v, heads, rows_per_batch
               _p(k), _p(v), _p(mlp), ldmlp, M, N, K, heads, rows_per_batch, row_offset, L_total, eps, _stream())
 
 
+def desc_linear(x, weight, bias, out, act=0):
+    """Descriptor of act(x @ weight.T + bias) -> out, for gemm_grouped()."""
+    _chk(x, "x"); _chk(weight, "weight"); _chk(bias, "bias"); _chk(out, "out")
+    M, lda = _rows(x)
+    N, K = weight.shape
+    return _lib.GemmDesc(kind=_lib.GEMM_BIAS_ACT, act=act, M=M, N=N, K=K, A=_p(x), W=_p(weight), bias=_p(bias), lda=lda,
+                         ldw=weight.stride(0), C=_p(out), ldc=_rows(out)[1])
+
+
+def desc_gate_residual(x, weight, bias, gate, residual, rows_per_batch, aux=None):
+    """Descriptor of residual += gate[b] * (x @ weight.T + bias) (in place); aux receives the un-gated value."""
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (gate, "gate"), (residual, "residual"), (aux, "aux")):
+        _chk(t, n)
+    M, lda = _rows(x)
+    N, K = weight.shape
+    ldr = _rows(residual)[1]
+    return _lib.GemmDesc(kind=_lib.GEMM_GATE_RESIDUAL, M=M, N=N, K=K, rows_per_batch=rows_per_batch, A=_p(x), W=_p(weight),
+                         bias=_p(bias), lda=lda, ldw=weight.stride(0), C=_p(residual), ldc=ldr, gate=_p(gate),
+                         residual=_p(residual), gate_stride=gate.stride(0), ldr=ldr, aux=_p(aux),
+                         ldaux=_rows(aux)[1] if aux is not None else 0)
+
+
+def desc_qkv_rope(x, weight, bias, rms_q, rms_k, rope, q, k, v, heads, rows_per_batch, row_offset, eps=1e-6, mlp=None):
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (rms_q, "rms_q"), (rms_k, "rms_k"), (q, "q"), (k, "k"), (v, "v"), (mlp, "mlp")):
+        _chk(t, n)
+    M, lda = _rows(x)
+    N, K = weight.shape
+    return _lib.GemmDesc(kind=_lib.GEMM_QKV_ROPE, M=M, N=N, K=K, rows_per_batch=rows_per_batch, heads=heads, row_offset=row_offset,
+                         L_total=q.shape[2], eps=eps, A=_p(x), W=_p(weight), bias=_p(bias), lda=lda, ldw=weight.stride(0),
+                         rms_q=_p(rms_q), rms_k=_p(rms_k), rope=_p(rope), q=_p(q), k=_p(k), v=_p(v), mlp=_p(mlp),
+                         ldmlp=_rows(mlp)[1] if mlp is not None else 0)
+
+
+def gemm_grouped(*descs):
+    """Run 1-2 GEMM descriptors of the same kind in ONE persistent CTA-pair launch (image + text stream of a block)."""
+    arr = (_lib.GemmDesc * len(descs))(*descs)
+    _lib.call("x2i_gemm_grouped", arr, len(descs), _stream())
+
+
 def matmul_kn(a, b_kn, bias=None):
     """a[M,K] @ b_kn[K,N] with b N-contiguous (exercises the MN-major tcgen05 operand path used for V)."""
     _chk(a, "a"); _chk(b_kn, "b"); _chk(bias, "bias")
