@@ -569,16 +569,15 @@ int x2i_proj_mix_ln(const void* x, int mode, const float* w, float conv_bias, co
                     float eps, void* y, int B, int C, int S, int H, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
-  if (B <= 0 || C <= 0 || S <= 0 || H <= 0 || H % 8 || H > 8 * PROJ_THREADS * 2 || mode < 0 || mode > 2) return fail(X2I_ERR_SHAPE, "proj_mix_ln: H must be a multiple of 8, <= 4096; mode in 0..2");
+  if (B <= 0 || C <= 0 || S <= 0 || H <= 0 || H % 8 || H > 8 * 512 || mode < 0 || mode > 2) return fail(X2I_ERR_SHAPE, "proj_mix_ln: H must be a multiple of 8, <= 4096; mode in 0..2");
   if (mode != 2 && !w) return fail(X2I_ERR_SHAPE, "proj_mix_ln: weights required for mode %d", mode);
   if (!aligned16(x) || !aligned16(y)) return fail(X2I_ERR_ALIGN, "proj_mix_ln: alignment");
-  const size_t smem = (((static_cast<size_t>(C) * 25 + 3) & ~size_t(3)) + H + 8 + 2 * (PROJ_THREADS / 32)) * sizeof(float);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  auto X = static_cast<const __nv_bfloat16*>(x);
-  auto Y = static_cast<__nv_bfloat16*>(y);
-  const int nchunk = H / 8;
-  if (nchunk <= PROJ_THREADS) proj_mix_ln_kernel<1><<<B * S, PROJ_THREADS, smem, st>>>(X, mode, w, conv_bias, gamma, beta, eps, Y, B, C, S, H);
-  else proj_mix_ln_kernel<2><<<B * S, PROJ_THREADS, smem, st>>>(X, mode, w, conv_bias, gamma, beta, eps, Y, B, C, S, H);
+  const int threads = ((H / 8 + 31) / 32) * 32;
+  const size_t smem = (((static_cast<size_t>(C) * 25 + 3) & ~size_t(3)) + 32) * sizeof(float);
+  if (smem > 48 * 1024) return fail(X2I_ERR_SHAPE, "proj_mix_ln: too many channels (C=%d)", C);
+  const int tiles = (S + PROJ_R - 1) / PROJ_R;
+  proj_mix_ln_kernel<<<B * tiles, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), mode, w, conv_bias, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), B, C, S, H);
   return check_launch("proj_mix_ln_kernel");
 }
 

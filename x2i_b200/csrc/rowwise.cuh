@@ -250,6 +250,14 @@ __global__ void gate_residual_kernel(__nv_bfloat16* __restrict__ x, long long ld
 // Forward writes row_kl[row]; a second deterministic kernel sums rows per layer.
 // Backward recomputes the row statistics and writes d loss / d student in bf16.
 constexpr int KD_THREADS = 128;
+__device__ __forceinline__ float sum_f32x2(uint64_t v) {
+  float a, b;
+  unpack_f32x2(v, a, b);
+  return a + b;
+}
+// All element-wise math runs on packed fp32x2 registers (FADD2 / FMUL2 / FFMA2): ~10 instructions per (teacher,
+// student) element pair instead of ~16, which is what keeps this kernel HBM-bound rather than issue-bound (2 MUFU.EX2 per
+// pair remain the next limiter: 384 clk per 3072-wide row per SM against 530 clk of HBM time).
 template <int MAXC, bool BWD>
 __global__ void __launch_bounds__(KD_THREADS) kd_row_kernel(const __nv_bfloat16* __restrict__ teacher,
                                                             const __nv_bfloat16* __restrict__ student, int D,
@@ -261,85 +269,123 @@ __global__ void __launch_bounds__(KD_THREADS) kd_row_kernel(const __nv_bfloat16*
   const int nchunk = D >> 3;
   const uint4* tr = reinterpret_cast<const uint4*>(teacher + row * D);
   const uint4* sr = reinterpret_cast<const uint4*>(student + row * D);
-  float t[MAXC][8], s[MAXC][8];
-  float r2[2] = {0.f, 0.f};
+  uint64_t t[MAXC][4], s[MAXC][4];  // fp32x2 pairs
+  uint4 tq[MAXC], sq[MAXC];
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
+  for (int i = 0; i < MAXC; ++i) {  // all loads first (2 * MAXC x 16 B in flight per thread)
     const int c = i * KD_THREADS + threadIdx.x;
     if (c < nchunk) {
-      unpack8(ld_stream(tr + c), t[i]);
-      unpack8(ld_stream(sr + c), s[i]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { r2[0] += t[i][j]; r2[1] += s[i][j]; }
+      tq[i] = ld_stream(tr + c);
+      sq[i] = ld_stream(sr + c);
     }
   }
+  uint64_t at = 0ull, as = 0ull;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    if (i * KD_THREADS + threadIdx.x < nchunk) {
+      t[i][0] = bf16x2_to_f32x2(tq[i].x); t[i][1] = bf16x2_to_f32x2(tq[i].y);
+      t[i][2] = bf16x2_to_f32x2(tq[i].z); t[i][3] = bf16x2_to_f32x2(tq[i].w);
+      s[i][0] = bf16x2_to_f32x2(sq[i].x); s[i][1] = bf16x2_to_f32x2(sq[i].y);
+      s[i][2] = bf16x2_to_f32x2(sq[i].z); s[i][3] = bf16x2_to_f32x2(sq[i].w);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { at = add_f32x2(at, t[i][j]); as = add_f32x2(as, s[i][j]); }
+    }
+  }
+  float r2[2] = {sum_f32x2(at), sum_f32x2(as)};
   block_sum<2, KD_THREADS / 32>(r2, red);
   const float mt = r2[0] / D, ms = r2[1] / D;
-  r2[0] = r2[1] = 0.f;
+  const uint64_t nmt2 = pack_f32x2(-mt, -mt), nms2 = pack_f32x2(-ms, -ms);
+  at = as = 0ull;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     if (i * KD_THREADS + threadIdx.x < nchunk) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        t[i][j] -= mt; s[i][j] -= ms;
-        r2[0] += t[i][j] * t[i][j]; r2[1] += s[i][j] * s[i][j];
+      for (int j = 0; j < 4; ++j) {
+        t[i][j] = add_f32x2(t[i][j], nmt2);
+        s[i][j] = add_f32x2(s[i][j], nms2);
+        at = fma_f32x2(t[i][j], t[i][j], at);
+        as = fma_f32x2(s[i][j], s[i][j], as);
       }
     }
   }
+  r2[0] = sum_f32x2(at); r2[1] = sum_f32x2(as);
   block_sum<2, KD_THREADS / 32>(r2, red);
   const float sd_t = sqrtf(r2[0] / (D - 1)), sd_s = sqrtf(r2[1] / (D - 1));
   const float kt = inv_T / (1e-7f + sd_t), ks = inv_T / (1e-7f + sd_s);
-  // u = z/T (logits); e = exp(u)
-  float r3[3] = {0.f, 0.f, 0.f};  // sum e_t, sum e_s, sum e_s (u_s - u_t)
+  // logits u = z/T, evaluated in the exp2 domain: e = 2^(u log2e)
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  const uint64_t kt2 = pack_f32x2(kt * LOG2E, kt * LOG2E), ks2 = pack_f32x2(ks * LOG2E, ks * LOG2E);
+  const uint64_t nkt2 = pack_f32x2(-kt * LOG2E, -kt * LOG2E);
+  uint64_t aet = 0ull, aes = 0ull, aeg = 0ull;  // sum e_t, sum e_s, sum e_s * gap   (gap = (u_s - u_t) log2e)
+  uint64_t es[BWD ? MAXC : 1][4];                // BWD keeps e_s (saves a second MUFU pass)
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     if (i * KD_THREADS + threadIdx.x < nchunk) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float ut = t[i][j] * kt, us = s[i][j] * ks;
-        const float es = __expf(us);
-        r3[0] += __expf(ut); r3[1] += es; r3[2] += es * (us - ut);
-        t[i][j] = us - ut;  // keep the logit gap; s stays centred
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t us2 = mul_f32x2(s[i][j], ks2);
+        const uint64_t ut2 = mul_f32x2(t[i][j], kt2);
+        const uint64_t gap2 = fma_f32x2(t[i][j], nkt2, us2);
+        float a0, a1, b0, b1;
+        unpack_f32x2(us2, a0, a1);
+        unpack_f32x2(ut2, b0, b1);
+        const uint64_t es2 = pack_f32x2(fast_exp2(a0), fast_exp2(a1));
+        const uint64_t et2 = pack_f32x2(fast_exp2(b0), fast_exp2(b1));
+        aet = add_f32x2(aet, et2);
+        aes = add_f32x2(aes, es2);
+        aeg = fma_f32x2(es2, gap2, aeg);
+        t[i][j] = gap2;  // keep the logit gap (log2 units); s stays centred
+        if constexpr (BWD) es[i][j] = es2;
       }
     }
   }
+  float r3[3] = {sum_f32x2(aet), sum_f32x2(aes), sum_f32x2(aeg)};
   block_sum<3, KD_THREADS / 32>(r3, red);
   const float lse_t = __logf(r3[0]), lse_s = __logf(r3[1]);
-  const float kl = r3[2] / r3[1] - lse_s + lse_t;
+  const float kl = LN2 * r3[2] / r3[1] - lse_s + lse_t;
   if constexpr (!BWD) {
     if (threadIdx.x == 0) row_kl[row] = kl;
   } else {
     // g_j = dKL/du_j = ps_j (a_j - kl), a_j = (us_j - ut_j) - lse_s + lse_t ; then back through normalize().
     const float inv_zs = 1.0f / r3[1];
     const float shift = lse_t - lse_s - kl;
-    float r[2] = {0.f, 0.f};  // sum g, sum g * (s - mean)
+    const uint64_t izs2 = pack_f32x2(inv_zs, inv_zs), ln2_2 = pack_f32x2(LN2, LN2), shift2 = pack_f32x2(shift, shift);
+    uint64_t ag = 0ull, ags = 0ull;  // sum g, sum g * (s - mean)
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
       if (i * KD_THREADS + threadIdx.x < nchunk) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float ps = __expf(s[i][j] * ks) * inv_zs;
-          const float g = ps * (t[i][j] + shift);
-          t[i][j] = g;
-          r[0] += g; r[1] += g * s[i][j];
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t ps2 = mul_f32x2(es[i][j], izs2);
+          const uint64_t g2 = mul_f32x2(ps2, fma_f32x2(t[i][j], ln2_2, shift2));
+          t[i][j] = g2;
+          ag = add_f32x2(ag, g2);
+          ags = fma_f32x2(g2, s[i][j], ags);
         }
       }
     }
+    float r[2] = {sum_f32x2(ag), sum_f32x2(ags)};
     block_sum<2, KD_THREADS / 32>(r, red);
     const float up = row_scale[row];
     const float gmean = r[0] / D;
     const bool dead = (up == 0.f);  // layer skipped by the inf/nan guard: exactly zero gradient, never 0 * NaN
     // du_j/ds_k = ks (delta_jk - 1/D) - (s_j-mean)(s_k-mean) * inv_T / ((eps+sd)^2 (D-1) sd)
     const float c2 = r[1] * inv_T / ((1e-7f + sd_s) * (1e-7f + sd_s) * (D - 1) * fmaxf(sd_s, 1e-30f));
+    const uint64_t ngm2 = pack_f32x2(-gmean, -gmean), a2 = pack_f32x2(up * ks, up * ks), b2 = pack_f32x2(-up * c2, -up * c2);
     uint4* gr = reinterpret_cast<uint4*>(grad + row * D);
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
       const int c = i * KD_THREADS + threadIdx.x;
       if (c < nchunk) {
-        float o[8];
+        uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = dead ? 0.f : up * (ks * (t[i][j] - gmean) - c2 * s[i][j]);
-        gr[c] = pack8(o);
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t v2 = fma_f32x2(add_f32x2(t[i][j], ngm2), a2, mul_f32x2(s[i][j], b2));
+          float v0, v1;
+          unpack_f32x2(v2, v0, v1);
+          o[j] = dead ? 0u : pack_bf16x2(v0, v1);
+        }
+        gr[c] = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
   }
@@ -398,121 +444,115 @@ __global__ void kd_row_scale_kernel(const long long* __restrict__ seg_row_start,
 //   y[b,s,:] = LayerNorm_H( mix(x[b,:,s,:]) ) * gamma + beta
 //   mode 0: Conv2d(C -> 1, 5x5, pad 2) over the (S, H) plane + bias
 //   mode 1: mean_c(cha_scale[c] * x)        mode 2: mean_c(x)
-// One CTA per (b, s) output row; thread i owns 8 consecutive h (16-byte loads of the 5 input rows s-2..s+2
-// for every channel, +-2 halo columns taken from the neighbours' registers via shared memory).
-constexpr int PROJ_THREADS = 256;
-template <int MAXC>
-__global__ void __launch_bounds__(PROJ_THREADS) proj_mix_ln_kernel(const __nv_bfloat16* __restrict__ x, int mode,
-                                                                   const float* __restrict__ w /* [C,5,5] | [C] */,
-                                                                   float conv_bias, const float* __restrict__ gamma,
-                                                                   const float* __restrict__ beta, float eps,
-                                                                   __nv_bfloat16* __restrict__ y, int B, int C, int S,
-                                                                   int H) {
-  extern __shared__ float sm[];
-  float* wsm = sm;                       // C*25
-  float* rowbuf = sm + ((C * 25 + 3) & ~3);  // [H + 8] one input row with halo, fp32 (16-byte aligned)
-  float* red = rowbuf + H + 8;           // 2 * warps
-  const int bs = blockIdx.x;
-  const int b = bs / S, s = bs - b * S;
-  const int nchunk = H >> 3;
-  const int nw = mode == 0 ? C * 25 : (mode == 1 ? C : 0);
-  for (int i = threadIdx.x; i < nw; i += PROJ_THREADS) wsm[i] = w[i];
-  float acc[MAXC][8];
-#pragma unroll
-  for (int i = 0; i < MAXC; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+// Register-blocked stencil: a CTA owns PROJ_R consecutive output rows of one batch element, thread i owns 8 consecutive
+// h.  Every input row s0-2 .. s0+R+1 of every channel is loaded ONCE per CTA (16 B + two 4 B halos per thread, no shared
+// memory, no barriers in the main loop) and feeds all output rows it overlaps: 40 FMAs per (input row, output row).
+// The op is FP32-FMA bound, not HBM bound: 25 MAC per input element = 25 FLOP/B.
+constexpr int PROJ_R = 2;
+__device__ __forceinline__ float block_sum_rt(float v, float* red, int nwarps) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  v = warp_sum(v);
   __syncthreads();
-  if (mode == 0) {
-    for (int c = 0; c < C; ++c) {
-      for (int dy = 0; dy < 5; ++dy) {
-        const int sy = s + dy - 2;
-        if (sy < 0 || sy >= S) continue;  // zero padding in S (uniform branch)
-        const uint4* xr = reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * C + c) * S + sy) * H);
-        __syncthreads();
-        if (threadIdx.x < 4) { rowbuf[threadIdx.x] = 0.f; rowbuf[H + 4 + threadIdx.x] = 0.f; }  // zero padding in H
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int j = 0; j < nwarps; ++j) s += red[j];  // fixed order
+  return s;
+}
+__global__ void __launch_bounds__(512) proj_mix_ln_kernel(const __nv_bfloat16* __restrict__ x, int mode,
+                                                          const float* __restrict__ w /* [C,5,5] | [C] */,
+                                                          float conv_bias, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps,
+                                                          __nv_bfloat16* __restrict__ y, int B, int C, int S, int H) {
+  extern __shared__ float sm[];
+  float* wsm = sm;                           // C*25 (mode 0) | C (mode 1)
+  float* red = sm + ((C * 25 + 3) & ~3);     // one float per warp
+  const int tiles = (S + PROJ_R - 1) / PROJ_R;
+  const int b = blockIdx.x / tiles, s0 = (blockIdx.x - b * tiles) * PROJ_R;
+  const int nwarps = blockDim.x >> 5;
+  const int h0 = threadIdx.x * 8;
+  const bool active = h0 < H;
+  const int nw = mode == 0 ? C * 25 : (mode == 1 ? C : 0);
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  float acc[PROJ_R][8];
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-          const int ch = i * PROJ_THREADS + threadIdx.x;
-          if (ch < nchunk) {
-            float f[8];
-            unpack8(ld_stream(xr + ch), f);
-            float4* d = reinterpret_cast<float4*>(rowbuf + 4 + ch * 8);
-            d[0] = make_float4(f[0], f[1], f[2], f[3]);
-            d[1] = make_float4(f[4], f[5], f[6], f[7]);
-          }
+  for (int o = 0; o < PROJ_R; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+  if (active) {
+    if (mode == 0) {
+      for (int c = 0; c < C; ++c) {
+        float wk[25];
+#pragma unroll
+        for (int i = 0; i < 25; ++i) wk[i] = wsm[c * 25 + i];
+        const __nv_bfloat16* xc = x + (static_cast<long long>(b) * C + c) * S * H;
+        // all rows of this channel are requested before any is consumed: 3 x (R+4) loads in flight per thread
+        uint4 raw[PROJ_R + 4];
+        uint32_t lft[PROJ_R + 4], rgt[PROJ_R + 4];
+#pragma unroll
+        for (int ri = 0; ri < PROJ_R + 4; ++ri) {
+          const int r = s0 + ri - 2;
+          const bool ok = r >= 0 && r < S;  // zero padding in S (CTA-uniform)
+          const __nv_bfloat16* xr = xc + static_cast<long long>(ok ? r : 0) * H + h0;
+          raw[ri] = ok ? ld_stream(xr) : make_uint4(0, 0, 0, 0);
+          lft[ri] = (ok && h0 > 0) ? __ldg(reinterpret_cast<const uint32_t*>(xr - 2)) : 0u;  // zero padding in H
+          rgt[ri] = (ok && h0 + 8 < H) ? __ldg(reinterpret_cast<const uint32_t*>(xr + 8)) : 0u;
         }
-        __syncthreads();
-        const float* wk = wsm + (c * 5 + dy) * 5;
-        const float w0 = wk[0], w1 = wk[1], w2 = wk[2], w3 = wk[3], w4 = wk[4];
 #pragma unroll
-        for (int i = 0; i < MAXC; ++i) {
-          const int ch = i * PROJ_THREADS + threadIdx.x;
-          if (ch < nchunk) {
-            const float* p = rowbuf + 4 + ch * 8 - 2;  // p[j + dx] = x[h0 + j + dx - 2]
-            float v[12];
+        for (int ri = 0; ri < PROJ_R + 4; ++ri) {
+          float v[12];
+          unpack8(raw[ri], v + 2);
+          v[0] = bf16_lo(lft[ri]); v[1] = bf16_hi(lft[ri]); v[10] = bf16_lo(rgt[ri]); v[11] = bf16_hi(rgt[ri]);
 #pragma unroll
-            for (int j = 0; j < 12; ++j) v[j] = p[j];
+          for (int o = 0; o < PROJ_R; ++o) {
+            const int dy = ri - o;  // = r - (s0 + o) + 2
+            if (dy < 0 || dy > 4) continue;  // compile-time after unrolling
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              acc[i][j] += w0 * v[j] + w1 * v[j + 1] + w2 * v[j + 2] + w3 * v[j + 3] + w4 * v[j + 4];
+              acc[o][j] += wk[dy * 5 + 0] * v[j] + wk[dy * 5 + 1] * v[j + 1] + wk[dy * 5 + 2] * v[j + 2] +
+                           wk[dy * 5 + 3] * v[j + 3] + wk[dy * 5 + 4] * v[j + 4];
           }
         }
       }
-    }
-  } else {
-    for (int c = 0; c < C; ++c) {
-      const float wc = mode == 1 ? wsm[c] : 1.0f;
-      const uint4* xr = reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * C + c) * S + s) * H);
+    } else {
+      for (int c = 0; c < C; ++c) {
+        const float wc = mode == 1 ? wsm[c] : 1.0f;
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        const int ch = i * PROJ_THREADS + threadIdx.x;
-        if (ch < nchunk) {
+        for (int o = 0; o < PROJ_R; ++o) {
+          if (s0 + o >= S) continue;
           float f[8];
-          unpack8(ld_stream(xr + ch), f);
+          unpack8(ld_stream(x + ((static_cast<long long>(b) * C + c) * S + s0 + o) * H + h0), f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] += wc * f[j];
+          for (int j = 0; j < 8; ++j) acc[o][j] += wc * f[j];
         }
       }
     }
   }
   const float post_mul = mode == 0 ? 1.0f : 1.0f / C;
   const float post_add = mode == 0 ? conv_bias : 0.f;
-  float r1[1] = {0.f};
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    if (i * PROJ_THREADS + threadIdx.x < nchunk) {
+  for (int o = 0; o < PROJ_R; ++o) {
+    if (s0 + o >= S) break;  // CTA-uniform
+    float part = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[i][j] = acc[i][j] * post_mul + post_add;
-        r1[0] += acc[i][j];
-      }
+    for (int j = 0; j < 8; ++j) {
+      acc[o][j] = active ? acc[o][j] * post_mul + post_add : 0.f;
+      part += acc[o][j];
     }
-  }
-  block_sum<1, PROJ_THREADS / 32>(r1, red);
-  const float mean = r1[0] / H;
-  r1[0] = 0.f;
+    const float mean = block_sum_rt(part, red, nwarps) / H;
+    part = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    if (i * PROJ_THREADS + threadIdx.x < nchunk) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[i][j] -= mean;
-        r1[0] += acc[i][j] * acc[i][j];
-      }
+    for (int j = 0; j < 8; ++j) {
+      acc[o][j] = active ? acc[o][j] - mean : 0.f;
+      part += acc[o][j] * acc[o][j];
     }
-  }
-  block_sum<1, PROJ_THREADS / 32>(r1, red);
-  const float rstd = rsqrtf(r1[0] / H + eps);
-  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<long long>(bs) * H);
+    const float rstd = rsqrtf(block_sum_rt(part, red, nwarps) / H + eps);
+    if (active) {
+      float ov[8];
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    const int ch = i * PROJ_THREADS + threadIdx.x;
-    if (ch < nchunk) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = acc[i][j] * rstd * gamma[ch * 8 + j] + beta[ch * 8 + j];
-      yr[ch] = pack8(o);
+      for (int j = 0; j < 8; ++j) ov[j] = acc[o][j] * rstd * gamma[h0 + j] + beta[h0 + j];
+      *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * S + s0 + o) * H + h0) = pack8(ov);
     }
   }
 }
