@@ -55,6 +55,8 @@ int x2i_gemm_gate_residual(const void* A, int64_t lda, const void* W, int64_t ld
                            int64_t ldc, void* aux, int64_t ldaux, int M, int N, int K, void* stream);
 
 /* Fused QKV (+ single-block proj_mlp) projection.  W = [Wq; Wk; Wv; (Wmlp)] is [N, K] with N = 3*heads*128 (+ F).
+ * (N may also stop after the q or k section; a q/k section whose rms weight is null is stored plain, like v -- used for
+ * the Resampler's in-projections.)
  * Epilogue per 128-column head: q,k: +bias, RMSNorm(128, eps) * rms_{q,k}, RoPE (adjacent pairs, table
  * rope[L_total,64] of (cos,sin) from x2i_rope_table), stored head-major into q/k[B, heads, L_total, 128] at token
  * row_offset + (m % rows_per_batch); v: +bias, same layout; columns >= 3*heads*128: GELU(tanh) -> mlp[m*ldmlp + ..].
@@ -103,11 +105,29 @@ int x2i_gemm_kn(const void* A, int64_t lda, const void* Bkn, int64_t ldb, const 
 int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0, int64_t ld0, int split, void* out1,
                         int64_t ld1, int B, int heads, int L, void* stream);
 
+/* Same kernel with different query / key lengths and an optional key-padding mask: q[B,heads,L,128],
+ * k,v[B,heads,Lkv,128]; kv_len (device int32 [B], nullable) = number of valid keys of batch b.  Replaces the
+ * cross-attention core of the MiniCPM-o Resampler (minicpm/resampler.py:170-176; MultiheadAttention :406-668 with
+ * key_padding_mask, softmax(q k^T / sqrt(128) + mask) v).                                                          */
+int x2i_cross_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out0, int64_t ld0, int split,
+                        void* out1, int64_t ld1, int B, int heads, int L, int Lkv, void* stream);
+
 /* ---- row-wise HBM-bound kernels -----------------------------------------------------------------------------
  * y = LayerNorm(x; no affine, eps) * (1 + scale[b]) + shift[b], b = row / rows_per_batch.  AdaLayerNormZero /
  * ZeroSingle / Continuous [D031] and norm2 + modulate (lightcontrol_flux.py:89, :166-170, :183-184, :196-197, :542). */
 int x2i_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride, void* y,
                     int64_t ldy, int rows, int D, int rows_per_batch, float eps, void* stream);
+
+/* y = LayerNorm(x) * gamma + beta (nn.LayerNorm with affine): Resampler ln_q / ln_kv / ln_post (minicpm/resampler.py:
+ * 116-119, :166-168, :184).                                                                                         */
+int x2i_layernorm_affine(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy, int rows, int D,
+                         float eps, void* stream);
+
+/* out[b,l,:] = x[b,l,:] + pos[l / w_b, l % w_b, :] for l < h_b*w_b else x[b,l,:]; tgt_sizes int32 [B,2] = (h_b, w_b), pos
+ * bf16 [max_h,max_w,D]: the per-image slice / flatten / zero-pad of the Resampler's 2-D sincos table that is added to
+ * the keys (minicpm/resampler.py:156-173).                                                                          */
+int x2i_add_pos2d(const void* x, const void* pos, const int* tgt_sizes, void* out, int B, int L, int D, int max_h, int max_w,
+                  void* stream);
 
 /* x[r,:] += gate[r / rows_per_batch, :] * y[r,:] -- the un-fused `gate.unsqueeze(1) * attn_output` + residual of
  * lightcontrol_flux.py:180-181, :193-194, used only behind a plug-in attention processor.                           */

@@ -15,6 +15,8 @@ TEST INFRASTRUCTURE ONLY.  What each fixture pins, and how:
                                this repo's oracle leaves (diffusers 0.31.0 is absent).  Pins the block
                                wiring (order of modulation chunks, gates, residuals, cat order, slicing);
                                does NOT pin the leaves.
+  resampler_small.pt           reference ``minicpm/resampler.py`` imported unmodified (with the 3 builtins it expects torch
+                               to leak); ragged tgt_sizes; output + its sincos table stored.
   crosscheck.json              oracle blocks vs the BFL-derived Flux blocks shipped in ``torchtitan``
                                (independent implementation, weights remapped) -- max-abs differences.
                                Sanity evidence for the leaves, not a parity authority.
@@ -350,6 +352,31 @@ def crosscheck_torchtitan():
     print("torchtitan cross-check:", res)
 
 
+# ----------------------------------------------------------------------------- E: MiniCPM resampler
+def golden_resampler():
+    import builtins
+    import math
+    import typing
+    # names the reference file expects torch.nn.functional's star-import to leak
+    builtins.List, builtins.DType, builtins.math = typing.List, int, math
+    sys.path.insert(0, os.path.join(REF, "minicpm"))
+    try:
+        ref_rs = importlib.import_module("resampler")  # the reference file, unmodified
+    finally:
+        sys.path.remove(os.path.join(REF, "minicpm"))
+    torch.manual_seed(0)
+    m = ref_rs.Resampler(num_queries=8, embed_dim=256, num_heads=2, kv_dim=48, adaptive=True, max_size=(6, 7)).eval()
+    sd = synth_state(m, 51, std=0.08)
+    sd["query"] = torch.randn(8, 256, generator=torch.Generator().manual_seed(52)) * 0.5
+    m.load_state_dict(sd)
+    tgt = torch.tensor([[3, 4], [2, 7], [5, 1]])
+    x = torch.randn(3, 14, 48, generator=torch.Generator().manual_seed(53))
+    with torch.no_grad():
+        y = m(x, tgt)
+    torch.save(dict(state=sd, x=x, tgt_sizes=tgt, out=y, pos_embed=m.pos_embed.clone()), os.path.join(OUT, "resampler_small.pt"))
+    print("resampler golden written", tuple(y.shape))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -357,3 +384,4 @@ if __name__ == "__main__":
     golden_helpers()
     golden_flux_structure()
     crosscheck_torchtitan()
+    golden_resampler()

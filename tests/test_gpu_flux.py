@@ -198,3 +198,32 @@ def test_kd_loss_module_matches_oracle_stacked(env):
     for a, b in zip(S_dev, S_ref):
         assert a.grad.shape == b.grad.shape
         assert env.rel(a.grad, b.grad) < TOL
+
+
+def test_resampler_matches_reference_golden_and_oracle(env, golden_dir):
+    from oracle import resampler_oracle as ro
+    from oracle.make_golden import synth_state
+    from x2i_b200.resampler import Resampler
+    # (1) the reference's own output (fixture minted from minicpm/resampler.py), ragged tgt_sizes incl. a 5x1 grid
+    g = torch.load(os.path.join(golden_dir, "resampler_small.pt"), weights_only=False)
+    m = Resampler(num_queries=8, embed_dim=256, num_heads=2, kv_dim=48, adaptive=True, max_size=(6, 7))
+    m.load_state_dict(g["state"])
+    m = m.to("cuda", torch.bfloat16)
+    y = m(g["x"].cuda(), g["tgt_sizes"].cuda())
+    assert y.shape == g["out"].shape
+    assert env.rel(y, g["out"]) < 2e-2   # reference fp32 weights/activations vs bf16 everywhere
+    # (2) MiniCPM-o-2.6 dimensions (64 queries, 3584 = 28 x 128, kv 1152), same bf16-rounded weights in the fp32 oracle
+    o = ro.Resampler(num_queries=64, embed_dim=3584, num_heads=28, kv_dim=1152, adaptive=True).eval()
+    sd = {k: v.bfloat16().float() for k, v in synth_state(o, 61, std=0.02).items()}
+    sd["query"] = (torch.randn(64, 3584, generator=torch.Generator().manual_seed(62)) * 0.5).bfloat16().float()
+    o.load_state_dict(sd)
+    m = Resampler(num_queries=64, embed_dim=3584, num_heads=28, kv_dim=1152, adaptive=True)
+    m.load_state_dict(sd)
+    m = m.to("cuda", torch.bfloat16)
+    tgt = torch.tensor([[20, 30], [24, 24], [7, 72]])  # 72 > default 70-wide table: exercises _adjust_pos_cache
+    x = torch.randn(3, 600, 1152, generator=torch.Generator().manual_seed(63)).bfloat16()
+    with torch.no_grad():
+        ref = o.cuda()(x.float().cuda(), tgt.cuda())
+    y = m(x.cuda(), tgt.cuda())
+    assert y.shape == (3, 64, 3584)
+    assert env.rel(y, ref) < TOL

@@ -114,3 +114,18 @@ def test_shard_range_covers_batch():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_resampler_surface_and_pos_table(golden_dir):
+    from x2i_b200.resampler import Resampler, get_2d_sincos_pos_embed
+    g = _load(golden_dir, "resampler_small.pt")
+    m = Resampler(num_queries=8, embed_dim=256, num_heads=2, kv_dim=48, adaptive=True, max_size=(6, 7))
+    assert set(m.state_dict()) == set(g["state"])          # same checkpoint keys as the reference module
+    m.load_state_dict(g["state"])
+    assert torch.equal(m.pos_embed, g["pos_embed"])          # bit-exact sincos table
+    assert "pos_embed" not in m.state_dict()                 # non-persistent buffer, like the reference
+    assert get_2d_sincos_pos_embed(8, (2, 3)).shape == (2, 3, 8)
+    with pytest.raises(X2IError):
+        Resampler(num_queries=8, embed_dim=96, num_heads=2)   # head_dim must be 128
+    with pytest.raises(X2IError):
+        m(torch.randn(3, 14, 48), g["tgt_sizes"])              # no CPU path

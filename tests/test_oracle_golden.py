@@ -113,3 +113,14 @@ def test_rope_identity_on_text_tokens():
     ids = fo.prepare_latent_image_ids(8, 8)
     cos, sin = fo.rope_table(ids)
     assert torch.equal(cos[:, :16], torch.ones(16, 16))  # axis 0 is always 0
+
+
+def test_resampler_oracle_matches_reference(golden_dir):
+    from oracle import resampler_oracle as ro
+    g = _load(golden_dir, "resampler_small.pt")
+    m = ro.Resampler(num_queries=8, embed_dim=256, num_heads=2, kv_dim=48, adaptive=True, max_size=(6, 7)).eval()
+    m.load_state_dict(g["state"])
+    assert torch.equal(m.pos_embed, g["pos_embed"])  # index-derived table: bit-exact
+    with torch.no_grad():
+        y = m(g["x"], g["tgt_sizes"])
+    torch.testing.assert_close(y, g["out"], rtol=1e-5, atol=1e-6)

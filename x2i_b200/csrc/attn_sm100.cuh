@@ -17,7 +17,9 @@
 namespace x2i {
 
 struct AttnParams {
-  int B, H, L;
+  int B, H, L;   // L = number of query rows per (batch, head)
+  int Lkv;       // number of key/value rows per (batch, head) (== L for self-attention)
+  const int* kv_len;  // optional device array [B]: valid keys of batch b (key-padding mask); null = Lkv
   float scale_log2;  // log2(e) / sqrt(head_dim)
   __nv_bfloat16* out0;  // rows with pos <  split: out0[(b*split + pos) * ld0 + h*128 + d]
   long long ld0;
@@ -133,7 +135,8 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int bh = b * p.H + h;
-  const int n_kv = (p.L + 127) / 128;
+  const int kv_valid = p.kv_len != nullptr ? min(max(p.kv_len[b], 1), p.Lkv) : p.Lkv;
+  const int n_kv = (kv_valid + 127) / 128;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_q);
@@ -254,12 +257,12 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
     float l_run = 0.f;
     const float sc = p.scale_log2;
 
-    const bool ragged = (p.L & 127) != 0;
+    const bool ragged = (kv_valid & 127) != 0;
     const int n_full = ragged ? n_kv - 1 : n_kv;
     for (int j = 0; j < n_full; ++j)
       softmax_step<POLY8, false>(t_s, t_o, &s_full[i], &p_full[i * 4], j, 128, sc, m_run, l_run, lane);
     if (ragged)
-      softmax_step<POLY8, true>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, p.L - (n_kv - 1) * 128, sc, m_run, l_run, lane);
+      softmax_step<POLY8, true>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, kv_valid - (n_kv - 1) * 128, sc, m_run, l_run, lane);
     // ---- epilogue: O_i / l -> bf16 -> global (token-major [.., H*128] so the out-projection GEMM reads it as A)
     mbar_wait(&o_full[i], 0);  // committed once, after the last PV MMA of this tile
     tc_fence_after();

@@ -260,9 +260,10 @@ int x2i_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, co
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   const int D = heads * 128;
-  if (heads <= 0 || N < 3 * D || N % 128 != 0) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: N=%d must be >= 3*heads*128 and a multiple of 128", N);
+  if (heads <= 0 || N < D || N % 128 != 0) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: N=%d must be >= heads*128 and a multiple of 128", N);
   if (N > 3 * D && !mlp) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: N > 3*D needs the mlp output");
-  if (!bias || !rms_q || !rms_k || !q || !k || !v) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: bias/rms/q/k/v required");
+  if (!bias || !q || (N > D && !k) || (N > 2 * D && !v)) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: bias and the outputs of every present section are required");
+  if (rope && (!rms_q || (N > D && !rms_k))) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: RoPE is applied only together with RMSNorm");
   if (rows_per_batch <= 0 || row_offset < 0 || row_offset + rows_per_batch > L_total) return fail(X2I_ERR_SHAPE, "gemm_qkv_rope: token window [%d,%d) outside L_total=%d", row_offset, row_offset + rows_per_batch, L_total);
   if (!aligned16(bias) || !aligned16(rms_q) || !aligned16(rms_k) || !aligned16(q) || !aligned16(k) || !aligned16(v) ||
       (rope && !aligned16(rope)) || (mlp && (!aligned16(mlp) || ldmlp % 8)))
@@ -337,8 +338,9 @@ int x2i_gemm_grouped(const x2i_gemm_desc* descs, int n, void* stream) {
     desc_to_params(ds, ps[i]);
     if (kind == X2I_GEMM_QKV_ROPE) {
       const int D = ds.heads * 128;
-      if (ds.heads <= 0 || ds.N < 3 * D || !ds.bias || !ds.rms_q || !ds.rms_k || !ds.q || !ds.k || !ds.v || (ds.N > 3 * D && !ds.mlp) ||
-          ds.rows_per_batch <= 0 || ds.row_offset < 0 || ds.row_offset + ds.rows_per_batch > ds.L_total)
+      if (ds.heads <= 0 || ds.N < D || ds.N % 128 || !ds.bias || !ds.q || (ds.N > D && !ds.k) || (ds.N > 2 * D && !ds.v) ||
+          (ds.N > 3 * D && !ds.mlp) || (ds.rope && (!ds.rms_q || (ds.N > D && !ds.rms_k))) || ds.rows_per_batch <= 0 ||
+          ds.row_offset < 0 || ds.row_offset + ds.rows_per_batch > ds.L_total)
         return fail(X2I_ERR_SHAPE, "gemm_grouped(qkv): inconsistent descriptor %d", i);
     } else if (kind == X2I_GEMM_GATE_RESIDUAL) {
       if (!ds.gate || !ds.residual || !ds.C || ds.rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "gemm_grouped(gate): descriptor %d", i);
@@ -389,8 +391,14 @@ int x2i_gemm_kn(const void* A, int64_t lda, const void* Bkn, int64_t ldb, const 
 
 int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0, int64_t ld0, int split, void* out1,
                         int64_t ld1, int B, int heads, int L, void* stream) {
+  return x2i_cross_attention(q, k, v, nullptr, out0, ld0, split, out1, ld1, B, heads, L, L, stream);
+}
+
+int x2i_cross_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out0, int64_t ld0, int split,
+                        void* out1, int64_t ld1, int B, int heads, int L, int Lkv, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
+  if (Lkv <= 0) return fail(X2I_ERR_SHAPE, "attention: Lkv must be positive");
   if (B <= 0 || heads <= 0 || L <= 0 || split < 0 || split > L) return fail(X2I_ERR_SHAPE, "attention: bad B/heads/L/split");
   if ((split > 0 && !out0) || (split < L && !out1)) return fail(X2I_ERR_SHAPE, "attention: missing output buffer");
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || (out0 && (!aligned16(out0) || ld0 % 8)) || (out1 && (!aligned16(out1) || ld1 % 8)))
@@ -398,11 +406,12 @@ int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0,
   CUtensorMap tq, tk, tv;
   uint64_t dims[3] = {128, (uint64_t)L, (uint64_t)B * heads}, str[3] = {1, 128, (uint64_t)L * 128};
   uint32_t box[3] = {64, 128, 1};
+  uint64_t dimk[3] = {128, (uint64_t)Lkv, (uint64_t)B * heads}, strk[3] = {1, 128, (uint64_t)Lkv * 128};
   if (int rc = make_map(d, &tq, q, 3, dims, str, box)) return rc;
-  if (int rc = make_map(d, &tk, k, 3, dims, str, box)) return rc;
-  if (int rc = make_map(d, &tv, v, 3, dims, str, box)) return rc;
+  if (int rc = make_map(d, &tk, k, 3, dimk, strk, box)) return rc;
+  if (int rc = make_map(d, &tv, v, 3, dimk, strk, box)) return rc;
   AttnParams p;
-  p.B = B; p.H = heads; p.L = L;
+  p.B = B; p.H = heads; p.L = L; p.Lkv = Lkv; p.kv_len = kv_len;
   p.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.ld0 = ld0; p.split = split;
   p.out1 = static_cast<__nv_bfloat16*>(out1); p.ld1 = ld1;
@@ -444,6 +453,39 @@ int x2i_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* s
   else if (nchunk <= 32 * 12) ln_modulate_kernel<12><<<grid, 256, 0, st>>>(X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps);
   else ln_modulate_kernel<16><<<grid, 256, 0, st>>>(X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps);
   return check_launch("ln_modulate_kernel");
+}
+
+int x2i_layernorm_affine(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy, int rows, int D,
+                         float eps, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || D <= 0 || D % 8 || D > 32 * 8 * 16) return fail(X2I_ERR_SHAPE, "layernorm_affine: D=%d must be a multiple of 8 and <= 4096", D);
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || ldx % 8 || ldy % 8) return fail(X2I_ERR_ALIGN, "layernorm_affine: alignment");
+  dim3 grid((rows + 7) / 8);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto G = static_cast<const __nv_bfloat16*>(gamma);
+  auto Bt = static_cast<const __nv_bfloat16*>(beta);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nchunk = D / 8;
+  // gamma / beta are shared by all rows: one "batch" spanning every row, modulation stride 0
+  if (nchunk <= 32 * 4) ln_modulate_kernel<4, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps);
+  else if (nchunk <= 32 * 12) ln_modulate_kernel<12, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps);
+  else ln_modulate_kernel<16, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps);
+  return check_launch("ln_modulate_kernel<affine>");
+}
+
+int x2i_add_pos2d(const void* x, const void* pos, const int* tgt_sizes, void* out, int B, int L, int D, int max_h, int max_w,
+                  void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || L <= 0 || D <= 0 || D % 8 || max_h <= 0 || max_w <= 0) return fail(X2I_ERR_SHAPE, "add_pos2d: bad shape");
+  if (!aligned16(x) || !aligned16(pos) || !aligned16(out)) return fail(X2I_ERR_ALIGN, "add_pos2d: alignment");
+  const long long n = static_cast<long long>(B) * L * (D / 8);
+  add_pos2d_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(pos), tgt_sizes, static_cast<__nv_bfloat16*>(out), B, L,
+      D, max_w);
+  return check_launch("add_pos2d_kernel");
 }
 
 int x2i_gate_residual(void* x, int64_t ldx, const void* y, int64_t ldy, const void* gate, int64_t gate_stride, int rows,

@@ -100,7 +100,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
       const int sec = n_h / D;  // 0 q, 1 k, 2 v, >=3 mlp
       uint32_t r[32];
       float x[32], bb[32];
-      if (sec < 2) {
+      const __nv_bfloat16* wnorm = sec == 0 ? p.rms_q : p.rms_k;
+      if (sec < 2 && wnorm != nullptr) {
         float ss = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -141,9 +142,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
           }
           if (row_ok) store_bf16x32(dst + c * 32, x);
         }
-      } else if (sec == 2) {
-        const int h = (n_h - 2 * D) >> 7;
-        __nv_bfloat16* dst = p.v + ((static_cast<long long>(b) * p.heads + h) * p.L_total + pos) * 128;
+      } else if (sec <= 2) {  // v, or a q / k section without RMSNorm+RoPE (plain head-major projection)
+        const int h = (n_h - sec * D) >> 7;
+        __nv_bfloat16* base = sec == 0 ? p.q : (sec == 1 ? p.k : p.v);
+        __nv_bfloat16* dst = base + ((static_cast<long long>(b) * p.heads + h) * p.L_total + pos) * 128;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           tmem_ld32(t_acc + hh * 128 + c * 32, r);

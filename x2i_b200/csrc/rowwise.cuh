@@ -54,7 +54,8 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red /* [NV * NW
 // ------------------------------------------------------------------------------------------------
 // y[r,:] = LayerNorm(x[r,:]) * (1 + scale[b,:]) + shift[b,:]     (no affine, eps inside sqrt), b = r / rows_per_batch
 // One warp per row, row kept in registers (D <= 32*8*MAXC).  AdaLayerNormZero / ZeroSingle / Continuous, norm2.
-template <int MAXC>
+// AFFINE: y = LN(x) * scale + shift (nn.LayerNorm weight / bias) instead of the AdaLN form LN(x) * (1 + scale) + shift.
+template <int MAXC, bool AFFINE = false>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                           const __nv_bfloat16* __restrict__ scale,
                                                           const __nv_bfloat16* __restrict__ shift, long long mod_stride,
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
       unpack8(__ldg(sc + c), a);
       unpack8(__ldg(sh + c), h);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * (1.0f + a[j]) + h[j];
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * (AFFINE ? a[j] : 1.0f + a[j]) + h[j];
       yr[c] = pack8(o);
     }
   }
@@ -221,6 +222,32 @@ __global__ void euler_step_kernel(__nv_bfloat16* __restrict__ x, const __nv_bflo
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] += dsigma * b[j];
   reinterpret_cast<uint4*>(x)[i] = pack8(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resampler key input (minicpm/resampler.py:156-177): out[b,l,:] = x[b,l,:] + pos[(l / w_b), (l % w_b), :] for
+// l < h_b * w_b (the 2-D sincos table sliced to the image's patch grid and flattened), else x[b,l,:] (zero padding).
+// tgt_sizes: int32 [B,2] = (h_b, w_b); pos: bf16 [max_h, max_w, D].  Index work is exact.
+__global__ void add_pos2d_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ pos,
+                                 const int* __restrict__ tgt_sizes, __nv_bfloat16* __restrict__ out, int B, int L, int D,
+                                 int max_w) {
+  const int nchunk = D >> 3;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * L * nchunk) return;
+  const int c = static_cast<int>(i % nchunk);
+  const long long row = i / nchunk;
+  const int b = static_cast<int>(row / L), l = static_cast<int>(row - static_cast<long long>(b) * L);
+  const int th = tgt_sizes[2 * b], tw = tgt_sizes[2 * b + 1];
+  float a[8];
+  unpack8(reinterpret_cast<const uint4*>(x + row * D)[c], a);
+  if (l < th * tw) {
+    const int ph = l / tw, pw = l - ph * tw;
+    float q[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(pos + (static_cast<long long>(ph) * max_w + pw) * D) + c), q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += q[j];
+  }
+  reinterpret_cast<uint4*>(out + row * D)[c] = pack8(a);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -82,6 +82,8 @@ def qkv_rope(x, weight, bias, rms_q, rms_k, rope, q, k, v, heads, rows_per_batch
     M, lda = _rows(x)
     N, K = weight.shape
     L_total = q.shape[2]
+    if not weight.is_contiguous() and weight.stride(1) != 1:
+        raise _lib.X2IError("qkv_rope: weight rows must be contiguous")
     ldmlp = _rows(mlp)[1] if mlp is not None else 0
     _lib.call("x2i_gemm_qkv_rope", _p(x), lda, _p(weight), weight.stride(0), _p(bias), _p(rms_q), _p(rms_k), _p(rope), _p(q),
               _p(k), _p(v), _p(mlp), ldmlp, M, N, K, heads, rows_per_batch, row_offset, L_total, eps, _stream())
@@ -161,6 +163,37 @@ def attention(q, k, v, split=0, out0=None, out1=None):
         e1.record()
         ATTN_EVENTS.append((e0, e1))
     return out0, out1
+
+
+def cross_attention(q, k, v, kv_len=None):
+    """softmax(q k^T / sqrt(128) [+ key padding mask]) v; q [B,H,Lq,128], k,v [B,H,Lkv,128]; kv_len int32 [B] or None.
+    Returns [B, Lq, H*128]."""
+    _chk(q, "q"); _chk(k, "k"); _chk(v, "v"); _chk(kv_len, "kv_len", torch.int32)
+    B, H, Lq, d = q.shape
+    Lkv = k.shape[2]
+    if d != 128 or not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()) or v.shape != k.shape:
+        raise _lib.X2IError("cross_attention: q [B,H,Lq,128], k,v [B,H,Lkv,128] contiguous")
+    out = torch.empty(B, Lq, H * 128, device=q.device, dtype=BF16)
+    _lib.call("x2i_cross_attention", _p(q), _p(k), _p(v), _p(kv_len), 0, 0, 0, _p(out), H * 128, B, H, Lq, Lkv, _stream())
+    return out
+
+
+def layernorm_affine(x, gamma, beta, eps=1e-6):
+    _chk(x, "x"); _chk(gamma, "gamma"); _chk(beta, "beta")
+    rows, ldx = _rows(x)
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.call("x2i_layernorm_affine", _p(x), ldx, _p(gamma), _p(beta), _p(y), x.shape[-1], rows, x.shape[-1], eps, _stream())
+    return y
+
+
+def add_pos2d(x, pos, tgt_sizes):
+    """x [B,L,D] + per-image slice of the 2-D table pos [max_h,max_w,D] (zero beyond h_b*w_b); tgt_sizes int32 [B,2]."""
+    _chk(x, "x"); _chk(pos, "pos"); _chk(tgt_sizes, "tgt_sizes", torch.int32)
+    B, L, D = x.shape
+    out = torch.empty_like(x)
+    _lib.call("x2i_add_pos2d", _p(x.contiguous()), _p(pos.contiguous()), _p(tgt_sizes.contiguous()), _p(out), B, L, D,
+              pos.shape[0], pos.shape[1], _stream())
+    return out
 
 
 def ln_modulate(x, scale, shift, rows_per_batch, eps=1e-6, out=None):
