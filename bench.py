@@ -46,6 +46,16 @@ def peaks():
     return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
 
 
+def attn_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the attention kernel, from the committed ncu --set full
+    capture of this same command (profiles/); None if no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_attn_traffic.json")))
+    if not files:
+        return None
+    return json.load(open(files[-1])).get("dram_bytes_per_launch")
+
+
 class ClockSampler:
     """nvidia-smi sampled every 200 ms during the timed region."""
 
@@ -285,7 +295,7 @@ def main():
             roof = {"kernel": "mmdit_attention_fwd_kernel", "bound": "tensor", "achieved": ach, "peak": pk_s,
                     "unit": "TFLOP/s", "frac": ach / pk_s, "frac_of_burst_peak": ach / pk["bf16"],
                     "peak_source": pk["source"] + " (sustained cuBLAS bf16: the kernel is timed inside long denoise steps)",
-                    "ms_per_launch": t_att * 1e3, "launches_timed": len(durs), "algorithmic_flops_per_launch": fl, "traffic": None,
+                    "ms_per_launch": t_att * 1e3, "launches_timed": len(durs), "algorithmic_flops_per_launch": fl, "traffic": attn_traffic(),
                     "step_share_attention": 57 * t_att / (t_local / args.steps)}
 
     if rank == 0:
@@ -302,7 +312,7 @@ def main():
                        "l2_policy": "per-step working set (24 GB weights) >> 126 MB L2; no flush needed"},
             "tflops_per_gpu": fl * B * args.steps / t_local / 1e12,
             "step_roofline_frac_bf16": fl * B * args.steps / t_local / 1e12 / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
-            "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
+            "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "x2i_b200.pipeline.FluxPipeline.__call__ (4-step schnell sampling per call, pinned host buffers)"},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clk,
         }

@@ -102,9 +102,9 @@ int make_map(DeviceInfo* d, CUtensorMap* m, const void* ptr, int rank, const uin
   return X2I_OK;
 }
 
-template <int BN, int EPI, bool B_MN>
+template <int BN, int EPI, bool B_MN, bool A_MN = false>
 int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_tcgen05_kernel<BN, EPI, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, B_MN, A_MN>;
   static std::atomic<bool> configured[16];  // per device, per instantiation (keeps the call out of graph captures)
   if (!configured[d->index].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
@@ -117,9 +117,9 @@ int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, c
   return check_launch("gemm_tcgen05_kernel");
 }
 
-template <int EPI>
+template <int EPI, bool B_MN = false>
 int launch_gemm2_t(DeviceInfo* d, const CUtensorMap* maps /* a0,b0,a1,b1 */, const GemmParams* ps, int n_prob, cudaStream_t st) {
-  auto kern = gemm2_tcgen05_kernel<EPI>;
+  auto kern = gemm2_tcgen05_kernel<EPI, B_MN>;
   static std::atomic<bool> configured[16];
   if (!configured[d->index].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES);
@@ -188,6 +188,33 @@ int launch_gemm(DeviceInfo* d, const void* A, int64_t lda, const void* W, int64_
     case 128: return launch_gemm_t<128, EPI, false>(d, ta, tb, p, st);
     default: return launch_gemm_t<64, EPI, false>(d, ta, tb, p, st);
   }
+}
+
+// dgrad / wgrad forms: A [M,K] K-contiguous (or A_MN: stored [K,M]); B stored [K,N] N-contiguous (B_MN).
+template <int EPI, bool A_MN>
+int launch_gemm_mn(DeviceInfo* d, const void* A, int64_t lda, const void* Bkn, int64_t ldb, GemmParams& p, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return fail(X2I_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  if (p.N % 64 != 0 || p.K % 8 != 0 || (A_MN && p.M % 8 != 0)) return fail(X2I_ERR_SHAPE, "gemm(kn): need N %% 64 == 0, K %% 8 == 0 (M=%d N=%d K=%d)", p.M, p.N, p.K);
+  if (!aligned16(A) || !aligned16(Bkn) || lda % 8 || ldb % 8) return fail(X2I_ERR_ALIGN, "gemm(kn): operands must be 16-byte aligned with ld %% 8 == 0");
+  CUtensorMap ta, tb;
+  uint32_t b64[2] = {64, 64};
+  uint64_t db[2] = {(uint64_t)p.N, (uint64_t)p.K}, sb[2] = {1, (uint64_t)ldb};
+  if (int rc = make_map(d, &tb, Bkn, 2, db, sb, b64)) return rc;
+  if (A_MN) {
+    uint64_t da[2] = {(uint64_t)p.M, (uint64_t)p.K}, sa[2] = {1, (uint64_t)lda};
+    if (int rc = make_map(d, &ta, A, 2, da, sa, b64)) return rc;
+  } else {
+    uint64_t da[2] = {(uint64_t)p.K, (uint64_t)p.M}, sa[2] = {1, (uint64_t)lda};
+    uint32_t ba[2] = {GEMM_BK, GEMM_BM};
+    if (int rc = make_map(d, &ta, A, 2, da, sa, ba)) return rc;
+    if (use_pair_kernel() && p.N % 256 == 0 && p.M > 128) {  // CTA-pair kernel, W halves staged as 64x64 boxes
+      CUtensorMap maps[2] = {ta, tb};
+      return launch_gemm2_t<EPI, true>(d, maps, &p, 1, st);
+    }
+  }
+  if (p.N % 256 == 0 && static_cast<long long>((p.M + 127) / 128) * (p.N / 256) >= 120) return launch_gemm_t<256, EPI, true, A_MN>(d, ta, tb, p, st);
+  if (p.N % 128 == 0) return launch_gemm_t<128, EPI, true, A_MN>(d, ta, tb, p, st);
+  return launch_gemm_t<64, EPI, true, A_MN>(d, ta, tb, p, st);
 }
 
 }  // namespace
@@ -295,6 +322,9 @@ int desc_to_params(const x2i_gemm_desc& ds, GemmParams& p) {
   p.rope = static_cast<const float2*>(ds.rope);
   p.L_total = ds.L_total; p.row_offset = ds.row_offset; p.heads = ds.heads; p.eps = ds.eps;
   p.mlp = static_cast<__nv_bfloat16*>(ds.mlp); p.ldmlp = ds.ldmlp;
+  p.qk_pre = static_cast<__nv_bfloat16*>(ds.qk_pre); p.ldqk = ds.ldqk;
+  p.mlp_pre = static_cast<__nv_bfloat16*>(ds.mlp_pre); p.ldmlp_pre = ds.ldmlp_pre;
+  p.aux_act = ds.aux_act;
   return X2I_OK;
 }
 }  // namespace
@@ -311,42 +341,46 @@ int x2i_gemm_grouped(const x2i_gemm_desc* descs, int n, void* stream) {
     if (ds.kind != kind) return fail(X2I_ERR_SHAPE, "gemm_grouped: all problems must share one epilogue kind");
     if (ds.M <= 0 || ds.N <= 0 || ds.K <= 0 || ds.N % 32 || ds.K % 8) return fail(X2I_ERR_SHAPE, "gemm_grouped: bad M/N/K");
     if (!aligned16(ds.A) || !aligned16(ds.W) || ds.lda % 8 || ds.ldw % 8) return fail(X2I_ERR_ALIGN, "gemm_grouped: A/W alignment");
-    pair_ok = pair_ok && ds.N % 256 == 0 && ds.M > 128;
-  }
-  if (!pair_ok || n == 1) {  // fall back to independent launches through the single-problem entry points
-    for (int i = 0; i < n; ++i) {
-      const x2i_gemm_desc& ds = descs[i];
-      int rc;
-      if (kind == X2I_GEMM_BIAS_ACT)
-        rc = x2i_gemm_bias_act(ds.A, ds.lda, ds.W, ds.ldw, ds.bias, ds.C, ds.ldc, ds.M, ds.N, ds.K, ds.act, stream);
-      else if (kind == X2I_GEMM_GATE_RESIDUAL)
-        rc = x2i_gemm_gate_residual(ds.A, ds.lda, ds.W, ds.ldw, ds.bias, ds.gate, ds.gate_stride, ds.rows_per_batch, ds.residual,
-                                    ds.ldr, ds.C, ds.ldc, ds.aux, ds.ldaux, ds.M, ds.N, ds.K, stream);
-      else if (kind == X2I_GEMM_QKV_ROPE)
-        rc = x2i_gemm_qkv_rope(ds.A, ds.lda, ds.W, ds.ldw, ds.bias, ds.rms_q, ds.rms_k, ds.rope, ds.q, ds.k, ds.v, ds.mlp, ds.ldmlp,
-                               ds.M, ds.N, ds.K, ds.heads, ds.rows_per_batch, ds.row_offset, ds.L_total, ds.eps, stream);
-      else
-        return fail(X2I_ERR_SHAPE, "gemm_grouped: unknown kind %d", kind);
-      if (rc) return rc;
-    }
-    return X2I_OK;
-  }
-  GemmParams ps[2];
-  CUtensorMap maps[4];
-  for (int i = 0; i < n; ++i) {
-    const x2i_gemm_desc& ds = descs[i];
-    desc_to_params(ds, ps[i]);
     if (kind == X2I_GEMM_QKV_ROPE) {
       const int D = ds.heads * 128;
       if (ds.heads <= 0 || ds.N < D || ds.N % 128 || !ds.bias || !ds.q || (ds.N > D && !ds.k) || (ds.N > 2 * D && !ds.v) ||
           (ds.N > 3 * D && !ds.mlp) || (ds.rope && (!ds.rms_q || (ds.N > D && !ds.rms_k))) || ds.rows_per_batch <= 0 ||
-          ds.row_offset < 0 || ds.row_offset + ds.rows_per_batch > ds.L_total)
+          ds.row_offset < 0 || ds.row_offset + ds.rows_per_batch > ds.L_total || (ds.qk_pre && ds.ldqk % 8) ||
+          (ds.mlp_pre && ds.ldmlp_pre % 8))
         return fail(X2I_ERR_SHAPE, "gemm_grouped(qkv): inconsistent descriptor %d", i);
     } else if (kind == X2I_GEMM_GATE_RESIDUAL) {
       if (!ds.gate || !ds.residual || !ds.C || ds.rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "gemm_grouped(gate): descriptor %d", i);
-    } else if (!ds.C) {
-      return fail(X2I_ERR_SHAPE, "gemm_grouped: C missing in descriptor %d", i);
+    } else if (kind == X2I_GEMM_BIAS_ACT) {
+      if (!ds.C) return fail(X2I_ERR_SHAPE, "gemm_grouped: C missing in descriptor %d", i);
+      if (ds.act != descs[0].act) return fail(X2I_ERR_SHAPE, "gemm_grouped: problems must share the activation");
+      if (ds.aux && ds.act != 0) return fail(X2I_ERR_SHAPE, "gemm_grouped: a second (activated) output needs act = 0 on the first");
+      if (ds.act < 0 || ds.act > 2) return fail(X2I_ERR_SHAPE, "gemm_grouped: unknown act %d", ds.act);
+    } else {
+      return fail(X2I_ERR_SHAPE, "gemm_grouped: unknown kind %d", kind);
     }
+    pair_ok = pair_ok && ds.N % 256 == 0 && ds.M > 128;
+  }
+  GemmParams ps[2];
+  for (int i = 0; i < n; ++i) desc_to_params(descs[i], ps[i]);
+  if (!pair_ok || n == 1) {  // independent launches (each still picks the CTA-pair kernel when its shape allows)
+    for (int i = 0; i < n; ++i) {
+      const x2i_gemm_desc& ds = descs[i];
+      int rc;
+      if (kind == X2I_GEMM_BIAS_ACT)
+        rc = ds.act == 0 ? launch_gemm<EPI_BIAS>(d, ds.A, ds.lda, ds.W, ds.ldw, ps[i], st)
+             : ds.act == 1 ? launch_gemm<EPI_BIAS_GELU_TANH>(d, ds.A, ds.lda, ds.W, ds.ldw, ps[i], st)
+                           : launch_gemm<EPI_BIAS_GELU_ERF>(d, ds.A, ds.lda, ds.W, ds.ldw, ps[i], st);
+      else if (kind == X2I_GEMM_GATE_RESIDUAL)
+        rc = launch_gemm<EPI_GATE_RESIDUAL>(d, ds.A, ds.lda, ds.W, ds.ldw, ps[i], st);
+      else
+        rc = launch_gemm<EPI_QKV>(d, ds.A, ds.lda, ds.W, ds.ldw, ps[i], st);
+      if (rc) return rc;
+    }
+    return X2I_OK;
+  }
+  CUtensorMap maps[4];
+  for (int i = 0; i < n; ++i) {
+    const x2i_gemm_desc& ds = descs[i];
     uint64_t da[2] = {(uint64_t)ds.K, (uint64_t)ds.M}, sa[2] = {1, (uint64_t)ds.lda};
     uint32_t ba[2] = {GEMM_BK, 128};
     if (int rc = make_map(d, &maps[2 * i], ds.A, 2, da, sa, ba)) return rc;
@@ -354,18 +388,59 @@ int x2i_gemm_grouped(const x2i_gemm_desc* descs, int n, void* stream) {
     if (int rc = make_map(d, &maps[2 * i + 1], ds.W, 2, db, sb, ba)) return rc;
   }
   if (kind == X2I_GEMM_BIAS_ACT) {
-    for (int i = 1; i < n; ++i)
-      if (descs[i].act != descs[0].act) return fail(X2I_ERR_SHAPE, "gemm_grouped: problems must share the activation");
     switch (descs[0].act) {
       case 0: return launch_gemm2_t<EPI_BIAS>(d, maps, ps, n, st);
       case 1: return launch_gemm2_t<EPI_BIAS_GELU_TANH>(d, maps, ps, n, st);
-      case 2: return launch_gemm2_t<EPI_BIAS_GELU_ERF>(d, maps, ps, n, st);
-      default: return fail(X2I_ERR_SHAPE, "gemm_grouped: unknown act");
+      default: return launch_gemm2_t<EPI_BIAS_GELU_ERF>(d, maps, ps, n, st);
     }
   }
   if (kind == X2I_GEMM_GATE_RESIDUAL) return launch_gemm2_t<EPI_GATE_RESIDUAL>(d, maps, ps, n, st);
-  if (kind == X2I_GEMM_QKV_ROPE) return launch_gemm2_t<EPI_QKV>(d, maps, ps, n, st);
-  return fail(X2I_ERR_SHAPE, "gemm_grouped: unknown kind %d", kind);
+  return launch_gemm2_t<EPI_QKV>(d, maps, ps, n, st);
+}
+
+int x2i_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* pre, int64_t ldpre, int n_split,
+                   int dact, const void* addend, int64_t ldadd, void* dX, int64_t lddx, int M, int Nout, int Kin, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!dX || !aligned16(dX) || lddx % 8 || (pre && (!aligned16(pre) || ldpre % 8)) || (addend && (!aligned16(addend) || ldadd % 8)))
+    return fail(X2I_ERR_ALIGN, "gemm_dgrad: alignment");
+  if (pre && (n_split < 0 || n_split % 32 || n_split > Kin || (dact != 1 && dact != 2)))
+    return fail(X2I_ERR_SHAPE, "gemm_dgrad: n_split must be a multiple of 32 in [0, Kin], dact 1 (tanh) or 2 (erf)");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = Kin; p.K = Nout;  // dX[M, Kin] = dY[M, Nout] @ W[Nout, Kin]: W is the [K, N] (N-contiguous) operand
+  p.C = static_cast<__nv_bfloat16*>(dX); p.ldc = lddx;
+  p.pre = static_cast<const __nv_bfloat16*>(pre); p.ldpre = ldpre; p.n_split = n_split; p.dact = dact;
+  p.residual = static_cast<const __nv_bfloat16*>(addend); p.ldr = ldadd;
+  return launch_gemm_mn<EPI_DACT, false>(d, dY, lddy, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+int x2i_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw, int M, int N, int K,
+                   int accumulate, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!dW || !aligned16(dW) || lddw % 8) return fail(X2I_ERR_ALIGN, "gemm_wgrad: alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = N; p.N = K; p.K = M;  // dW[N, K] = dY[M, N]^T @ X[M, K]: contraction over the M rows, both operands MN-major
+  p.C = static_cast<__nv_bfloat16*>(dW); p.ldc = lddw;
+  if (accumulate) { p.residual = p.C; p.ldr = lddw; }
+  return launch_gemm_mn<EPI_DACT, true>(d, dY, lddy, X, ldx, p, static_cast<cudaStream_t>(stream));
+}
+
+int x2i_gemm_bias_act_save(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C_pre, int64_t ldc,
+                           void* C_act, int64_t ldg, int M, int N, int K, int act, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!C_pre || !C_act || (act != 1 && act != 2)) return fail(X2I_ERR_SHAPE, "gemm_bias_act_save: both outputs required; act 1 (tanh) or 2 (erf)");
+  if (!aligned16(C_pre) || !aligned16(C_act) || ldc % 8 || ldg % 8 || (bias && !aligned16(bias))) return fail(X2I_ERR_ALIGN, "gemm_bias_act_save: alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.C = static_cast<__nv_bfloat16*>(C_pre); p.ldc = ldc;
+  p.aux = static_cast<__nv_bfloat16*>(C_act); p.ldaux = ldg; p.aux_act = act;
+  return launch_gemm<EPI_BIAS>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
 int x2i_gemm_kn(const void* A, int64_t lda, const void* Bkn, int64_t ldb, const void* bias, void* C, int64_t ldc, int M,

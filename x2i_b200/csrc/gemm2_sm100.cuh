@@ -88,7 +88,8 @@ __device__ __forceinline__ TileRef locate_tile(const GemmGroup& g, int tile) {
   return t;
 }
 
-template <int EPI>
+// B_MN: W given as [K, N] (N contiguous) -- each CTA stages its 128-column half as two 64 x 64 boxes (dgrad GEMMs).
+template <int EPI, bool B_MN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_constant__ CUtensorMap tma_b0,
                      const __grid_constant__ CUtensorMap tma_a1, const __grid_constant__ CUtensorMap tma_b1,
@@ -151,7 +152,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
           uint8_t* sa = smem + stage * GEMM2_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * GEMM2_STAGE_BYTES);
           tma_load_2d_pair(sa, ma, &full_bar[stage], kb * GEMM_BK, row_a);
-          tma_load_2d_pair(sa + 16384, mb, &full_bar[stage], kb * GEMM_BK, row_b);
+          if constexpr (!B_MN) {
+            tma_load_2d_pair(sa + 16384, mb, &full_bar[stage], kb * GEMM_BK, row_b);
+          } else {
+            tma_load_2d_pair(sa + 16384, mb, &full_bar[stage], row_b, kb * GEMM_BK);
+            tma_load_2d_pair(sa + 16384 + 8192, mb, &full_bar[stage], row_b + 64, kb * GEMM_BK);
+          }
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
@@ -159,7 +165,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -177,7 +183,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
           const uint32_t b_base = a_base + 16384;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_ss_pair(d_tmem, make_smem_desc_sw128(a_base + k * 32, 16, 1024), make_smem_desc_sw128(b_base + k * 32, 16, 1024),
+            umma_ss_pair(d_tmem, make_smem_desc_sw128(a_base + k * 32, 16, 1024),
+                         B_MN ? make_smem_desc_sw128(b_base + k * 2048, 8192, 1024) : make_smem_desc_sw128(b_base + k * 32, 16, 1024),
                          idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage]);
           if (++stage == NS) { stage = 0; phase ^= 1; }

@@ -13,13 +13,20 @@
 //   EPI_BIAS_GELU_ERF   C = gelu_erf(acc + bias)                         projector MLP3
 //   EPI_GATE_RESIDUAL   C = residual + gate[b,:] * (acc + bias); aux = acc + bias (optional, KD hook tensor)
 //   EPI_QKV             per 128-column head tile: q,k -> +bias, RMSNorm(128)*w, RoPE, head-major store;
-//                       v -> +bias, head-major store; columns >= 3D -> gelu_tanh -> mlp buffer (single block)
+//                       v -> +bias, head-major store; columns >= 3D -> gelu_tanh -> mlp buffer (single block);
+//                       training: also the pre-norm q,k (token-major) and the pre-GELU mlp values the backward needs
+//   EPI_DACT            backward of a Linear followed by GELU: C = addend + acc * act'(pre) for columns >= n_split,
+//                       C = addend + acc below it (dgrad GEMMs of the distillation step)
+//
+// Operand forms: B_MN takes B as [K, N] (N contiguous) and A_MN takes A as [K, M] (M contiguous) -- the "MN-major"
+// UMMA operands.  dgrad (dX = dY W) uses B_MN on the weights exactly as nn.Linear stores them; wgrad (dW = dY^T X) uses
+// both, so no tensor is ever transposed in memory.
 #pragma once
 #include "common.cuh"
 
 namespace x2i {
 
-enum { EPI_BIAS = 0, EPI_BIAS_GELU_TANH = 1, EPI_BIAS_GELU_ERF = 2, EPI_GATE_RESIDUAL = 3, EPI_QKV = 4 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU_TANH = 1, EPI_BIAS_GELU_ERF = 2, EPI_GATE_RESIDUAL = 3, EPI_QKV = 4, EPI_DACT = 5 };
 
 struct GemmParams {
   int M, N, K;
@@ -42,6 +49,17 @@ struct GemmParams {
   float eps;
   __nv_bfloat16* mlp;  // [M, ldmlp]
   long long ldmlp;
+  // training-mode saves of EPI_QKV (nullable): pre-norm q|k token-major [M, ldqk] and pre-GELU mlp [M, ldmlp_pre]
+  __nv_bfloat16* qk_pre;
+  long long ldqk;
+  __nv_bfloat16* mlp_pre;
+  long long ldmlp_pre;
+  // EPI_BIAS: aux_act selects the activation of the second output (0/2 gelu_erf, 1 gelu_tanh)
+  int aux_act;
+  // EPI_DACT: pre-activation [M, ldpre] (column n - n_split), derivative kind dact (1 tanh-GELU, 2 erf-GELU), addend = residual
+  const __nv_bfloat16* pre;
+  long long ldpre;
+  int n_split, dact;
 };
 
 constexpr int GEMM_BM = 128;
@@ -110,9 +128,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float t = __uint_as_float(r[j]) + bb[j];
-            ss += t * t;
+            x[j] = __uint_as_float(r[j]) + bb[j];
+            ss += x[j] * x[j];
           }
+          if (p.qk_pre != nullptr && row_ok) store_bf16x32(p.qk_pre + static_cast<long long>(m) * p.ldqk + n_h + c * 32, x);
         }
         const float rinv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
         const int h = (n_h - sec * D) >> 7;
@@ -163,7 +182,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
           load_bf16x32(p.bias + n_h + c * 32, bb);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(__uint_as_float(r[j]) + bb[j]);
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) + bb[j];
+          if (p.mlp_pre != nullptr && row_ok)
+            store_bf16x32(p.mlp_pre + static_cast<long long>(m) * p.ldmlp_pre + (n_h - 3 * D) + c * 32, x);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = gelu_tanh_f(x[j]);
           if (row_ok) store_bf16x32(dst + c * 32, x);
         }
       }
@@ -201,9 +224,33 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
         if constexpr (EPI == EPI_BIAS) {
           if (p.aux != nullptr) {  // second output: gelu_erf(C) (projector: MLP3.fc consumes GELU(x2), utils/proj.py:31)
             float g[32];
+            if (p.aux_act == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) g[j] = gelu_erf_f(x[j]);
+              for (int j = 0; j < 32; ++j) g[j] = gelu_tanh_f(x[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) g[j] = gelu_erf_f(x[j]);
+            }
             store_bf16x32(p.aux + static_cast<long long>(m) * p.ldaux + n0, g);
+          }
+        }
+        if constexpr (EPI == EPI_DACT) {
+          if (p.pre != nullptr && n0 >= p.n_split) {
+            float pr[32];
+            load_bf16x32(p.pre + static_cast<long long>(m) * p.ldpre + (n0 - p.n_split), pr);
+            if (p.dact == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] *= dgelu_tanh_f(pr[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] *= dgelu_erf_f(pr[j]);
+            }
+          }
+          if (p.residual != nullptr) {
+            float res[32];
+            load_bf16x32(p.residual + static_cast<long long>(m) * p.ldr + n0, res);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += res[j];
           }
         }
         if constexpr (EPI == EPI_GATE_RESIDUAL) {
@@ -220,7 +267,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
   }
 }
 
-template <int BN, int EPI, bool B_MN>
+template <int BN, int EPI, bool B_MN, bool A_MN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -274,7 +321,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+          } else {
+#pragma unroll
+            for (int g = 0; g < GEMM_BM / 64; ++g)  // A stored [K, M]: boxes of 64 (m) x 64 (k rows)
+              tma_load_2d(sa + g * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + g * 64, kb * GEMM_BK);
+          }
           if constexpr (!B_MN) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           } else {
@@ -289,7 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -306,7 +359,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           const uint32_t b_base = a_base + Cfg::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * 2048, 8192, 1024)
+                                        : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, 8192, 1024)
                                         : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
             umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
