@@ -91,6 +91,12 @@ typedef struct x2i_gemm_desc {
   const void *rms_q, *rms_k, *rope;
   void *q, *k, *v, *mlp;
   int64_t ldmlp;
+  /* training-mode saves (all nullable; see x2i_gemm_qkv_rope_save / x2i_gemm_bias_act_save): */
+  void* qk_pre;   /* QKV: pre-norm q|k, token-major [M, ldqk] */
+  int64_t ldqk;
+  void* mlp_pre;  /* QKV: pre-GELU proj_mlp values [M, ldmlp_pre] */
+  int64_t ldmlp_pre;
+  int aux_act;    /* BIAS_ACT with act = 0 and aux set: aux = aux_act(C), 1 GELU(tanh), 0/2 GELU(erf) */
 } x2i_gemm_desc;
 int x2i_gemm_grouped(const x2i_gemm_desc* descs, int n, void* stream);
 
@@ -98,12 +104,67 @@ int x2i_gemm_grouped(const x2i_gemm_desc* descs, int n, void* stream);
 int x2i_gemm_kn(const void* A, int64_t lda, const void* Bkn, int64_t ldb, const void* bias, void* C, int64_t ldc,
                 int M, int N, int K, void* stream);
 
+/* ---- dense contractions of the backward pass (distillation training, train/train_qwenvl.py:625) -----------------
+ * The FLUX weights are frozen (requires_grad_(False), train_qwenvl.py:417-429), so the student pass needs only
+ * activation gradients (dgrad) through the 57 blocks; weight gradients (wgrad) exist for the projector alone.
+ *
+ * dgrad of y = x W^T:   dX[M, Kin] = addend + (dY[M, Nout] @ W[Nout, Kin]) * act'(pre[M, Kin - n_split])
+ * W is consumed exactly as nn.Linear stores it (as the N-contiguous tcgen05 B operand; nothing is transposed in memory).
+ * pre (nullable) holds the pre-activation of the Linear+GELU that PRODUCED x: columns >= n_split are multiplied by
+ * GELU'(pre) (dact 1 tanh -- FeedForward / proj_mlp, 2 erf -- MLP3), columns < n_split pass through (the attention part
+ * of a single block's [attn | mlp] concat, lightcontrol_flux.py:97).  addend (nullable) is added last; may alias dX.      */
+int x2i_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* pre, int64_t ldpre, int n_split,
+                   int dact, const void* addend, int64_t ldadd, void* dX, int64_t lddx, int M, int Nout, int Kin, void* stream);
+
+/* wgrad of y = x W^T:   dW[N, K] (+)= dY[M, N]^T @ X[M, K]   (contraction over the M token rows; both operands are read
+ * as MN-major tcgen05 operands).  Projector linears: utils/proj.py:22-25 trained at train_qwenvl.py:453-459.            */
+int x2i_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw, int M, int N, int K,
+                   int accumulate, void* stream);
+
+/* Forward Linear + GELU that keeps the pre-activation for the backward: C_pre = A W^T + bias, C_act = act(C_pre);
+ * act 1 GELU(tanh), 2 GELU(erf).                                                                                    */
+int x2i_gemm_bias_act_save(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C_pre, int64_t ldc,
+                           void* C_act, int64_t ldg, int M, int N, int K, int act, void* stream);
+
 /* ---- fused MMDiT attention ----------------------------------------------------------------------------------
  * O = softmax(Q K^T / sqrt(128)) V over q,k,v[B, heads, L, 128]; output token-major: rows with token < split go to
  * out0[(b*split + t) * ld0 + h*128], the rest to out1[(b*(L-split) + t-split) * ld1 + h*128].
  * Replaces F.scaled_dot_product_attention + transpose/reshape + the txt/img split in FluxAttnProcessor2_0 [D031].  */
 int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0, int64_t ld0, int split, void* out1,
                         int64_t ld1, int B, int heads, int L, void* stream);
+
+/* Training forward: same as x2i_mmdit_attention, additionally lse fp32 [B*heads, Lpad] (Lpad = L rounded up to 128):
+ * log2-domain log-sum-exp of every score row (+inf in the padding), consumed by x2i_mmdit_attention_bwd.             */
+int x2i_mmdit_attention_lse(const void* q, const void* k, const void* v, void* out0, int64_t ld0, int split, void* out1,
+                            int64_t ld1, float* lse, int B, int heads, int L, void* stream);
+
+/* Backward of the fused attention (autograd of F.scaled_dot_product_attention in FluxAttnProcessor2_0 [D031]):
+ * q,k,v,dout,dq,dk,dv head-major [B, heads, L, 128] bf16; lse from the forward, delta from x2i_attention_bwd_prep.
+ * Two launches (dK/dV per key tile, dQ per query tile), no atomics, bit-reproducible.                               */
+int x2i_mmdit_attention_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
+                            void* dq, void* dk, void* dv, int B, int heads, int L, void* stream);
+
+/* Prologue of the attention backward: token-major dO (+ optional addend = the KD-loss gradient of a hooked single-block
+ * attention output, train_qwenvl.py:214) and token-major O -> head-major dO [B,heads,L,128] and
+ * delta[b,h,t] = sum_d dO*O ([B*heads, Lpad] fp32).  Token-major tensors are split like the forward outputs: tokens
+ * t < split in *0 (row (b*split + t) * ld), the rest in *1 (row (b*(L-split) + t-split) * ld).                      */
+int x2i_attention_bwd_prep(const void* do0, int64_t lddo0, const void* do1, int64_t lddo1, const void* o0, int64_t ldo0,
+                           const void* o1, int64_t ldo1, const void* add0, int64_t ldadd0, const void* add1, int64_t ldadd1,
+                           void* do_hm, float* delta, int B, int heads, int L, int split, void* stream);
+
+/* Backward of the QKV epilogue (per-head RMSNorm(128)*w then RoPE) + head-major -> token-major: dq,dk,dv
+ * [B,heads,L_total,128] -> out[M, ldo] = [dq_pre | dk_pre | dv] for the M = B*rows_per_batch tokens at row_offset;
+ * qk_pre = the pre-norm q|k saved by x2i_gemm_qkv_rope_save.  (norm_q/norm_k + apply_rotary_emb)   */
+int x2i_qk_norm_rope_bwd(const void* dq, const void* dk, const void* dv, const void* qk_pre, int64_t ldqk, const void* rms_q,
+                         const void* rms_k, const void* rope, void* out, int64_t ldo, int M, int heads, int rows_per_batch,
+                         int row_offset, int L_total, float eps, void* stream);
+
+/* x2i_gemm_qkv_rope that also stores what the backward needs: qk_pre [M, ldqk] (pre-norm q|k) and mlp_pre [M, ldmlp_pre]
+ * (pre-GELU proj_mlp; nullable when N == 3*heads*128).                                                                */
+int x2i_gemm_qkv_rope_save(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* rms_q,
+                           const void* rms_k, const void* rope, void* q, void* k, void* v, void* mlp, int64_t ldmlp,
+                           void* qk_pre, int64_t ldqk, void* mlp_pre, int64_t ldmlp_pre, int M, int N, int K, int heads,
+                           int rows_per_batch, int row_offset, int L_total, float eps, void* stream);
 
 /* Same kernel with different query / key lengths and an optional key-padding mask: q[B,heads,L,128],
  * k,v[B,heads,Lkv,128]; kv_len (device int32 [B], nullable) = number of valid keys of batch b.  Replaces the
@@ -133,6 +194,34 @@ int x2i_add_pos2d(const void* x, const void* pos, const int* tgt_sizes, void* ou
  * lightcontrol_flux.py:180-181, :193-194, used only behind a plug-in attention processor.                           */
 int x2i_gate_residual(void* x, int64_t ldx, const void* y, int64_t ldy, const void* gate, int64_t gate_stride, int rows,
                       int D, int rows_per_batch, void* stream);
+
+/* ---- row-wise backward kernels (distillation training) --------------------------------------------------------
+ * dy = gate[b] * dx (+ addend): backward of x' = x + gate * y towards y (lightcontrol_flux.py:100, :180-181, :187-189);
+ * addend = KD-loss gradient arriving at the hooked y.                                                               */
+int x2i_gate_bwd(const void* dx, int64_t lddx, const void* gate, int64_t gate_stride, const void* addend, int64_t ldadd, void* dy,
+                 int64_t lddy, int rows, int D, int rows_per_batch, void* stream);
+
+/* dx = dres + dLN: backward of x2i_ln_modulate (affine = 0, `scale` = the AdaLN scale) or x2i_layernorm_affine (affine = 1,
+ * `scale` = gamma, mod_stride 0) towards x; stats (nullable) float2 [rows] receives (mean, rstd) for x2i_colsum.      */
+int x2i_ln_modulate_bwd(const void* dn, int64_t lddn, const void* x, int64_t ldx, const void* scale, int64_t mod_stride,
+                        const void* dres, int64_t ldr, void* dx, int64_t lddx, void* stats, int rows, int D, int rows_per_batch,
+                        float eps, int affine, void* stream);
+
+/* Per-batch column sums (deterministic two-stage): out0[b, :] (+)= sum_t A[b,t,:];  out1[b, :] (+)= sum_t A[b,t,:] * Bv[b,t,:]
+ * with Bv = B or, when stats is given, (B - mean_t) * rstd_t.  fp32 outputs with row strides ldo0/ldo1; workspace of
+ * x2i_colsum_workspace_floats() floats.  dshift/dscale/dgate of the AdaLN modulations, dgamma/dbeta, bias gradients.  */
+int x2i_colsum(const void* A, int64_t lda, const void* Bm, int64_t ldb, const void* stats, float* out0, int64_t ldo0, float* out1,
+               int64_t ldo1, float* workspace, int nbatch, int rows_per_batch, int D, int accumulate, void* stream);
+int64_t x2i_colsum_workspace_floats(int nbatch, int rows_per_batch, int D);
+
+/* out[b,k] (+)= act'(pre[b,k]) * sum_n g[b,n] W[n,k]  (g, out fp32; dact 0 none, 1 SiLU'): the backward of
+ * x2i_skinny_linear -- all AdaLN modulation linears of a step in one pass over the concatenated weights, and the
+ * time/text embedding MLPs.  workspace: x2i_skinny_linear_t_workspace_floats() floats.                              */
+int x2i_skinny_linear_t(const float* g, int64_t ldg, const void* W, int64_t ldw, const void* pre, int64_t ldpre, float* out,
+                        int64_t ldo, float* workspace, int B, int N, int K, int dact, int accumulate, void* stream);
+int64_t x2i_skinny_linear_t_workspace_floats(int N, int K);
+
+int x2i_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 
 /* out[b,n] (+)= bias[n] + sum_k act_in(x[b,k]) W[n,k];  B <= 64, act_in: 0 none, 1 SiLU.  All AdaLN modulation
  * linears of a step in one launch (weights concatenated), and the CombinedTimestep*TextProjEmbeddings MLPs [D031]. */

@@ -12,7 +12,7 @@ def _declared():
     src = open(os.path.join(ROOT, "include", "x2i_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(?:int|long long|const char\*)\s+(x2i_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(?:int|int64_t|long long|const char\*)\s+(x2i_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         decls[m.group(1)] = 0 if args == "void" else len([a for a in args.split(",") if a.strip()])
     return decls
@@ -39,7 +39,9 @@ def test_bindings_match_header(built):
     for name, argtypes in built.SIGNATURES.items():
         assert name in decls, f"{name} bound in _lib.py but not declared in the header"
         assert len(argtypes) == decls[name], f"{name}: {len(argtypes)} bound args vs {decls[name]} declared"
-    unbound = set(decls) - set(built.SIGNATURES) - {"x2i_version", "x2i_last_error", "x2i_launch_count"}
+    for name, argtypes in built.SIZE_FUNCS.items():
+        assert name in decls and len(argtypes) == decls[name]
+    unbound = set(decls) - set(built.SIGNATURES) - set(built.SIZE_FUNCS) - {"x2i_version", "x2i_last_error", "x2i_launch_count"}
     assert not unbound, f"declared but unbound: {unbound}"
 
 

@@ -1,0 +1,207 @@
+"""-m gpu: the backward kernels of the distillation step, each against fp32 PyTorch autograd of the same op on the same
+seeded bf16 inputs.  Tolerance: relative Frobenius error <= 1e-2 (BASELINE.json north_star), typically one bf16 rounding."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import __graft_entry__ as g
+    g.build()
+    from x2i_b200 import ops
+    return ops
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def rn(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(BF)
+
+
+def gelu_tanh(x):
+    return torch.nn.functional.gelu(x, approximate="tanh")
+
+
+@pytest.mark.parametrize("M,Nout,Kin", [(512, 768, 256), (300, 256, 128), (1024, 512, 1024), (64, 128, 64), (4608, 3072, 3072)])
+def test_dgrad_plain(ops, M, Nout, Kin):
+    dy, w = rn(M, Nout, seed=1), rn(Nout, Kin, seed=2, scale=0.05)
+    out = ops.linear_dgrad(dy, w)
+    assert rel(out, dy.float() @ w.float()) < 4e-3
+
+
+@pytest.mark.parametrize("dact", [1, 2])
+def test_dgrad_with_activation_derivative_split_and_addend(ops, dact):
+    M, Nout, D, F = 384, 256, 256, 512
+    dy, w = rn(M, Nout, seed=3), rn(Nout, D + F, seed=4, scale=0.05)
+    pre, add = rn(M, F, seed=5), rn(M, D + F, seed=6)
+    out = ops.linear_dgrad(dy, w, pre=pre, n_split=D, dact=dact, addend=add)
+    pf = pre.float().requires_grad_(True)
+    act = gelu_tanh(pf) if dact == 1 else torch.nn.functional.gelu(pf)
+    (dgelu,) = torch.autograd.grad(act.sum(), pf)
+    ref = dy.float() @ w.float()
+    ref[:, D:] *= dgelu
+    ref += add.float()
+    assert rel(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(2048, 256, 512), (520, 768, 256), (1024, 4096, 2048)])
+def test_wgrad(ops, M, N, K):
+    dy, x = rn(M, N, seed=7), rn(M, K, seed=8)
+    ref = dy.float().t() @ x.float()
+    out = ops.linear_wgrad(dy, x)
+    assert out.shape == (N, K) and rel(out, ref) < 4e-3
+    acc = out.clone()
+    ops.linear_wgrad(dy, x, out=acc, accumulate=True)
+    assert rel(acc, 2 * ref) < 6e-3
+
+
+def test_linear_act_save(ops):
+    x, w, b = rn(640, 256, seed=9), rn(1024, 256, seed=10, scale=0.05), rn(1024, seed=11, scale=0.1)
+    pre, act = ops.linear_act_save(x, w, b, 1)
+    ref = x.float() @ w.float().t() + b.float()
+    assert rel(pre, ref) < 4e-3 and rel(act, gelu_tanh(ref)) < 4e-3
+
+
+def _attn_ref(q, k, v, do):
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) / math.sqrt(128)
+    o = torch.softmax(s, -1) @ vf
+    lse2 = torch.logsumexp(s, -1) * 1.4426950408889634
+    dq, dk, dv = torch.autograd.grad(o, (qf, kf, vf), do.float())
+    return o, lse2, dq, dk, dv
+
+
+@pytest.mark.parametrize("B,H,L", [(1, 2, 256), (2, 3, 333), (1, 2, 1000), (1, 1, 64), (1, 4, 1536)])
+def test_attention_backward(ops, B, H, L):
+    q, k, v = rn(B, H, L, 128, seed=12), rn(B, H, L, 128, seed=13), rn(B, H, L, 128, seed=14)
+    do_tok = rn(B, L, H * 128, seed=15)  # token-major, as the out-projection dgrad produces it
+    split = 40 if L > 64 else 0
+    o0, o1, lse = ops.attention_lse(q, k, v, split=split)
+    do_hm_ref = do_tok.view(B, L, H, 128).permute(0, 2, 1, 3).contiguous()
+    o_ref, lse_ref, dq_r, dk_r, dv_r = _attn_ref(q, k, v, do_hm_ref)
+    o_tok = torch.cat([t for t in (o0, o1) if t is not None], 1)
+    assert rel(o_tok.view(B, L, H, 128).permute(0, 2, 1, 3), o_ref) < 6e-3
+    assert torch.allclose(lse[:, :, :L], lse_ref, atol=2e-2, rtol=1e-3)
+    assert torch.isinf(lse[:, :, L:]).all()
+    do0 = do_tok[:, :split].contiguous() if split else None
+    do1 = do_tok[:, split:].contiguous()
+    do_hm, delta = ops.attention_bwd_prep(do0, do1, o0, o1, B, H, L, split)
+    assert torch.equal(do_hm, do_hm_ref)
+    assert torch.allclose(delta[:, :, :L], (do_hm_ref.float() * o_ref).sum(-1), atol=0.15, rtol=2e-2)
+    assert (delta[:, :, L:] == 0).all()
+    dq, dk, dv = ops.attention_bwd(q, k, v, do_hm, lse, delta)
+    assert rel(dv, dv_r) < 8e-3
+    assert rel(dq, dq_r) < 1e-2
+    assert rel(dk, dk_r) < 1e-2
+
+
+def test_attention_bwd_prep_addend(ops):
+    B, H, L = 2, 2, 130
+    do, o, add = rn(B, L, 256, seed=16), rn(B, L, 256, seed=17), rn(B, L, 256, seed=18)
+    do_hm, delta = ops.attention_bwd_prep(None, do, None, o, B, H, L, 0, add1=add)
+    s = (do.float() + add.float()).to(BF)
+    assert torch.equal(do_hm, s.view(B, L, H, 128).permute(0, 2, 1, 3))
+    ref = (s.float() * o.float()).view(B, L, H, 128).sum(-1).permute(0, 2, 1)
+    assert torch.allclose(delta[:, :, :L], ref, atol=1e-2, rtol=1e-3)
+
+
+def test_qkv_save_and_norm_rope_backward(ops):
+    """Forward saves (pre-norm q|k, pre-GELU mlp) and the backward of RMSNorm*w -> RoPE against autograd."""
+    B, H, S, Lt, K, F = 2, 2, 24, 88, 256, 512
+    D = H * 128
+    M = B * S
+    off = 40
+    x, w, b = rn(M, K, seed=19), rn(3 * D + F, K, seed=20, scale=0.06), rn(3 * D + F, seed=21, scale=0.1)
+    wq, wk = (1 + 0.2 * rn(128, seed=22).float()).to(BF), (1 + 0.2 * rn(128, seed=23).float()).to(BF)
+    ids = torch.zeros(Lt, 3, device="cuda")
+    ids[:, 1] = torch.arange(Lt, device="cuda") // 8
+    ids[:, 2] = torch.arange(Lt, device="cuda") % 8
+    cos, sin, rope = ops.rope_table(ids)
+    q = torch.zeros(B, H, Lt, 128, device="cuda", dtype=BF); k = torch.zeros_like(q); v = torch.zeros_like(q)
+    mlp, mlp_pre, qk_pre = (torch.empty(M, F, device="cuda", dtype=BF), torch.empty(M, F, device="cuda", dtype=BF),
+                            torch.empty(M, 2 * D, device="cuda", dtype=BF))
+    ops.gemm_grouped(ops.desc_qkv_rope_save(x, w, b, wq, wk, rope, q, k, v, H, S, off, qk_pre, mlp=mlp, mlp_pre=mlp_pre))
+    y = x.float() @ w.float().t() + b.float()
+    assert rel(qk_pre, y[:, :2 * D]) < 4e-3 and rel(mlp_pre, y[:, 3 * D:]) < 4e-3 and rel(mlp, gelu_tanh(y[:, 3 * D:])) < 4e-3
+
+    # reference forward of the epilogue from the SAVED pre-norm values, with autograd
+    t = qk_pre.float().requires_grad_(True)
+    cs, sn = cos[off:off + S], sin[off:off + S]
+
+    def norm_rope(z, wn):  # z [B, S, H, 128]
+        z = z * torch.rsqrt(z.pow(2).mean(-1, keepdim=True) + 1e-6) * wn.float()
+        zr = torch.stack([-z[..., 1::2], z[..., 0::2]], -1).flatten(-2)
+        return z * cs[None, :, None, :] + zr * sn[None, :, None, :]
+
+    qr = norm_rope(t[:, :D].reshape(B, S, H, 128), wq).permute(0, 2, 1, 3)
+    kr = norm_rope(t[:, D:].reshape(B, S, H, 128), wk).permute(0, 2, 1, 3)
+    assert rel(q[:, :, off:off + S], qr) < 6e-3 and rel(k[:, :, off:off + S], kr) < 6e-3
+    dq, dk, dv = rn(B, H, Lt, 128, seed=24), rn(B, H, Lt, 128, seed=25), rn(B, H, Lt, 128, seed=26)
+    (gt,) = torch.autograd.grad([qr, kr], t, [dq[:, :, off:off + S].float(), dk[:, :, off:off + S].float()])
+    out = torch.zeros(M, 3 * D + F, device="cuda", dtype=BF)
+    ops.qk_norm_rope_bwd(dq, dk, dv, qk_pre, wq, wk, rope, out, S, off)
+    assert rel(out[:, :2 * D], gt) < 6e-3
+    assert torch.equal(out[:, 2 * D:3 * D], dv[:, :, off:off + S].permute(0, 2, 1, 3).reshape(M, D))
+
+
+@pytest.mark.parametrize("D,affine", [(256, False), (3072, False), (3584, True), (2048, True)])
+def test_ln_modulate_backward_and_colsums(ops, D, affine):
+    B, L = 2, 200
+    x, dn, dres = rn(B * L, D, seed=27), rn(B * L, D, seed=28), rn(B * L, D, seed=29)
+    if affine:
+        scale = (1 + 0.1 * rn(1, D, seed=30).float()).to(BF)
+        shift = rn(1, D, seed=31)
+    else:
+        scale, shift = rn(B, D, seed=30, scale=0.3), rn(B, D, seed=31, scale=0.3)
+    xf = x.float().requires_grad_(True)
+    sf, hf = scale.float().requires_grad_(True), shift.float().requires_grad_(True)
+    ln = torch.nn.functional.layer_norm(xf, (D,), eps=1e-6).view(-1, L, D) if not affine else torch.nn.functional.layer_norm(xf, (D,), eps=1e-6).view(1, -1, D)
+    y = ln * (sf[:, None] if affine else 1 + sf[:, None]) + hf[:, None]
+    gx, gs, gh = torch.autograd.grad(y, (xf, sf, hf), dn.float().view(y.shape))
+    nb, rpb = (1, B * L) if affine else (B, L)
+    stats = torch.empty(B * L, 2, device="cuda", dtype=torch.float32)
+    out = ops.ln_modulate_bwd(dn, x, scale, rpb, dres=dres, stats=stats, affine=affine)
+    assert rel(out, gx + dres.float()) < 5e-3
+    dshift = torch.zeros(nb, D, device="cuda"); dscale = torch.zeros(nb, D, device="cuda")
+    ops.colsum(dn, nb, rpb, out0=dshift, b=x, out1=dscale, stats=stats)
+    assert rel(dshift, gh) < 1e-4 and rel(dscale, gs) < 1e-3
+    ops.colsum(dn, nb, rpb, out0=dshift, accumulate=True)
+    assert rel(dshift, 2 * gh) < 1e-4
+
+
+def test_gate_backward_and_dgate(ops):
+    B, L, D = 2, 130, 256
+    dx, y, gate, add = rn(B * L, D, seed=32), rn(B * L, D, seed=33), rn(B, D, seed=34), rn(B * L, D, seed=35)
+    out = ops.gate_bwd(dx, gate, L, addend=add)
+    ref = dx.float().view(B, L, D) * gate.float()[:, None] + add.float().view(B, L, D)
+    assert rel(out.view(B, L, D), ref) < 4e-3
+    dgate = torch.zeros(B, D, device="cuda")
+    ops.colsum(dx, B, L, b=y, out1=dgate)
+    assert rel(dgate, (dx.float() * y.float()).view(B, L, D).sum(1)) < 1e-4
+
+
+@pytest.mark.parametrize("B,N,K,dact", [(2, 5000, 256, 0), (3, 3072, 3072, 1), (9, 777, 768, 0)])
+def test_skinny_linear_transposed(ops, B, N, K, dact):
+    g = torch.randn(B, N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(36))
+    w, pre = rn(N, K, seed=37, scale=0.05), rn(B, K, seed=38)
+    out = ops.skinny_linear_t(g, w, pre=pre if dact else None, dact=dact)
+    ref = g @ w.float()
+    if dact:
+        pf = pre.float().requires_grad_(True)
+        (ds,) = torch.autograd.grad(torch.nn.functional.silu(pf).sum(), pf)
+        ref = ref * ds
+    assert rel(out, ref) < 1e-4
+    ops.skinny_linear_t(g, w, pre=pre if dact else None, dact=dact, out=out, accumulate=True)
+    assert rel(out, 2 * ref) < 1e-4
+    assert rel(ops.f32_to_bf16(out), out) < 4e-3

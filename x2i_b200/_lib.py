@@ -17,7 +17,7 @@ class GemmDesc(ctypes.Structure):
                 ("A", _vp), ("W", _vp), ("bias", _vp), ("lda", _i64), ("ldw", _i64), ("C", _vp), ("ldc", _i64),
                 ("gate", _vp), ("residual", _vp), ("gate_stride", _i64), ("ldr", _i64), ("aux", _vp), ("ldaux", _i64),
                 ("rms_q", _vp), ("rms_k", _vp), ("rope", _vp), ("q", _vp), ("k", _vp), ("v", _vp), ("mlp", _vp),
-                ("ldmlp", _i64)]
+                ("ldmlp", _i64), ("qk_pre", _vp), ("ldqk", _i64), ("mlp_pre", _vp), ("ldmlp_pre", _i64), ("aux_act", _i)]
 
 
 GEMM_BIAS_ACT, GEMM_GATE_RESIDUAL, GEMM_QKV_ROPE = 0, 1, 2
@@ -44,6 +44,26 @@ SIGNATURES = {
     "x2i_kd_loss_bwd": [_vp, _vp, _i64, _i, _f, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp],
     "x2i_proj_mix_ln": [_vp, _i, _vp, _f, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],
     "x2i_mean_over_s": [_vp, _vp, _i, _i, _i, _vp],
+    # ---- backward / training
+    "x2i_gemm_dgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _vp, _i64, _i, _i, _i, _vp],
+    "x2i_gemm_wgrad": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp],
+    "x2i_gemm_bias_act_save": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp],
+    "x2i_gemm_qkv_rope_save": [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64,
+                               _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "x2i_mmdit_attention_lse": [_vp, _vp, _vp, _vp, _i64, _i, _vp, _i64, _vp, _i, _i, _i, _vp],
+    "x2i_mmdit_attention_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "x2i_attention_bwd_prep": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp],
+    "x2i_qk_norm_rope_bwd": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp],
+    "x2i_gate_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _vp],
+    "x2i_ln_modulate_bwd": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _f, _i, _vp],
+    "x2i_colsum": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp],
+    "x2i_skinny_linear_t": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
+    "x2i_f32_to_bf16": [_vp, _vp, _i64, _vp],
+}
+# helpers that return a size instead of a status code
+SIZE_FUNCS = {
+    "x2i_colsum_workspace_floats": [_i, _i, _i],
+    "x2i_skinny_linear_t_workspace_floats": [_i, _i],
 }
 
 
@@ -67,6 +87,10 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = argtypes
             fn.restype = ctypes.c_int
+        for name, argtypes in SIZE_FUNCS.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int64
         L.x2i_version.restype = ctypes.c_int
         L.x2i_last_error.restype = ctypes.c_char_p
         L.x2i_launch_count.restype = ctypes.c_longlong

@@ -1,0 +1,285 @@
+// Backward of the fused MMDiT joint attention for sm_100a (head_dim 128, non-causal, no mask) -- the student pass of
+// the attention-distillation step back-propagates through 57 of these (train/train_qwenvl.py:625).
+//
+//   P = softmax(Q K^T / sqrt(128)),  dV = P^T dO,  dP = dO V^T,  dS = P o (dP - delta),  delta_i = sum_d dO_id O_id
+//   dQ = dS K / sqrt(128),  dK = dS^T Q / sqrt(128)
+//
+// Two launches of ONE kernel template, no atomics, bit-reproducible:
+//   KV = true : a CTA owns 128 keys   (X0 = K_j, X1 = V_j resident), streams 64-query tiles (Y0 = Q, Y1 = dO):
+//               T1 = S^T = X0 Y0^T, T2 = dP^T = X1 Y1^T; dK_j += dS~ Y0, dV_j += P~ Y1
+//   KV = false: a CTA owns 128 queries (X0 = Q_i, X1 = dO_i resident), streams 64-key tiles  (Y0 = K, Y1 = V):
+//               T1 = S = X0 Y0^T,   T2 = dP = X1 Y1^T;   dQ_i += dS~ Y0
+// so both modes issue the same MMAs: two SS products into a double-buffered TMEM region (2 x (64 + 64) columns), the
+// soft-max warpgroup turns them into bf16 P~ / dS~ IN TMEM (aliasing T1 / T2), and the accumulating products read them
+// as the A operand from TMEM (TS form) with the streamed tile as an MN-major B operand.  The MMAs of stream tile y+2
+// and the accumulation of tile y overlap the soft-max math of tile y+1.
+//
+// 192 threads: warp 0 TMA producer, warp 1 MMA issuer (one lane), warps 2..5 soft-max / epilogue (one owner row per
+// thread).  lse / delta are [B*H, Lpad] fp32 (log2 domain, +inf / 0 in the padding) written by the forward kernel and
+// by attn_bwd_prep_kernel.  All tensors are head-major [B*H, L, 128] bf16.
+#pragma once
+#include "common.cuh"
+
+namespace x2i {
+
+struct AttnBwdParams {
+  int B, H, L, Lpad;
+  float scale_log2;  // log2(e) / sqrt(128)
+  float scale;       // 1 / sqrt(128)
+  const float* lse;
+  const float* delta;
+  __nv_bfloat16* out0;  // KV: dK, else dQ
+  __nv_bfloat16* out1;  // KV: dV
+};
+
+constexpr int ABW_THREADS = 192;
+constexpr int ABW_STAGES = 4;
+constexpr int ABW_OWNER_BYTES = 2 * 32768;  // X0 | X1, 128 x 128 bf16 each (two 128B-swizzled column halves of 16 KB)
+constexpr int ABW_STAGE_BYTES = 2 * 16384;  // Y0 | Y1, 64 x 128 bf16 each (two column halves of 8 KB)
+constexpr int ABW_STATS_BYTES = 512;        // per stage: lse[64] | delta[64] of the streamed queries (KV mode)
+constexpr int ABW_SMEM_BYTES = ABW_OWNER_BYTES + ABW_STAGES * (ABW_STAGE_BYTES + ABW_STATS_BYTES) + 256 + 1024;
+
+template <bool KV>
+__global__ void __launch_bounds__(ABW_THREADS, 1)
+mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __grid_constant__ CUtensorMap tma_x1,
+                           const __grid_constant__ CUtensorMap tma_y0, const __grid_constant__ CUtensorMap tma_y1,
+                           const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sx = smem;
+  uint8_t* sy = smem + ABW_OWNER_BYTES;
+  float* sstat = reinterpret_cast<float*>(sy + ABW_STAGES * ABW_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sstat) + ABW_STAGES * ABW_STATS_BYTES);
+  uint64_t* x_full = bars;         // 1
+  uint64_t* y_full = bars + 1;     // 4
+  uint64_t* y_empty = bars + 5;    // 4
+  uint64_t* t_full = bars + 9;     // 2
+  uint64_t* pd_full = bars + 11;   // 2
+  uint64_t* acc_full = bars + 13;  // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 128;
+  const int bh = blockIdx.z * p.H + blockIdx.y;
+  const int n_y = (p.L + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_x0);
+    tma_prefetch_desc(&tma_x1);
+    tma_prefetch_desc(&tma_y0);
+    tma_prefetch_desc(&tma_y1);
+    mbar_init(x_full, 1);
+    for (int i = 0; i < ABW_STAGES; ++i) {
+      mbar_init(&y_full[i], 1);
+      mbar_init(&y_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&pd_full[i], 4);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: [0,128) T buffer 0 (T1 | T2), [128,256) T buffer 1, [256,384) acc0, [384,512) acc1
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(x_full, ABW_OWNER_BYTES);
+#pragma unroll
+      for (int op = 0; op < 2; ++op)
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int rb = 0; rb < 2; ++rb)
+            tma_load_3d(sx + op * 32768 + g * 16384 + rb * 8192, op ? &tma_x1 : &tma_x0, x_full, g * 64, r0 + rb * 64, bh);
+      for (int y = 0; y < n_y; ++y) {
+        const int stage = y & (ABW_STAGES - 1);
+        const uint32_t ph = (y / ABW_STAGES) & 1;
+        mbar_wait(&y_empty[stage], ph ^ 1);
+        mbar_expect_tx(&y_full[stage], ABW_STAGE_BYTES + (KV ? ABW_STATS_BYTES : 0));
+        uint8_t* dst = sy + stage * ABW_STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; ++op)
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            tma_load_3d(dst + op * 16384 + g * 8192, op ? &tma_y1 : &tma_y0, &y_full[stage], g * 64, y * 64, bh);
+        if constexpr (KV) {
+          float* st = sstat + stage * (ABW_STATS_BYTES / 4);
+          const long long off = static_cast<long long>(bh) * p.Lpad + y * 64;
+          bulk_load_1d(st, p.lse + off, 256, &y_full[stage]);
+          bulk_load_1d(st + 64, p.delta + off, 256, &y_full[stage]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, 0, 1);
+      const uint32_t x_base = smem_u32(sx);
+      const uint32_t y_base = smem_u32(sy);
+      auto issue_t = [&](int y, int buf) {  // T1 = X0 Y0^T, T2 = X1 Y1^T  (128 x 64 each, K = 128)
+        const uint32_t ys = y_base + (y & (ABW_STAGES - 1)) * ABW_STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; ++op)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t ox = op * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32;
+            const uint32_t oy = op * 16384 + (kk >> 2) * 8192 + (kk & 3) * 32;
+            umma_ss(tmem_base + buf * 128 + op * 64, make_smem_desc_sw128(x_base + ox, 16, 1024),
+                    make_smem_desc_sw128(ys + oy, 16, 1024), idesc_t, kk != 0);
+          }
+      };
+      auto issue_acc = [&](int y, int buf) {  // acc0 += dS~ Y0 ; KV: acc1 += P~ Y1   (A from TMEM, K = 64 streamed rows)
+        const uint32_t ys = y_base + (y & (ABW_STAGES - 1)) * ABW_STAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          umma_ts(tmem_base + 256, tmem_base + buf * 128 + 64 + kk * 8, make_smem_desc_sw128(ys + kk * 2048, 8192, 1024), idesc_acc,
+                  (y > 0 || kk > 0) ? 1u : 0u);
+          if constexpr (KV)
+            umma_ts(tmem_base + 384, tmem_base + buf * 128 + kk * 8, make_smem_desc_sw128(ys + 16384 + kk * 2048, 8192, 1024),
+                    idesc_acc, (y > 0 || kk > 0) ? 1u : 0u);
+        }
+      };
+      auto y_wait = [&](int y) { mbar_wait(&y_full[y & (ABW_STAGES - 1)], (y / ABW_STAGES) & 1); };
+
+      mbar_wait(x_full, 0);
+      y_wait(0);
+      tc_fence_after();
+      issue_t(0, 0);
+      umma_commit(&t_full[0]);
+      if (n_y > 1) {
+        y_wait(1);
+        tc_fence_after();
+        issue_t(1, 1);
+        umma_commit(&t_full[1]);
+      }
+      for (int y = 0; y < n_y; ++y) {
+        const int buf = y & 1;
+        mbar_wait(&pd_full[buf], (y >> 1) & 1);
+        tc_fence_after();
+        issue_acc(y, buf);
+        umma_commit(&y_empty[y & (ABW_STAGES - 1)]);
+        if (y + 2 < n_y) {
+          y_wait(y + 2);
+          tc_fence_after();
+          issue_t(y + 2, buf);
+          umma_commit(&t_full[buf]);
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ---------------------------------------------------------------- soft-max warpgroup (one owner row per thread)
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int grow = r0 + quad * 32 + lane;  // owner row (key in KV mode, query otherwise)
+    const float sc = p.scale_log2;
+    float my_lse = 0.f, my_delta = 0.f;
+    if constexpr (!KV) {
+      my_lse = p.lse[static_cast<long long>(bh) * p.Lpad + grow];
+      my_delta = p.delta[static_cast<long long>(bh) * p.Lpad + grow];
+    }
+    for (int y = 0; y < n_y; ++y) {
+      const int buf = y & 1;
+      const uint32_t t1 = tmem_base + buf * 128 + lane_off, t2 = t1 + 64;
+      mbar_wait(&t_full[buf], (y >> 1) & 1);
+      tc_fence_after();
+      uint32_t a[2][32], d[2][32];
+      tmem_ld32(t1, a[0]);
+      tmem_ld32(t1 + 32, a[1]);
+      tmem_ld32(t2, d[0]);
+      tmem_ld32(t2 + 32, d[1]);
+      const float* st = sstat + (y & (ABW_STAGES - 1)) * (ABW_STATS_BYTES / 4);
+      if constexpr (KV) mbar_wait(&y_full[y & (ABW_STAGES - 1)], (y / ABW_STAGES) & 1);  // lse / delta of this tile landed
+      tmem_ld_wait();
+      const int valid = p.L - y * 64;  // streamed rows beyond L: zero-filled by TMA
+      uint32_t pk[2][16], dk[2][16];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          float l4[4], dl4[4];
+          if constexpr (KV) {
+            const float4 lv = *reinterpret_cast<const float4*>(st + c * 32 + k);
+            const float4 dv = *reinterpret_cast<const float4*>(st + 64 + c * 32 + k);
+            l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
+            dl4[0] = dv.x; dl4[1] = dv.y; dl4[2] = dv.z; dl4[3] = dv.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { l4[e] = my_lse; dl4[e] = my_delta; }
+          }
+          float pv[4], dsv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            pv[e] = fast_exp2(fmaf(__uint_as_float(a[c][k + e]), sc, -l4[e]));
+            if constexpr (!KV) {
+              if (c * 32 + k + e >= valid) pv[e] = 0.f;  // padded keys
+            }
+            dsv[e] = pv[e] * (__uint_as_float(d[c][k + e]) - dl4[e]);
+          }
+          pk[c][k >> 1] = pack_bf16x2(pv[0], pv[1]);
+          pk[c][(k >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+          dk[c][k >> 1] = pack_bf16x2(dsv[0], dsv[1]);
+          dk[c][(k >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if constexpr (KV) tmem_st16(t1 + c * 16, pk[c]);
+        tmem_st16(t2 + c * 16, dk[c]);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pd_full[buf]);
+    }
+    // ---- epilogue: accumulators -> bf16, head-major
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool ok = grow < p.L;
+    const long long orow = (static_cast<long long>(bh) * p.L + grow) * 128;
+#pragma unroll 1
+    for (int which = 0; which < (KV ? 2 : 1); ++which) {
+      const float mul = which == 0 ? p.scale : 1.0f;
+      __nv_bfloat16* dst = (which == 0 ? p.out0 : p.out1) + orow;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tmem_base + 256 + which * 128 + lane_off + c * 32, o);
+        tmem_ld_wait();
+        if (ok) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * mul, __uint_as_float(o[8 * k + 1]) * mul);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * mul, __uint_as_float(o[8 * k + 3]) * mul);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul);
+            d4[k] = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace x2i

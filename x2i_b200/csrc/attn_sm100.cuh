@@ -26,6 +26,8 @@ struct AttnParams {
   int split;
   __nv_bfloat16* out1;  // rows with pos >= split: out1[(b*(L-split) + pos-split) * ld1 + h*128 + d]
   long long ld1;
+  float* lse;  // optional (training): lse[(b*H + h) * Lpad + pos] = log2-domain log-sum-exp of row pos (+inf for pos >= L)
+  int Lpad;    // row stride of lse (L rounded up to 128)
 };
 
 constexpr int ATT_THREADS = 320;
@@ -268,6 +270,7 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const bool ok = pos < p.L;
+    if (p.lse != nullptr && pos < p.Lpad) p.lse[static_cast<long long>(bh) * p.Lpad + pos] = ok ? m_run + log2f(l_run) : INFINITY;
     __nv_bfloat16* dst;
     if (pos < p.split)
       dst = p.out0 + (static_cast<long long>(b) * p.split + pos) * p.ld0 + h * 128;

@@ -7,10 +7,12 @@
 #include <mutex>
 
 #include "../../include/x2i_b200.h"
+#include "attn_bwd_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "rowwise.cuh"
+#include "rowwise_bwd.cuh"
 
 using namespace x2i;
 
@@ -307,6 +309,23 @@ int x2i_gemm_qkv_rope(const void* A, int64_t lda, const void* W, int64_t ldw, co
   return launch_gemm<EPI_QKV>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
 }
 
+int x2i_gemm_qkv_rope_save(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* rms_q,
+                           const void* rms_k, const void* rope, void* q, void* k, void* v, void* mlp, int64_t ldmlp,
+                           void* qk_pre, int64_t ldqk, void* mlp_pre, int64_t ldmlp_pre, int M, int N, int K, int heads,
+                           int rows_per_batch, int row_offset, int L_total, float eps, void* stream) {
+  x2i_gemm_desc ds;
+  memset(&ds, 0, sizeof(ds));
+  ds.kind = X2I_GEMM_QKV_ROPE;
+  ds.M = M; ds.N = N; ds.K = K; ds.rows_per_batch = rows_per_batch; ds.heads = heads; ds.row_offset = row_offset;
+  ds.L_total = L_total; ds.eps = eps; ds.A = A; ds.W = W; ds.bias = bias; ds.lda = lda; ds.ldw = ldw;
+  ds.rms_q = rms_q; ds.rms_k = rms_k; ds.rope = rope; ds.q = q; ds.k = k; ds.v = v; ds.mlp = mlp; ds.ldmlp = ldmlp;
+  ds.qk_pre = qk_pre; ds.ldqk = ldqk; ds.mlp_pre = mlp_pre; ds.ldmlp_pre = ldmlp_pre;
+  if (!qk_pre || !aligned16(qk_pre) || (mlp_pre && !aligned16(mlp_pre)) || !aligned16(bias) || !aligned16(rms_q) || !aligned16(rms_k) ||
+      !aligned16(q) || !aligned16(k) || !aligned16(v) || (rope && !aligned16(rope)) || (mlp && (!aligned16(mlp) || ldmlp % 8)))
+    return fail(X2I_ERR_ALIGN, "gemm_qkv_rope_save: qk_pre required; alignment");
+  return x2i_gemm_grouped(&ds, 1, stream);
+}
+
 namespace {
 int desc_to_params(const x2i_gemm_desc& ds, GemmParams& p) {
   memset(&p, 0, sizeof(p));
@@ -469,8 +488,22 @@ int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0,
   return x2i_cross_attention(q, k, v, nullptr, out0, ld0, split, out1, ld1, B, heads, L, L, stream);
 }
 
+namespace {
+int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len, void* out0, int64_t ld0, int split,
+                  void* out1, int64_t ld1, float* lse, int B, int heads, int L, int Lkv, void* stream);
+}
 int x2i_cross_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out0, int64_t ld0, int split,
                         void* out1, int64_t ld1, int B, int heads, int L, int Lkv, void* stream) {
+  return attention_fwd(q, k, v, kv_len, out0, ld0, split, out1, ld1, nullptr, B, heads, L, Lkv, stream);
+}
+int x2i_mmdit_attention_lse(const void* q, const void* k, const void* v, void* out0, int64_t ld0, int split, void* out1,
+                            int64_t ld1, float* lse, int B, int heads, int L, void* stream) {
+  if (!lse) return fail(X2I_ERR_SHAPE, "mmdit_attention_lse: lse buffer required");
+  return attention_fwd(q, k, v, nullptr, out0, ld0, split, out1, ld1, lse, B, heads, L, L, stream);
+}
+namespace {
+int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len, void* out0, int64_t ld0, int split,
+                  void* out1, int64_t ld1, float* lse, int B, int heads, int L, int Lkv, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   if (Lkv <= 0) return fail(X2I_ERR_SHAPE, "attention: Lkv must be positive");
@@ -490,6 +523,7 @@ int x2i_cross_attention(const void* q, const void* k, const void* v, const int* 
   p.scale_log2 = 1.4426950408889634f / sqrtf(128.0f);
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.ld0 = ld0; p.split = split;
   p.out1 = static_cast<__nv_bfloat16*>(out1); p.ld1 = ld1;
+  p.lse = lse; p.Lpad = (L + 127) / 128 * 128;
   static const int poly8 = []() { const char* e = getenv("X2I_ATTN_POLY8"); return e ? atoi(e) : 0; }();
   auto kern = mmdit_attention_fwd_kernel<0>;
   switch (poly8) {
@@ -509,6 +543,7 @@ int x2i_cross_attention(const void* q, const void* k, const void* v, const int* 
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   return check_launch("mmdit_attention_fwd_kernel");
 }
+}  // namespace
 
 int x2i_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride, void* y,
                     int64_t ldy, int rows, int D, int rows_per_batch, float eps, void* stream) {
@@ -706,6 +741,190 @@ int x2i_mean_over_s(const void* y, void* out, int B, int S, int N, void* stream)
   mean_over_s_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(y),
                                                                                     static_cast<__nv_bfloat16*>(out), B, S, N);
   return check_launch("mean_over_s_kernel");
+}
+
+// ================================================================================================ backward (training)
+int x2i_mmdit_attention_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
+                            void* dq, void* dk, void* dv, int B, int heads, int L, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || heads <= 0 || L <= 0) return fail(X2I_ERR_SHAPE, "attention_bwd: bad B/heads/L");
+  if (!q || !k || !v || !dout || !lse || !delta || !dq || !dk || !dv) return fail(X2I_ERR_SHAPE, "attention_bwd: null buffer");
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(dout) || !aligned16(lse) || !aligned16(delta) || !aligned16(dq) ||
+      !aligned16(dk) || !aligned16(dv))
+    return fail(X2I_ERR_ALIGN, "attention_bwd: alignment");
+  CUtensorMap tq, tk, tv, tdo;
+  uint64_t dims[3] = {128, (uint64_t)L, (uint64_t)B * heads}, str[3] = {1, 128, (uint64_t)L * 128};
+  uint32_t box[3] = {64, 64, 1};
+  if (int rc = make_map(d, &tq, q, 3, dims, str, box)) return rc;
+  if (int rc = make_map(d, &tk, k, 3, dims, str, box)) return rc;
+  if (int rc = make_map(d, &tv, v, 3, dims, str, box)) return rc;
+  if (int rc = make_map(d, &tdo, dout, 3, dims, str, box)) return rc;
+  AttnBwdParams p;
+  p.B = B; p.H = heads; p.L = L; p.Lpad = (L + 127) / 128 * 128;
+  p.scale = 1.0f / sqrtf(128.0f);
+  p.scale_log2 = 1.4426950408889634f * p.scale;
+  p.lse = lse; p.delta = delta;
+  static std::atomic<bool> configured[16];
+  if (!configured[d->index].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(mmdit_attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mmdit_attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
+    configured[d->index].store(true, std::memory_order_release);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((L + 127) / 128, heads, B);
+  p.out0 = static_cast<__nv_bfloat16*>(dk); p.out1 = static_cast<__nv_bfloat16*>(dv);
+  mmdit_attention_bwd_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
+  if (int rc = check_launch("mmdit_attention_bwd_kernel<kv>")) return rc;
+  p.out0 = static_cast<__nv_bfloat16*>(dq); p.out1 = nullptr;
+  mmdit_attention_bwd_kernel<false><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tq, tdo, tk, tv, p);
+  return check_launch("mmdit_attention_bwd_kernel<q>");
+}
+
+int x2i_attention_bwd_prep(const void* do0, int64_t lddo0, const void* do1, int64_t lddo1, const void* o0, int64_t ldo0, const void* o1,
+                           int64_t ldo1, const void* add0, int64_t ldadd0, const void* add1, int64_t ldadd1, void* do_hm, float* delta,
+                           int B, int heads, int L, int split, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || heads <= 0 || L <= 0 || split < 0 || split > L) return fail(X2I_ERR_SHAPE, "attention_bwd_prep: bad shape");
+  if ((split > 0 && (!do0 || !o0)) || (split < L && (!do1 || !o1)) || !do_hm || !delta) return fail(X2I_ERR_SHAPE, "attention_bwd_prep: missing buffer");
+  if (lddo0 % 8 || lddo1 % 8 || ldo0 % 8 || ldo1 % 8 || ldadd0 % 8 || ldadd1 % 8 || !aligned16(do0) || !aligned16(do1) || !aligned16(o0) ||
+      !aligned16(o1) || !aligned16(add0) || !aligned16(add1) || !aligned16(do_hm))
+    return fail(X2I_ERR_ALIGN, "attention_bwd_prep: alignment");
+  auto bp = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+  TokSrc sdo{bp(do0), lddo0, bp(do1), lddo1}, so{bp(o0), ldo0, bp(o1), ldo1}, sa{bp(add0), ldadd0, bp(add1), ldadd1};
+  const int Lpad = (L + 127) / 128 * 128;
+  const long long units = static_cast<long long>(B) * Lpad * heads;
+  attn_bwd_prep_kernel<<<static_cast<unsigned>((units + 15) / 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sdo, so, sa, static_cast<__nv_bfloat16*>(do_hm), delta, B, heads, L, Lpad, split);
+  return check_launch("attn_bwd_prep_kernel");
+}
+
+int x2i_qk_norm_rope_bwd(const void* dq, const void* dk, const void* dv, const void* qk_pre, int64_t ldqk, const void* rms_q,
+                         const void* rms_k, const void* rope, void* out, int64_t ldo, int M, int heads, int rows_per_batch,
+                         int row_offset, int L_total, float eps, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (M <= 0 || heads <= 0 || rows_per_batch <= 0 || row_offset < 0 || row_offset + rows_per_batch > L_total || M % rows_per_batch)
+    return fail(X2I_ERR_SHAPE, "qk_norm_rope_bwd: bad shape");
+  if (!dq || !dk || !dv || !qk_pre || !rms_q || !rms_k || !out) return fail(X2I_ERR_SHAPE, "qk_norm_rope_bwd: null buffer");
+  if (ldqk % 8 || ldo % 8 || !aligned16(dq) || !aligned16(dk) || !aligned16(dv) || !aligned16(qk_pre) || !aligned16(rms_q) ||
+      !aligned16(rms_k) || !aligned16(rope) || !aligned16(out))
+    return fail(X2I_ERR_ALIGN, "qk_norm_rope_bwd: alignment");
+  auto bp = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+  const long long units = static_cast<long long>(M) * heads;
+  qk_norm_rope_bwd_kernel<<<static_cast<unsigned>((units + 15) / 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bp(dq), bp(dk), bp(dv), bp(qk_pre), ldqk, bp(rms_q), bp(rms_k), static_cast<const float2*>(rope),
+      static_cast<__nv_bfloat16*>(out), ldo, M, heads, rows_per_batch, row_offset, L_total, eps);
+  return check_launch("qk_norm_rope_bwd_kernel");
+}
+
+int x2i_gate_bwd(const void* dx, int64_t lddx, const void* gate, int64_t gate_stride, const void* addend, int64_t ldadd, void* dy,
+                 int64_t lddy, int rows, int D, int rows_per_batch, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || D <= 0 || D % 8 || rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "gate_bwd: D must be a multiple of 8");
+  if (!aligned16(dx) || !aligned16(gate) || !aligned16(addend) || !aligned16(dy) || lddx % 8 || gate_stride % 8 || ldadd % 8 || lddy % 8)
+    return fail(X2I_ERR_ALIGN, "gate_bwd: alignment");
+  auto bp = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+  const long long n = static_cast<long long>(rows) * (D / 8);
+  gate_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      bp(dx), lddx, bp(gate), gate_stride, bp(addend), ldadd, static_cast<__nv_bfloat16*>(dy), lddy, rows, D, rows_per_batch);
+  return check_launch("gate_bwd_kernel");
+}
+
+int x2i_ln_modulate_bwd(const void* dn, int64_t lddn, const void* x, int64_t ldx, const void* scale, int64_t mod_stride,
+                        const void* dres, int64_t ldr, void* dx, int64_t lddx, void* stats, int rows, int D, int rows_per_batch,
+                        float eps, int affine, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || D <= 0 || D % 8 || D > 32 * 8 * 16 || rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "ln_modulate_bwd: D=%d must be a multiple of 8 and <= 4096", D);
+  if (!aligned16(dn) || !aligned16(x) || !aligned16(scale) || !aligned16(dres) || !aligned16(dx) || lddn % 8 || ldx % 8 || mod_stride % 8 ||
+      ldr % 8 || lddx % 8 || (reinterpret_cast<uintptr_t>(stats) & 7))
+    return fail(X2I_ERR_ALIGN, "ln_modulate_bwd: alignment");
+  auto bp = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
+  dim3 grid((rows + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nchunk = D / 8;
+#define X2I_LNB(MC, AF)                                                                                                      \
+  ln_mod_bwd_kernel<MC, AF><<<grid, 256, 0, st>>>(bp(dn), lddn, bp(x), ldx, bp(scale), mod_stride, bp(dres), ldr,            \
+                                                  static_cast<__nv_bfloat16*>(dx), lddx, static_cast<float2*>(stats), rows, D, \
+                                                  rows_per_batch, eps)
+  if (affine) {
+    if (nchunk <= 32 * 4) X2I_LNB(4, true); else if (nchunk <= 32 * 12) X2I_LNB(12, true); else X2I_LNB(16, true);
+  } else {
+    if (nchunk <= 32 * 4) X2I_LNB(4, false); else if (nchunk <= 32 * 12) X2I_LNB(12, false); else X2I_LNB(16, false);
+  }
+#undef X2I_LNB
+  return check_launch("ln_mod_bwd_kernel");
+}
+
+int x2i_colsum(const void* A, int64_t lda, const void* Bm, int64_t ldb, const void* stats, float* out0, int64_t ldo0, float* out1,
+               int64_t ldo1, float* workspace, int nbatch, int rows_per_batch, int D, int accumulate, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (nbatch <= 0 || rows_per_batch <= 0 || D <= 0 || D % 8) return fail(X2I_ERR_SHAPE, "colsum: D must be a multiple of 8");
+  if (!A || (!out0 && !out1) || (out1 && !Bm) || !workspace) return fail(X2I_ERR_SHAPE, "colsum: missing buffer");
+  if (!aligned16(A) || !aligned16(Bm) || lda % 8 || ldb % 8 || !aligned16(workspace)) return fail(X2I_ERR_ALIGN, "colsum: alignment");
+  const int nsplit = (rows_per_batch + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  const long long per = static_cast<long long>(nbatch) * nsplit * D;
+  float* p0 = out0 ? workspace : nullptr;
+  float* p1 = out1 ? workspace + (out0 ? per : 0) : nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 g1((D / 8 + 127) / 128, nsplit, nbatch);
+  colsum_partial_kernel<<<g1, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(Bm), ldb,
+                                            static_cast<const float2*>(stats), p0, p1, rows_per_batch, D, nsplit);
+  if (int rc = check_launch("colsum_partial_kernel")) return rc;
+  dim3 g2((D + 255) / 256, nbatch);
+  if (out0) {
+    colsum_final_kernel<<<g2, 256, 0, st>>>(p0, out0, ldo0, D, nsplit, accumulate);
+    if (int rc = check_launch("colsum_final_kernel")) return rc;
+  }
+  if (out1) {
+    colsum_final_kernel<<<g2, 256, 0, st>>>(p1, out1, ldo1, D, nsplit, accumulate);
+    if (int rc = check_launch("colsum_final_kernel")) return rc;
+  }
+  return X2I_OK;
+}
+int64_t x2i_colsum_workspace_floats(int nbatch, int rows_per_batch, int D) {
+  const int nsplit = (rows_per_batch + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  return 2LL * nbatch * nsplit * D;
+}
+
+int x2i_skinny_linear_t(const float* g, int64_t ldg, const void* W, int64_t ldw, const void* pre, int64_t ldpre, float* out,
+                        int64_t ldo, float* workspace, int B, int N, int K, int dact, int accumulate, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || B > 64 || N <= 0 || K <= 0 || K % 8 || K > 4096) return fail(X2I_ERR_SHAPE, "skinny_linear_t: need 1 <= B <= 64, K %% 8 == 0, K <= 4096");
+  if (!g || !W || !out || !workspace || (dact && !pre)) return fail(X2I_ERR_SHAPE, "skinny_linear_t: missing buffer");
+  if (!aligned16(W) || ldw % 8 || !aligned16(workspace)) return fail(X2I_ERR_ALIGN, "skinny_linear_t: alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int nslab = d->sms * 4;
+  if (nslab > N) nslab = N;
+  const int rows_per_slab = (N + nslab - 1) / nslab;
+  nslab = (N + rows_per_slab - 1) / rows_per_slab;
+  const int threads = ((K / 8 + 31) / 32) * 32;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    const int nb = (B - b0) < 8 ? (B - b0) : 8;
+    skinny_linear_t_kernel<8><<<nslab, threads, 0, st>>>(g + b0 * ldg, ldg, static_cast<const __nv_bfloat16*>(W), ldw, workspace, nb, N, K,
+                                                         rows_per_slab);
+    if (int rc = check_launch("skinny_linear_t_kernel")) return rc;
+    dim3 g2((K + 255) / 256, nb);
+    skinny_linear_t_final_kernel<<<g2, 256, 0, st>>>(workspace, pre ? static_cast<const __nv_bfloat16*>(pre) + b0 * ldpre : nullptr, ldpre,
+                                                      out + b0 * ldo, ldo, nb, K, nslab, dact, accumulate);
+    if (int rc = check_launch("skinny_linear_t_final_kernel")) return rc;
+  }
+  return X2I_OK;
+}
+int64_t x2i_skinny_linear_t_workspace_floats(int N, int K) { return 148LL * 4 * 8 * K + 8LL * K; }
+
+int x2i_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (n <= 0) return fail(X2I_ERR_SHAPE, "f32_to_bf16: empty");
+  f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  return check_launch("f32_to_bf16_kernel");
 }
 
 }  // extern "C"

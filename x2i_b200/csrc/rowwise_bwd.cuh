@@ -1,0 +1,353 @@
+// Row-wise (HBM-bound) backward kernels of the attention-distillation step: everything between the dgrad GEMMs and the
+// attention backward of a FLUX block, plus the reductions that carry gradient into the AdaLN modulation (-> temb ->
+// pooled projection -> projector).  The reference gets these from autograd over ~35 eager ops per block
+// (train/train_qwenvl.py:625 through lightcontrol_flux.py:82-104, :159-204); here each is one fused pass.
+// All column reductions are two-stage with a fixed summation order (deterministic).
+#pragma once
+#include "rowwise.cuh"
+
+namespace x2i {
+
+// ------------------------------------------------------------------------------------------------
+// dy[r,:] = gate[b,:] * dx[r,:] (+ addend[r,:])       backward of  x' = x + gate * y  towards y (b = r / rows_per_batch);
+// addend = the KD-loss gradient arriving at the hooked tensor y (train_qwenvl.py:186-214).
+__global__ void gate_bwd_kernel(const __nv_bfloat16* __restrict__ dx, long long lddx, const __nv_bfloat16* __restrict__ gate,
+                                long long gate_stride, const __nv_bfloat16* __restrict__ addend, long long ldadd,
+                                __nv_bfloat16* __restrict__ dy, long long lddy, int rows, int D, int rows_per_batch) {
+  const int nchunk = D >> 3;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * nchunk) return;
+  const int r = static_cast<int>(i / nchunk), c = static_cast<int>(i - static_cast<long long>(r) * nchunk);
+  float a[8], g[8];
+  unpack8(reinterpret_cast<const uint4*>(dx + r * lddx)[c], a);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(gate + (r / rows_per_batch) * gate_stride) + c), g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] *= g[j];
+  if (addend != nullptr) {
+    float e[8];
+    unpack8(reinterpret_cast<const uint4*>(addend + r * ldadd)[c], e);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += e[j];
+  }
+  reinterpret_cast<uint4*>(dy + r * lddy)[c] = pack8(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of y = LN(x) * (1 + scale[b]) + shift[b]  (AFFINE: y = LN(x) * gamma + beta) towards x:
+//   g = dn * (1 + scale);  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) + dres
+// One warp per row (row in registers).  Also writes stats[r] = (mean, rstd) for the column reductions (dscale/dshift).
+template <int MAXC, bool AFFINE>
+__global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dn, long long lddn,
+                                                         const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                         const __nv_bfloat16* __restrict__ scale, long long mod_stride,
+                                                         const __nv_bfloat16* __restrict__ dres, long long ldr,
+                                                         __nv_bfloat16* __restrict__ dx, long long lddx,
+                                                         float2* __restrict__ stats, int rows, int D, int rows_per_batch,
+                                                         float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nchunk = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
+  const uint4* gr = reinterpret_cast<const uint4*>(dn + static_cast<long long>(row) * lddn);
+  const uint4* sc = reinterpret_cast<const uint4*>(scale + static_cast<long long>(row / rows_per_batch) * mod_stride);
+  float v[MAXC][8], g[MAXC][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nchunk) {
+      unpack8(xr[c], v[i]);
+      unpack8(gr[c], g[i]);
+      float a[8];
+      unpack8(__ldg(sc + c), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s += v[i][j];
+        g[i][j] *= AFFINE ? a[j] : 1.0f + a[j];
+      }
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (i * 32 + lane < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] -= mean;
+        q += v[i][j] * v[i][j];
+      }
+    }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (i * 32 + lane < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] *= rstd;  // xhat
+        sg += g[i][j];
+        sgx += g[i][j] * v[i][j];
+      }
+    }
+  const float mg = warp_sum(sg) / D, mgx = warp_sum(sgx) / D;
+  if (lane == 0 && stats != nullptr) stats[row] = make_float2(mean, rstd);
+  uint4* outr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
+  const uint4* rr = dres != nullptr ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * ldr) : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nchunk) {
+      float o[8], e[8];
+      if (rr != nullptr) {
+        unpack8(rr[c], e);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - mg - v[i][j] * mgx) + e[j];
+      outr[c] = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column reductions over the rows of each batch element (stage 1): a CTA owns 1024 columns x COLSUM_ROWS rows.
+//   part0[b, split, col] = sum_r A[r, col]                      (if part0)
+//   part1[b, split, col] = sum_r A[r, col] * Bv[r, col]         (if part1);  Bv = B, or (B - mean_r) * rstd_r with stats
+// Used for dshift / dscale of every AdaLN (A = dn, B = LN input), dgate (A = dx, B = the un-gated branch output),
+// the affine LayerNorm's dbeta / dgamma and bias gradients.
+constexpr int COLSUM_ROWS = 64;
+__global__ void __launch_bounds__(128) colsum_partial_kernel(const __nv_bfloat16* __restrict__ A, long long lda,
+                                                             const __nv_bfloat16* __restrict__ Bm, long long ldb,
+                                                             const float2* __restrict__ stats, float* __restrict__ part0,
+                                                             float* __restrict__ part1, int rows_per_batch, int D, int nsplit) {
+  const int c = blockIdx.x * 128 + threadIdx.x;  // 16-byte chunk index
+  if (c * 8 >= D) return;
+  const int split = blockIdx.y, b = blockIdx.z;
+  const int t0 = split * COLSUM_ROWS, t1 = min(t0 + COLSUM_ROWS, rows_per_batch);
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const long long r = static_cast<long long>(b) * rows_per_batch + t;
+    float a[8];
+    unpack8(ld_stream(A + r * lda + c * 8), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0[j] += a[j];
+    if (part1 != nullptr) {
+      float v[8];
+      unpack8(ld_stream(Bm + r * ldb + c * 8), v);
+      if (stats != nullptr) {
+        const float2 st = stats[r];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - st.x) * st.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s1[j] += a[j] * v[j];
+    }
+  }
+  const long long o = (static_cast<long long>(b) * nsplit + split) * D + c * 8;
+  if (part0 != nullptr) {
+    *reinterpret_cast<float4*>(part0 + o) = make_float4(s0[0], s0[1], s0[2], s0[3]);
+    *reinterpret_cast<float4*>(part0 + o + 4) = make_float4(s0[4], s0[5], s0[6], s0[7]);
+  }
+  if (part1 != nullptr) {
+    *reinterpret_cast<float4*>(part1 + o) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    *reinterpret_cast<float4*>(part1 + o + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+  }
+}
+// stage 2: out[b * ldo + col] (+)= sum over splits, fixed order.
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, long long ldo, int D, int nsplit,
+                                    int accumulate) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= D) return;
+  const int b = blockIdx.y;
+  float s = 0.f;
+  for (int i = 0; i < nsplit; ++i) s += part[(static_cast<long long>(b) * nsplit + i) * D + col];
+  float* o = out + static_cast<long long>(b) * ldo + col;
+  *o = accumulate ? *o + s : s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the QKV epilogue (per-head RMSNorm(128) * w, then RoPE) + head-major -> token-major transposition:
+//   dq, dk, dv [B, H, L_total, 128] (grads w.r.t. the post-RoPE q, k and v the attention consumed)
+//   qk_pre [M, ldqk]: pre-norm q | k of this stream's tokens (saved by the forward epilogue)
+//   out [M, ldo]: [dq_pre | dk_pre | dv] (the A operand of the QKV dgrad GEMM)
+// One half-warp per (token, head): 8 elements per lane.
+__global__ void __launch_bounds__(256) qk_norm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dq, const __nv_bfloat16* __restrict__ dk,
+                                                               const __nv_bfloat16* __restrict__ dv,
+                                                               const __nv_bfloat16* __restrict__ qk_pre, long long ldqk,
+                                                               const __nv_bfloat16* __restrict__ rms_q,
+                                                               const __nv_bfloat16* __restrict__ rms_k,
+                                                               const float2* __restrict__ rope, __nv_bfloat16* __restrict__ out,
+                                                               long long ldo, int M, int H, int rows_per_batch, int row_offset,
+                                                               int L_total, float eps) {
+  const long long unit = static_cast<long long>(blockIdx.x) * 16 + (threadIdx.x >> 4);
+  const bool live = unit < static_cast<long long>(M) * H;
+  const long long u = live ? unit : 0;
+  const int m = static_cast<int>(u / H), h = static_cast<int>(u - static_cast<long long>(m) * H);
+  const int l16 = threadIdx.x & 15;
+  const int b = m / rows_per_batch, pos = row_offset + (m - b * rows_per_batch);
+  const int D = H * 128;
+  const long long src = ((static_cast<long long>(b) * H + h) * L_total + pos) * 128 + l16 * 8;
+  __nv_bfloat16* orow = out + static_cast<long long>(m) * ldo + h * 128 + l16 * 8;
+#pragma unroll
+  for (int sec = 0; sec < 2; ++sec) {
+    float dy[8], t[8], w[8];
+    unpack8(*reinterpret_cast<const uint4*>((sec == 0 ? dq : dk) + src), dy);
+    if (rope != nullptr) {
+      const float4* rp = reinterpret_cast<const float4*>(rope + static_cast<long long>(pos) * 64 + l16 * 4);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float4 cs = __ldg(rp + j);  // (cos0, sin0, cos1, sin1)
+        const float a0 = dy[4 * j], a1 = dy[4 * j + 1], a2 = dy[4 * j + 2], a3 = dy[4 * j + 3];
+        dy[4 * j] = a0 * cs.x + a1 * cs.y;
+        dy[4 * j + 1] = a1 * cs.x - a0 * cs.y;
+        dy[4 * j + 2] = a2 * cs.z + a3 * cs.w;
+        dy[4 * j + 3] = a3 * cs.z - a2 * cs.w;
+      }
+    }
+    unpack8(*reinterpret_cast<const uint4*>(qk_pre + static_cast<long long>(m) * ldqk + sec * D + h * 128 + l16 * 8), t);
+    unpack8(__ldg(reinterpret_cast<const uint4*>((sec == 0 ? rms_q : rms_k) + l16 * 8)), w);
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += t[j] * t[j];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rinv = rsqrtf(ss * (1.0f / 128.0f) + eps);
+    float gx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dy[j] *= w[j];     // g
+      t[j] *= rinv;      // xhat
+      gx += dy[j] * t[j];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) gx += __shfl_xor_sync(0xffffffffu, gx, o);
+    gx *= (1.0f / 128.0f);
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = rinv * (dy[j] - t[j] * gx);
+    if (live) *reinterpret_cast<uint4*>(orow + sec * D) = pack8(r);
+  }
+  if (live) *reinterpret_cast<uint4*>(orow + 2 * D) = *reinterpret_cast<const uint4*>(dv + src);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prologue of the attention backward: token-major dO (+ optional addend, the KD gradient of a hooked single-block
+// attention output) and O  ->  head-major dO [B, H, L, 128] and delta[b, h, pos] = sum_d dO * O  ([B*H, Lpad], 0 in the pad).
+// Token-major sources are split like the forward's outputs: rows pos < split live in p0 (row (b*split + pos) * ld0), the
+// rest in p1 (row (b*(L-split) + pos-split) * ld1).
+struct TokSrc {
+  const __nv_bfloat16* p0;
+  long long ld0;
+  const __nv_bfloat16* p1;
+  long long ld1;
+};
+__device__ __forceinline__ const __nv_bfloat16* tok_ptr(const TokSrc& s, int b, int pos, int split, int L) {
+  return pos < split ? s.p0 + (static_cast<long long>(b) * split + pos) * s.ld0
+                     : s.p1 + (static_cast<long long>(b) * (L - split) + (pos - split)) * s.ld1;
+}
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const TokSrc dO, const TokSrc O, const TokSrc add,
+                                                            __nv_bfloat16* __restrict__ do_hm, float* __restrict__ delta, int B,
+                                                            int H, int L, int Lpad, int split) {
+  const long long unit = static_cast<long long>(blockIdx.x) * 16 + (threadIdx.x >> 4);
+  const bool live = unit < static_cast<long long>(B) * Lpad * H;
+  const long long u = live ? unit : 0;
+  const int h = static_cast<int>(u % H);
+  const long long bp = u / H;
+  const int pos = static_cast<int>(bp % Lpad), b = static_cast<int>(bp / Lpad);
+  const int l16 = threadIdx.x & 15;
+  const bool real = pos < L;
+  float g[8], o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = o[j] = 0.f;
+  if (real) {
+    const int col = h * 128 + l16 * 8;
+    unpack8(*reinterpret_cast<const uint4*>(tok_ptr(dO, b, pos, split, L) + col), g);
+    unpack8(*reinterpret_cast<const uint4*>(tok_ptr(O, b, pos, split, L) + col), o);
+    if (add.p0 != nullptr || add.p1 != nullptr) {
+      float e[8];
+      unpack8(*reinterpret_cast<const uint4*>(tok_ptr(add, b, pos, split, L) + col), e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += e[j];
+    }
+  }
+  const uint4 packed = pack8(g);
+  // delta from the bf16-rounded dO the MMAs will consume
+  float gr[8];
+  unpack8(packed, gr);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += gr[j] * o[j];
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (live) {
+    if (real) *reinterpret_cast<uint4*>(do_hm + ((static_cast<long long>(b) * H + h) * L + pos) * 128 + l16 * 8) = packed;
+    if (l16 == 0) delta[(static_cast<long long>(b) * H + h) * Lpad + pos] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transposed skinny linear: out[b, k] = act'(pre[b, k]) * sum_n g[b, n] * W[n, k]      (B <= 8 rows per launch)
+// -- the backward of every AdaLN modulation linear of a step in one pass over the concatenated weights (6.5 GB, read
+// once), and of the time/text embedding MLPs.  Stage 1: CTA `s` reduces its slab of n rows, thread t owns columns
+// [8t, 8t+8) (W rows are read fully coalesced); stage 2 sums the slabs in a fixed order.  g fp32, W bf16, out fp32.
+template <int MAXB>
+__global__ void __launch_bounds__(512) skinny_linear_t_kernel(const float* __restrict__ g, long long ldg,
+                                                               const __nv_bfloat16* __restrict__ W, long long ldw,
+                                                               float* __restrict__ part /* [nslab, B, K] */, int B, int N, int K,
+                                                               int rows_per_slab) {
+  const int c = threadIdx.x;
+  if (c * 8 >= K) return;
+  const int n0 = blockIdx.x * rows_per_slab, n1 = min(n0 + rows_per_slab, N);
+  float acc[MAXB][8];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[b][j] = 0.f;
+  for (int n = n0; n < n1; ++n) {
+    float w[8];
+    unpack8(ld_stream(W + static_cast<long long>(n) * ldw + c * 8), w);
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+      if (b < B) {
+        const float gv = __ldg(g + static_cast<long long>(b) * ldg + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[b][j] += gv * w[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) {
+    if (b < B) {
+      float* o = part + (static_cast<long long>(blockIdx.x) * B + b) * K + c * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[b][4], acc[b][5], acc[b][6], acc[b][7]);
+    }
+  }
+}
+// dact: 0 none, 1 SiLU'(pre)
+__global__ void skinny_linear_t_final_kernel(const float* __restrict__ part, const __nv_bfloat16* __restrict__ pre, long long ldpre,
+                                             float* __restrict__ out, long long ldo, int B, int K, int nslab, int dact,
+                                             int accumulate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int b = blockIdx.y;
+  float s = 0.f;
+  for (int i = 0; i < nslab; ++i) s += part[(static_cast<long long>(i) * B + b) * K + k];
+  if (dact == 1) s *= dsilu_f(__bfloat162float(pre[static_cast<long long>(b) * ldpre + k]));
+  float* o = out + static_cast<long long>(b) * ldo + k;
+  *o = accumulate ? *o + s : s;
+}
+
+// fp32 -> bf16 row copy (gradients leave the fp32 reduction buffers as bf16 tensors)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+
+}  // namespace x2i

@@ -305,3 +305,199 @@ def kd_loss_bwd(teacher, student, seg_row_start, seg_layer, max_seg_rows, batch,
     _lib.call("x2i_kd_loss_bwd", _p(teacher), _p(student), rows, D, float(temperature), _p(seg_row_start), _p(seg_layer),
               seg_layer.numel(), int(max_seg_rows), batch, _p(valid), _p(dloss), _p(row_scale), _p(grad), _stream())
     return grad
+
+
+# ================================================================================================ backward / training
+F32 = torch.float32
+
+
+def linear_dgrad(dy, weight, pre=None, n_split=0, dact=1, addend=None, out=None):
+    """dX = addend + (dy @ weight) * act'(pre) on columns >= n_split  (backward of y = x @ weight.T towards x).
+    dy [.., Nout], weight [Nout, Kin] as stored by nn.Linear; pre [.., Kin - n_split] = pre-activation that produced x."""
+    _chk(dy, "dy"); _chk(weight, "weight"); _chk(pre, "pre"); _chk(addend, "addend"); _chk(out, "out")
+    M, lddy = _rows(dy)
+    Nout, Kin = weight.shape
+    if out is None:
+        out = torch.empty(*dy.shape[:-1], Kin, device=dy.device, dtype=BF16)
+    ldpre = _rows(pre)[1] if pre is not None else 0
+    ldadd = _rows(addend)[1] if addend is not None else 0
+    _lib.call("x2i_gemm_dgrad", _p(dy), lddy, _p(weight), weight.stride(0), _p(pre), ldpre, n_split, dact, _p(addend), ldadd,
+              _p(out), _rows(out)[1], M, Nout, Kin, _stream())
+    return out
+
+
+def linear_wgrad(dy, x, out=None, accumulate=False):
+    """dW[N, K] (+)= dy[M, N]^T @ x[M, K]  (weight gradient of y = x @ W.T)."""
+    _chk(dy, "dy"); _chk(x, "x"); _chk(out, "out")
+    M, lddy = _rows(dy)
+    M2, ldx = _rows(x)
+    if M != M2:
+        raise _lib.X2IError("linear_wgrad: dy and x must have the same number of rows")
+    N, K = dy.shape[-1], x.shape[-1]
+    if out is None:
+        out = torch.empty(N, K, device=dy.device, dtype=BF16)
+        accumulate = False
+    _lib.call("x2i_gemm_wgrad", _p(dy), lddy, _p(x), ldx, _p(out), out.stride(0), M, N, K, 1 if accumulate else 0, _stream())
+    return out
+
+
+def linear_act_save(x, weight, bias, act, pre_out=None, act_out=None):
+    """(pre, act(pre)) with pre = x @ weight.T + bias; act 1 gelu-tanh, 2 gelu-erf."""
+    _chk(x, "x"); _chk(weight, "weight"); _chk(bias, "bias"); _chk(pre_out, "pre_out"); _chk(act_out, "act_out")
+    M, lda = _rows(x)
+    N, K = weight.shape
+    if pre_out is None:
+        pre_out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=BF16)
+    if act_out is None:
+        act_out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=BF16)
+    _lib.call("x2i_gemm_bias_act_save", _p(x), lda, _p(weight), weight.stride(0), _p(bias), _p(pre_out), _rows(pre_out)[1],
+              _p(act_out), _rows(act_out)[1], M, N, K, act, _stream())
+    return pre_out, act_out
+
+
+def desc_linear_act_save(x, weight, bias, pre_out, act_out, act=1):
+    d = desc_linear(x, weight, bias, pre_out, act=0)
+    _chk(act_out, "act_out")
+    d.aux = _p(act_out); d.ldaux = _rows(act_out)[1]; d.aux_act = act
+    return d
+
+
+def desc_qkv_rope_save(x, weight, bias, rms_q, rms_k, rope, q, k, v, heads, rows_per_batch, row_offset, qk_pre, eps=1e-6, mlp=None,
+                       mlp_pre=None):
+    d = desc_qkv_rope(x, weight, bias, rms_q, rms_k, rope, q, k, v, heads, rows_per_batch, row_offset, eps, mlp)
+    _chk(qk_pre, "qk_pre"); _chk(mlp_pre, "mlp_pre")
+    d.qk_pre = _p(qk_pre); d.ldqk = _rows(qk_pre)[1]
+    if mlp_pre is not None:
+        d.mlp_pre = _p(mlp_pre); d.ldmlp_pre = _rows(mlp_pre)[1]
+    return d
+
+
+def lse_pad(L):
+    return (L + 127) // 128 * 128
+
+
+def attention_lse(q, k, v, split=0, out0=None, out1=None, lse=None):
+    """attention() that also returns the log2-domain row log-sum-exp [B, H, Lpad] fp32 for the backward."""
+    _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
+    B, H, L, d = q.shape
+    if d != 128 or not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        raise _lib.X2IError("attention: q,k,v must be contiguous [B,H,L,128]")
+    if split > 0 and out0 is None:
+        out0 = torch.empty(B, split, H * 128, device=q.device, dtype=BF16)
+    if split < L and out1 is None:
+        out1 = torch.empty(B, L - split, H * 128, device=q.device, dtype=BF16)
+    if lse is None:
+        lse = torch.empty(B, H, lse_pad(L), device=q.device, dtype=F32)
+    _chk(out0, "out0"); _chk(out1, "out1"); _chk(lse, "lse", F32)
+    ld0 = out0.stride(-2) if out0 is not None else 0
+    ld1 = out1.stride(-2) if out1 is not None else 0
+    _lib.call("x2i_mmdit_attention_lse", _p(q), _p(k), _p(v), _p(out0), ld0, split, _p(out1), ld1, _p(lse), B, H, L, _stream())
+    return out0, out1, lse
+
+
+def attention_bwd_prep(do0, do1, o0, o1, B, H, L, split, add0=None, add1=None, do_hm=None, delta=None):
+    """token-major dO (+addend) and O -> head-major dO [B,H,L,128] and delta [B,H,Lpad]; *0 = tokens < split, *1 = the rest."""
+    for t, n in ((do0, "do0"), (do1, "do1"), (o0, "o0"), (o1, "o1"), (add0, "add0"), (add1, "add1")):
+        _chk(t, n)
+    dev = (do1 if do1 is not None else do0).device
+    if do_hm is None:
+        do_hm = torch.empty(B, H, L, 128, device=dev, dtype=BF16)
+    if delta is None:
+        delta = torch.empty(B, H, lse_pad(L), device=dev, dtype=F32)
+    ld = lambda t: t.stride(-2) if t is not None else 0  # noqa: E731
+    _lib.call("x2i_attention_bwd_prep", _p(do0), ld(do0), _p(do1), ld(do1), _p(o0), ld(o0), _p(o1), ld(o1), _p(add0), ld(add0),
+              _p(add1), ld(add1), _p(do_hm), _p(delta), B, H, L, split, _stream())
+    return do_hm, delta
+
+
+def attention_bwd(q, k, v, do_hm, lse, delta, dq=None, dk=None, dv=None):
+    """(dq, dk, dv) head-major for softmax(q k^T / sqrt(128)) v."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (do_hm, "do_hm")):
+        _chk(t, n)
+        if not t.is_contiguous():
+            raise _lib.X2IError(f"attention_bwd: {n} must be contiguous [B,H,L,128]")
+    _chk(lse, "lse", F32); _chk(delta, "delta", F32)
+    B, H, L, _ = q.shape
+    if lse.shape != (B, H, lse_pad(L)) or delta.shape != lse.shape or not (lse.is_contiguous() and delta.is_contiguous()):
+        raise _lib.X2IError("attention_bwd: lse / delta must be contiguous [B, H, Lpad] fp32")
+    dq = torch.empty_like(q) if dq is None else dq
+    dk = torch.empty_like(q) if dk is None else dk
+    dv = torch.empty_like(q) if dv is None else dv
+    _lib.call("x2i_mmdit_attention_bwd", _p(q), _p(k), _p(v), _p(do_hm), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), B, H, L, _stream())
+    return dq, dk, dv
+
+
+def qk_norm_rope_bwd(dq, dk, dv, qk_pre, rms_q, rms_k, rope, out, rows_per_batch, row_offset, eps=1e-6):
+    """head-major dq,dk,dv -> out[M, >=3D] = [dq_pre | dk_pre | dv] token-major for the stream's tokens."""
+    for t, n in ((dq, "dq"), (dk, "dk"), (dv, "dv"), (qk_pre, "qk_pre"), (rms_q, "rms_q"), (rms_k, "rms_k"), (out, "out")):
+        _chk(t, n)
+    B, H, L_total, _ = dq.shape
+    M = _rows(qk_pre)[0]
+    _lib.call("x2i_qk_norm_rope_bwd", _p(dq), _p(dk), _p(dv), _p(qk_pre), _rows(qk_pre)[1], _p(rms_q), _p(rms_k), _p(rope), _p(out),
+              _rows(out)[1], M, H, rows_per_batch, row_offset, L_total, eps, _stream())
+    return out
+
+
+def gate_bwd(dx, gate, rows_per_batch, addend=None, out=None):
+    _chk(dx, "dx"); _chk(gate, "gate"); _chk(addend, "addend"); _chk(out, "out")
+    rows, lddx = _rows(dx)
+    if out is None:
+        out = torch.empty(dx.shape, device=dx.device, dtype=BF16)
+    _lib.call("x2i_gate_bwd", _p(dx), lddx, _p(gate), gate.stride(0), _p(addend), _rows(addend)[1] if addend is not None else 0,
+              _p(out), _rows(out)[1], rows, dx.shape[-1], rows_per_batch, _stream())
+    return out
+
+
+def ln_modulate_bwd(dn, x, scale, rows_per_batch, dres=None, out=None, stats=None, eps=1e-6, affine=False):
+    """dx = dres + d/dx [LN(x) * (1 + scale) + shift] . dn   (affine: LN(x) * scale + shift); stats float2 [rows] optional."""
+    _chk(dn, "dn"); _chk(x, "x"); _chk(scale, "scale"); _chk(dres, "dres"); _chk(out, "out"); _chk(stats, "stats", F32)
+    rows, lddn = _rows(dn)
+    if out is None:
+        out = torch.empty(dn.shape, device=dn.device, dtype=BF16)
+    mod_stride = 0 if affine else scale.stride(0)
+    _lib.call("x2i_ln_modulate_bwd", _p(dn), lddn, _p(x), _rows(x)[1], _p(scale), mod_stride, _p(dres),
+              _rows(dres)[1] if dres is not None else 0, _p(out), _rows(out)[1], _p(stats), rows, dn.shape[-1], rows_per_batch,
+              eps, 1 if affine else 0, _stream())
+    return out
+
+
+_COLSUM_WS = {}
+
+
+def _ws_f32(key, n, device):
+    t = _COLSUM_WS.get((key, str(device)))
+    if t is None or t.numel() < n:
+        t = torch.empty(int(n), device=device, dtype=F32)
+        _COLSUM_WS[(key, str(device))] = t
+    return t
+
+
+def colsum(a, nbatch, rows_per_batch, out0=None, b=None, out1=None, stats=None, accumulate=False):
+    """out0[nb, D] (+)= sum_t a;  out1[nb, D] (+)= sum_t a * (b, or (b - mean) * rstd with stats).  fp32 outputs (row-strided ok)."""
+    _chk(a, "a"); _chk(b, "b"); _chk(out0, "out0", F32); _chk(out1, "out1", F32); _chk(stats, "stats", F32)
+    D = a.shape[-1]
+    ws = _ws_f32("colsum", _lib.lib().x2i_colsum_workspace_floats(nbatch, rows_per_batch, D), a.device)
+    _lib.call("x2i_colsum", _p(a), _rows(a)[1], _p(b), _rows(b)[1] if b is not None else 0, _p(stats), _p(out0),
+              out0.stride(0) if out0 is not None else 0, _p(out1), out1.stride(0) if out1 is not None else 0, _p(ws), nbatch,
+              rows_per_batch, D, 1 if accumulate else 0, _stream())
+
+
+def skinny_linear_t(g, weight, pre=None, dact=0, out=None, accumulate=False):
+    """out[b, k] (+)= act'(pre[b, k]) * sum_n g[b, n] * weight[n, k]; g, out fp32; dact 1 = SiLU'."""
+    _chk(g, "g", F32); _chk(weight, "weight"); _chk(pre, "pre"); _chk(out, "out", F32)
+    B, N = g.shape
+    K = weight.shape[1]
+    if out is None:
+        out = torch.empty(B, K, device=g.device, dtype=F32)
+        accumulate = False
+    ws = _ws_f32("skinny_t", _lib.lib().x2i_skinny_linear_t_workspace_floats(N, K), g.device)
+    _lib.call("x2i_skinny_linear_t", _p(g), g.stride(0), _p(weight), weight.stride(0), _p(pre), pre.stride(0) if pre is not None else 0,
+              _p(out), out.stride(0), _p(ws), B, N, K, dact, 1 if accumulate else 0, _stream())
+    return out
+
+
+def f32_to_bf16(x):
+    _chk(x, "x", F32)
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.call("x2i_f32_to_bf16", _p(x.contiguous()), _p(out), x.numel(), _stream())
+    return out
