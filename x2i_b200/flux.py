@@ -14,8 +14,9 @@ Mirrors the interface the reference consumes:
     image_rotary_emb)`` (``lightcontrol_flux.py:286-384``).
 
 Every FLOP of the forward runs in libx2i_b200.so (tcgen05 GEMMs with fused epilogues, the fused attention kernel and
-the row-wise kernels); PyTorch only owns the buffers.  Forward only (inference / teacher): the backward kernels for
-distillation training are a later scope row.  There is no CPU or eager fallback.
+the row-wise kernels); PyTorch only owns the buffers.  When an input requires grad (the student pass of distillation
+training) the forward runs in a saving mode and the backward through all blocks runs on the hand-written backward
+kernels (flux_train.py).  There is no CPU or eager fallback.
 """
 from __future__ import annotations
 
@@ -576,7 +577,6 @@ class FluxTransformer2DModel(nn.Module):
 
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
                 txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=True):
-        _no_grad_needed(hidden_states, encoder_hidden_states, pooled_projections)
         self._pack()
         if txt_ids.ndim == 3:
             txt_ids = txt_ids[0]
@@ -584,7 +584,10 @@ class FluxTransformer2DModel(nn.Module):
             img_ids = img_ids[0]
         if guidance is not None and not self.config.guidance_embeds:
             guidance = None
-        if self._graphable():
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                           for t in (hidden_states, encoder_hidden_states, pooled_projections)):
+            out = self._forward_train(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance)
+        elif self._graphable():
             out = self._forward_graphed(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
                                         guidance)
         else:
@@ -593,6 +596,27 @@ class FluxTransformer2DModel(nn.Module):
         if not return_dict:
             return (out,)
         return SimpleNamespace(sample=out)
+
+    def _forward_train(self, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance):
+        """Differentiable forward (student pass of the distillation step, train/train_qwenvl.py:578-587): one autograd node
+        for the whole transformer (flux_train.FluxTrainFn); the forward hooks registered on every ``blk.attn``
+        (train_qwenvl.py:206-214) are then invoked, in block order, with outputs that carry autograd history."""
+        from . import flux_train
+        for m in self.modules():
+            if isinstance(m, Attention) and not _default_proc(m):
+                raise X2IError("training through a plug-in attention processor is not supported (no backward for user code "
+                               "inside the fused block); use the default FluxAttnProcessor2_0")
+        outs = flux_train.FluxTrainFn.apply(self, 0, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids,
+                                            guidance)
+        nd, ns = len(self.transformer_blocks), len(self.single_transformer_blocks)
+        out, hi, ht, hs = outs[0], outs[1:1 + nd], outs[1 + nd:1 + 2 * nd], outs[1 + 2 * nd:1 + 2 * nd + ns]
+        for i, blk in enumerate(self.transformer_blocks):
+            for hook in list(blk.attn._forward_hooks.values()):
+                hook(blk.attn, (), (hi[i], ht[i]))
+        for i, blk in enumerate(self.single_transformer_blocks):
+            for hook in list(blk.attn._forward_hooks.values()):
+                hook(blk.attn, (), hs[i])
+        return out
 
     def _graphable(self):
         if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():

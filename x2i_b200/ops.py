@@ -98,15 +98,18 @@ def desc_linear(x, weight, bias, out, act=0):
                          ldw=weight.stride(0), C=_p(out), ldc=_rows(out)[1])
 
 
-def desc_gate_residual(x, weight, bias, gate, residual, rows_per_batch, aux=None):
-    """Descriptor of residual += gate[b] * (x @ weight.T + bias) (in place); aux receives the un-gated value."""
-    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (gate, "gate"), (residual, "residual"), (aux, "aux")):
+def desc_gate_residual(x, weight, bias, gate, residual, rows_per_batch, aux=None, out=None):
+    """Descriptor of out = residual + gate[b] * (x @ weight.T + bias) (out defaults to residual: in place); aux receives the
+    un-gated value."""
+    for t, n in ((x, "x"), (weight, "weight"), (bias, "bias"), (gate, "gate"), (residual, "residual"), (aux, "aux"), (out, "out")):
         _chk(t, n)
     M, lda = _rows(x)
     N, K = weight.shape
     ldr = _rows(residual)[1]
+    if out is None:
+        out = residual
     return _lib.GemmDesc(kind=_lib.GEMM_GATE_RESIDUAL, M=M, N=N, K=K, rows_per_batch=rows_per_batch, A=_p(x), W=_p(weight),
-                         bias=_p(bias), lda=lda, ldw=weight.stride(0), C=_p(residual), ldc=ldr, gate=_p(gate),
+                         bias=_p(bias), lda=lda, ldw=weight.stride(0), C=_p(out), ldc=_rows(out)[1], gate=_p(gate),
                          residual=_p(residual), gate_stride=gate.stride(0), ldr=ldr, aux=_p(aux),
                          ldaux=_rows(aux)[1] if aux is not None else 0)
 
