@@ -264,6 +264,19 @@ int x2i_proj_mix_ln(const void* x, int mode, const float* w, float conv_bias, co
 /* pooled[b,n] = mean_s y[b,s,n]  (utils/proj.py:32)                                                                */
 int x2i_mean_over_s(const void* y, void* out, int B, int S, int N, void* stream);
 
+/* ---- projector backward (the only trained module: train/train_qwenvl.py:453-459) --------------------------------
+ * x2i_proj_mix_ln that also stores xm bf16 [B,S,H], the mixed plane BEFORE the LayerNorm (needed by its backward).    */
+int x2i_proj_mix_ln_save(const void* x, int mode, const float* w, float conv_bias, const float* gamma, const float* beta,
+                         float eps, void* y, void* xm, int B, int C, int S, int H, void* stream);
+/* dy[b,s,:] = dpooled[b,:] / S : backward of the mean over S (utils/proj.py:32).                                    */
+int x2i_mean_over_s_bwd(const void* dpooled, void* dy, int B, int S, int N, void* stream);
+/* Weight gradient of the layer-mixing front end w.r.t. g = d loss / d mixed plane [B,S,H] (bf16):
+ * mode 0: dw fp32 [C,5,5] of Conv2d(C->1, 5x5, pad 2) (utils/proj.py:69; the conv bias gradient is sum(g));
+ * mode 1: dw fp32 [C] of cha_scale (utils/proj.py:67, includes the 1/C of the mean).
+ * workspace: x2i_proj_mix_wgrad_workspace_floats() floats.  Deterministic two-stage reduction.                      */
+int x2i_proj_mix_wgrad(const void* x, const void* g, int mode, float* dw, float* workspace, int B, int C, int S, int H, void* stream);
+int64_t x2i_proj_mix_wgrad_workspace_floats(int B, int C, int S);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,7 +196,7 @@ int launch_gemm(DeviceInfo* d, const void* A, int64_t lda, const void* W, int64_
 template <int EPI, bool A_MN>
 int launch_gemm_mn(DeviceInfo* d, const void* A, int64_t lda, const void* Bkn, int64_t ldb, GemmParams& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return fail(X2I_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
-  if (p.N % 64 != 0 || p.K % 8 != 0 || (A_MN && p.M % 8 != 0)) return fail(X2I_ERR_SHAPE, "gemm(kn): need N %% 64 == 0, K %% 8 == 0 (M=%d N=%d K=%d)", p.M, p.N, p.K);
+  if (p.N % 64 != 0) return fail(X2I_ERR_SHAPE, "gemm(kn): need N %% 64 == 0 (M=%d N=%d K=%d)", p.M, p.N, p.K);
   if (!aligned16(A) || !aligned16(Bkn) || lda % 8 || ldb % 8) return fail(X2I_ERR_ALIGN, "gemm(kn): operands must be 16-byte aligned with ld %% 8 == 0");
   CUtensorMap ta, tb;
   uint32_t b64[2] = {64, 64};
@@ -717,8 +717,22 @@ int x2i_kd_loss_bwd(const void* teacher, const void* student, int64_t rows, int 
   return check_launch("kd_row_kernel<bwd>");
 }
 
+namespace {
+int proj_mix_ln_impl(const void* x, int mode, const float* w, float conv_bias, const float* gamma, const float* beta,
+                     float eps, void* y, void* xm, int B, int C, int S, int H, void* stream);
+}
 int x2i_proj_mix_ln(const void* x, int mode, const float* w, float conv_bias, const float* gamma, const float* beta,
                     float eps, void* y, int B, int C, int S, int H, void* stream) {
+  return proj_mix_ln_impl(x, mode, w, conv_bias, gamma, beta, eps, y, nullptr, B, C, S, H, stream);
+}
+int x2i_proj_mix_ln_save(const void* x, int mode, const float* w, float conv_bias, const float* gamma, const float* beta,
+                         float eps, void* y, void* xm, int B, int C, int S, int H, void* stream) {
+  if (!xm || !aligned16(xm)) return fail(X2I_ERR_ALIGN, "proj_mix_ln_save: xm buffer required (16-byte aligned)");
+  return proj_mix_ln_impl(x, mode, w, conv_bias, gamma, beta, eps, y, xm, B, C, S, H, stream);
+}
+namespace {
+int proj_mix_ln_impl(const void* x, int mode, const float* w, float conv_bias, const float* gamma, const float* beta,
+                     float eps, void* y, void* xm, int B, int C, int S, int H, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   if (B <= 0 || C <= 0 || S <= 0 || H <= 0 || H % 8 || H > 8 * 512 || mode < 0 || mode > 2) return fail(X2I_ERR_SHAPE, "proj_mix_ln: H must be a multiple of 8, <= 4096; mode in 0..2");
@@ -729,9 +743,44 @@ int x2i_proj_mix_ln(const void* x, int mode, const float* w, float conv_bias, co
   if (smem > 48 * 1024) return fail(X2I_ERR_SHAPE, "proj_mix_ln: too many channels (C=%d)", C);
   const int tiles = (S + PROJ_R - 1) / PROJ_R;
   proj_mix_ln_kernel<<<B * tiles, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), mode, w, conv_bias, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), B, C, S, H);
+      static_cast<const __nv_bfloat16*>(x), mode, w, conv_bias, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), B, C, S, H,
+      static_cast<__nv_bfloat16*>(xm));
   return check_launch("proj_mix_ln_kernel");
 }
+}  // namespace
+
+int x2i_mean_over_s_bwd(const void* dpooled, void* dy, int B, int S, int N, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || S <= 0 || N <= 0 || N % 8) return fail(X2I_ERR_SHAPE, "mean_over_s_bwd: N must be a multiple of 8");
+  if (!aligned16(dpooled) || !aligned16(dy)) return fail(X2I_ERR_ALIGN, "mean_over_s_bwd: alignment");
+  const long long n = static_cast<long long>(B) * S * (N / 8);
+  mean_over_s_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dpooled), static_cast<__nv_bfloat16*>(dy), B, S, N);
+  return check_launch("mean_over_s_bwd_kernel");
+}
+
+int x2i_proj_mix_wgrad(const void* x, const void* g, int mode, float* dw, float* workspace, int B, int C, int S, int H, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || C <= 0 || S <= 0 || H <= 0 || H % 8 || H > 8 * 512 || (mode != 0 && mode != 1)) return fail(X2I_ERR_SHAPE, "proj_mix_wgrad: H %% 8, H <= 4096, mode 0 (conv) or 1 (cha_scale)");
+  if (!x || !g || !dw || !workspace) return fail(X2I_ERR_SHAPE, "proj_mix_wgrad: null buffer");
+  if (!aligned16(x) || !aligned16(g)) return fail(X2I_ERR_ALIGN, "proj_mix_wgrad: alignment");
+  const int tiles = (S + PROJB_R - 1) / PROJB_R;
+  const int threads = ((H / 8 + 31) / 32) * 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(tiles, C, B);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto G = static_cast<const __nv_bfloat16*>(g);
+  const int nt = mode == 0 ? 25 : 1;
+  if (mode == 0) proj_mix_wgrad_kernel<true><<<grid, threads, 0, st>>>(X, G, workspace, B, C, S, H);
+  else proj_mix_wgrad_kernel<false><<<grid, threads, 0, st>>>(X, G, workspace, B, C, S, H);
+  if (int rc = check_launch("proj_mix_wgrad_kernel")) return rc;
+  const int n_out = C * nt;
+  proj_mix_wgrad_final_kernel<<<(n_out + 127) / 128, 128, 0, st>>>(workspace, dw, B * tiles, n_out, mode == 0 ? 1.0f : 1.0f / C);
+  return check_launch("proj_mix_wgrad_final_kernel");
+}
+int64_t x2i_proj_mix_wgrad_workspace_floats(int B, int C, int S) { return 25LL * B * ((S + PROJB_R - 1) / PROJB_R) * C; }
 
 int x2i_mean_over_s(const void* y, void* out, int B, int S, int N, void* stream) {
   DeviceInfo* d;

@@ -490,7 +490,8 @@ __global__ void __launch_bounds__(512) proj_mix_ln_kernel(const __nv_bfloat16* _
                                                           const float* __restrict__ w /* [C,5,5] | [C] */,
                                                           float conv_bias, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps,
-                                                          __nv_bfloat16* __restrict__ y, int B, int C, int S, int H) {
+                                                          __nv_bfloat16* __restrict__ y, int B, int C, int S, int H,
+                                                          __nv_bfloat16* __restrict__ xm /* optional: pre-LN mix (training) */) {
   extern __shared__ float sm[];
   float* wsm = sm;                           // C*25 (mode 0) | C (mode 1)
   float* red = sm + ((C * 25 + 3) & ~3);     // one float per warp
@@ -567,6 +568,7 @@ __global__ void __launch_bounds__(512) proj_mix_ln_kernel(const __nv_bfloat16* _
       acc[o][j] = active ? acc[o][j] * post_mul + post_add : 0.f;
       part += acc[o][j];
     }
+    if (xm != nullptr && active) *reinterpret_cast<uint4*>(xm + (static_cast<long long>(b) * S + s0 + o) * H + h0) = pack8(acc[o]);
     const float mean = block_sum_rt(part, red, nwarps) / H;
     part = 0.f;
 #pragma unroll

@@ -344,6 +344,109 @@ __global__ void skinny_linear_t_final_kernel(const float* __restrict__ part, con
   *o = accumulate ? *o + s : s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of pooled = mean_s y[b, s, :]  (utils/proj.py:32):  dy[b, s, :] = dpooled[b, :] / S
+__global__ void mean_over_s_bwd_kernel(const __nv_bfloat16* __restrict__ dpooled, __nv_bfloat16* __restrict__ dy, int B, int S, int N) {
+  const int nchunk = N >> 3;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * S * nchunk) return;
+  const int c = static_cast<int>(i % nchunk);
+  const int b = static_cast<int>(i / (static_cast<long long>(S) * nchunk));
+  float a[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(dpooled + static_cast<long long>(b) * N) + c), a);
+  const float inv = 1.0f / S;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] *= inv;
+  reinterpret_cast<uint4*>(dy)[i] = pack8(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of the projector's layer-mixing front end (utils/proj.py:62-72):
+//   CONV : dW[c, ky, kx] = sum_{b,s,h} g[b,s,h] * x[b, c, s+ky-2, h+kx-2]     (Conv2d(C -> 1, 5x5, pad 2))
+//   !CONV: dW[c]         = sum_{b,s,h} g[b,s,h] * x[b, c, s, h]               (cha_scale; caller divides by C)
+// g = gradient w.r.t. the mixed [B,S,H] plane.  Same register-blocked stencil as the forward: a CTA owns PROJB_R rows of
+// one (b, c) plane, thread i owns 8 consecutive h; every x row is loaded once and meets the 5 g rows it overlaps.
+// Stage 1 writes part[(b * tiles + tile) * C + c][25]; stage 2 sums b and tiles in a fixed order.
+constexpr int PROJB_R = 4;
+template <bool CONV>
+__global__ void __launch_bounds__(512) proj_mix_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ g,
+                                                             float* __restrict__ part, int B, int C, int S, int H) {
+  __shared__ float red[16][25];
+  const int tiles = gridDim.x;
+  const int tile = blockIdx.x, c = blockIdx.y, b = blockIdx.z;
+  const int s0 = tile * PROJB_R;
+  const int h0 = threadIdx.x * 8;
+  const bool active = h0 < H;
+  constexpr int NT = CONV ? 25 : 1;
+  float acc[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) acc[i] = 0.f;
+  if (active) {
+    const __nv_bfloat16* xc = x + (static_cast<long long>(b) * C + c) * S * H;
+    const __nv_bfloat16* gb = g + static_cast<long long>(b) * S * H;
+    float gv[PROJB_R][8];
+#pragma unroll
+    for (int o = 0; o < PROJB_R; ++o) {
+      if (s0 + o < S) {
+        unpack8(*reinterpret_cast<const uint4*>(gb + static_cast<long long>(s0 + o) * H + h0), gv[o]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[o][j] = 0.f;
+      }
+    }
+    if constexpr (CONV) {
+#pragma unroll
+      for (int ri = 0; ri < PROJB_R + 4; ++ri) {
+        const int r = s0 + ri - 2;
+        if (r < 0 || r >= S) continue;  // zero padding (CTA-uniform)
+        const __nv_bfloat16* xr = xc + static_cast<long long>(r) * H + h0;
+        float v[12];
+        unpack8(ld_stream(xr), v + 2);
+        const uint32_t lft = h0 > 0 ? __ldg(reinterpret_cast<const uint32_t*>(xr - 2)) : 0u;
+        const uint32_t rgt = h0 + 8 < H ? __ldg(reinterpret_cast<const uint32_t*>(xr + 8)) : 0u;
+        v[0] = bf16_lo(lft); v[1] = bf16_hi(lft); v[10] = bf16_lo(rgt); v[11] = bf16_hi(rgt);
+#pragma unroll
+        for (int o = 0; o < PROJB_R; ++o) {
+          const int ky = ri - o;  // x row r = (s0 + o) + ky - 2
+          if (ky < 0 || ky > 4) continue;
+#pragma unroll
+          for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[ky * 5 + kx] += gv[o][j] * v[j + kx];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int o = 0; o < PROJB_R; ++o) {
+        if (s0 + o >= S) continue;
+        float v[8];
+        unpack8(ld_stream(xc + static_cast<long long>(s0 + o) * H + h0), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[0] += gv[o][j] * v[j];
+      }
+    }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    const float sres = warp_sum(acc[i]);
+    if (l == 0) red[w][i] = sres;
+  }
+  __syncthreads();
+  if (threadIdx.x < NT) {
+    float sres = 0.f;
+    for (int j = 0; j < nw; ++j) sres += red[j][threadIdx.x];
+    part[((static_cast<long long>(b) * tiles + tile) * C + c) * NT + threadIdx.x] = sres;
+  }
+}
+__global__ void proj_mix_wgrad_final_kernel(const float* __restrict__ part, float* __restrict__ out, int n_parts, int n_out, float mul) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (c, tap)
+  if (i >= n_out) return;
+  float sres = 0.f;
+  for (int p = 0; p < n_parts; ++p) sres += part[static_cast<long long>(p) * n_out + i];
+  out[i] = sres * mul;
+}
+
 // fp32 -> bf16 row copy (gradients leave the fp32 reduction buffers as bf16 tensors)
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -91,3 +91,52 @@ def attention_distillation_loss(KD_teacher: Sequence, KD_student: Sequence, temp
             for i in bad:
                 print(f"down_feature{['', '1', '2'][gi]}:{i}")
     return total
+
+
+class _KDLayers(torch.autograd.Function):
+    """Sum over layers of the reference's per-layer KL term, straight from the hook LISTS (no torch.stack copies of the
+    1.6 GB/sample hook tensors, train_qwenvl.py:590-592): tensors = (teacher_0..n-1, student_0..n-1), each [B, L_i, D]."""
+
+    @staticmethod
+    def forward(ctx, temperature, n, *tensors):
+        teachers, students = tensors[:n], tensors[n:]
+        dev = teachers[0].device
+        total = torch.zeros((), device=dev, dtype=torch.float32)
+        saved, metas = [], []
+        valids = []
+        for t, s in zip(teachers, students):
+            B, L, D = t.shape
+            t2 = t.detach().to(torch.bfloat16).contiguous().view(-1, D)
+            s2 = s.detach().to(torch.bfloat16).contiguous().view(-1, D)
+            starts = torch.arange(0, B + 1, device=dev, dtype=torch.int64) * L
+            layer = torch.zeros(B, device=dev, dtype=torch.int32)
+            loss, _terms, valid = ops.kd_loss_fwd(t2, s2, starts, layer, 1, B, temperature)
+            total = total + loss
+            saved += [t2, s2, starts, layer, valid]
+            metas.append((B, L, s.shape, s.dtype))
+            valids.append(valid)
+        ctx.save_for_backward(*saved)
+        ctx.meta = (temperature, n, metas)
+        valid_all = torch.cat(valids)
+        ctx.mark_non_differentiable(valid_all)
+        return total, valid_all
+
+    @staticmethod
+    def backward(ctx, dloss, _dvalid):
+        temperature, n, metas = ctx.meta
+        sv = ctx.saved_tensors
+        dl = dloss.float().contiguous()
+        grads = []
+        for i, (B, L, shape, dtype) in enumerate(metas):
+            t2, s2, starts, layer, valid = sv[5 * i:5 * i + 5]
+            g = ops.kd_loss_bwd(t2, s2, starts, layer, L, B, valid, dl, temperature)
+            grads.append(g.view(shape).to(dtype))
+        return (None, None) + (None,) * n + tuple(grads)
+
+
+def kd_loss_layers(teacher_layers: Sequence[torch.Tensor], student_layers: Sequence[torch.Tensor], temperature: float = 3.0):
+    """(loss, valid[n_layers]) over per-layer hook tensors [B, L_i, D]; same value as the stacked form (each layer's term is
+    sum / B, inf/nan layers skipped) without stacking."""
+    if len(teacher_layers) != len(student_layers) or not teacher_layers:
+        raise X2IError("kd_loss_layers: need equally long, non-empty teacher / student lists")
+    return _KDLayers.apply(float(temperature), len(teacher_layers), *teacher_layers, *student_layers)

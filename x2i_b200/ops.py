@@ -504,3 +504,33 @@ def f32_to_bf16(x):
     out = torch.empty(x.shape, device=x.device, dtype=BF16)
     _lib.call("x2i_f32_to_bf16", _p(x.contiguous()), _p(out), x.numel(), _stream())
     return out
+
+
+def proj_mix_ln_save(x, mode, w, conv_bias, gamma, beta, eps):
+    """proj_mix_ln that also returns the pre-LayerNorm mixed plane xm [B,S,H] (bf16) for the backward."""
+    _chk(x, "x"); _chk(w, "w", F32); _chk(gamma, "gamma", F32); _chk(beta, "beta", F32)
+    x = x.contiguous()
+    B, C, S, H = x.shape
+    y = torch.empty(B, S, H, device=x.device, dtype=BF16)
+    xm = torch.empty_like(y)
+    _lib.call("x2i_proj_mix_ln_save", _p(x), mode, _p(w), float(conv_bias), _p(gamma), _p(beta), float(eps), _p(y), _p(xm), B, C, S, H,
+              _stream())
+    return y, xm
+
+
+def mean_over_s_bwd(dpooled, S):
+    _chk(dpooled, "dpooled")
+    B, N = dpooled.shape
+    dy = torch.empty(B, S, N, device=dpooled.device, dtype=BF16)
+    _lib.call("x2i_mean_over_s_bwd", _p(dpooled.contiguous()), _p(dy), B, S, N, _stream())
+    return dy
+
+
+def proj_mix_wgrad(x, g, mode):
+    """fp32 gradient of the conv weight [C,5,5] (mode 0) or of cha_scale [C] (mode 1); x bf16 [B,C,S,H], g bf16 [B,S,H]."""
+    _chk(x, "x"); _chk(g, "g")
+    B, C, S, H = x.shape
+    dw = torch.empty((C, 5, 5) if mode == 0 else (C,), device=x.device, dtype=F32)
+    ws = _ws_f32("proj_mix_wgrad", _lib.lib().x2i_proj_mix_wgrad_workspace_floats(B, C, S), x.device)
+    _lib.call("x2i_proj_mix_wgrad", _p(x.contiguous()), _p(g.contiguous()), mode, _p(dw), _p(ws), B, C, S, H, _stream())
+    return dw

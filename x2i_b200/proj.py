@@ -8,8 +8,10 @@ Same classes, constructor arguments, parameter names and return values as the re
       --GELU--> Linear(4096,4096,no bias) = prompt_embeds[B,S,4096] --GELU--> Linear(4096,768)+b --mean_S--> pooled[B,768]
 
 Kernels: one HBM-streaming stencil+LayerNorm kernel for the front end (x2i_proj_mix_ln), tcgen05 GEMMs with GELU
-epilogues for the three linears, a column-mean kernel.  Forward only for now (the projector's backward / wgrad is a
-later scope row).  ``use_t5=True`` raises exactly like the reference (NameError there).
+epilogues for the three linears, a column-mean kernel.  With trainable parameters and grad enabled the module runs as one
+autograd node (``_ProjFn``) whose backward is hand-written too: wgrad / dgrad tcgen05 GEMMs (MN-major operands, GELU'
+epilogues), LayerNorm backward, a stencil weight-gradient kernel for the 5x5 layer-mixing conv, deterministic reductions.
+``use_t5=True`` raises exactly like the reference (NameError there).
 """
 import torch
 import torch.nn as nn
@@ -18,6 +20,64 @@ from . import ops
 from ._lib import X2IError
 
 BF16 = torch.bfloat16
+
+
+class _ProjFn(torch.autograd.Function):
+    """Projector forward + backward on the sm_100a kernels (the only trained module of the distillation step,
+    train/train_qwenvl.py:453-459, :576, :625).  Inputs: x [B,C,S,H] and the parameters; outputs (pooled, seq).
+    mode 0 conv, 1 cha_scale, 2 plain mean.  Gradients for every parameter (x is the frozen MLLM's output: no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, mode, mix_w, mix_b, ln_w, ln_b, eps, w0, w2, w3, b3):
+        xb = x.detach().to(BF16).contiguous()
+        B, C, S, H = xb.shape
+        gamma, beta = ln_w.detach().float(), ln_b.detach().float()
+        if mode == 0:
+            wf, cb = mix_w.detach().float().reshape(C, 25).contiguous(), float(mix_b.detach().float())
+        elif mode == 1:
+            wf, cb = mix_w.detach().float().reshape(C).contiguous(), 0.0
+        else:
+            wf, cb = gamma, 0.0
+        xn, xm = ops.proj_mix_ln_save(xb, mode, wf, cb, gamma, beta, eps)
+        M = B * S
+        h1, g1 = ops.linear_act_save(xn.view(M, H), w0.detach(), None, 2)
+        x2, g2 = ops.linear_dual_gelu(g1, w2.detach(), None)
+        x1 = ops.mean_over_s(ops.linear(g2, w3.detach(), b3.detach()).view(B, S, -1))
+        ctx.save_for_backward(xb, xm, xn, h1, g1, x2, g2, ln_w, w0, w2, w3)
+        ctx.meta = (mode, eps, B, C, S, H, None if mix_w is None else (mix_w.shape, mix_w.dtype), ln_w.dtype, w0.dtype, b3.dtype)
+        return x1, x2.view(B, S, -1)
+
+    @staticmethod
+    def backward(ctx, dx1, dx2):
+        xb, xm, xn, h1, g1, x2, g2, ln_w, w0, w2, w3 = ctx.saved_tensors
+        mode, eps, B, C, S, H, mixmeta, ln_dt, w_dt, b_dt = ctx.meta
+        M = B * S
+        dev = xb.device
+        dy = ops.mean_over_s_bwd(dx1.to(BF16), S).view(M, -1)                     # through mean over S
+        db3 = torch.empty(1, dy.shape[1], device=dev, dtype=torch.float32)
+        ops.colsum(dy, 1, M, out0=db3)
+        dw3 = ops.linear_wgrad(dy, g2)
+        dx2t = ops.linear_dgrad(dy, w3.detach(), pre=x2, n_split=0, dact=2, addend=dx2.to(BF16).contiguous().view(M, -1))
+        dw2 = ops.linear_wgrad(dx2t, g1)
+        dh1 = ops.linear_dgrad(dx2t, w2.detach(), pre=h1, n_split=0, dact=2)
+        dw0 = ops.linear_wgrad(dh1, xn.view(M, H))
+        dxn = ops.linear_dgrad(dh1, w0.detach())
+        stats = torch.empty(M, 2, device=dev, dtype=torch.float32)
+        gamma_b = ln_w.detach().to(BF16).reshape(1, H).contiguous()
+        dxm = ops.ln_modulate_bwd(dxn, xm.view(M, H), gamma_b, M, stats=stats, eps=eps, affine=True)
+        dbeta = torch.empty(1, H, device=dev, dtype=torch.float32)
+        dgamma = torch.empty(1, H, device=dev, dtype=torch.float32)
+        ops.colsum(dxn, 1, M, out0=dbeta, b=xm.view(M, H), out1=dgamma, stats=stats)
+        d_mix_w = d_mix_b = None
+        if mode in (0, 1):
+            shape, dt = mixmeta
+            d_mix_w = ops.proj_mix_wgrad(xb, dxm.view(B, S, H), mode).view(shape).to(dt)
+            if mode == 0:
+                tot = torch.empty(1, H, device=dev, dtype=torch.float32)
+                ops.colsum(dxm, 1, M, out0=tot)
+                d_mix_b = tot.sum().reshape(1).to(dt)
+        return (None, None, d_mix_w, d_mix_b, dgamma.view(H).to(ln_dt), dbeta.view(H).to(ln_dt), None, dw0.to(w_dt), dw2.to(w_dt),
+                dw3.to(w_dt), db3.view(-1).to(b_dt))
 
 
 class MLP3(nn.Module):
@@ -63,12 +123,19 @@ class Proj7Exp(nn.Module):
         self.mlp = MLP3(input_dim, output_dim1, output_dim1, output_dim0, norm_eps)
 
     def forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise X2IError("x2i_b200.proj: backward is not implemented yet; call under torch.no_grad()")
         if self.mlp.projector[0].weight.dtype != BF16 or not x.is_cuda:
             raise X2IError("Proj7Exp runs in bf16 on a CUDA device (x2i_b200 has no CPU path): .to('cuda', torch.bfloat16)")
         B, C, S, H = x.shape
         ln = self.mlp.layernorm
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if x.requires_grad:
+                raise X2IError("Proj7Exp: no gradient towards the MLLM hidden states (the MLLM is frozen in X2I training)")
+            m = self.mlp
+            mode = 1 if self.use_scale else (0 if self.use_cnn else 2)
+            mix_w = self.cha_scale if mode == 1 else (self.conv.weight if mode == 0 else None)
+            mix_b = self.conv.bias if mode == 0 else None
+            return _ProjFn.apply(x, mode, mix_w, mix_b, ln.weight, ln.bias, ln.eps, m.projector[0].weight, m.projector[2].weight,
+                                 m.fc[1].weight, m.fc[1].bias)
         gamma, beta = ln.weight.float(), ln.bias.float()
         xb = x.to(BF16)
         if self.use_scale:
