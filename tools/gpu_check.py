@@ -311,6 +311,65 @@ def check_perf():
     return out
 
 
+def check_perf_bwd():
+    """Backward kernels at the FLUX shapes, timed alone (CUDA events, 20 iterations after warm-up)."""
+    torch, ops = _imports()
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(10)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()  # noqa: E731
+    for (M, Nout, Kin) in [(4608, 3072, 15360), (4608, 21504, 3072), (4096, 3072, 12288), (4096, 12288, 3072), (4096, 9216, 3072), (4096, 3072, 3072)]:
+        dy, w = rn(M, Nout), rn(Nout, Kin) * 0.02
+        pre = rn(M, Kin)
+        o = torch.empty(M, Kin, device="cuda", dtype=torch.bfloat16)
+        t = timeit(lambda: ops.linear_dgrad(dy, w, out=o))
+        t2 = timeit(lambda: ops.linear_dgrad(dy, w, pre=pre, n_split=0, dact=1, out=o))
+        t_ref = timeit(lambda: torch.matmul(dy, w))
+        fl = 2 * M * Nout * Kin
+        out[f"dgrad_{M}x{Nout}x{Kin}"] = {"ms": t * 1e3, "tflops": fl / t / 1e12, "with_dgelu_ms": t2 * 1e3, "cublas_tflops": fl / t_ref / 1e12}
+    for (M, N, K) in [(2048, 4096, 4096), (2048, 4096, 2048), (2048, 768, 4096)]:
+        dy, x = rn(M, N), rn(M, K)
+        t = timeit(lambda: ops.linear_wgrad(dy, x))
+        t_ref = timeit(lambda: torch.matmul(dy.t(), x))
+        out[f"wgrad_{M}x{N}x{K}"] = {"ms": t * 1e3, "tflops": 2 * M * N * K / t / 1e12, "cublas_tflops": 2 * M * N * K / t_ref / 1e12}
+    for (B, H, L) in [(1, 24, 4608), (2, 24, 4608)]:
+        q, k, v, do = rn(B, H, L, 128), rn(B, H, L, 128), rn(B, H, L, 128), rn(B, H, L, 128)
+        _, o1, lse = ops.attention_lse(q, k, v)
+        do_tok = rn(B, L, H * 128)
+        do_hm, delta = ops.attention_bwd_prep(None, do_tok, None, o1, B, H, L, 0)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+        t = timeit(lambda: ops.attention_bwd(q, k, v, do_hm, lse, delta, dq, dk, dv))
+        tp = timeit(lambda: ops.attention_bwd_prep(None, do_tok, None, o1, B, H, L, 0, do_hm=do_hm, delta=delta))
+        tf = timeit(lambda: ops.attention_lse(q, k, v, out1=o1, lse=lse))
+        fl = 4 * L * L * 128 * H * B
+        qf, kf, vf = (t_.detach().clone().requires_grad_(True) for t_ in (q, k, v))
+        of = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf)
+        t_ref = timeit(lambda: torch.autograd.grad(of, (qf, kf, vf), do, retain_graph=True), iters=10)
+        out[f"attn_bwd_B{B}_L{L}"] = {"ms": t * 1e3, "tflops_5gemm": 2.5 * fl / t / 1e12, "tflops_issued_7gemm": 3.5 * fl / t / 1e12,
+                                      "prep_ms": tp * 1e3, "fwd_lse_ms": tf * 1e3, "sdpa_bwd_ms": t_ref * 1e3}
+    B, L, D = 1, 4608, 3072
+    x, dn, dres = rn(B * L, D), rn(B * L, D), rn(B * L, D)
+    sc = rn(B, D)
+    stats = torch.empty(B * L, 2, device="cuda")
+    o = torch.empty_like(x)
+    t = timeit(lambda: ops.ln_modulate_bwd(dn, x, sc, L, dres=dres, out=o, stats=stats))
+    out["ln_mod_bwd_4608x3072"] = {"ms": t * 1e3, "gbs": 4 * x.numel() * 2 / t / 1e9}
+    d0, d1 = torch.zeros(B, D, device="cuda"), torch.zeros(B, D, device="cuda")
+    t = timeit(lambda: ops.colsum(dn, B, L, out0=d0, b=x, out1=d1, stats=stats))
+    out["colsum2_4608x3072"] = {"ms": t * 1e3, "gbs": 2 * x.numel() * 2 / t / 1e9}
+    t = timeit(lambda: ops.colsum(dn, B, L, b=x, out1=d1))
+    out["colsum1_4608x3072"] = {"ms": t * 1e3, "gbs": 2 * x.numel() * 2 / t / 1e9}
+    N = 300000
+    w = rn(N, 3072) * 0.02
+    gg = torch.randn(1, N, device="cuda", generator=g)
+    t = timeit(lambda: ops.skinny_linear_t(gg, w))
+    out["skinny_t_1x300000x3072"] = {"ms": t * 1e3, "gbs": w.numel() * 2 / t / 1e9}
+    xx = rn(1, 37, 512, 2048)
+    gm = rn(1, 512, 2048)
+    t = timeit(lambda: ops.proj_mix_wgrad(xx, gm, 0))
+    out["proj_conv_wgrad_37x512x2048"] = {"ms": t * 1e3, "gbs": xx.numel() * 2 / t / 1e9}
+    return out
+
+
 def check_attn_variants():
     """Times the attention kernel for the POLY8 variant selected by the X2I_ATTN_POLY8 env var of this process."""
     torch, ops = _imports()

@@ -14,8 +14,8 @@
 // as the A operand from TMEM (TS form) with the streamed tile as an MN-major B operand.  The MMAs of stream tile y+2
 // and the accumulation of tile y overlap the soft-max math of tile y+1.
 //
-// 192 threads: warp 0 TMA producer, warp 1 MMA issuer (one lane), warps 2..5 soft-max / epilogue (one owner row per
-// thread).  lse / delta are [B*H, Lpad] fp32 (log2 domain, +inf / 0 in the padding) written by the forward kernel and
+// 320 threads: warp 0 TMA producer, warp 1 MMA issuer (one lane), warps 2..5 / 6..9 two soft-max + epilogue
+// warpgroups (one owner row per thread; warpgroup g owns T buffer g).  lse / delta are [B*H, Lpad] fp32 (log2 domain, +inf / 0 in the padding) written by the forward kernel and
 // by attn_bwd_prep_kernel.  All tensors are head-major [B*H, L, 128] bf16.
 #pragma once
 #include "common.cuh"
@@ -32,7 +32,7 @@ struct AttnBwdParams {
   __nv_bfloat16* out1;  // KV: dV
 };
 
-constexpr int ABW_THREADS = 192;
+constexpr int ABW_THREADS = 320;
 constexpr int ABW_STAGES = 4;
 constexpr int ABW_OWNER_BYTES = 2 * 32768;  // X0 | X1, 128 x 128 bf16 each (two 128B-swizzled column halves of 16 KB)
 constexpr int ABW_STAGE_BYTES = 2 * 16384;  // Y0 | Y1, 64 x 128 bf16 each (two column halves of 8 KB)
@@ -58,7 +58,7 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
   uint64_t* acc_full = bars + 13;  // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 128;
   const int bh = blockIdx.z * p.H + blockIdx.y;
@@ -122,33 +122,33 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (whole warp, elected lane issues)
+    {
       constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 0, 0);
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, 0, 1);
       const uint32_t x_base = smem_u32(sx);
       const uint32_t y_base = smem_u32(sy);
+      // descriptors are built once; per MMA only the 14-bit start-address field moves (a 64-bit add of a constant)
+      const uint64_t xdesc = make_smem_desc_sw128(x_base, 16, 1024);
       auto issue_t = [&](int y, int buf) {  // T1 = X0 Y0^T, T2 = X1 Y1^T  (128 x 64 each, K = 128)
-        const uint32_t ys = y_base + (y & (ABW_STAGES - 1)) * ABW_STAGE_BYTES;
+        const uint64_t ydesc = make_smem_desc_sw128(y_base + (y & (ABW_STAGES - 1)) * ABW_STAGE_BYTES, 16, 1024);
 #pragma unroll
         for (int op = 0; op < 2; ++op)
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const uint32_t ox = op * 32768 + (kk >> 2) * 16384 + (kk & 3) * 32;
             const uint32_t oy = op * 16384 + (kk >> 2) * 8192 + (kk & 3) * 32;
-            umma_ss(tmem_base + buf * 128 + op * 64, make_smem_desc_sw128(x_base + ox, 16, 1024),
-                    make_smem_desc_sw128(ys + oy, 16, 1024), idesc_t, kk != 0);
+            umma_ss_w(tmem_base + buf * 128 + op * 64, xdesc + (ox >> 4), ydesc + (oy >> 4), idesc_t, kk != 0);
           }
       };
       auto issue_acc = [&](int y, int buf) {  // acc0 += dS~ Y0 ; KV: acc1 += P~ Y1   (A from TMEM, K = 64 streamed rows)
-        const uint32_t ys = y_base + (y & (ABW_STAGES - 1)) * ABW_STAGE_BYTES;
+        const uint64_t ydesc = make_smem_desc_sw128(y_base + (y & (ABW_STAGES - 1)) * ABW_STAGE_BYTES, 8192, 1024);
+        const uint32_t acc = y > 0 ? 1u : 0u;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          umma_ts(tmem_base + 256, tmem_base + buf * 128 + 64 + kk * 8, make_smem_desc_sw128(ys + kk * 2048, 8192, 1024), idesc_acc,
-                  (y > 0 || kk > 0) ? 1u : 0u);
+          umma_ts_w(tmem_base + 256, tmem_base + buf * 128 + 64 + kk * 8, ydesc + ((kk * 2048) >> 4), idesc_acc, kk > 0 ? 1u : acc);
           if constexpr (KV)
-            umma_ts(tmem_base + 384, tmem_base + buf * 128 + kk * 8, make_smem_desc_sw128(ys + 16384 + kk * 2048, 8192, 1024),
-                    idesc_acc, (y > 0 || kk > 0) ? 1u : 0u);
+            umma_ts_w(tmem_base + 384, tmem_base + buf * 128 + kk * 8, ydesc + ((16384 + kk * 2048) >> 4), idesc_acc, kk > 0 ? 1u : acc);
         }
       };
       auto y_wait = [&](int y) { mbar_wait(&y_full[y & (ABW_STAGES - 1)], (y / ABW_STAGES) & 1); };
@@ -157,30 +157,33 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
       y_wait(0);
       tc_fence_after();
       issue_t(0, 0);
-      umma_commit(&t_full[0]);
+      umma_commit_w(&t_full[0]);
       if (n_y > 1) {
         y_wait(1);
         tc_fence_after();
         issue_t(1, 1);
-        umma_commit(&t_full[1]);
+        umma_commit_w(&t_full[1]);
       }
       for (int y = 0; y < n_y; ++y) {
         const int buf = y & 1;
         mbar_wait(&pd_full[buf], (y >> 1) & 1);
         tc_fence_after();
         issue_acc(y, buf);
-        umma_commit(&y_empty[y & (ABW_STAGES - 1)]);
+        umma_commit_w(&y_empty[y & (ABW_STAGES - 1)]);
         if (y + 2 < n_y) {
           y_wait(y + 2);
           tc_fence_after();
           issue_t(y + 2, buf);
-          umma_commit(&t_full[buf]);
+          umma_commit_w(&t_full[buf]);
         }
       }
-      umma_commit(acc_full);
+      umma_commit_w(acc_full);
     }
   } else {
-    // ---------------------------------------------------------------- soft-max warpgroup (one owner row per thread)
+    // ---------------------------------------------------------------- two soft-max warpgroups (one owner row per thread);
+    // warpgroup g owns the stream tiles with y % 2 == g, i.e. T buffer g, so every SM sub-partition always has two
+    // soft-max warps to interleave (TMEM-load and MUFU latency of one hides behind the other).
+    const int wg = (warp - 2) >> 2;
     const int quad = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int grow = r0 + quad * 32 + lane;  // owner row (key in KV mode, query otherwise)
@@ -190,23 +193,20 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
       my_lse = p.lse[static_cast<long long>(bh) * p.Lpad + grow];
       my_delta = p.delta[static_cast<long long>(bh) * p.Lpad + grow];
     }
-    for (int y = 0; y < n_y; ++y) {
-      const int buf = y & 1;
-      const uint32_t t1 = tmem_base + buf * 128 + lane_off, t2 = t1 + 64;
-      mbar_wait(&t_full[buf], (y >> 1) & 1);
+    const uint32_t t1 = tmem_base + wg * 128 + lane_off, t2 = t1 + 64;
+    for (int y = wg; y < n_y; y += 2) {
+      mbar_wait(&t_full[wg], (y >> 1) & 1);
       tc_fence_after();
-      uint32_t a[2][32], d[2][32];
-      tmem_ld32(t1, a[0]);
-      tmem_ld32(t1 + 32, a[1]);
-      tmem_ld32(t2, d[0]);
-      tmem_ld32(t2 + 32, d[1]);
       const float* st = sstat + (y & (ABW_STAGES - 1)) * (ABW_STATS_BYTES / 4);
       if constexpr (KV) mbar_wait(&y_full[y & (ABW_STAGES - 1)], (y / ABW_STAGES) & 1);  // lse / delta of this tile landed
-      tmem_ld_wait();
       const int valid = p.L - y * 64;  // streamed rows beyond L: zero-filled by TMA
-      uint32_t pk[2][16], dk[2][16];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        uint32_t a[32], d[32];
+        tmem_ld32(t1 + c * 32, a);
+        tmem_ld32(t2 + c * 32, d);
+        tmem_ld_wait();
+        uint32_t pk[16], dk[16];
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
           float l4[4], dl4[4];
@@ -222,53 +222,51 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
           float pv[4], dsv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            pv[e] = fast_exp2(fmaf(__uint_as_float(a[c][k + e]), sc, -l4[e]));
+            pv[e] = fast_exp2(fmaf(__uint_as_float(a[k + e]), sc, -l4[e]));
             if constexpr (!KV) {
               if (c * 32 + k + e >= valid) pv[e] = 0.f;  // padded keys
             }
-            dsv[e] = pv[e] * (__uint_as_float(d[c][k + e]) - dl4[e]);
+            dsv[e] = pv[e] * (__uint_as_float(d[k + e]) - dl4[e]);
           }
-          pk[c][k >> 1] = pack_bf16x2(pv[0], pv[1]);
-          pk[c][(k >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-          dk[c][k >> 1] = pack_bf16x2(dsv[0], dsv[1]);
-          dk[c][(k >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
+          pk[k >> 1] = pack_bf16x2(pv[0], pv[1]);
+          pk[(k >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+          dk[k >> 1] = pack_bf16x2(dsv[0], dsv[1]);
+          dk[(k >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
         }
-      }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if constexpr (KV) tmem_st16(t1 + c * 16, pk[c]);
-        tmem_st16(t2 + c * 16, dk[c]);
+        // P~ / dS~ alias the first 32 columns of T1 / T2: half c lands in columns [16c, 16c+16), which this thread has
+        // already consumed (c = 0: columns 0..15 were loaded above; c = 1: columns 16..31 were loaded in the first half)
+        if constexpr (KV) tmem_st16(t1 + c * 16, pk);
+        tmem_st16(t2 + c * 16, dk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pd_full[buf]);
+      if (lane == 0) mbar_arrive(&pd_full[wg]);
     }
-    // ---- epilogue: accumulators -> bf16, head-major
+    // ---- epilogue: accumulators -> bf16, head-major.  KV: warpgroup 0 drains dK, warpgroup 1 dV; else each takes 64 columns of dQ
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const bool ok = grow < p.L;
     const long long orow = (static_cast<long long>(bh) * p.L + grow) * 128;
+    const int which = KV ? wg : 0;
+    const int c_lo = KV ? 0 : wg * 2, c_hi = KV ? 4 : wg * 2 + 2;
+    const float mul = which == 0 ? p.scale : 1.0f;
+    __nv_bfloat16* dst = (which == 0 ? p.out0 : p.out1) + orow;
 #pragma unroll 1
-    for (int which = 0; which < (KV ? 2 : 1); ++which) {
-      const float mul = which == 0 ? p.scale : 1.0f;
-      __nv_bfloat16* dst = (which == 0 ? p.out0 : p.out1) + orow;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tmem_base + 256 + which * 128 + lane_off + c * 32, o);
-        tmem_ld_wait();
-        if (ok) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+    for (int c = c_lo; c < c_hi; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem_base + 256 + which * 128 + lane_off + c * 32, o);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * mul, __uint_as_float(o[8 * k + 1]) * mul);
-            u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * mul, __uint_as_float(o[8 * k + 3]) * mul);
-            u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul);
-            u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul);
-            d4[k] = u;
-          }
+        for (int k = 0; k < 4; ++k) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * mul, __uint_as_float(o[8 * k + 1]) * mul);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * mul, __uint_as_float(o[8 * k + 3]) * mul);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul);
+          d4[k] = u;
         }
       }
     }

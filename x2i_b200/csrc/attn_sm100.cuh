@@ -131,7 +131,7 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
   uint64_t* o_full = bars + 19;         // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
   const int h = blockIdx.y;
@@ -187,31 +187,32 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (whole warp, elected lane issues)
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);
       const uint32_t q_base = smem_u32(sq);
       const uint32_t kv_base = smem_u32(skv);
+      // descriptors are built once per tile; per MMA only the start-address field moves (a 64-bit add of a constant)
+      const uint64_t qdesc = make_smem_desc_sw128(q_base, 16, 1024);
       auto issue_s = [&](int i, int slot) {  // S_i = Q_i K^T
-        const uint32_t a = q_base + i * ATT_TILE_BYTES, bsm = kv_base + slot * ATT_TILE_BYTES;
+        const uint64_t ad = qdesc + ((i * ATT_TILE_BYTES) >> 4);
+        const uint64_t bd = make_smem_desc_sw128(kv_base + slot * ATT_TILE_BYTES, 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * 16384 + (kk & 3) * 32;
-          umma_ss(tmem_base + i * 128, make_smem_desc_sw128(a + off, 16, 1024), make_smem_desc_sw128(bsm + off, 16, 1024),
-                  idesc_s, kk != 0);
+          const uint32_t off = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4;
+          umma_ss_w(tmem_base + i * 128, ad + off, bd + off, idesc_s, kk != 0);
         }
       };
       auto issue_pv = [&](int i, int slot, bool acc, uint32_t ph) {  // O_i += P_i V, quarter by quarter as P lands
-        const uint32_t bsm = kv_base + slot * ATT_TILE_BYTES;
+        const uint64_t bd = make_smem_desc_sw128(kv_base + slot * ATT_TILE_BYTES, 16384, 1024);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           mbar_wait(&p_full[i * 4 + c], ph);
           tc_fence_after();
 #pragma unroll
           for (int kk = 2 * c; kk < 2 * c + 2; ++kk)
-            umma_ts(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8,
-                    make_smem_desc_sw128(bsm + kk * 2048, 16384, 1024), idesc_o, (acc || kk != 0) ? 1u : 0u);
+            umma_ts_w(tmem_base + 256 + i * 128, tmem_base + i * 128 + kk * 8, bd + ((kk * 2048) >> 4), idesc_o, (acc || kk != 0) ? 1u : 0u);
         }
       };
       auto kv_wait = [&](int seq) { mbar_wait(&kv_full[seq & (ATT_KV_SLOTS - 1)], (seq / ATT_KV_SLOTS) & 1); };
@@ -220,30 +221,30 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
       kv_wait(0);
       tc_fence_after();
       issue_s(0, 0);
-      umma_commit(&s_full[0]);
+      umma_commit_w(&s_full[0]);
       issue_s(1, 0);
-      umma_commit(&s_full[1]);
-      umma_commit(&kv_empty[0]);
+      umma_commit_w(&s_full[1]);
+      umma_commit_w(&kv_empty[0]);
       for (int j = 0; j < n_kv; ++j) {
         const int vseq = 2 * j + 1, kseq = 2 * j + 2;
         const int vslot = vseq & (ATT_KV_SLOTS - 1), kslot = kseq & (ATT_KV_SLOTS - 1);
         const bool more = (j + 1 < n_kv);
         kv_wait(vseq);
         issue_pv(0, vslot, j > 0, j & 1);
-        if (!more) umma_commit(&o_full[0]);
+        if (!more) umma_commit_w(&o_full[0]);
         if (more) {
           kv_wait(kseq);
           tc_fence_after();
           issue_s(0, kslot);
-          umma_commit(&s_full[0]);
+          umma_commit_w(&s_full[0]);
         }
         issue_pv(1, vslot, j > 0, j & 1);
-        if (!more) umma_commit(&o_full[1]);
-        umma_commit(&kv_empty[vslot]);
+        if (!more) umma_commit_w(&o_full[1]);
+        umma_commit_w(&kv_empty[vslot]);
         if (more) {
           issue_s(1, kslot);
-          umma_commit(&s_full[1]);
-          umma_commit(&kv_empty[kslot]);
+          umma_commit_w(&s_full[1]);
+          umma_commit_w(&kv_empty[kslot]);
         }
       }
     }

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __
 //   part1[b, split, col] = sum_r A[r, col] * Bv[r, col]         (if part1);  Bv = B, or (B - mean_r) * rstd_r with stats
 // Used for dshift / dscale of every AdaLN (A = dn, B = LN input), dgate (A = dx, B = the un-gated branch output),
 // the affine LayerNorm's dbeta / dgamma and bias gradients.
-constexpr int COLSUM_ROWS = 64;
+constexpr int COLSUM_ROWS = 32;
 __global__ void __launch_bounds__(128) colsum_partial_kernel(const __nv_bfloat16* __restrict__ A, long long lda,
                                                              const __nv_bfloat16* __restrict__ Bm, long long ldb,
                                                              const float2* __restrict__ stats, float* __restrict__ part0,
@@ -128,25 +128,35 @@ __global__ void __launch_bounds__(128) colsum_partial_kernel(const __nv_bfloat16
   if (c * 8 >= D) return;
   const int split = blockIdx.y, b = blockIdx.z;
   const int t0 = split * COLSUM_ROWS, t1 = min(t0 + COLSUM_ROWS, rows_per_batch);
+  const bool two = part1 != nullptr;
   float s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
-  for (int t = t0; t < t1; ++t) {
-    const long long r = static_cast<long long>(b) * rows_per_batch + t;
-    float a[8];
-    unpack8(ld_stream(A + r * lda + c * 8), a);
+  constexpr int U = 8;  // rows in flight per thread (2 x U independent 16-byte loads)
+  for (int t = t0; t < t1; t += U) {
+    uint4 ra[U], rb[U];
+    float2 st[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s0[j] += a[j];
-    if (part1 != nullptr) {
-      float v[8];
-      unpack8(ld_stream(Bm + r * ldb + c * 8), v);
-      if (stats != nullptr) {
-        const float2 st = stats[r];
+    for (int u = 0; u < U; ++u) {
+      const long long r = static_cast<long long>(b) * rows_per_batch + min(t + u, t1 - 1);
+      ra[u] = ld_stream(A + r * lda + c * 8);
+      if (two) rb[u] = ld_stream(Bm + r * ldb + c * 8);
+      st[u] = (two && stats != nullptr) ? stats[r] : make_float2(0.f, 1.f);
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (v[j] - st.x) * st.y;
+    for (int u = 0; u < U; ++u) {
+      if (t + u < t1) {
+        float a[8];
+        unpack8(ra[u], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s0[j] += a[j];
+        if (two) {
+          float v[8];
+          unpack8(rb[u], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s1[j] += a[j] * ((v[j] - st[u].x) * st[u].y);
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s1[j] += a[j] * v[j];
     }
   }
   const long long o = (static_cast<long long>(b) * nsplit + split) * D + c * 8;
