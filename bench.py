@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="images per GPU")
     ap.add_argument("--impl", default="x2i_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary distillation-train-step measurement")
+    ap.add_argument("--train-batch", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -298,6 +300,37 @@ def main():
                     "ms_per_launch": t_att * 1e3, "launches_timed": len(durs), "algorithmic_flops_per_launch": fl, "traffic": attn_traffic(),
                     "step_share_attention": 57 * t_att / (t_local / args.steps)}
 
+    # ---- secondary workload (BASELINE config 4, N=1 only): the attention-distillation train step on the same frozen FLUX --
+    # teacher pass + projector + student pass (saving mode) + KD loss + backward through all 57 blocks + projector wgrad +
+    # AdamW.  Reported as an extra object; the headline metric above is unchanged.  tools/bench_train.py runs it under torchrun.
+    train_info = None
+    if world == 1 and not args.no_train:
+        from x2i_b200 import proj as xproj, train as xtrain
+        model.use_cuda_graph = False
+        proj = xproj.create_proj3_qwen3b(37, use_t5=False, use_scale=False, use_cnn=True).to(dev, torch.bfloat16)
+        opt = torch.optim.AdamW(proj.parameters(), lr=1e-4, fused=True)
+        tb = xtrain.synthetic_batch(args.train_batch, dev, FLUX_SCHNELL, seed=7)
+        for _ in range(2):
+            xtrain.distill_step(proj, model, tb, optimizer=opt)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        n_train = 3
+        for _ in range(n_train):
+            tl = xtrain.distill_step(proj, model, tb, optimizer=opt)
+        t1e.record()
+        torch.cuda.synchronize()
+        tt = t0e.elapsed_time(t1e) * 1e-3 / n_train
+        train_info = {"workload": "attention-distillation train step (train_qwenvl.py:559-651 + teacher :717-816), 1024px latents, "
+                                  "projector qwen3b [B,37,512,2048], teacher+student on the same GPU",
+                      "batch_per_gpu": args.train_batch, "ms_per_step": tt * 1e3, "samples_per_s": args.train_batch / tt,
+                      "approx_tflops": args.train_batch * step_flops() * 4.3 / tt / 1e12, "loss": float(tl),
+                      "gpu_launches_per_step": (_lib.launch_count() - n0) / n_train,
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        model.use_cuda_graph = True
+        del proj, opt, tb
+
     if rank == 0:
         total_steps = world * B * args.steps
         value = total_steps / t
@@ -314,7 +347,7 @@ def main():
             "step_roofline_frac_bf16": fl * B * args.steps / t_local / 1e12 / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
             "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "x2i_b200.pipeline.FluxPipeline.__call__ (4-step schnell sampling per call, pinned host buffers)"},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clk,
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clk, "distill_train": train_info,
         }
         print(json.dumps(out))
     if world > 1:

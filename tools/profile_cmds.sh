@@ -3,7 +3,7 @@
 # X2I_NCU=1 makes bench.py bracket its timed region with cudaProfilerStart/Stop.
 set -x
 export X2I_NCU=1
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train"
 # 1) launch list: every kernel of the timed steps with its device time
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/ncu_launches.log 2>&1
 # 2) full captures: fused attention kernel, the dominant GEMMs, the row-wise kernels

@@ -893,17 +893,17 @@ int x2i_ln_modulate_bwd(const void* dn, int64_t lddn, const void* x, int64_t ldx
       ldr % 8 || lddx % 8 || (reinterpret_cast<uintptr_t>(stats) & 7))
     return fail(X2I_ERR_ALIGN, "ln_modulate_bwd: alignment");
   auto bp = [](const void* p) { return static_cast<const __nv_bfloat16*>(p); };
-  dim3 grid((rows + 7) / 8);
+  dim3 grid(rows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nchunk = D / 8;
-#define X2I_LNB(MC, AF)                                                                                                      \
-  ln_mod_bwd_kernel<MC, AF><<<grid, 256, 0, st>>>(bp(dn), lddn, bp(x), ldx, bp(scale), mod_stride, bp(dres), ldr,            \
-                                                  static_cast<__nv_bfloat16*>(dx), lddx, static_cast<float2*>(stats), rows, D, \
-                                                  rows_per_batch, eps)
+#define X2I_LNB(MC, AF)                                                                                                              \
+  ln_mod_bwd_kernel<MC, AF><<<grid, LNB_THREADS, 0, st>>>(bp(dn), lddn, bp(x), ldx, bp(scale), mod_stride, bp(dres), ldr,             \
+                                                          static_cast<__nv_bfloat16*>(dx), lddx, static_cast<float2*>(stats), rows, D, \
+                                                          rows_per_batch, eps)
   if (affine) {
-    if (nchunk <= 32 * 4) X2I_LNB(4, true); else if (nchunk <= 32 * 12) X2I_LNB(12, true); else X2I_LNB(16, true);
+    if (nchunk <= LNB_THREADS) X2I_LNB(1, true); else if (nchunk <= LNB_THREADS * 3) X2I_LNB(3, true); else X2I_LNB(4, true);
   } else {
-    if (nchunk <= 32 * 4) X2I_LNB(4, false); else if (nchunk <= 32 * 12) X2I_LNB(12, false); else X2I_LNB(16, false);
+    if (nchunk <= LNB_THREADS) X2I_LNB(1, false); else if (nchunk <= LNB_THREADS * 3) X2I_LNB(3, false); else X2I_LNB(4, false);
   }
 #undef X2I_LNB
   return check_launch("ln_mod_bwd_kernel");
@@ -949,15 +949,19 @@ int x2i_skinny_linear_t(const float* g, int64_t ldg, const void* W, int64_t ldw,
   if (!g || !W || !out || !workspace || (dact && !pre)) return fail(X2I_ERR_SHAPE, "skinny_linear_t: missing buffer");
   if (!aligned16(W) || ldw % 8 || !aligned16(workspace)) return fail(X2I_ERR_ALIGN, "skinny_linear_t: alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int nslab = d->sms * 4;
+  int nslab = d->sms * 8;
   if (nslab > N) nslab = N;
   const int rows_per_slab = (N + nslab - 1) / nslab;
   nslab = (N + rows_per_slab - 1) / rows_per_slab;
   const int threads = ((K / 8 + 31) / 32) * 32;
   for (int b0 = 0; b0 < B; b0 += 8) {
     const int nb = (B - b0) < 8 ? (B - b0) : 8;
-    skinny_linear_t_kernel<8><<<nslab, threads, 0, st>>>(g + b0 * ldg, ldg, static_cast<const __nv_bfloat16*>(W), ldw, workspace, nb, N, K,
-                                                         rows_per_slab);
+    auto Wb = static_cast<const __nv_bfloat16*>(W);
+    // fewer accumulators per thread for small batches -> more CTAs resident per SM -> more bytes in flight
+    if (nb == 1) skinny_linear_t_kernel<1><<<nslab, threads, 0, st>>>(g + b0 * ldg, ldg, Wb, ldw, workspace, nb, N, K, rows_per_slab);
+    else if (nb == 2) skinny_linear_t_kernel<2><<<nslab, threads, 0, st>>>(g + b0 * ldg, ldg, Wb, ldw, workspace, nb, N, K, rows_per_slab);
+    else if (nb <= 4) skinny_linear_t_kernel<4><<<nslab, threads, 0, st>>>(g + b0 * ldg, ldg, Wb, ldw, workspace, nb, N, K, rows_per_slab);
+    else skinny_linear_t_kernel<8><<<nslab, threads, 0, st>>>(g + b0 * ldg, ldg, Wb, ldw, workspace, nb, N, K, rows_per_slab);
     if (int rc = check_launch("skinny_linear_t_kernel")) return rc;
     dim3 g2((K + 255) / 256, nb);
     skinny_linear_t_final_kernel<<<g2, 256, 0, st>>>(workspace, pre ? static_cast<const __nv_bfloat16*>(pre) + b0 * ldpre : nullptr, ldpre,
@@ -966,7 +970,7 @@ int x2i_skinny_linear_t(const float* g, int64_t ldg, const void* W, int64_t ldw,
   }
   return X2I_OK;
 }
-int64_t x2i_skinny_linear_t_workspace_floats(int N, int K) { return 148LL * 4 * 8 * K + 8LL * K; }
+int64_t x2i_skinny_linear_t_workspace_floats(int N, int K) { return 160LL * 8 * 8 * K + 8LL * K; }
 
 int x2i_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
   DeviceInfo* d;

@@ -49,6 +49,25 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {  // arrives on
                "h"(static_cast<uint16_t>(3))
                : "memory");
 }
+// whole-warp forms (see common.cuh): all 32 lanes call, one elected lane issues
+__device__ __forceinline__ void umma_ss_pair_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar_local) {  // arrive on the leader CTA's copy of `bar`
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
@@ -104,7 +123,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -164,7 +183,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // whole warp runs the loop, the elected lane issues (uniform-register descriptors)
       constexpr uint32_t idesc = make_idesc_bf16(256, BN, 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -180,16 +199,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * GEMM2_STAGE_BYTES);
-          const uint32_t b_base = a_base + 16384;
+          const uint64_t adesc = make_smem_desc_sw128(a_base, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(a_base + 16384, 8192, 1024) : make_smem_desc_sw128(a_base + 16384, 16, 1024);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_ss_pair(d_tmem, make_smem_desc_sw128(a_base + k * 32, 16, 1024),
-                         B_MN ? make_smem_desc_sw128(b_base + k * 2048, 8192, 1024) : make_smem_desc_sw128(b_base + k * 32, 16, 1024),
-                         idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage]);
+            umma_ss_pair_w(d_tmem, adesc + ((k * 32) >> 4), bdesc + ((B_MN ? k * 2048 : k * 32) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair_w(&empty_bar[stage]);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tfull_bar[as]);
+        umma_commit_pair_w(&tfull_bar[as]);
       }
     }
   } else {

@@ -280,7 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int num_n = (p.N + BN - 1) / BN;
@@ -340,8 +340,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -357,18 +357,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t b_base = a_base + Cfg::A_BYTES;
+          const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base, 8192, 1024) : make_smem_desc_sw128(a_base, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base, 8192, 1024) : make_smem_desc_sw128(b_base, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_base + k * 2048, 8192, 1024)
-                                        : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_base + k * 2048, 8192, 1024)
-                                        : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_ss_w(d_tmem, adesc + ((A_MN ? k * 2048 : k * 32) >> 4), bdesc + ((B_MN ? k * 2048 : k * 32) >> 4), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit_w(&empty_bar[stage]);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
+        umma_commit_w(&tfull_bar[as]);
       }
     }
   } else {

@@ -35,77 +35,87 @@ __global__ void gate_bwd_kernel(const __nv_bfloat16* __restrict__ dx, long long 
 // ------------------------------------------------------------------------------------------------
 // Backward of y = LN(x) * (1 + scale[b]) + shift[b]  (AFFINE: y = LN(x) * gamma + beta) towards x:
 //   g = dn * (1 + scale);  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) + dres
-// One warp per row (row in registers).  Also writes stats[r] = (mean, rstd) for the column reductions (dscale/dshift).
+// Also writes stats[r] = (mean, rstd) for the column reductions (dscale/dshift).
+// One 128-thread CTA per row (row in registers, MAXC 16-byte chunks per thread): small register footprint -> many rows in
+// flight per SM, which is what an HBM-bound kernel with 3 reads + 1 write per element needs.
+constexpr int LNB_THREADS = 128;
 template <int MAXC, bool AFFINE>
-__global__ void __launch_bounds__(256) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dn, long long lddn,
-                                                         const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                         const __nv_bfloat16* __restrict__ scale, long long mod_stride,
-                                                         const __nv_bfloat16* __restrict__ dres, long long ldr,
-                                                         __nv_bfloat16* __restrict__ dx, long long lddx,
-                                                         float2* __restrict__ stats, int rows, int D, int rows_per_batch,
-                                                         float eps) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(LNB_THREADS) ln_mod_bwd_kernel(const __nv_bfloat16* __restrict__ dn, long long lddn,
+                                                                 const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                                 const __nv_bfloat16* __restrict__ scale, long long mod_stride,
+                                                                 const __nv_bfloat16* __restrict__ dres, long long ldr,
+                                                                 __nv_bfloat16* __restrict__ dx, long long lddx,
+                                                                 float2* __restrict__ stats, int rows, int D, int rows_per_batch,
+                                                                 float eps) {
+  __shared__ float red[2 * (LNB_THREADS / 32)];
+  const int row = blockIdx.x;
   const int nchunk = D >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
   const uint4* gr = reinterpret_cast<const uint4*>(dn + static_cast<long long>(row) * lddn);
   const uint4* sc = reinterpret_cast<const uint4*>(scale + static_cast<long long>(row / rows_per_batch) * mod_stride);
+  const uint4* rr = dres != nullptr ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * ldr) : nullptr;
+  uint4 qx[MAXC], qg[MAXC], qr[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {  // all loads first
+    const int c = i * LNB_THREADS + threadIdx.x;
+    if (c < nchunk) {
+      qx[i] = ld_stream(xr + c);
+      qg[i] = ld_stream(gr + c);
+      qr[i] = rr != nullptr ? ld_stream(rr + c) : make_uint4(0, 0, 0, 0);
+    }
+  }
   float v[MAXC][8], g[MAXC][8];
-  float s = 0.f;
+  float s2[2] = {0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
-    const int c = i * 32 + lane;
+    const int c = i * LNB_THREADS + threadIdx.x;
     if (c < nchunk) {
-      unpack8(xr[c], v[i]);
-      unpack8(gr[c], g[i]);
+      unpack8(qx[i], v[i]);
+      unpack8(qg[i], g[i]);
       float a[8];
       unpack8(__ldg(sc + c), a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s += v[i][j];
+        s2[0] += v[i][j];
         g[i][j] *= AFFINE ? a[j] : 1.0f + a[j];
+        s2[1] += g[i][j];
       }
     }
   }
-  const float mean = warp_sum(s) / D;
-  float q = 0.f;
+  block_sum<2, LNB_THREADS / 32>(s2, red);
+  const float mean = s2[0] / D, mg = s2[1] / D;
+  float q1[1] = {0.f};
 #pragma unroll
   for (int i = 0; i < MAXC; ++i)
-    if (i * 32 + lane < nchunk) {
+    if (i * LNB_THREADS + threadIdx.x < nchunk) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[i][j] -= mean;
-        q += v[i][j] * v[i][j];
+        q1[0] += v[i][j] * v[i][j];
       }
     }
-  const float rstd = rsqrtf(warp_sum(q) / D + eps);
-  float sg = 0.f, sgx = 0.f;
+  block_sum<1, LNB_THREADS / 32>(q1, red);
+  const float rstd = rsqrtf(q1[0] / D + eps);
+  float sgx[1] = {0.f};
 #pragma unroll
   for (int i = 0; i < MAXC; ++i)
-    if (i * 32 + lane < nchunk) {
+    if (i * LNB_THREADS + threadIdx.x < nchunk) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[i][j] *= rstd;  // xhat
-        sg += g[i][j];
-        sgx += g[i][j] * v[i][j];
+        sgx[0] += g[i][j] * v[i][j];
       }
     }
-  const float mg = warp_sum(sg) / D, mgx = warp_sum(sgx) / D;
-  if (lane == 0 && stats != nullptr) stats[row] = make_float2(mean, rstd);
+  block_sum<1, LNB_THREADS / 32>(sgx, red);
+  const float mgx = sgx[0] / D;
+  if (threadIdx.x == 0 && stats != nullptr) stats[row] = make_float2(mean, rstd);
   uint4* outr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
-  const uint4* rr = dres != nullptr ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * ldr) : nullptr;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
-    const int c = i * 32 + lane;
+    const int c = i * LNB_THREADS + threadIdx.x;
     if (c < nchunk) {
       float o[8], e[8];
-      if (rr != nullptr) {
-        unpack8(rr[c], e);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = 0.f;
-      }
+      unpack8(qr[i], e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - mg - v[i][j] * mgx) + e[j];
       outr[c] = pack8(o);
@@ -319,9 +329,30 @@ __global__ void __launch_bounds__(512) skinny_linear_t_kernel(const float* __res
   for (int b = 0; b < MAXB; ++b)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[b][j] = 0.f;
-  for (int n = n0; n < n1; ++n) {
+  constexpr int U = 8;  // W rows in flight per thread
+  const __nv_bfloat16* wp = W + static_cast<long long>(n0) * ldw + c * 8;
+  int n = n0;
+  for (; n + U <= n1; n += U, wp += U * ldw) {  // full groups: U independent 16-byte loads, then the math
+    uint4 wq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) wq[u] = __ldcs(reinterpret_cast<const uint4*>(wp + u * ldw));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float w[8];
+      unpack8(wq[u], w);
+#pragma unroll
+      for (int b = 0; b < MAXB; ++b) {
+        if (b < B) {
+          const float gv = __ldg(g + static_cast<long long>(b) * ldg + n + u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[b][j] += gv * w[j];
+        }
+      }
+    }
+  }
+  for (; n < n1; ++n, wp += ldw) {
     float w[8];
-    unpack8(ld_stream(W + static_cast<long long>(n) * ldw + c * 8), w);
+    unpack8(__ldcs(reinterpret_cast<const uint4*>(wp)), w);
 #pragma unroll
     for (int b = 0; b < MAXB; ++b) {
       if (b < B) {
