@@ -21,8 +21,8 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
-def launches(tag, steps=2):
-    src = os.path.join(GP, "launches.csv")
+def launches(tag, steps=2, src_name="launches.csv", out_name="launch_list_summary.md", title=None):
+    src = os.path.join(GP, src_name)
     if not os.path.exists(src):
         return
     lines = [l for l in open(src) if not l.startswith("==")]
@@ -43,8 +43,8 @@ def launches(tag, steps=2):
         a[1] += v
         tot += v
         n += 1
-    with open(os.path.join(OUT, f"{tag}_launch_list_summary.md"), "w") as f:
-        f.write(f"# {tag}: kernels of the timed region of `python bench.py --steps {steps} --warmup 3` under ncu\n\n"
+    with open(os.path.join(OUT, f"{tag}_{out_name}"), "w") as f:
+        f.write((title or f"# {tag}: kernels of the timed region of `python bench.py --steps {steps} --warmup 3` under ncu") + "\n\n"
                 "`ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised, no power cap:\n"
                 "compare SHARES, not absolutes).  Raw list: gpurun_out/launches.csv (scratch).\n\n"
                 f"{n} launches, {tot / 1e3:.2f} ms kernel time over {steps} steps = {tot / steps / 1e3:.2f} ms/step\n\n"
@@ -75,5 +75,8 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
-    for rep in ("prof_attn", "prof_gemm", "prof_rowwise"):
+    launches(tag, steps=3, src_name="train_launches.csv", out_name="train_launch_list_summary.md",
+             title=f"# {tag}: every kernel of `python tools/bench_train.py --batch 1 --steps 1 --warmup 1 --layers 2 4` under ncu "
+                   "(whole process: model init + 3 train-step passes over 2 double + 4 single blocks; per-step columns = totals / 3)")
+    for rep in ("prof_attn", "prof_gemm", "prof_rowwise", "prof_bwd"):
         raw(tag, rep)

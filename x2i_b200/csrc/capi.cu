@@ -925,7 +925,7 @@ int x2i_colsum(const void* A, int64_t lda, const void* Bm, int64_t ldb, const vo
   colsum_partial_kernel<<<g1, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(Bm), ldb,
                                             static_cast<const float2*>(stats), p0, p1, rows_per_batch, D, nsplit);
   if (int rc = check_launch("colsum_partial_kernel")) return rc;
-  dim3 g2((D + 255) / 256, nbatch);
+  dim3 g2((D + 31) / 32, nbatch);
   if (out0) {
     colsum_final_kernel<<<g2, 256, 0, st>>>(p0, out0, ldo0, D, nsplit, accumulate);
     if (int rc = check_launch("colsum_final_kernel")) return rc;
@@ -963,7 +963,7 @@ int x2i_skinny_linear_t(const float* g, int64_t ldg, const void* W, int64_t ldw,
     else if (nb <= 4) skinny_linear_t_kernel<4><<<nslab, threads, 0, st>>>(g + b0 * ldg, ldg, Wb, ldw, workspace, nb, N, K, rows_per_slab);
     else skinny_linear_t_kernel<8><<<nslab, threads, 0, st>>>(g + b0 * ldg, ldg, Wb, ldw, workspace, nb, N, K, rows_per_slab);
     if (int rc = check_launch("skinny_linear_t_kernel")) return rc;
-    dim3 g2((K + 255) / 256, nb);
+    dim3 g2((K + 31) / 32, nb);
     skinny_linear_t_final_kernel<<<g2, 256, 0, st>>>(workspace, pre ? static_cast<const __nv_bfloat16*>(pre) + b0 * ldpre : nullptr, ldpre,
                                                       out + b0 * ldo, ldo, nb, K, nslab, dact, accumulate);
     if (int rc = check_launch("skinny_linear_t_final_kernel")) return rc;

@@ -179,16 +179,26 @@ __global__ void __launch_bounds__(128) colsum_partial_kernel(const __nv_bfloat16
     *reinterpret_cast<float4*>(part1 + o + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
   }
 }
-// stage 2: out[b * ldo + col] (+)= sum over splits, fixed order.
-__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, long long ldo, int D, int nsplit,
-                                    int accumulate) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= D) return;
+// stage 2: out[b * ldo + col] (+)= sum over splits.  A 256-thread CTA owns 32 columns: 8 thread groups each sum every
+// 8th partial (coalesced 128-byte rows), then the 8 group sums are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, long long ldo,
+                                                           int D, int nsplit, int accumulate) {
+  __shared__ float red[8][32];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cl;
   const int b = blockIdx.y;
   float s = 0.f;
-  for (int i = 0; i < nsplit; ++i) s += part[(static_cast<long long>(b) * nsplit + i) * D + col];
-  float* o = out + static_cast<long long>(b) * ldo + col;
-  *o = accumulate ? *o + s : s;
+  if (col < D)
+    for (int i = grp; i < nsplit; i += 8) s += part[(static_cast<long long>(b) * nsplit + i) * D + col];
+  red[grp][cl] = s;
+  __syncthreads();
+  if (grp == 0 && col < D) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][cl];
+    float* o = out + static_cast<long long>(b) * ldo + col;
+    *o = accumulate ? *o + t : t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,18 +381,27 @@ __global__ void __launch_bounds__(512) skinny_linear_t_kernel(const float* __res
     }
   }
 }
-// dact: 0 none, 1 SiLU'(pre)
-__global__ void skinny_linear_t_final_kernel(const float* __restrict__ part, const __nv_bfloat16* __restrict__ pre, long long ldpre,
-                                             float* __restrict__ out, long long ldo, int B, int K, int nslab, int dact,
-                                             int accumulate) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+// dact: 0 none, 1 SiLU'(pre).  Same 32-column x 8-group layout as colsum_final_kernel.
+__global__ void __launch_bounds__(256) skinny_linear_t_final_kernel(const float* __restrict__ part, const __nv_bfloat16* __restrict__ pre,
+                                                                    long long ldpre, float* __restrict__ out, long long ldo, int B, int K,
+                                                                    int nslab, int dact, int accumulate) {
+  __shared__ float red[8][32];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + cl;
   const int b = blockIdx.y;
   float s = 0.f;
-  for (int i = 0; i < nslab; ++i) s += part[(static_cast<long long>(i) * B + b) * K + k];
-  if (dact == 1) s *= dsilu_f(__bfloat162float(pre[static_cast<long long>(b) * ldpre + k]));
-  float* o = out + static_cast<long long>(b) * ldo + k;
-  *o = accumulate ? *o + s : s;
+  if (k < K)
+    for (int i = grp; i < nslab; i += 8) s += part[(static_cast<long long>(i) * B + b) * K + k];
+  red[grp][cl] = s;
+  __syncthreads();
+  if (grp == 0 && k < K) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][cl];
+    if (dact == 1) t *= dsilu_f(__bfloat162float(pre[static_cast<long long>(b) * ldpre + k]));
+    float* o = out + static_cast<long long>(b) * ldo + k;
+    *o = accumulate ? *o + t : t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
