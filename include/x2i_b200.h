@@ -277,6 +277,25 @@ int x2i_mean_over_s_bwd(const void* dpooled, void* dy, int B, int S, int N, void
 int x2i_proj_mix_wgrad(const void* x, const void* g, int mode, float* dw, float* workspace, int B, int C, int S, int H, void* stream);
 int64_t x2i_proj_mix_wgrad_workspace_floats(int B, int C, int S);
 
+/* ---- ControlNeXt nets of the LightControl editing branch (lightcontrol/lightcontrol_flux.py:575-749) -------------------
+ * Implicit-GEMM convolution on tcgen05, NHWC bf16: out[n,y,x,co] = relu?(conv(x, w)[..] + bias[co] + rowvec[n,co]) + residual.
+ * x [N,H,W,Cin], w pre-packed [Cout, KH, KW, Cin], out / residual [N,Ho,Wo,Cout]; KH,KW <= 3, stride 1 or 2, pad 0 or 1,
+ * Cin and Cout multiples of 64.  No im2col buffer: the A operand of each (tap, channel-chunk) k-block is one shifted
+ * tensor-map box of the input, out-of-image rows zero-filled by TMA.  Replaces nn.Conv2d (cuDNN) in ControlNeXtModel.embedding
+ * [3], [6] (:596-601), ResnetBlock2D.conv1/conv2/conv_shortcut and Downsample2D.conv [D031] (:605-624), mid_convs (:626-668);
+ * rowvec = time_emb_proj(silu(temb)) of ResnetBlock2D; residual = shortcut / the FLUX hidden states for the final conv
+ * (the injection hidden_states += out * scale of :505-507 fused into its epilogue; out may alias residual).             */
+int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
+                    void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, void* stream);
+/* ControlNeXtModel.embedding[0]: Conv2d(3 -> 64, 3x3, stride 2, pad 1) on the NCHW bf16 hint image -> NHWC bf16 [N,H/2,W/2,64];
+ * w fp32 [64,3,3,3] (PyTorch layout), bias fp32 [64].                                                                  */
+int x2i_conv_first(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, void* stream);
+/* nn.GroupNorm on NHWC bf16 + activation (0 none, 1 ReLU, 2 SiLU) + optional residual add: y = act(GN(x)) + residual.
+ * gamma/beta bf16 [C]; C in {64,128,256}; workspace of x2i_groupnorm_workspace_floats() floats.  Deterministic.        */
+int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
+                       int HW, int C, int G, float eps, int act, void* stream);
+int64_t x2i_groupnorm_workspace_floats(int Nimg, int HW, int G);
+
 #ifdef __cplusplus
 }
 #endif

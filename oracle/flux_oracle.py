@@ -343,7 +343,7 @@ class FluxTransformerBlock(nn.Module):
 
 
 class FluxTransformer2DModel(nn.Module):
-    """lightcontrol_flux.py:208-553 without the ControlNeXt injection (:504-507)."""
+    """lightcontrol_flux.py:208-553; the ControlNeXt injection (:504-507) runs when control_nets is given."""
 
     def __init__(self, patch_size=1, in_channels=64, num_layers=19, num_single_layers=38, attention_head_dim=128,
                  num_attention_heads=24, joint_attention_dim=4096, pooled_projection_dim=768, guidance_embeds=False,
@@ -374,7 +374,8 @@ class FluxTransformer2DModel(nn.Module):
         return self.x_embedder.weight.dtype
 
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None,
-                img_ids=None, txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=True):
+                img_ids=None, txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=True,
+                guided_hint=None, control_nets=None):
         x = self.x_embedder(hidden_states)
         timestep = timestep.to(x.dtype) * 1000
         if guidance is not None:
@@ -388,8 +389,11 @@ class FluxTransformer2DModel(nn.Module):
         if img_ids.ndim == 3:
             img_ids = img_ids[0]
         rope = self.pos_embed(torch.cat((txt_ids, img_ids), dim=0))
-        for blk in self.transformer_blocks:
+        for i, blk in enumerate(self.transformer_blocks):
             c, x = blk(hidden_states=x, encoder_hidden_states=c, temb=temb, image_rotary_emb=rope)
+            if control_nets is not None and i < len(control_nets):  # LightControl injection, lightcontrol_flux.py:504-507
+                control = control_nets[i](guided_hint, timestep)    # note: timestep is already x1000 here (:447)
+                x = x + control["out"].flatten(2).transpose(1, 2).to(x.dtype) * control["scale"]
         h = torch.cat([c, x], dim=1)
         for blk in self.single_transformer_blocks:
             h = blk(hidden_states=h, temb=temb, image_rotary_emb=rope)

@@ -289,6 +289,57 @@ def golden_flux_structure():
     print("flux structure golden written")
 
 
+# ----------------------------------------------------------------------------- C2: ControlNeXt (LightControl branch)
+def golden_controlnext():
+    """The reference's ControlNeXtModel class + its injection into the transformer, imported unmodified with the diffusers
+    leaves (ResnetBlock2D, Downsample2D, Timesteps, TimestepEmbedding) taken from the oracle."""
+    from oracle import controlnext_oracle as co
+    fakes = _fake_diffusers()
+    fakes["diffusers.models.resnet"].ResnetBlock2D = co.ResnetBlock2D
+    fakes["diffusers.models.resnet"].Downsample2D = co.Downsample2D
+    fakes["diffusers.utils"].BaseOutput = dict
+    sys.modules.update(fakes)
+    sys.modules.pop("lightcontrol_flux", None)
+    sys.path.insert(0, os.path.join(REF, "lightcontrol"))
+    try:
+        ref_flux = importlib.import_module("lightcontrol_flux")  # the reference file, unmodified
+    finally:
+        sys.path.remove(os.path.join(REF, "lightcontrol"))
+        for k in fakes:
+            sys.modules.pop(k, None)
+    g = torch.Generator().manual_seed(51)
+    net = ref_flux.ControlNeXtModel().eval()
+    sd = synth_state(net, 52, std=0.05)
+    net.load_state_dict(sd)
+    hint = torch.rand(2, 3, 64, 96, generator=g) * 2 - 1
+    t = torch.tensor([1000.0, 250.0])
+    with torch.no_grad():
+        o = net(hint, t)
+    # the 6.7 M-parameter state is regenerated from its seed by the tests (synth_state(net, 52, std=0.05)), not stored
+    out = dict(seed=52, std=0.05, hint=hint, timestep=t, out=o["out"], scale=o["scale"], n_params=sum(v.numel() for v in sd.values()),
+               keys=sorted(sd.keys()))
+    # injection inside the reference transformer (2 double blocks, 2 control nets; hidden width 3072 is fixed by mid_convs[1])
+    cfg = dict(patch_size=1, in_channels=8, num_layers=2, num_single_layers=0, attention_head_dim=128,
+               num_attention_heads=24, joint_attention_dim=16, pooled_projection_dim=8, guidance_embeds=True,
+               axes_dims_rope=(16, 56, 56))
+    ref = ref_flux.FluxTransformer2DModel(**cfg).eval()
+    tsd = synth_state(ref, 53, std=0.02)
+    ref.load_state_dict(tsd)
+    nets = nn.ModuleList([ref_flux.ControlNeXtModel().eval() for _ in range(1)])  # 1 net, 2 blocks: exercises i < len(control_nets)
+    for i, n in enumerate(nets):
+        n.load_state_dict(synth_state(n, 54 + i, std=0.05))
+    hl, wl, S = 4, 6, 4  # 64 x 96 hint pixels -> 4 x 6 control tokens (one per 16 x 16 pixels) = the packed-latent grid
+    inp = dict(hidden_states=torch.randn(2, hl * wl, 8, generator=g), encoder_hidden_states=torch.randn(2, S, 16, generator=g),
+               pooled_projections=torch.randn(2, 8, generator=g), timestep=torch.tensor([1.0, 0.25]),
+               img_ids=fo.prepare_latent_image_ids(2 * hl, 2 * wl), txt_ids=torch.zeros(S, 3), guidance=torch.tensor([3.5, 3.5]))
+    with torch.no_grad():
+        y = ref(**inp, guided_hint=hint, control_nets=nets, return_dict=False)
+    out["transformer"] = dict(cfg=cfg, seeds=dict(transformer=53, nets=[54], std_t=0.02, std_n=0.05), inputs=inp,
+                              output=y)
+    torch.save(out, os.path.join(OUT, "controlnext.pt"))
+    print("controlnext golden written:", tuple(o["out"].shape), tuple(y.shape))
+
+
 # ----------------------------------------------------------------------------- D: torchtitan cross-check
 def crosscheck_torchtitan():
     try:
@@ -380,8 +431,13 @@ def golden_resampler():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:  # regenerate selected fixtures only:  python oracle/make_golden.py controlnext
+        for name in sys.argv[1:]:
+            globals()["golden_" + name]()
+        sys.exit(0)
     golden_projector()
     golden_helpers()
     golden_flux_structure()
     crosscheck_torchtitan()
     golden_resampler()
+    golden_controlnext()

@@ -62,12 +62,17 @@ SIGNATURES = {
     "x2i_proj_mix_ln_save": [_vp, _i, _vp, _f, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp],
     "x2i_mean_over_s_bwd": [_vp, _vp, _i, _i, _i, _vp],
     "x2i_proj_mix_wgrad": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp],
+    # ---- ControlNeXt
+    "x2i_conv2d_nhwc": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "x2i_conv_first": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "x2i_groupnorm_nhwc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
 }
 # helpers that return a size instead of a status code
 SIZE_FUNCS = {
     "x2i_colsum_workspace_floats": [_i, _i, _i],
     "x2i_skinny_linear_t_workspace_floats": [_i, _i],
     "x2i_proj_mix_wgrad_workspace_floats": [_i, _i, _i],
+    "x2i_groupnorm_workspace_floats": [_i, _i, _i],
 }
 
 

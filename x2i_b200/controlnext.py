@@ -1,0 +1,149 @@
+"""Drop-in ``ControlNeXtModel`` (the LightControl editing branch of X2I, ``lightcontrol/lightcontrol_flux.py:575-749``) on
+sm_100a kernels, and its injection into the FLUX double blocks (``:504-507``).
+
+Same constructor, parameter names / state-dict keys and ``forward(sample, timestep) -> {'out': [B,3072,h,w], 'scale': 1.0}``
+as the reference, so ``nn.ModuleList([ControlNeXtModel() for _ in range(19)])`` and a trained ``controlnet.state_dict()``
+(``lightcontrol/train_lightcontrol.py:517-522,:785-791``) work unchanged.  Inside, activations are NHWC bf16 and every
+convolution except the 3-channel stem is an implicit-GEMM tcgen05 kernel (``x2i_conv2d_nhwc``: shifted tensor-map boxes as
+the A operand, no im2col), GroupNorm + activation (+ residual) is one fused deterministic kernel pair, the time embedding uses
+the skinny-linear kernels.  The final 2x2/stride-2 conv emits [B, h*w, 3072] token-major -- exactly
+``control['out'].flatten(2).transpose(1, 2)`` -- and, when called from the transformer, adds straight into the image
+stream in its epilogue.  Forward only (inference, BASELINE config 5); no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import X2IError
+
+BF16 = torch.bfloat16
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise X2IError(f"{type(self).__name__} is a parameter holder inside the fused ControlNeXtModel")
+
+
+class TimestepEmbedding(_Holder):
+    def __init__(self, in_channels, time_embed_dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+
+
+class ResnetBlock2D(_Holder):
+    """Parameter layout of diffusers' ResnetBlock2D as configured by the reference (oracle/controlnext_oracle.py)."""
+
+    def __init__(self, *, in_channels, out_channels=None, temb_channels=512, groups=32, eps=1e-6):
+        super().__init__()
+        out_channels = in_channels if out_channels is None else out_channels
+        self.groups, self.eps = groups, eps
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels)
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
+
+
+class Downsample2D(_Holder):
+    def __init__(self, channels, use_conv=True, out_channels=None, padding=1, name="op"):
+        super().__init__()
+        if not use_conv:
+            raise X2IError("Downsample2D: only the conv form (use_conv=True) is used by ControlNeXt")
+        self.conv = nn.Conv2d(channels, out_channels or channels, 3, stride=2, padding=padding)
+
+
+class ControlNeXtModel(nn.Module):
+    _supports_gradient_checkpointing = True
+
+    def __init__(self, in_channels: List[int] = (128, 128), out_channels: List[int] = (128, 256), groups: List[int] = (4, 8),
+                 time_embed_dim: int = 256, final_out_channels: int = 320):
+        super().__init__()
+        self.time_embedding = TimestepEmbedding(128, time_embed_dim)
+        self.embedding = nn.Sequential(
+            nn.Conv2d(3, 64, 3, stride=2, padding=1), nn.GroupNorm(2, 64), nn.ReLU(),
+            nn.Conv2d(64, 64, 3, padding=1), nn.GroupNorm(2, 64), nn.ReLU(),
+            nn.Conv2d(64, 128, 3, padding=1), nn.GroupNorm(2, 128), nn.ReLU())
+        self.down_res = nn.ModuleList([ResnetBlock2D(in_channels=i, out_channels=o, temb_channels=time_embed_dim, groups=g)
+                                       for i, o, g in zip(in_channels, out_channels, groups)])
+        self.down_sample = nn.ModuleList([Downsample2D(o, use_conv=True, out_channels=o, padding=1, name="op") for o in out_channels])
+        c = out_channels[-1]
+        self.mid_convs = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(c, c, 3, padding=1), nn.ReLU(), nn.GroupNorm(8, c), nn.Conv2d(c, c, 3, padding=1), nn.GroupNorm(8, c)),
+            nn.Conv2d(c, 3072, kernel_size=2, stride=2)])
+        self.scale = 1.0
+        self._packed = {}
+
+    # -- weights in the layout the implicit-GEMM kernel reads, packed once per parameter version ------------------------
+    def _w(self, conv: nn.Conv2d):
+        key = id(conv)
+        ver = (conv.weight.data_ptr(), conv.weight._version)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.pack_conv_weight(conv.weight))
+            self._packed[key] = hit
+        return hit[1]
+
+    def _conv(self, x, conv: nn.Conv2d, **kw):
+        return ops.conv2d_nhwc(x, self._w(conv), conv.bias, conv.kernel_size[0], conv.kernel_size[1], stride=conv.stride[0],
+                               pad=conv.padding[0], **kw)
+
+    @staticmethod
+    def _gn(x, gn: nn.GroupNorm, act, residual=None):
+        return ops.groupnorm_nhwc(x, gn.weight, gn.bias, gn.num_groups, gn.eps, act=act, residual=residual)
+
+    def forward_tokens(self, sample, timestep, add_to=None):
+        """[B, h*w, 3072] token-major control signal; with add_to ([B, h*w, 3072] bf16, contiguous) the signal is added to it in
+        place (scale == 1.0) by the last conv's epilogue and add_to is returned."""
+        w0 = self.embedding[0]
+        if w0.weight.dtype != BF16 or not sample.is_cuda:
+            raise X2IError("ControlNeXtModel runs in bf16 on a CUDA device (x2i_b200 has no CPU path): .to('cuda', torch.bfloat16)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and sample.requires_grad:
+            raise X2IError("ControlNeXtModel: forward only (LightControl inference); call under torch.no_grad()")
+        B = sample.shape[0]
+        t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=sample.device)
+        t = t.reshape(-1).to(sample.device).expand(B).float().contiguous()
+        te = self.time_embedding
+        h = ops.skinny_linear(ops.timestep_sinusoid(t, 128), te.linear_1.weight, te.linear_1.bias)
+        emb = ops.skinny_linear(h, te.linear_2.weight, te.linear_2.bias, act_in=1)                       # [B, 256]
+        e = self.embedding
+        x = ops.conv_first(sample.to(BF16), w0.weight.float(), w0.bias.float())                          # [B, H/2, W/2, 64]
+        x = self._gn(x, e[1], 1)
+        x = self._gn(self._conv(x, e[3]), e[4], 1)
+        x = self._gn(self._conv(x, e[6]), e[7], 1)
+        for res, down in zip(self.down_res, self.down_sample):
+            tproj = ops.skinny_linear(emb, res.time_emb_proj.weight, res.time_emb_proj.bias, act_in=1)   # Linear(SiLU(emb))
+            hcur = self._conv(self._gn(x, res.norm1, 2), res.conv1, rowvec=tproj)
+            hcur = self._conv(self._gn(hcur, res.norm2, 2), res.conv2, residual=x if res.conv_shortcut is None else None)
+            if res.conv_shortcut is not None:
+                hcur = self._conv(x, res.conv_shortcut, residual=hcur)
+            x = self._conv(hcur, down.conv)
+        m = self.mid_convs[0]
+        y = self._conv(x, m[0], relu=True)
+        y = self._conv(self._gn(y, m[2], 0), m[3])
+        x = self._gn(y, m[4], 0, residual=x)                                                             # mid(sample) + sample
+        last = self.mid_convs[1]
+        if add_to is not None:
+            if add_to.dtype != BF16 or not add_to.is_contiguous():
+                raise X2IError("ControlNeXtModel: add_to must be a contiguous bf16 [B, h*w, 3072] tensor")
+            if self.scale != 1.0:
+                raise X2IError("ControlNeXtModel: fused injection assumes scale == 1.0 (the reference's constant)")
+            Ho, Wo = x.shape[1] // 2, x.shape[2] // 2
+            if add_to.shape != (B, Ho * Wo, 3072):
+                raise X2IError(f"ControlNeXtModel: control grid {Ho}x{Wo} does not match the image stream {tuple(add_to.shape)}")
+            self._conv(x, last, residual=add_to.view(B, Ho, Wo, 3072), out=add_to.view(B, Ho, Wo, 3072))
+            return add_to
+        out = self._conv(x, last)
+        return out.view(B, -1, out.shape[-1])
+
+    def forward(self, sample, timestep):
+        tok = self.forward_tokens(sample, timestep)
+        B, _, C = tok.shape
+        hh, ww = sample.shape[2] // 16, sample.shape[3] // 16
+        # NCHW *view* of the NHWC result: values and shape of the reference's control['out'] without a transposing copy
+        return {"out": tok.view(B, hh, ww, C).permute(0, 3, 1, 2), "scale": self.scale}

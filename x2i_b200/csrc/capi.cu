@@ -9,6 +9,7 @@
 #include "../../include/x2i_b200.h"
 #include "attn_bwd_sm100.cuh"
 #include "attn_sm100.cuh"
+#include "conv_sm100.cuh"
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "rowwise.cuh"
@@ -90,8 +91,8 @@ int device_info(DeviceInfo** out) {
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides in elements (dim 0 is dense).
 int make_map(DeviceInfo* d, CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
              const uint32_t* box) {
-  cuuint64_t gdim[3], gstr[2];
-  cuuint32_t bx[3], es[3] = {1, 1, 1};
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
@@ -978,6 +979,111 @@ int x2i_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
   if (n <= 0) return fail(X2I_ERR_SHAPE, "f32_to_bf16: empty");
   f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, static_cast<__nv_bfloat16*>(out), n);
   return check_launch("f32_to_bf16_kernel");
+}
+
+}  // extern "C"
+
+// ================================================================================================ ControlNeXt (LightControl)
+namespace {
+template <int BN>
+int launch_conv_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& cp, cudaStream_t st) {
+  auto kern = conv2d_tcgen05_kernel<BN, EPI_CONV>;
+  static std::atomic<bool> configured[16];
+  if (!configured[d->index].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(conv): %s", cudaGetErrorString(e));
+    configured[d->index].store(true, std::memory_order_release);
+  }
+  const int tiles = cp.Nimg * cp.tiles_x * cp.tiles_y * ((cp.g.N + BN - 1) / BN);
+  const int grid = tiles < d->sms ? tiles : d->sms;
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, cp);
+  return check_launch("conv2d_tcgen05_kernel");
+}
+}  // namespace
+
+extern "C" {
+
+int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
+                    void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (Nimg <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin % 64 || Cout <= 0 || Cout % 64 || KH <= 0 || KW <= 0 || KH > 3 || KW > 3 || pad < 0 ||
+      pad > 1 || (stride != 1 && stride != 2))
+    return fail(X2I_ERR_SHAPE, "conv2d_nhwc: need Cin %% 64 == 0, Cout %% 64 == 0, kernel <= 3x3, pad <= 1, stride 1 or 2");
+  if (stride == 2 && ((H | W) & 1)) return fail(X2I_ERR_SHAPE, "conv2d_nhwc: stride 2 needs even H and W");
+  if (!x || !w || !out) return fail(X2I_ERR_SHAPE, "conv2d_nhwc: null buffer");
+  if (!aligned16(x) || !aligned16(w) || !aligned16(out) || !aligned16(bias) || !aligned16(rowvec) || !aligned16(residual) || rowvec_stride % 8)
+    return fail(X2I_ERR_ALIGN, "conv2d_nhwc: alignment");
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  ConvParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.Nimg = Nimg; cp.Ho = Ho; cp.Wo = Wo; cp.Cin = Cin; cp.KH = KH; cp.KW = KW; cp.stride = stride; cp.pad = pad;
+  cp.tiles_x = (Wo + CONV_TW - 1) / CONV_TW; cp.tiles_y = (Ho + CONV_TH - 1) / CONV_TH;
+  GemmParams& p = cp.g;
+  p.M = Nimg * Ho * Wo; p.N = Cout; p.K = KH * KW * Cin;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.C = static_cast<__nv_bfloat16*>(out); p.ldc = Cout;
+  p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
+  p.rowvec = static_cast<const __nv_bfloat16*>(rowvec); p.rowvec_stride = rowvec_stride; p.rows_per_batch = Ho * Wo; p.relu = relu;
+  CUtensorMap ta, tb;
+  if (stride == 1) {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+    uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
+    uint32_t box[4] = {GEMM_BK, CONV_TW, CONV_TH, 1};
+    if (int rc = make_map(d, &ta, x, 4, dims, str, box)) return rc;
+  } else {  // parity view [2C, W/2, 2, H/2, N]
+    uint64_t dims[5] = {(uint64_t)2 * Cin, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)Nimg};
+    uint64_t str[5] = {1, (uint64_t)2 * Cin, (uint64_t)W * Cin, (uint64_t)2 * W * Cin, (uint64_t)H * W * Cin};
+    uint32_t box[5] = {GEMM_BK, CONV_TW, 1, CONV_TH, 1};
+    if (int rc = make_map(d, &ta, x, 5, dims, str, box)) return rc;
+  }
+  const int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  uint64_t db[2] = {(uint64_t)p.K, (uint64_t)Cout}, sb[2] = {1, (uint64_t)p.K};
+  uint32_t bb[2] = {GEMM_BK, (uint32_t)bn};
+  if (int rc = make_map(d, &tb, w, 2, db, sb, bb)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 256: return launch_conv_t<256>(d, ta, tb, cp, st);
+    case 128: return launch_conv_t<128>(d, ta, tb, cp, st);
+    default: return launch_conv_t<64>(d, ta, tb, cp, st);
+  }
+}
+
+int x2i_conv_first(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (Nimg <= 0 || H <= 0 || W <= 0 || ((H | W) & 1)) return fail(X2I_ERR_SHAPE, "conv_first: even H and W required");
+  if (!x || !w || !bias || !out || !aligned16(out)) return fail(X2I_ERR_SHAPE, "conv_first: null / unaligned buffer");
+  const long long pix = static_cast<long long>(Nimg) * (H / 2) * (W / 2);
+  conv_first_kernel<<<static_cast<unsigned>((pix + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), w, bias, static_cast<__nv_bfloat16*>(out), Nimg, H, W);
+  return check_launch("conv_first_kernel");
+}
+
+int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
+                       int HW, int C, int G, float eps, int act, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (Nimg <= 0 || HW <= 0 || (C != 64 && C != 128 && C != 256) || G <= 0 || (C / 8) % G) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: C in {64,128,256}, (C/8) %% G == 0");
+  if (!x || !gamma || !beta || !y || !workspace) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: null buffer");
+  if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(residual) || !aligned16(y) || !aligned16(workspace)) return fail(X2I_ERR_ALIGN, "groupnorm_nhwc: alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nsplit = (HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA;
+  float* part = workspace;
+  float2* stats = reinterpret_cast<float2*>(workspace + static_cast<long long>(Nimg) * nsplit * G * 2);
+  gn_stats_partial_kernel<<<dim3(nsplit, Nimg), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, nsplit);
+  if (int rc = check_launch("gn_stats_partial_kernel")) return rc;
+  gn_stats_final_kernel<<<(Nimg * G + 63) / 64, 64, 0, st>>>(part, stats, G, nsplit, static_cast<double>(HW) * (C / G), eps, Nimg * G);
+  if (int rc = check_launch("gn_stats_final_kernel")) return rc;
+  const long long total8 = static_cast<long long>(Nimg) * HW * (C / 8);
+  gn_apply_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x), stats, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta),
+      static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), total8, HW, C, G, act);
+  return check_launch("gn_apply_kernel");
+}
+int64_t x2i_groupnorm_workspace_floats(int Nimg, int HW, int G) {
+  const int nsplit = (HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA;
+  return 2LL * Nimg * nsplit * G + 2LL * Nimg * G + 8;
 }
 
 }  // extern "C"

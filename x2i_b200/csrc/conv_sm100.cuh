@@ -1,0 +1,272 @@
+// Implicit-GEMM 2-D convolution on tcgen05 for sm_100a (NHWC activations, bf16, fp32 accumulation in TMEM) -- the
+// ControlNeXt nets of the LightControl editing branch (lightcontrol/lightcontrol_flux.py:575-749: 3x3 / 1x1 / 2x2 convs,
+// stride 1 or 2), which the reference runs through cuDNN.
+//
+//   out[n, y, x, co] = epilogue( sum_{ky,kx,ci} in[n, y*s + ky - pad, x*s + kx - pad, ci] * w[co, ky, kx, ci] )
+//
+// There is no im2col buffer: the persistent GEMM of gemm_sm100.cuh is kept (TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// -> double-buffered TMEM accumulators -> fused epilogue) and only the A-operand load changes.  An M tile is an 8 x 16 patch
+// of output pixels of one image; for k-block (tap, 64-channel chunk) the producer issues ONE tensor-map load whose box is
+// the patch shifted by the tap -- [64 ch, 16 x, 8 y, 1 n] of the NHWC tensor -- which lands in shared memory exactly as a
+// 128-row x 64-column K-major tile; rows that fall outside the image are zero-filled by TMA (= the conv's zero padding).
+// Stride-2 convs read a parity view of the same tensor, [2C, W/2, 2, H/2, N] (x parity folded into the channel dim), where a
+// tap has a fixed (row parity, column parity), so the box is again dense.  Weights are pre-packed [Cout, KH*KW*Cin].
+#pragma once
+#include "gemm_sm100.cuh"
+#include "rowwise.cuh"
+
+namespace x2i {
+
+struct ConvParams {
+  GemmParams g;  // g.M = Nimg * Ho * Wo (output pixels), g.N = Cout, g.K = KH * KW * Cin; g.rows_per_batch = Ho * Wo
+  int Nimg, Ho, Wo, Cin, KH, KW, stride, pad;
+  int tiles_x, tiles_y;  // 16-wide / 8-high output patches per image
+};
+
+constexpr int CONV_TW = 16, CONV_TH = 8;
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const ConvParams cp) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int NS = Cfg::STAGES;
+  const GemmParams& p = cp.g;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + NS;
+  uint64_t* tfull_bar = empty_bar + NS;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+  const int tiles_img = cp.tiles_x * cp.tiles_y;
+  const int num_m = cp.Nimg * tiles_img;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int cchunks = cp.Cin / GEMM_BK;
+  const int num_kb = cp.KH * cp.KW * cchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % num_m, n_blk = tile / num_m;
+        const int img = m_blk / tiles_img, t = m_blk - img * tiles_img;
+        const int y0 = (t / cp.tiles_x) * CONV_TH, x0 = (t % cp.tiles_x) * CONV_TW;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / cchunks, cc = kb - tap * cchunks;
+          const int ky = tap / cp.KW, kx = tap - ky * cp.KW;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (cp.stride == 1) {
+            tma_load_4d(sa, &tma_a, &full_bar[stage], cc * GEMM_BK, x0 + kx - cp.pad, y0 + ky - cp.pad, img);
+          } else {  // stride 2: input column 2x + kx - pad = 2 * (x + (vx >> 1)) + (vx & 1)
+            const int vx = kx - cp.pad, vy = ky - cp.pad;
+            tma_load_5d(sa, &tma_a, &full_bar[stage], (vx & 1) * cp.Cin + cc * GEMM_BK, x0 + (vx >> 1), vy & 1, y0 + (vy >> 1), img);
+          }
+          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t adesc = make_smem_desc_sw128(a_base, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(a_base + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k)
+          umma_ss_w(d_tmem, adesc + ((k * 32) >> 4), bdesc + ((k * 32) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit_w(&empty_bar[stage]);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_w(&tfull_bar[as]);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..5): one output pixel per thread
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int img = m_blk / tiles_img, t = m_blk - img * tiles_img;
+      const int r = quad * 32 + lane;
+      const int y = (t / cp.tiles_x) * CONV_TH + r / CONV_TW, x = (t % cp.tiles_x) * CONV_TW + r % CONV_TW;
+      const int m = (y < cp.Ho && x < cp.Wo) ? (img * cp.Ho + y) * cp.Wo + x : p.M;  // p.M = "row out of range"
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      gemm_epilogue_tile<BN, EPI>(p, tmem_base + as * BN + lane_off, m, n_blk * BN);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// First ControlNeXt conv: Conv2d(3 -> 64, 3x3, stride 2, pad 1) on the NCHW hint image (lightcontrol_flux.py:594),
+// output NHWC.  K = 27 is far too small for the tensor cores: direct form, one output pixel per thread, 64 channels.
+__global__ void __launch_bounds__(128) conv_first_kernel(const __nv_bfloat16* __restrict__ x /* [N,3,H,W] */,
+                                                         const float* __restrict__ w /* [64][27] (co, ci, ky, kx) */,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /* [N,H/2,W/2,64] */,
+                                                         int Nimg, int H, int W) {
+  __shared__ float ws[27 * 64 + 64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[(i % 27) * 64 + i / 27] = w[i];  // [tap][co]
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) ws[27 * 64 + i] = bias[i];
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= static_cast<long long>(Nimg) * Ho * Wo) return;
+  const int xo = static_cast<int>(pix % Wo), yo = static_cast<int>((pix / Wo) % Ho), n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  float v[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yi = 2 * yo + ky - 1, xi = 2 * xo + kx - 1;
+        v[ci * 9 + ky * 3 + kx] = (yi >= 0 && yi < H && xi >= 0 && xi < W)
+                                      ? __bfloat162float(x[((static_cast<long long>(n) * 3 + ci) * H + yi) * W + xi]) : 0.f;
+      }
+  uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll 1
+  for (int c8 = 0; c8 < 8; ++c8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = ws[27 * 64 + c8 * 8 + j];
+#pragma unroll
+    for (int t = 0; t < 27; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[t] * ws[t * 64 + c8 * 8 + j];
+    o4[c8] = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm on NHWC bf16 (nn.GroupNorm of ControlNeXt: 2 / 4 / 8 groups): deterministic two-stage statistics + one
+// fused apply pass  y = act((x - mean) * rstd * gamma + beta) (+ residual).  act: 0 none, 1 ReLU, 2 SiLU.
+constexpr int GN_PIX_PER_CTA = 1024;
+__global__ void __launch_bounds__(256) gn_stats_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part /* [N, nsplit, G, 2] */,
+                                                               int HW, int C, int G, int nsplit) {
+  __shared__ float red[256][2];
+  const int tpp = C >> 3;            // threads per pixel (16-byte chunks)
+  const int ppi = 256 / tpp;         // pixels per CTA iteration
+  const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const int split = blockIdx.x, n = blockIdx.y;
+  const int p0 = split * GN_PIX_PER_CTA, p1 = min(p0 + GN_PIX_PER_CTA, HW);
+  float s = 0.f, ss = 0.f;
+  if (pl < ppi)
+    for (int pp = p0 + pl; pp < p1; pp += ppi) {
+      float f[8];
+      unpack8(ld_stream(x + (static_cast<long long>(n) * HW + pp) * C + cg * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += f[j]; ss += f[j] * f[j]; }
+    }
+  red[threadIdx.x][0] = s;
+  red[threadIdx.x][1] = ss;
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int tpg = tpp / G;  // chunk-threads per group within a pixel
+    float a = 0.f, b = 0.f;
+    for (int t = 0; t < ppi * tpp; ++t)
+      if ((t % tpp) / tpg == static_cast<int>(threadIdx.x)) { a += red[t][0]; b += red[t][1]; }
+    float* o = part + ((static_cast<long long>(n) * nsplit + split) * G + threadIdx.x) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+__global__ void gn_stats_final_kernel(const float* __restrict__ part, float2* __restrict__ stats /* [N, G] (mean, rstd) */, int G,
+                                      int nsplit, double count, float eps, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n * G + g
+  if (i >= total) return;
+  const int n = i / G, g = i - n * G;
+  double a = 0.0, b = 0.0;
+  for (int sidx = 0; sidx < nsplit; ++sidx) {
+    const float* o = part + ((static_cast<long long>(n) * nsplit + sidx) * G + g) * 2;
+    a += o[0]; b += o[1];
+  }
+  const double mean = a / count;
+  const double var = fmax(b / count - mean * mean, 0.0);
+  stats[i] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+}
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
+                                                       const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                                                       const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, long long total8,
+                                                       int HW, int C, int G, int act) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int tpp = C >> 3;
+  const int cg = static_cast<int>(i % tpp);
+  const int n = static_cast<int>(i / (static_cast<long long>(HW) * tpp));
+  const float2 st = stats[n * G + cg / (tpp / G)];
+  float f[8], ga[8], be[8];
+  unpack8(ld_stream(reinterpret_cast<const uint4*>(x) + i), f);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + cg), ga);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + cg), be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = (f[j] - st.x) * st.y * ga[j] + be[j];
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) v = silu_f(v);
+    f[j] = v;
+  }
+  if (residual != nullptr) {
+    float r[8];
+    unpack8(ld_stream(reinterpret_cast<const uint4*>(residual) + i), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += r[j];
+  }
+  reinterpret_cast<uint4*>(y)[i] = pack8(f);
+}
+
+}  // namespace x2i

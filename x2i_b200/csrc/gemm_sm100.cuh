@@ -18,6 +18,8 @@
 //   EPI_DACT            backward of a Linear followed by GELU: C = addend + acc * act'(pre) for columns >= n_split,
 //                       C = addend + acc below it (dgrad GEMMs of the distillation step)
 //
+//   EPI_CONV            implicit-GEMM convolution (conv_sm100.cuh): C = relu?(acc + bias + rowvec[b, :]) + residual
+//
 // Operand forms: B_MN takes B as [K, N] (N contiguous) and A_MN takes A as [K, M] (M contiguous) -- the "MN-major"
 // UMMA operands.  dgrad (dX = dY W) uses B_MN on the weights exactly as nn.Linear stores them; wgrad (dW = dY^T X) uses
 // both, so no tensor is ever transposed in memory.
@@ -26,7 +28,7 @@
 
 namespace x2i {
 
-enum { EPI_BIAS = 0, EPI_BIAS_GELU_TANH = 1, EPI_BIAS_GELU_ERF = 2, EPI_GATE_RESIDUAL = 3, EPI_QKV = 4, EPI_DACT = 5 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU_TANH = 1, EPI_BIAS_GELU_ERF = 2, EPI_GATE_RESIDUAL = 3, EPI_QKV = 4, EPI_DACT = 5, EPI_CONV = 6 };
 
 struct GemmParams {
   int M, N, K;
@@ -60,6 +62,10 @@ struct GemmParams {
   const __nv_bfloat16* pre;
   long long ldpre;
   int n_split, dact;
+  // EPI_CONV: per-image channel vector added before the activation (ResnetBlock2D time embedding), ReLU flag; residual/ldr
+  const __nv_bfloat16* rowvec;
+  long long rowvec_stride;
+  int relu;
 };
 
 constexpr int GEMM_BM = 128;
@@ -245,6 +251,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
 #pragma unroll
               for (int j = 0; j < 32; ++j) x[j] *= dgelu_erf_f(pr[j]);
             }
+          }
+          if (p.residual != nullptr) {
+            float res[32];
+            load_bf16x32(p.residual + static_cast<long long>(m) * p.ldr + n0, res);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += res[j];
+          }
+        }
+        if constexpr (EPI == EPI_CONV) {
+          if (p.rowvec != nullptr) {
+            float rv[32];
+            load_bf16x32(p.rowvec + static_cast<long long>(m / p.rows_per_batch) * p.rowvec_stride + n0, rv);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += rv[j];
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
           }
           if (p.residual != nullptr) {
             float res[32];

@@ -576,7 +576,9 @@ class FluxTransformer2DModel(nn.Module):
     use_cuda_graph = True  # replay one captured graph per step instead of ~410 launches (inference, default processors)
 
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
-                txt_ids=None, guidance=None, joint_attention_kwargs=None, return_dict=True):
+                txt_ids=None, guidance=None, joint_attention_kwargs=None, guided_hint=None, control_nets=None, return_dict=True):
+        """guided_hint / control_nets: the LightControl editing branch (lightcontrol_flux.py:400-401, :504-507): after each of the
+        first len(control_nets) double blocks the image stream receives control_nets[i](guided_hint, timestep)['out']."""
         self._pack()
         if txt_ids.ndim == 3:
             txt_ids = txt_ids[0]
@@ -584,8 +586,12 @@ class FluxTransformer2DModel(nn.Module):
             img_ids = img_ids[0]
         if guidance is not None and not self.config.guidance_embeds:
             guidance = None
-        if torch.is_grad_enabled() and any(t is not None and t.requires_grad
-                                           for t in (hidden_states, encoder_hidden_states, pooled_projections)):
+        if control_nets is not None and len(control_nets) > 0:
+            _no_grad_needed(hidden_states, encoder_hidden_states, pooled_projections)
+            out = self._forward_eager(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+                                      guided_hint=guided_hint, control_nets=control_nets)
+        elif torch.is_grad_enabled() and any(t is not None and t.requires_grad
+                                             for t in (hidden_states, encoder_hidden_states, pooled_projections)):
             out = self._forward_train(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance)
         elif self._graphable():
             out = self._forward_graphed(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
@@ -669,7 +675,8 @@ class FluxTransformer2DModel(nn.Module):
         if sin["g"] is not None:
             sin["g"].copy_(guidance.expand(sin["g"].shape[0]) if guidance.dim() > 0 else guidance, non_blocking=True)
 
-    def _forward_eager(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance):
+    def _forward_eager(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+                       guided_hint=None, control_nets=None):
         B, L_img, _ = hidden_states.shape
         S = encoder_hidden_states.shape[1]
         D = self.inner_dim
@@ -688,10 +695,18 @@ class FluxTransformer2DModel(nn.Module):
         mod = ops.skinny_linear(temb, self._w_mod, self._b_mod, act_in=1)  # every AdaLN modulation of this step
 
         off = 0
-        for blk in self.transformer_blocks:
+        for i, blk in enumerate(self.transformer_blocks):
             c, x = blk(hidden_states=x, encoder_hidden_states=c, temb=temb, image_rotary_emb=rope_full,
                        _mod=mod[:, off:off + 12 * D], _rope=rope, _ws=ws)
             off += 12 * D
+            if control_nets is not None and i < len(control_nets):  # lightcontrol_flux.py:504-507
+                net = control_nets[i]
+                if hasattr(net, "forward_tokens"):   # x2i_b200 ControlNeXtModel: adds in the epilogue of its last conv
+                    net.forward_tokens(guided_hint, t1000, add_to=x)
+                else:                                # any other control net: the reference's protocol, then a fused axpy
+                    control = net(guided_hint, t1000)
+                    sig = control["out"].flatten(2).transpose(1, 2).to(BF16).contiguous()
+                    ops.euler_step_(x, sig, float(control["scale"]))
         h = ws["h"]
         h[:, :S].copy_(c)
         h[:, S:].copy_(x)

@@ -534,3 +534,52 @@ def proj_mix_wgrad(x, g, mode):
     ws = _ws_f32("proj_mix_wgrad", _lib.lib().x2i_proj_mix_wgrad_workspace_floats(B, C, S), x.device)
     _lib.call("x2i_proj_mix_wgrad", _p(x.contiguous()), _p(g.contiguous()), mode, _p(dw), _p(ws), B, C, S, H, _stream())
     return dw
+
+
+# ================================================================================================ ControlNeXt (LightControl)
+def conv2d_nhwc(x, w_packed, bias, kh, kw, stride=1, pad=1, rowvec=None, residual=None, relu=False, out=None):
+    """NHWC implicit-GEMM conv: x [N,H,W,Cin], w_packed [Cout, kh*kw*Cin] (from pack_conv_weight), bias [Cout];
+    out = relu?(conv + bias + rowvec[n]) + residual, [N,Ho,Wo,Cout]."""
+    for t, n in ((x, "x"), (w_packed, "w"), (bias, "bias"), (rowvec, "rowvec"), (residual, "residual"), (out, "out")):
+        _chk(t, n)
+    N, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    if w_packed.shape[1] != kh * kw * Cin or not x.is_contiguous() or not w_packed.is_contiguous():
+        raise _lib.X2IError("conv2d_nhwc: x must be contiguous NHWC and w packed [Cout, kh*kw*Cin]")
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    if out is None:
+        out = torch.empty(N, Ho, Wo, Cout, device=x.device, dtype=BF16)
+    if residual is not None and (residual.numel() != out.numel() or not residual.is_contiguous()):
+        raise _lib.X2IError("conv2d_nhwc: residual must be contiguous with the output's shape")
+    _lib.call("x2i_conv2d_nhwc", _p(x), _p(w_packed), _p(bias), _p(rowvec), rowvec.stride(0) if rowvec is not None else 0, _p(residual),
+              _p(out), N, H, W, Cin, Cout, kh, kw, stride, pad, 1 if relu else 0, _stream())
+    return out
+
+
+def pack_conv_weight(w):
+    """[Cout, Cin, KH, KW] -> bf16 [Cout, KH*KW*Cin] (tap-major, channels innermost): the B operand of conv2d_nhwc."""
+    return w.detach().permute(0, 2, 3, 1).contiguous().view(w.shape[0], -1).to(BF16).contiguous()
+
+
+def conv_first(x_nchw, w, bias):
+    """Conv2d(3->64, 3x3, s2, p1): x bf16 [N,3,H,W] -> NHWC bf16 [N,H/2,W/2,64]; w fp32 [64,3,3,3], bias fp32 [64]."""
+    _chk(x_nchw, "x"); _chk(w, "w", F32); _chk(bias, "bias", F32)
+    N, C, H, W = x_nchw.shape
+    if C != 3 or tuple(w.shape) != (64, 3, 3, 3):
+        raise _lib.X2IError("conv_first: x [N,3,H,W], w [64,3,3,3]")
+    out = torch.empty(N, H // 2, W // 2, 64, device=x_nchw.device, dtype=BF16)
+    _lib.call("x2i_conv_first", _p(x_nchw.contiguous()), _p(w.contiguous()), _p(bias.contiguous()), _p(out), N, H, W, _stream())
+    return out
+
+
+def groupnorm_nhwc(x, gamma, beta, groups, eps, act=0, residual=None, out=None):
+    """act(GroupNorm(x)) + residual on NHWC bf16; act 0 none, 1 relu, 2 silu."""
+    for t, n in ((x, "x"), (gamma, "gamma"), (beta, "beta"), (residual, "residual"), (out, "out")):
+        _chk(t, n)
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    ws = _ws_f32("groupnorm", _lib.lib().x2i_groupnorm_workspace_floats(N, H * W, groups), x.device)
+    _lib.call("x2i_groupnorm_nhwc", _p(x), _p(gamma), _p(beta), _p(residual), _p(out), _p(ws), N, H * W, C, groups, float(eps), act,
+              _stream())
+    return out
