@@ -1073,10 +1073,10 @@ int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const
   float2* stats = reinterpret_cast<float2*>(workspace + static_cast<long long>(Nimg) * nsplit * G * 2);
   gn_stats_partial_kernel<<<dim3(nsplit, Nimg), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, nsplit);
   if (int rc = check_launch("gn_stats_partial_kernel")) return rc;
-  gn_stats_final_kernel<<<(Nimg * G + 63) / 64, 64, 0, st>>>(part, stats, G, nsplit, static_cast<double>(HW) * (C / G), eps, Nimg * G);
+  gn_stats_final_kernel<<<(Nimg * G + 3) / 4, 128, 0, st>>>(part, stats, G, nsplit, static_cast<double>(HW) * (C / G), eps, Nimg * G);
   if (int rc = check_launch("gn_stats_final_kernel")) return rc;
   const long long total8 = static_cast<long long>(Nimg) * HW * (C / 8);
-  gn_apply_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, st>>>(
+  gn_apply_kernel<<<static_cast<unsigned>((total8 + 1023) / 1024), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), stats, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta),
       static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), total8, HW, C, G, act);
   return check_launch("gn_apply_kernel");

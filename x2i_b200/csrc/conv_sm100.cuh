@@ -196,77 +196,113 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const __nv_bfloat16* __
 // ------------------------------------------------------------------------------------------------
 // GroupNorm on NHWC bf16 (nn.GroupNorm of ControlNeXt: 2 / 4 / 8 groups): deterministic two-stage statistics + one
 // fused apply pass  y = act((x - mean) * rstd * gamma + beta) (+ residual).  act: 0 none, 1 ReLU, 2 SiLU.
-constexpr int GN_PIX_PER_CTA = 1024;
+constexpr int GN_PIX_PER_CTA = 256;
 __global__ void __launch_bounds__(256) gn_stats_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part /* [N, nsplit, G, 2] */,
                                                                int HW, int C, int G, int nsplit) {
-  __shared__ float red[256][2];
-  const int tpp = C >> 3;            // threads per pixel (16-byte chunks)
+  __shared__ float red[2][256];
+  const int tpp = C >> 3;            // threads per pixel (16-byte chunks): 8, 16 or 32
   const int ppi = 256 / tpp;         // pixels per CTA iteration
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   const int split = blockIdx.x, n = blockIdx.y;
   const int p0 = split * GN_PIX_PER_CTA, p1 = min(p0 + GN_PIX_PER_CTA, HW);
   float s = 0.f, ss = 0.f;
-  if (pl < ppi)
-    for (int pp = p0 + pl; pp < p1; pp += ppi) {
+  const __nv_bfloat16* xb = x + static_cast<long long>(n) * HW * C + cg * 8;
+  for (int pp = p0 + pl; pp < p1; pp += 4 * ppi) {  // 4 independent 16-byte loads in flight
+    uint4 q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = (pp + u * ppi < p1) ? ld_stream(xb + static_cast<long long>(pp + u * ppi) * C) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
       float f[8];
-      unpack8(ld_stream(x + (static_cast<long long>(n) * HW + pp) * C + cg * 8), f);
+      unpack8(q[u], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s += f[j]; ss += f[j] * f[j]; }
     }
-  red[threadIdx.x][0] = s;
-  red[threadIdx.x][1] = ss;
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = ss;
   __syncthreads();
-  if (threadIdx.x < G) {
-    const int tpg = tpp / G;  // chunk-threads per group within a pixel
+  // fold the pixel dimension (stride stays a multiple of tpp, so a thread keeps its channel chunk); fixed order
+  for (int stride = 128; stride >= tpp; stride >>= 1) {
+    if (static_cast<int>(threadIdx.x) < stride) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + stride];
+      red[1][threadIdx.x] += red[1][threadIdx.x + stride];
+    }
+    __syncthreads();
+  }
+  if (static_cast<int>(threadIdx.x) < G) {
+    const int tpg = tpp / G;  // channel chunks per group
     float a = 0.f, b = 0.f;
-    for (int t = 0; t < ppi * tpp; ++t)
-      if ((t % tpp) / tpg == static_cast<int>(threadIdx.x)) { a += red[t][0]; b += red[t][1]; }
+    for (int t = 0; t < tpg; ++t) { a += red[0][threadIdx.x * tpg + t]; b += red[1][threadIdx.x * tpg + t]; }
     float* o = part + ((static_cast<long long>(n) * nsplit + split) * G + threadIdx.x) * 2;
     o[0] = a; o[1] = b;
   }
 }
-__global__ void gn_stats_final_kernel(const float* __restrict__ part, float2* __restrict__ stats /* [N, G] (mean, rstd) */, int G,
-                                      int nsplit, double count, float eps, int total) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n * G + g
+// one warp per (image, group): fp64 accumulation of the per-slab partials, fixed order within a lane + shuffle tree
+__global__ void __launch_bounds__(128) gn_stats_final_kernel(const float* __restrict__ part, float2* __restrict__ stats /* [N, G] (mean, rstd) */,
+                                                             int G, int nsplit, double count, float eps, int total) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // n * G + g
+  const int lane = threadIdx.x & 31;
   if (i >= total) return;
   const int n = i / G, g = i - n * G;
   double a = 0.0, b = 0.0;
-  for (int sidx = 0; sidx < nsplit; ++sidx) {
+  for (int sidx = lane; sidx < nsplit; sidx += 32) {
     const float* o = part + ((static_cast<long long>(n) * nsplit + sidx) * G + g) * 2;
     a += o[0]; b += o[1];
   }
-  const double mean = a / count;
-  const double var = fmax(b / count - mean * mean, 0.0);
-  stats[i] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+  }
+  if (lane == 0) {
+    const double mean = a / count;
+    const double var = fmax(b / count - mean * mean, 0.0);
+    stats[i] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+  }
 }
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
                                                        const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                                                        const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, long long total8,
                                                        int HW, int C, int G, int act) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
+  constexpr int U = 4;  // 16-byte chunks per thread, a CTA-wide stride apart (coalesced), all loads issued first
+  const long long base = static_cast<long long>(blockIdx.x) * (blockDim.x * U) + threadIdx.x;
   const int tpp = C >> 3;
-  const int cg = static_cast<int>(i % tpp);
-  const int n = static_cast<int>(i / (static_cast<long long>(HW) * tpp));
-  const float2 st = stats[n * G + cg / (tpp / G)];
-  float f[8], ga[8], be[8];
-  unpack8(ld_stream(reinterpret_cast<const uint4*>(x) + i), f);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + cg), ga);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + cg), be);
+  uint4 q[U], r[U];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float v = (f[j] - st.x) * st.y * ga[j] + be[j];
-    if (act == 1) v = fmaxf(v, 0.f);
-    else if (act == 2) v = silu_f(v);
-    f[j] = v;
+  for (int u = 0; u < U; ++u) {
+    const long long i = base + static_cast<long long>(u) * blockDim.x;
+    if (i < total8) {
+      q[u] = ld_stream(reinterpret_cast<const uint4*>(x) + i);
+      if (residual != nullptr) r[u] = ld_stream(reinterpret_cast<const uint4*>(residual) + i);
+    }
   }
-  if (residual != nullptr) {
-    float r[8];
-    unpack8(ld_stream(reinterpret_cast<const uint4*>(residual) + i), r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] += r[j];
+  for (int u = 0; u < U; ++u) {
+    const long long i = base + static_cast<long long>(u) * blockDim.x;
+    if (i >= total8) continue;
+    const int cg = static_cast<int>(i % tpp);
+    const int n = static_cast<int>(i / (static_cast<long long>(HW) * tpp));
+    const float2 st = stats[n * G + cg / (tpp / G)];
+    float f[8], ga[8], be[8];
+    unpack8(q[u], f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + cg), ga);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + cg), be);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = (f[j] - st.x) * st.y * ga[j] + be[j];
+      if (act == 1) v = fmaxf(v, 0.f);
+      else if (act == 2) v = silu_f(v);
+      f[j] = v;
+    }
+    if (residual != nullptr) {
+      float rr[8];
+      unpack8(r[u], rr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += rr[j];
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(f);
   }
-  reinterpret_cast<uint4*>(y)[i] = pack8(f);
 }
 
 }  // namespace x2i

@@ -203,7 +203,11 @@ class FluxPipeline:
     def __call__(self, prompt=None, prompt_2=None, height: Optional[int] = None, width: Optional[int] = None,
                  num_inference_steps: int = 28, timesteps=None, guidance_scale: float = 3.5, num_images_per_prompt: int = 1,
                  generator=None, latents=None, prompt_embeds=None, pooled_prompt_embeds=None, output_type: str = "pil",
-                 return_dict: bool = True, joint_attention_kwargs=None, max_sequence_length: int = 512, **kw):
+                 return_dict: bool = True, joint_attention_kwargs=None, max_sequence_length: int = 512, guided_hint=None,
+                 control_nets=None, **kw):
+        """guided_hint [B,3,H,W] / control_nets (ModuleList of ControlNeXtModel): the LightControl editing branch; they are handed
+        to the transformer every step exactly as lightcontrol/train_lightcontrol.py:732-743 does (the reference ships no
+        LightControl inference script; BASELINE config 5 = 20 Euler steps of this call)."""
         if prompt is not None or prompt_embeds is None or pooled_prompt_embeds is None:
             raise X2IError("FluxPipeline (x2i_b200): text encoders are out of scope; pass prompt_embeds and "
                            "pooled_prompt_embeds as the X2I inference scripts do")
@@ -235,7 +239,8 @@ class FluxPipeline:
             noise_pred = self.transformer(hidden_states=latents, timestep=timestep / 1000, guidance=guidance,
                                           pooled_projections=pooled_prompt_embeds, encoder_hidden_states=prompt_embeds,
                                           txt_ids=text_ids, img_ids=latent_image_ids,
-                                          joint_attention_kwargs=joint_attention_kwargs, return_dict=False)[0]
+                                          joint_attention_kwargs=joint_attention_kwargs, guided_hint=guided_hint,
+                                          control_nets=control_nets, return_dict=False)[0]
             latents = self.scheduler.step(noise_pred, ts[i], latents, return_dict=False)[0]
         if not return_dict:
             return (latents,)
