@@ -129,3 +129,26 @@ def test_resampler_surface_and_pos_table(golden_dir):
         Resampler(num_queries=8, embed_dim=96, num_heads=2)   # head_dim must be 128
     with pytest.raises(X2IError):
         m(torch.randn(3, 14, 48), g["tgt_sizes"])              # no CPU path
+
+
+def test_projector_bundle_and_checkpoint_formats(tmp_path):
+    """On-disk contracts: the trainer's {step}/diffusion_pytorch_model.bin with DDP 'module.' prefixes
+    (train_qwenvl.py:641-647, inference_qwenvl.py:85-91) and the ComfyUI {"config","state_dict"} bundle (x2i_comfyui/model.py:33-39)."""
+    import torch
+    from x2i_b200 import proj as xproj, train
+    p = xproj.create_proj_internvl1b(5, use_t5=False, use_scale=False, use_cnn=True)
+    fn = train.save_projector_checkpoint(p, str(tmp_path), 1300)
+    assert fn.endswith("1300/diffusion_pytorch_model.bin")
+    sd = torch.load(fn)
+    q = xproj.create_proj_internvl1b(5, use_t5=False, use_scale=False, use_cnn=True)
+    xproj.load_projector_state(q, {"module." + k: v for k, v in sd.items()})
+    for a, b in zip(p.state_dict().values(), q.state_dict().values()):
+        assert torch.equal(a, b)
+    bundle = str(tmp_path / "proj.pt")
+    xproj.save_projector_bundle(p, bundle)
+    r = xproj.load_projector_bundle(bundle, device=None)
+    assert type(r) is xproj.Proj7Exp and r.use_cnn and not r.use_scale
+    for a, b in zip(p.state_dict().values(), r.state_dict().values()):
+        assert torch.equal(a, b)
+    d = torch.load(bundle, weights_only=True)
+    assert set(d) == {"config", "state_dict"} and d["config"]["in_channels"] == 5 and d["config"]["input_dim"] == 896

@@ -180,3 +180,23 @@ def load_projector_state(module: nn.Module, state_dict) -> nn.Module:
     sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in state_dict.items()}
     module.load_state_dict(sd)
     return module
+
+
+# ---- ComfyUI bundle format (x2i_comfyui/model.py:33-39, :89-97): {"config": ctor kwargs, "state_dict": ...} in one .pt -------
+def load_projector_bundle(path: str, device="cuda") -> Proj7Exp:
+    """``Proj.load(path)`` of the ComfyUI nodes: build the projector from the bundle's config and load its weights."""
+    all_dict = torch.load(path, map_location="cpu", weights_only=True)
+    proj = Proj7Exp(**all_dict["config"])
+    load_projector_state(proj, all_dict["state_dict"])
+    return proj.eval().to(device, BF16) if device is not None else proj.eval()
+
+
+def save_projector_bundle(proj: Proj7Exp, path: str, config: dict | None = None) -> None:
+    """``Proj.transfrom(config, state_path, save_path)``: write {"config", "state_dict"}; config defaults to the module's own."""
+    if config is None:
+        m = proj.mlp
+        config = dict(in_channels=(proj.cha_scale.shape[1] if proj.use_scale else proj.conv.in_channels if proj.use_cnn else 1),
+                      kernel_size=5, input_dim=m.layernorm.normalized_shape[0], output_dim0=m.fc[1].out_features,
+                      output_dim1=m.projector[2].out_features, num_layers=2, num_heads=16, norm_eps=m.layernorm.eps, head_dim=128,
+                      use_t5=False, use_scale=proj.use_scale, use_cnn=proj.use_cnn)
+    torch.save({"config": config, "state_dict": {k: v.detach().cpu() for k, v in proj.state_dict().items()}}, path)
