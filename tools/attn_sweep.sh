@@ -1,0 +1,7 @@
+#!/bin/bash
+# Times the attention kernel variants (env-selected instantiations) in separate processes; output in gpurun_out/attn_sweep.log
+out=gpurun_out/attn_sweep.log; : > $out
+run() { echo "### $*" >> $out; env "$@" timeout 120 python tools/gpu_check.py --one attn_variants 2>&1 | grep -E "RESULT|ATTTRACE|rror" >> $out; }
+if [ $# -eq 0 ]; then set -- "X2I_ATTN_POLY8=0"; fi
+for v in "$@"; do run $v; done
+cat $out

@@ -28,24 +28,52 @@ struct AttnParams {
   long long ld1;
   float* lse;  // optional (training): lse[(b*H + h) * Lpad + pos] = log2-domain log-sum-exp of row pos (+inf for pos >= L)
   int Lpad;    // row stride of lse (L rounded up to 128)
+  long long* trace;  // diagnostics only (DBG == 1 instantiation): clock64 stamps of CTA (0,0,0)
 };
+#define ATT_STAMP(slot) do { if constexpr (DBG == 1) { if (trace != nullptr && lane == 0) trace[slot] = clock64(); } } while (0)
 
 constexpr int ATT_THREADS = 320;
+constexpr int ATT_DEFAULT_POLY8 = 1;  // production instantiation (see capi.cu)
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 128B-swizzled boxes of [128 rows x 64 cols]
 constexpr int ATT_KV_SLOTS = 4;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + ATT_KV_SLOTS * ATT_TILE_BYTES + 1024 + 256;
 
+// exp2(x * sc - m) of one half (HALF = 0 / 1) of a 32-score quarter -> 8 of its 16 packed bf16x2 words + packed partial sums
+template <int POLY8, int DBG, int HALF>
+__device__ __forceinline__ void exp_half(const uint32_t (&x)[32], uint64_t sc2, uint64_t nm2, uint64_t (&sum2)[4], uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int k = 8 * HALF; k < 8 * HALF + 8; ++k) {
+    const uint64_t a2 = fma_f32x2(pack_f32x2(__uint_as_float(x[2 * k]), __uint_as_float(x[2 * k + 1])), sc2, nm2);
+    float a0, a1, p0, p1;
+    unpack_f32x2(a2, a0, a1);
+    if constexpr (DBG == 2) {  // timing experiment: no exponentials at all
+      p0 = a0;
+      p1 = a1;
+    } else if ((k & 3) < POLY8) {  // POLY8 of every 4 pairs: exp2 on the FMA pipe instead of MUFU
+      poly_exp2_x2(a0, a1, p0, p1);
+    } else {
+      p0 = fast_exp2(a0);
+      p1 = fast_exp2(a1);
+    }
+    sum2[k & 3] = add_f32x2(sum2[k & 3], pack_f32x2(p0, p1));
+    pk[k] = pack_bf16x2(p0, p1);
+  }
+}
+
 // One online-softmax step of one query row over a 128-key tile (executed by the 128 threads of a softmax warpgroup).
 // MASKED is instantiated only for the last, ragged key tile so the common path carries no masking instructions.
-template <int POLY8, bool MASKED>
+template <int POLY8, bool MASKED, int DBG>
 __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, int j, int valid,
-                                             float sc, float& m_run, float& l_run, int lane) {
+                                             float sc, float& m_run, float& l_run, int lane, long long* trace) {
+  ATT_STAMP(0);
   mbar_wait(s_full_i, j & 1);
   tc_fence_after();
+  ATT_STAMP(1);
   uint32_t r[4][32];
 #pragma unroll
   for (int c = 0; c < 4; ++c) tmem_ld32(t_s + c * 32, r[c]);
   tmem_ld_wait();
+  ATT_STAMP(2);
   if constexpr (MASKED) {  // keys >= valid were zero-filled by TMA: exclude them
 #pragma unroll
     for (int c = 0; c < 4; ++c)
@@ -59,7 +87,8 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
 #pragma unroll
     for (int k = 0; k < 32; k += 2)
       mx4[(k >> 1) & 3] = max3f(mx4[(k >> 1) & 3], __uint_as_float(r[c][k]), __uint_as_float(r[c][k + 1]));
-  const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+  float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+  if constexpr (DBG == 3) mx = 4.0f / sc;  // timing experiment: no max phase
   const float m_cand = fmaxf(m_run, mx * sc);
   float alpha = 1.0f;
   bool rescale = false;
@@ -83,38 +112,53 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
       tmem_st32(t_o + c * 32, o);
     }
   }
+  ATT_STAMP(3);
   const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_run, -m_run);
   uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};  // packed (FADD2) partial row sums, 4 independent chains
+  // Second pass, quarter by quarter (32 keys each), software-pipelined by hand because the TMEM store -> wait::st -> fence ->
+  // mbarrier arrive sequence costs ~120 cycles in which the MUFU pipe would idle:
+  //   * quarter 0 is still in registers from the max pass; quarter c+1 is re-read from TMEM in the MIDDLE of quarter c, after
+  //     the store of P quarter c-1 in program order, so ptxas cannot hoist its exponentials above that store (with all 128
+  //     scores live in registers it sank every store to the end of the step and serialised the PV MMAs behind the soft-max);
+  //   * the completion wait + hand-off of quarter c-1 is deferred to the middle of quarter c, when its store has long landed.
+  // P quarter c (columns [16c,16c+16)) only overwrites S columns of quarters <= c/2, which have been consumed.
+  uint32_t rq[2][32];
+  uint32_t pk[16];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    uint32_t pk[16];
+    const uint32_t(&x)[32] = c == 0 ? r[0] : rq[c & 1];
+    if (c > 0) {
+      tmem_ld_wait();
+      if constexpr (MASKED) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const uint64_t a2 = fma_f32x2(pack_f32x2(__uint_as_float(r[c][2 * k]), __uint_as_float(r[c][2 * k + 1])), sc2, nm2);
-      float a0, a1, p0, p1;
-      unpack_f32x2(a2, a0, a1);
-      if ((k & 3) < POLY8) {  // POLY8 of every 4 pairs: exp2 on the FMA pipe instead of MUFU
-        poly_exp2_x2(a0, a1, p0, p1);
-      } else {
-        p0 = fast_exp2(a0);
-        p1 = fast_exp2(a1);
+        for (int k = 0; k < 32; ++k)
+          if (c * 32 + k >= valid) rq[c & 1][k] = 0xff800000u;
       }
-      sum2[k & 3] = add_f32x2(sum2[k & 3], pack_f32x2(p0, p1));
-      pk[k] = pack_bf16x2(p0, p1);
     }
+    exp_half<POLY8, DBG, 0>(x, sc2, nm2, sum2, pk);
+    if (c > 0) {
+      tmem_st_wait();  // store of quarter c-1, issued half a quarter ago
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full_i[c - 1]);
+      ATT_STAMP(3 + c);
+    }
+    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, rq[(c + 1) & 1]);
+    exp_half<POLY8, DBG, 1>(x, sc2, nm2, sum2, pk);
     tmem_st16(t_s + c * 16, pk);  // P_i aliases S_i columns [0, 64)
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&p_full_i[c]);  // this quarter of P is ready for its two PV MMAs
   }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&p_full_i[3]);
+  ATT_STAMP(7);
   float s0, s1;
   unpack_f32x2(add_f32x2(add_f32x2(sum2[0], sum2[1]), add_f32x2(sum2[2], sum2[3])), s0, s1);
   l_run = l_run * alpha + (s0 + s1);
 }
 
 // POLY8: how many of every 4 element PAIRS of the softmax use the FMA-pipe poly_exp2_x2 instead of MUFU.EX2.
-template <int POLY8>
+template <int POLY8, int DBG = 0>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                            const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -225,12 +269,17 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
       issue_s(1, 0);
       umma_commit_w(&s_full[1]);
       umma_commit_w(&kv_empty[0]);
+      long long* const trace_base = (DBG == 1 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.trace : nullptr;
       for (int j = 0; j < n_kv; ++j) {
+        long long* const trace = (trace_base != nullptr && j < 16) ? trace_base + 512 + j * 8 : nullptr;
         const int vseq = 2 * j + 1, kseq = 2 * j + 2;
         const int vslot = vseq & (ATT_KV_SLOTS - 1), kslot = kseq & (ATT_KV_SLOTS - 1);
         const bool more = (j + 1 < n_kv);
+        ATT_STAMP(0);
         kv_wait(vseq);
+        ATT_STAMP(1);
         issue_pv(0, vslot, j > 0, j & 1);
+        ATT_STAMP(2);
         if (!more) umma_commit_w(&o_full[0]);
         if (more) {
           kv_wait(kseq);
@@ -238,7 +287,9 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
           issue_s(0, kslot);
           umma_commit_w(&s_full[0]);
         }
+        ATT_STAMP(3);
         issue_pv(1, vslot, j > 0, j & 1);
+        ATT_STAMP(4);
         if (!more) umma_commit_w(&o_full[1]);
         umma_commit_w(&kv_empty[vslot]);
         if (more) {
@@ -246,6 +297,7 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
           umma_commit_w(&s_full[1]);
           umma_commit_w(&kv_empty[kslot]);
         }
+        ATT_STAMP(5);
       }
     }
   } else {
@@ -262,16 +314,20 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
 
     const bool ragged = (kv_valid & 127) != 0;
     const int n_full = ragged ? n_kv - 1 : n_kv;
+    const bool traced = DBG == 1 && quad == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && p.trace != nullptr;
     for (int j = 0; j < n_full; ++j)
-      softmax_step<POLY8, false>(t_s, t_o, &s_full[i], &p_full[i * 4], j, 128, sc, m_run, l_run, lane);
+      softmax_step<POLY8, false, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], j, 128, sc, m_run, l_run, lane,
+                                      (traced && j < 16) ? p.trace + (i * 16 + j) * 8 : nullptr);
     if (ragged)
-      softmax_step<POLY8, true>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, kv_valid - (n_kv - 1) * 128, sc, m_run, l_run, lane);
+      softmax_step<POLY8, true, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, kv_valid - (n_kv - 1) * 128, sc, m_run, l_run, lane,
+                                     nullptr);
     // ---- epilogue: O_i / l -> bf16 -> global (token-major [.., H*128] so the out-projection GEMM reads it as A)
     mbar_wait(&o_full[i], 0);  // committed once, after the last PV MMA of this tile
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const bool ok = pos < p.L;
-    if (p.lse != nullptr && pos < p.Lpad) p.lse[static_cast<long long>(bh) * p.Lpad + pos] = ok ? m_run + log2f(l_run) : INFINITY;
+    if (p.lse != nullptr && pos < p.Lpad)
+      p.lse[static_cast<long long>(bh) * p.Lpad + pos] = ok ? m_run + log2f(l_run) : INFINITY;
     __nv_bfloat16* dst;
     if (pos < p.split)
       dst = p.out0 + (static_cast<long long>(b) * p.split + pos) * p.ld0 + h * 128;

@@ -1,5 +1,6 @@
 // C ABI of libx2i_b200.so (see include/x2i_b200.h).  Host side only: argument checks, TMA descriptors, launches.
 #include <atomic>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -525,14 +526,23 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.ld0 = ld0; p.split = split;
   p.out1 = static_cast<__nv_bfloat16*>(out1); p.ld1 = ld1;
   p.lse = lse; p.Lpad = (L + 127) / 128 * 128;
-  static const int poly8 = []() { const char* e = getenv("X2I_ATTN_POLY8"); return e ? atoi(e) : 0; }();
-  auto kern = mmdit_attention_fwd_kernel<0>;
-  switch (poly8) {
-    case 1: kern = mmdit_attention_fwd_kernel<1>; break;
-    case 2: kern = mmdit_attention_fwd_kernel<2>; break;
-    case 3: kern = mmdit_attention_fwd_kernel<3>; break;
-    case 4: kern = mmdit_attention_fwd_kernel<4>; break;
-    default: break;
+  // Variant selection.  Production = the defaults; the env overrides exist for tools/attn_sweep.sh.  X2I_ATTN_DBG=1 prints
+  // a clock64 trace of CTA (0,0,0) to stderr after a synchronous launch; 2 / 3 are timing experiments with wrong results.
+  static const int poly8 = []() { const char* e = getenv("X2I_ATTN_POLY8"); return e ? atoi(e) : ATT_DEFAULT_POLY8; }();
+  static const int dbg = []() { const char* e = getenv("X2I_ATTN_DBG"); return e ? atoi(e) : 0; }();
+  using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
+  KernT kern = nullptr;
+#define ATT_PICK(P, D) if (poly8 == P && dbg == D) kern = mmdit_attention_fwd_kernel<P, D>
+  ATT_PICK(0, 0); ATT_PICK(1, 0); ATT_PICK(2, 0);
+  ATT_PICK(0, 1); ATT_PICK(1, 1); ATT_PICK(0, 2); ATT_PICK(0, 3);
+#undef ATT_PICK
+  if (!kern) return fail(X2I_ERR_SHAPE, "attention: no kernel instantiation for POLY8=%d DBG=%d", poly8, dbg);
+  static long long* trace_dev = nullptr;
+  p.trace = nullptr;
+  if (dbg == 1) {
+    if (!trace_dev) cudaMalloc(&trace_dev, 1024 * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, 1024 * sizeof(long long), static_cast<cudaStream_t>(stream));
+    p.trace = trace_dev;
   }
   static std::atomic<bool> att_configured[16];
   if (!att_configured[d->index].load(std::memory_order_acquire)) {
@@ -542,6 +552,24 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
   }
   dim3 grid((L + 255) / 256, heads, B);
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  if (dbg == 1) {
+    static int dumps = 0;
+    std::vector<long long> h(1024);
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    cudaMemcpy(h.data(), trace_dev, 1024 * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (++dumps == 3) {  // third launch: warm
+      long long t0 = h[512];
+      for (int j = 0; j < 16; ++j) {
+        fprintf(stderr, "ATTTRACE j=%2d mma:", j);
+        for (int s = 0; s < 6; ++s) fprintf(stderr, " %6lld", h[512 + j * 8 + s] - t0);
+        for (int i = 0; i < 2; ++i) {
+          fprintf(stderr, " | sm%d:", i);
+          for (int s = 0; s < 8; ++s) fprintf(stderr, " %6lld", h[(i * 16 + j) * 8 + s] - t0);
+        }
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return check_launch("mmdit_attention_fwd_kernel");
 }
 }  // namespace
