@@ -291,10 +291,22 @@ int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* 
  * w fp32 [64,3,3,3] (PyTorch layout), bias fp32 [64].                                                                  */
 int x2i_conv_first(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, void* stream);
 /* nn.GroupNorm on NHWC bf16 + activation (0 none, 1 ReLU, 2 SiLU) + optional residual add: y = act(GN(x)) + residual.
- * gamma/beta bf16 [C]; C in {64,128,256}; workspace of x2i_groupnorm_workspace_floats() floats.  Deterministic.        */
+ * gamma/beta bf16 [C]; C % 64 == 0, C <= 2048, groups of 4 or a multiple of 8 channels; workspace of
+ * x2i_groupnorm_workspace_floats() floats.  Deterministic.                                                                */
 int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
                        int HW, int C, int G, float eps, int act, void* stream);
 int64_t x2i_groupnorm_workspace_floats(int Nimg, int HW, int G);
+
+/* ---- VAE decoder (reference call site infer/inference_qwenvl.py:209-216: vae.decode(latents)) ----------
+ * The decoder's convolutions and GroupNorms run through x2i_conv2d_nhwc / x2i_groupnorm_nhwc (C up to 2048, groups of 4 or a
+ * multiple of 8 channels); these three cover what is left of diffusers' AutoencoderKL decoder [D031].
+ * C32[M, ldc] (fp32) = alpha * A[M,K] W[N,K]^T: the attention scores of the single-head d=512 mid-block attention.           */
+int x2i_gemm_f32(const void* A, int64_t lda, const void* W, int64_t ldw, float* C32, int64_t ldc, int M, int N, int K, float alpha,
+                 void* stream);
+/* P[r, :] (bf16) = softmax(S[r, :]) over fp32 scores; cols % 4 == 0, cols <= 16384.                                           */
+int x2i_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int rows, int cols, void* stream);
+/* Upsample2D's F.interpolate(scale_factor=2, mode="nearest") on NHWC bf16: out [N, 2H, 2W, C].                              */
+int x2i_upsample2x_nhwc(const void* x, void* out, int Nimg, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1092,23 +1092,61 @@ int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const
                        int HW, int C, int G, float eps, int act, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
-  if (Nimg <= 0 || HW <= 0 || (C != 64 && C != 128 && C != 256) || G <= 0 || (C / 8) % G) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: C in {64,128,256}, (C/8) %% G == 0");
+  const bool sub2 = G > 0 && C == 4 * G;  // groups of 4 channels
+  if (Nimg <= 0 || HW <= 0 || C % 64 || C <= 0 || C > 2048 || G <= 0 || (!sub2 && (C / 8) % G))
+    return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: C %% 64 == 0, C <= 2048 and groups of 4 or a multiple of 8 channels (C=%d G=%d)", C, G);
   if (!x || !gamma || !beta || !y || !workspace) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: null buffer");
   if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(residual) || !aligned16(y) || !aligned16(workspace)) return fail(X2I_ERR_ALIGN, "groupnorm_nhwc: alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nsplit = (HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA;
   float* part = workspace;
   float2* stats = reinterpret_cast<float2*>(workspace + static_cast<long long>(Nimg) * nsplit * G * 2);
-  gn_stats_partial_kernel<<<dim3(nsplit, Nimg), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, nsplit);
+  if (sub2)
+    gn_stats_partial_kernel<2><<<dim3(nsplit, Nimg), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, nsplit);
+  else
+    gn_stats_partial_kernel<1><<<dim3(nsplit, Nimg), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, nsplit);
   if (int rc = check_launch("gn_stats_partial_kernel")) return rc;
   gn_stats_final_kernel<<<(Nimg * G + 3) / 4, 128, 0, st>>>(part, stats, G, nsplit, static_cast<double>(HW) * (C / G), eps, Nimg * G);
   if (int rc = check_launch("gn_stats_final_kernel")) return rc;
   const long long total8 = static_cast<long long>(Nimg) * HW * (C / 8);
-  gn_apply_kernel<<<static_cast<unsigned>((total8 + 1023) / 1024), 256, 0, st>>>(
+  auto apply = sub2 ? gn_apply_kernel<2> : gn_apply_kernel<1>;
+  apply<<<static_cast<unsigned>((total8 + 1023) / 1024), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), stats, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta),
       static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), total8, HW, C, G, act);
   return check_launch("gn_apply_kernel");
 }
+int x2i_gemm_f32(const void* A, int64_t lda, const void* W, int64_t ldw, float* C32, int64_t ldc, int M, int N, int K, float alpha,
+                 void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!C32 || !aligned16(C32) || ldc % 4) return fail(X2I_ERR_ALIGN, "gemm_f32: C alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.c32 = C32; p.ldc32 = ldc; p.alpha = alpha;
+  return launch_gemm<EPI_BIAS>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+int x2i_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int rows, int cols, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || cols <= 0 || cols % 4 || cols > 256 * 4 * SM_VEC) return fail(X2I_ERR_SHAPE, "softmax_rows: cols %% 4 == 0 and cols <= %d", 256 * 4 * SM_VEC);
+  if (!S || !P || !aligned16(S) || !aligned16(P) || lds % 4 || ldp % 8) return fail(X2I_ERR_ALIGN, "softmax_rows: alignment");
+  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, static_cast<__nv_bfloat16*>(P), ldp, cols);
+  return check_launch("softmax_rows_kernel");
+}
+
+int x2i_upsample2x_nhwc(const void* x, void* out, int Nimg, int H, int W, int C, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (Nimg <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return fail(X2I_ERR_SHAPE, "upsample2x_nhwc: C %% 8 == 0");
+  if (!x || !out || !aligned16(x) || !aligned16(out)) return fail(X2I_ERR_ALIGN, "upsample2x_nhwc: alignment");
+  const long long total8 = 4LL * Nimg * H * W * (C / 8);
+  upsample2x_nhwc_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(out), total8, H, W, C / 8);
+  return check_launch("upsample2x_nhwc_kernel");
+}
+
 int64_t x2i_groupnorm_workspace_floats(int Nimg, int HW, int G) {
   const int nsplit = (HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA;
   return 2LL * Nimg * nsplit * G + 2LL * Nimg * G + 8;

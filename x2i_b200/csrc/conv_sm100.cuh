@@ -197,15 +197,17 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const __nv_bfloat16* __
 // GroupNorm on NHWC bf16 (nn.GroupNorm of ControlNeXt: 2 / 4 / 8 groups): deterministic two-stage statistics + one
 // fused apply pass  y = act((x - mean) * rstd * gamma + beta) (+ residual).  act: 0 none, 1 ReLU, 2 SiLU.
 constexpr int GN_PIX_PER_CTA = 256;
+// SUB == 2: groups of 4 channels (the VAE's GroupNorm(32, 128)): a thread's 8-channel chunk covers two groups.
+template <int SUB>
 __global__ void __launch_bounds__(256) gn_stats_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part /* [N, nsplit, G, 2] */,
                                                                int HW, int C, int G, int nsplit) {
-  __shared__ float red[2][256];
+  __shared__ float red[2 * SUB][256];
   const int tpp = C >> 3;            // threads per pixel (16-byte chunks): 8, 16 or 32
   const int ppi = 256 / tpp;         // pixels per CTA iteration
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   const int split = blockIdx.x, n = blockIdx.y;
   const int p0 = split * GN_PIX_PER_CTA, p1 = min(p0 + GN_PIX_PER_CTA, HW);
-  float s = 0.f, ss = 0.f;
+  float s = 0.f, ss = 0.f, s_hi = 0.f, ss_hi = 0.f;
   const __nv_bfloat16* xb = x + static_cast<long long>(n) * HW * C + cg * 8;
   for (int pp = p0 + pl; pp < p1; pp += 4 * ppi) {  // 4 independent 16-byte loads in flight
     uint4 q[4];
@@ -215,20 +217,37 @@ __global__ void __launch_bounds__(256) gn_stats_partial_kernel(const __nv_bfloat
     for (int u = 0; u < 4; ++u) {
       float f[8];
       unpack8(q[u], f);
+      if constexpr (SUB == 1) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s += f[j]; ss += f[j] * f[j]; }
+        for (int j = 0; j < 8; ++j) { s += f[j]; ss += f[j] * f[j]; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s += f[j]; ss += f[j] * f[j]; s_hi += f[j + 4]; ss_hi += f[j + 4] * f[j + 4]; }
+      }
     }
   }
   red[0][threadIdx.x] = s;
   red[1][threadIdx.x] = ss;
+  if constexpr (SUB == 2) {
+    red[2][threadIdx.x] = s_hi;
+    red[3][threadIdx.x] = ss_hi;
+  }
   __syncthreads();
   // fold the pixel dimension (stride stays a multiple of tpp, so a thread keeps its channel chunk); fixed order
   for (int stride = 128; stride >= tpp; stride >>= 1) {
     if (static_cast<int>(threadIdx.x) < stride) {
-      red[0][threadIdx.x] += red[0][threadIdx.x + stride];
-      red[1][threadIdx.x] += red[1][threadIdx.x + stride];
+#pragma unroll
+      for (int q = 0; q < 2 * SUB; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + stride];
     }
     __syncthreads();
+  }
+  if constexpr (SUB == 2) {
+    if (static_cast<int>(threadIdx.x) < G) {  // group g = channel chunk g / 2, half g & 1
+      float* o = part + ((static_cast<long long>(n) * nsplit + split) * G + threadIdx.x) * 2;
+      o[0] = red[2 * (threadIdx.x & 1)][threadIdx.x >> 1];
+      o[1] = red[2 * (threadIdx.x & 1) + 1][threadIdx.x >> 1];
+    }
+    return;
   }
   if (static_cast<int>(threadIdx.x) < G) {
     const int tpg = tpp / G;  // channel chunks per group
@@ -261,6 +280,7 @@ __global__ void __launch_bounds__(128) gn_stats_final_kernel(const float* __rest
     stats[i] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
   }
 }
+template <int SUB>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
                                                        const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                                                        const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, long long total8,
@@ -283,14 +303,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
     if (i >= total8) continue;
     const int cg = static_cast<int>(i % tpp);
     const int n = static_cast<int>(i / (static_cast<long long>(HW) * tpp));
-    const float2 st = stats[n * G + cg / (tpp / G)];
+    float2 st, st_hi;
+    if constexpr (SUB == 1) {
+      st = stats[n * G + cg / (tpp / G)];
+      st_hi = st;
+    } else {
+      st = stats[n * G + 2 * cg];
+      st_hi = stats[n * G + 2 * cg + 1];
+    }
     float f[8], ga[8], be[8];
     unpack8(q[u], f);
     unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + cg), ga);
     unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + cg), be);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = (f[j] - st.x) * st.y * ga[j] + be[j];
+      float v = (f[j] - (j < 4 ? st.x : st_hi.x)) * (j < 4 ? st.y : st_hi.y) * ga[j] + be[j];
       if (act == 1) v = fmaxf(v, 0.f);
       else if (act == 2) v = silu_f(v);
       f[j] = v;
@@ -302,6 +329,84 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
       for (int j = 0; j < 8; ++j) f[j] += rr[j];
     }
     reinterpret_cast<uint4*>(y)[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Nearest-neighbour 2x upsampling on NHWC bf16 (Upsample2D of the VAE decoder, F.interpolate(scale_factor=2, mode="nearest")):
+// out[n, y, x, :] = in[n, y / 2, x / 2, :].  One 16-byte chunk per thread, writes coalesced.
+__global__ void __launch_bounds__(256) upsample2x_nhwc_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long total8, int H, int W,
+                                                              int c8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c = static_cast<int>(i % c8);
+  long long pix = i / c8;
+  const int xo = static_cast<int>(pix % (2 * W));
+  pix /= 2 * W;
+  const int yo = static_cast<int>(pix % (2 * H));
+  const long long n = pix / (2 * H);
+  out[i] = __ldg(in + ((n * H + (yo >> 1)) * W + (xo >> 1)) * c8 + c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row soft-max of fp32 scores -> bf16 probabilities (the single-head, d = 512 self-attention of the VAE mid block, whose
+// scores come from a GEMM with fp32 output): P[r, :] = softmax(S[r, :]).  One CTA per row, the row lives in registers
+// (cols <= 256 * 4 * SM_VEC).
+constexpr int SM_VEC = 16;  // float4 loads per thread -> up to 16384 columns
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* __restrict__ P, long long ldp,
+                                                           int cols) {
+  __shared__ float red[8];
+  const float* s = S + static_cast<long long>(blockIdx.x) * lds;
+  __nv_bfloat16* o = P + static_cast<long long>(blockIdx.x) * ldp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 v[SM_VEC];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < SM_VEC; ++u) {
+    const int c = (u * 256 + threadIdx.x) * 4;
+    if (c < cols) {
+      v[u] = *reinterpret_cast<const float4*>(s + c);
+      mx = fmaxf(fmaxf(mx, fmaxf(v[u].x, v[u].y)), fmaxf(v[u].z, v[u].w));
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  const float l2e = 1.4426950408889634f;
+#pragma unroll
+  for (int u = 0; u < SM_VEC; ++u) {
+    const int c = (u * 256 + threadIdx.x) * 4;
+    if (c < cols) {
+      v[u].x = fast_exp2((v[u].x - mx) * l2e);
+      v[u].y = fast_exp2((v[u].y - mx) * l2e);
+      v[u].z = fast_exp2((v[u].z - mx) * l2e);
+      v[u].w = fast_exp2((v[u].w - mx) * l2e);
+      sum += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];  // fixed order: deterministic
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int u = 0; u < SM_VEC; ++u) {
+    const int c = (u * 256 + threadIdx.x) * 4;
+    if (c < cols) {
+      uint2 w2;
+      w2.x = pack_bf16x2(v[u].x * inv, v[u].y * inv);
+      w2.y = pack_bf16x2(v[u].z * inv, v[u].w * inv);
+      *reinterpret_cast<uint2*>(o + c) = w2;
+    }
   }
 }
 

@@ -58,6 +58,10 @@ struct GemmParams {
   long long ldmlp_pre;
   // EPI_BIAS: aux_act selects the activation of the second output (0/2 gelu_erf, 1 gelu_tanh)
   int aux_act;
+  // EPI_BIAS with an fp32 destination (attention scores of the VAE mid block): C32 = alpha * (acc + bias); C is not written
+  float* c32;
+  long long ldc32;
+  float alpha;
   // EPI_DACT: pre-activation [M, ldpre] (column n - n_split), derivative kind dact (1 tanh-GELU, 2 erf-GELU), addend = residual
   const __nv_bfloat16* pre;
   long long ldpre;
@@ -228,6 +232,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
       }
       if (row_ok) {
         if constexpr (EPI == EPI_BIAS) {
+          if (p.c32 != nullptr) {
+            float4* d4 = reinterpret_cast<float4*>(p.c32 + static_cast<long long>(m) * p.ldc32 + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d4[j] = make_float4(x[4 * j] * p.alpha, x[4 * j + 1] * p.alpha, x[4 * j + 2] * p.alpha, x[4 * j + 3] * p.alpha);
+            continue;
+          }
           if (p.aux != nullptr) {  // second output: gelu_erf(C) (projector: MLP3.fc consumes GELU(x2), utils/proj.py:31)
             float g[32];
             if (p.aux_act == 1) {

@@ -583,3 +583,39 @@ def groupnorm_nhwc(x, gamma, beta, groups, eps, act=0, residual=None, out=None):
     _lib.call("x2i_groupnorm_nhwc", _p(x), _p(gamma), _p(beta), _p(residual), _p(out), _p(ws), N, H * W, C, groups, float(eps), act,
               _stream())
     return out
+
+
+# ================================================================================================ VAE decoder
+def linear_f32(x, weight, alpha=1.0, out=None):
+    """fp32 out[M, N] = alpha * x[M, K] @ weight[N, K]^T (attention scores that must not be rounded to bf16)."""
+    _chk(x, "x"); _chk(weight, "weight")
+    M, K = x.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=F32)
+    _chk(out, "out", F32)
+    _lib.call("x2i_gemm_f32", _p(x), x.stride(0), _p(weight), weight.stride(0), _p(out), out.stride(0), M, N, K, float(alpha), _stream())
+    return out
+
+
+def softmax_rows(s, out=None):
+    """bf16 softmax over the last dim of fp32 scores [R, C]."""
+    _chk(s, "s", F32)
+    R, C = s.shape
+    if out is None:
+        out = torch.empty(R, C, device=s.device, dtype=BF16)
+    _chk(out, "out")
+    _lib.call("x2i_softmax_rows", _p(s), s.stride(0), _p(out), out.stride(0), R, C, _stream())
+    return out
+
+
+def upsample2x_nhwc(x, out=None):
+    """Nearest 2x upsampling of NHWC bf16."""
+    _chk(x, "x")
+    N, H, W, C = x.shape
+    if not x.is_contiguous():
+        raise _lib.X2IError("upsample2x_nhwc: x must be contiguous NHWC")
+    if out is None:
+        out = torch.empty(N, 2 * H, 2 * W, C, device=x.device, dtype=BF16)
+    _lib.call("x2i_upsample2x_nhwc", _p(x), _p(out), N, H, W, C, _stream())
+    return out

@@ -211,8 +211,9 @@ class FluxPipeline:
         if prompt is not None or prompt_embeds is None or pooled_prompt_embeds is None:
             raise X2IError("FluxPipeline (x2i_b200): text encoders are out of scope; pass prompt_embeds and "
                            "pooled_prompt_embeds as the X2I inference scripts do")
-        if output_type != "latent":
-            raise X2IError("FluxPipeline (x2i_b200): only output_type='latent' is supported (vae=None in X2I)")
+        if output_type != "latent" and self.vae is None:
+            raise X2IError("FluxPipeline (x2i_b200): output_type != 'latent' needs a vae (x2i_b200.vae.AutoencoderKL); the X2I "
+                           "scripts construct the pipeline with vae=None and decode themselves")
         height = height or self.default_sample_size * self.vae_scale_factor
         width = width or self.default_sample_size * self.vae_scale_factor
         device = self.transformer.device
@@ -242,6 +243,12 @@ class FluxPipeline:
                                           joint_attention_kwargs=joint_attention_kwargs, guided_hint=guided_hint,
                                           control_nets=control_nets, return_dict=False)[0]
             latents = self.scheduler.step(noise_pred, ts[i], latents, return_dict=False)[0]
+        if output_type != "latent":  # diffusers' tail: unpack -> un-scale -> vae.decode -> image_processor.postprocess
+            from .vae import VaeImageProcessor
+            scale = 2 ** len(self.vae.config.block_out_channels)
+            z = self._unpack_latents(latents, height, width, scale)
+            z = (z / self.vae.config.scaling_factor) + self.vae.config.shift_factor
+            latents = VaeImageProcessor(vae_scale_factor=scale).postprocess(self.vae.decode(z, return_dict=False)[0], output_type=output_type)
         if not return_dict:
             return (latents,)
         return SimpleNamespace(images=latents)
