@@ -291,7 +291,7 @@ int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* 
  * w fp32 [64,3,3,3] (PyTorch layout), bias fp32 [64].                                                                  */
 int x2i_conv_first(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, void* stream);
 /* nn.GroupNorm on NHWC bf16 + activation (0 none, 1 ReLU, 2 SiLU) + optional residual add: y = act(GN(x)) + residual.
- * gamma/beta bf16 [C]; C % 64 == 0, C <= 2048, groups of 4 or a multiple of 8 channels; workspace of
+ * gamma/beta bf16 [C]; C a power of two in [64, 2048], groups of 4 or a multiple of 8 channels; workspace of
  * x2i_groupnorm_workspace_floats() floats.  Deterministic.                                                                */
 int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
                        int HW, int C, int G, float eps, int act, void* stream);

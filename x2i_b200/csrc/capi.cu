@@ -1093,12 +1093,13 @@ int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   const bool sub2 = G > 0 && C == 4 * G;  // groups of 4 channels
-  if (Nimg <= 0 || HW <= 0 || C % 64 || C <= 0 || C > 2048 || G <= 0 || (!sub2 && (C / 8) % G))
-    return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: C %% 64 == 0, C <= 2048 and groups of 4 or a multiple of 8 channels (C=%d G=%d)", C, G);
+  if (Nimg <= 0 || HW <= 0 || C % 64 || C <= 0 || C > 2048 || (C & (C - 1)) || G <= 0 || (!sub2 && (C / 8) % G))
+    return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: C a power of two in [64, 2048] and groups of 4 or a multiple of 8 channels (C=%d G=%d)", C, G);
   if (!x || !gamma || !beta || !y || !workspace) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: null buffer");
   if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(residual) || !aligned16(y) || !aligned16(workspace)) return fail(X2I_ERR_ALIGN, "groupnorm_nhwc: alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int nsplit = (HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA;
+  const int ppc = gn_pix_per_cta(HW);
+  const int nsplit = (HW + ppc - 1) / ppc;
   float* part = workspace;
   float2* stats = reinterpret_cast<float2*>(workspace + static_cast<long long>(Nimg) * nsplit * G * 2);
   if (sub2)
@@ -1108,11 +1109,12 @@ int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const
   if (int rc = check_launch("gn_stats_partial_kernel")) return rc;
   gn_stats_final_kernel<<<(Nimg * G + 3) / 4, 128, 0, st>>>(part, stats, G, nsplit, static_cast<double>(HW) * (C / G), eps, Nimg * G);
   if (int rc = check_launch("gn_stats_final_kernel")) return rc;
-  const long long total8 = static_cast<long long>(Nimg) * HW * (C / 8);
+  const long long cpi = static_cast<long long>(HW) * (C / 8);  // 16-byte chunks per image
+  if (cpi > 0x7fffffffLL - 4096) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: image too large");
   auto apply = sub2 ? gn_apply_kernel<2> : gn_apply_kernel<1>;
-  apply<<<static_cast<unsigned>((total8 + 1023) / 1024), 256, 0, st>>>(
+  apply<<<dim3(static_cast<unsigned>((cpi + 2047) / 2048), Nimg), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), stats, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta),
-      static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), total8, HW, C, G, act);
+      static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), static_cast<int>(cpi), C, G, act);
   return check_launch("gn_apply_kernel");
 }
 int x2i_gemm_f32(const void* A, int64_t lda, const void* W, int64_t ldw, float* C32, int64_t ldc, int M, int N, int K, float alpha,
@@ -1148,7 +1150,8 @@ int x2i_upsample2x_nhwc(const void* x, void* out, int Nimg, int H, int W, int C,
 }
 
 int64_t x2i_groupnorm_workspace_floats(int Nimg, int HW, int G) {
-  const int nsplit = (HW + GN_PIX_PER_CTA - 1) / GN_PIX_PER_CTA;
+  const int ppc = gn_pix_per_cta(HW);
+  const int nsplit = (HW + ppc - 1) / ppc;
   return 2LL * Nimg * nsplit * G + 2LL * Nimg * G + 8;
 }
 

@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const __nv_bfloat16* __
 // ------------------------------------------------------------------------------------------------
 // GroupNorm on NHWC bf16 (nn.GroupNorm of ControlNeXt: 2 / 4 / 8 groups): deterministic two-stage statistics + one
 // fused apply pass  y = act((x - mean) * rstd * gamma + beta) (+ residual).  act: 0 none, 1 ReLU, 2 SiLU.
-constexpr int GN_PIX_PER_CTA = 256;
+// pixels per statistics slab: at least 256, grown so that an image has at most ~1024 slabs (keeps the final reduction short)
+__host__ __device__ inline int gn_pix_per_cta(int HW) { const int p = (HW / 1024 + 255) / 256 * 256; return p < 256 ? 256 : p; }
 // SUB == 2: groups of 4 channels (the VAE's GroupNorm(32, 128)): a thread's 8-channel chunk covers two groups.
 template <int SUB>
 __global__ void __launch_bounds__(256) gn_stats_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ part /* [N, nsplit, G, 2] */,
@@ -206,7 +207,8 @@ __global__ void __launch_bounds__(256) gn_stats_partial_kernel(const __nv_bfloat
   const int ppi = 256 / tpp;         // pixels per CTA iteration
   const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   const int split = blockIdx.x, n = blockIdx.y;
-  const int p0 = split * GN_PIX_PER_CTA, p1 = min(p0 + GN_PIX_PER_CTA, HW);
+  const int ppc = gn_pix_per_cta(HW);
+  const int p0 = split * ppc, p1 = min(p0 + ppc, HW);
   float s = 0.f, ss = 0.f, s_hi = 0.f, ss_hi = 0.f;
   const __nv_bfloat16* xb = x + static_cast<long long>(n) * HW * C + cg * 8;
   for (int pp = p0 + pl; pp < p1; pp += 4 * ppi) {  // 4 independent 16-byte loads in flight
@@ -265,9 +267,15 @@ __global__ void __launch_bounds__(128) gn_stats_final_kernel(const float* __rest
   if (i >= total) return;
   const int n = i / G, g = i - n * G;
   double a = 0.0, b = 0.0;
-  for (int sidx = lane; sidx < nsplit; sidx += 32) {
-    const float* o = part + ((static_cast<long long>(n) * nsplit + sidx) * G + g) * 2;
-    a += o[0]; b += o[1];
+  for (int s0 = lane; s0 < nsplit; s0 += 128) {  // 4 independent loads in flight; fixed summation order
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int sidx = s0 + 32 * u;
+      v[u] = sidx < nsplit ? *reinterpret_cast<const float2*>(part + ((static_cast<long long>(n) * nsplit + sidx) * G + g) * 2) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a += v[u].x; b += v[u].y; }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -280,29 +288,25 @@ __global__ void __launch_bounds__(128) gn_stats_final_kernel(const float* __rest
     stats[i] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
   }
 }
+// Apply pass.  grid = (slabs of 256 * U chunks, image); a CTA-wide stride is a multiple of the chunks per pixel, so a thread
+// keeps its 8 channels for all its chunks: gamma/beta/statistics are folded ONCE into a per-channel (scale, shift) pair and the
+// inner loop is load -> 8 FMA (+ activation) -> store, with 32-bit indexing.
+__device__ __forceinline__ float silu_fast(float x) {  // x * sigmoid(x), sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5: one MUFU op
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
 template <int SUB>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
                                                        const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
-                                                       const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, long long total8,
-                                                       int HW, int C, int G, int act) {
-  constexpr int U = 4;  // 16-byte chunks per thread, a CTA-wide stride apart (coalesced), all loads issued first
-  const long long base = static_cast<long long>(blockIdx.x) * (blockDim.x * U) + threadIdx.x;
+                                                       const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, int chunks_per_img,
+                                                       int C, int G, int act) {
+  constexpr int U = 8;  // 16-byte chunks per thread, a CTA-wide stride apart (coalesced), loads issued in two batches of 4
   const int tpp = C >> 3;
-  uint4 q[U], r[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const long long i = base + static_cast<long long>(u) * blockDim.x;
-    if (i < total8) {
-      q[u] = ld_stream(reinterpret_cast<const uint4*>(x) + i);
-      if (residual != nullptr) r[u] = ld_stream(reinterpret_cast<const uint4*>(residual) + i);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const long long i = base + static_cast<long long>(u) * blockDim.x;
-    if (i >= total8) continue;
-    const int cg = static_cast<int>(i % tpp);
-    const int n = static_cast<int>(i / (static_cast<long long>(HW) * tpp));
+  const int cg = threadIdx.x % tpp;
+  const int n = blockIdx.y;
+  float sc[8], sh[8];
+  {
     float2 st, st_hi;
     if constexpr (SUB == 1) {
       st = stats[n * G + cg / (tpp / G)];
@@ -311,24 +315,55 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
       st = stats[n * G + 2 * cg];
       st_hi = stats[n * G + 2 * cg + 1];
     }
-    float f[8], ga[8], be[8];
-    unpack8(q[u], f);
+    float ga[8], be[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + cg), ga);
     unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + cg), be);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = (f[j] - (j < 4 ? st.x : st_hi.x)) * (j < 4 ? st.y : st_hi.y) * ga[j] + be[j];
-      if (act == 1) v = fmaxf(v, 0.f);
-      else if (act == 2) v = silu_f(v);
-      f[j] = v;
+      const float mean = j < 4 ? st.x : st_hi.x, rstd = j < 4 ? st.y : st_hi.y;
+      sc[j] = rstd * ga[j];
+      sh[j] = be[j] - mean * sc[j];
     }
-    if (residual != nullptr) {
-      float rr[8];
-      unpack8(r[u], rr);
+  }
+  const long long img_off = static_cast<long long>(n) * chunks_per_img;
+  const uint4* xin = reinterpret_cast<const uint4*>(x) + img_off;
+  const uint4* rin = residual != nullptr ? reinterpret_cast<const uint4*>(residual) + img_off : nullptr;
+  uint4* yout = reinterpret_cast<uint4*>(y) + img_off;
+  const int base = blockIdx.x * (256 * U) + threadIdx.x;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += rr[j];
+  for (int h = 0; h < U / 4; ++h) {
+    uint4 q[4], r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + (h * 4 + u) * 256;
+      if (i < chunks_per_img) {
+        q[u] = ld_stream(xin + i);
+        if (rin != nullptr) r[u] = ld_stream(rin + i);
+      }
     }
-    reinterpret_cast<uint4*>(y)[i] = pack8(f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = base + (h * 4 + u) * 256;
+      if (i >= chunks_per_img) continue;
+      float f[8];
+      unpack8(q[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu_fast(f[j]);
+      }
+      if (rin != nullptr) {
+        float rr[8];
+        unpack8(r[u], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += rr[j];
+      }
+      yout[i] = pack8(f);
+    }
   }
 }
 
