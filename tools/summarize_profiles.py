@@ -56,9 +56,13 @@ def launches(tag, steps=2, src_name="launches.csv", out_name="launch_list_summar
 
 def raw(tag, rep):
     src = os.path.join(GP, rep + ".ncu-rep")
-    if not os.path.exists(src):
+    pre = os.path.join(GP, rep + "_raw.csv")  # exported on the GPU box by tools/profile_cmds.sh
+    if os.path.exists(pre):
+        out = open(pre).read()
+    elif os.path.exists(src):
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     cols = [i for i, h in enumerate(hdr) if h in KEYS or h == "Kernel Name"]
@@ -78,5 +82,10 @@ if __name__ == "__main__":
     launches(tag, steps=3, src_name="train_launches.csv", out_name="train_launch_list_summary.md",
              title=f"# {tag}: every kernel of `python tools/bench_train.py --batch 1 --steps 1 --warmup 1 --layers 2 4` under ncu "
                    "(whole process: model init + 3 train-step passes over 2 double + 4 single blocks; per-step columns = totals / 3)")
-    for rep in ("prof_attn", "prof_gemm", "prof_rowwise", "prof_bwd"):
+    launches(tag, steps=2, src_name="vae_launches.csv", out_name="vae_launch_list_summary.md",
+             title=f"# {tag}: every kernel of `python tools/bench_vae.py --steps 1 --warmup 1` under ncu (2 decodes of one 1024px image "
+                   "+ model init; per-step columns = totals / 2)")
+    launches(tag, steps=1, src_name="cn_launches.csv", out_name="controlnext_launch_list_summary.md",
+             title=f"# {tag}: one ControlNeXt net on a 1024x1024 hint (`tools/profile_controlnext.py`, profiled pass only) under ncu")
+    for rep in ("prof_attn", "prof_gemm", "prof_rowwise", "prof_bwd", "prof_vae"):
         raw(tag, rep)
