@@ -1013,18 +1013,20 @@ int x2i_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
 
 // ================================================================================================ ControlNeXt (LightControl)
 namespace {
-template <int BN>
-int launch_conv_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& cp, cudaStream_t st) {
-  auto kern = conv2d_tcgen05_kernel<BN, EPI_CONV>;
+template <int BN, int MT>
+int launch_conv_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, ConvParams cp, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, MT>;
+  auto kern = conv2d_tcgen05_kernel<BN, EPI_CONV, MT>;
   static std::atomic<bool> configured[16];
   if (!configured[d->index].load(std::memory_order_acquire)) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(conv): %s", cudaGetErrorString(e));
     configured[d->index].store(true, std::memory_order_release);
   }
+  cp.tiles_y = (cp.Ho + CONV_TH * MT - 1) / (CONV_TH * MT);
   const int tiles = cp.Nimg * cp.tiles_x * cp.tiles_y * ((cp.g.N + BN - 1) / BN);
   const int grid = tiles < d->sms ? tiles : d->sms;
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, cp);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, cp);
   return check_launch("conv2d_tcgen05_kernel");
 }
 }  // namespace
@@ -1053,27 +1055,35 @@ int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* 
   p.C = static_cast<__nv_bfloat16*>(out); p.ldc = Cout;
   p.residual = static_cast<const __nv_bfloat16*>(residual); p.ldr = Cout;
   p.rowvec = static_cast<const __nv_bfloat16*>(rowvec); p.rowvec_stride = rowvec_stride; p.rows_per_batch = Ho * Wo; p.relu = relu;
+  const int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  // M tiles per CTA (see ConvCfg): as many as the TMEM budget allows, unless that would leave SMs without a tile
+  static const int mt_override = []() { const char* e = getenv("X2I_CONV_MT"); return e ? atoi(e) : 0; }();
+  int mt = bn == 256 ? 1 : (bn == 128 ? 2 : 4);
+  while (mt > 1 && static_cast<long long>(Nimg) * cp.tiles_x * ((Ho + CONV_TH * mt - 1) / (CONV_TH * mt)) * (Cout / bn) < d->sms) mt >>= 1;
+  if (mt_override > 0 && mt_override <= mt) mt = mt_override;
   CUtensorMap ta, tb;
   if (stride == 1) {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
     uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
-    uint32_t box[4] = {GEMM_BK, CONV_TW, CONV_TH, 1};
+    uint32_t box[4] = {GEMM_BK, CONV_TW, (uint32_t)(CONV_TH * mt), 1};
     if (int rc = make_map(d, &ta, x, 4, dims, str, box)) return rc;
   } else {  // parity view [2C, W/2, 2, H/2, N]
     uint64_t dims[5] = {(uint64_t)2 * Cin, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)Nimg};
     uint64_t str[5] = {1, (uint64_t)2 * Cin, (uint64_t)W * Cin, (uint64_t)2 * W * Cin, (uint64_t)H * W * Cin};
-    uint32_t box[5] = {GEMM_BK, CONV_TW, 1, CONV_TH, 1};
+    uint32_t box[5] = {GEMM_BK, CONV_TW, 1, (uint32_t)(CONV_TH * mt), 1};
     if (int rc = make_map(d, &ta, x, 5, dims, str, box)) return rc;
   }
-  const int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : 64);
   uint64_t db[2] = {(uint64_t)p.K, (uint64_t)Cout}, sb[2] = {1, (uint64_t)p.K};
   uint32_t bb[2] = {GEMM_BK, (uint32_t)bn};
   if (int rc = make_map(d, &tb, w, 2, db, sb, bb)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (bn) {
-    case 256: return launch_conv_t<256>(d, ta, tb, cp, st);
-    case 128: return launch_conv_t<128>(d, ta, tb, cp, st);
-    default: return launch_conv_t<64>(d, ta, tb, cp, st);
+  switch (bn * 8 + mt) {
+    case 256 * 8 + 1: return launch_conv_t<256, 1>(d, ta, tb, cp, st);
+    case 128 * 8 + 2: return launch_conv_t<128, 2>(d, ta, tb, cp, st);
+    case 128 * 8 + 1: return launch_conv_t<128, 1>(d, ta, tb, cp, st);
+    case 64 * 8 + 4: return launch_conv_t<64, 4>(d, ta, tb, cp, st);
+    case 64 * 8 + 2: return launch_conv_t<64, 2>(d, ta, tb, cp, st);
+    default: return launch_conv_t<64, 1>(d, ta, tb, cp, st);
   }
 }
 

@@ -20,16 +20,33 @@ namespace x2i {
 struct ConvParams {
   GemmParams g;  // g.M = Nimg * Ho * Wo (output pixels), g.N = Cout, g.K = KH * KW * Cin; g.rows_per_batch = Ho * Wo
   int Nimg, Ho, Wo, Cin, KH, KW, stride, pad;
-  int tiles_x, tiles_y;  // 16-wide / 8-high output patches per image
+  int tiles_x, tiles_y;  // 16-wide / (8 * MT)-high output tiles per image
 };
 
 constexpr int CONV_TW = 16, CONV_TH = 8;
 
-template <int BN, int EPI>
+// MT = vertically adjacent 8x16 pixel patches per CTA tile.  With MT > 1 ONE tensor-map box [64 ch, 16 x, 8*MT y] lands as MT
+// consecutive 128-row K-major A tiles, the weight tile of the k-block is staged once and feeds MT MMAs (MT accumulators of BN
+// columns each, all double-buffered: 2 * MT * BN <= 512 TMEM columns).  Narrow convs (Cout 64 / 128) are bound by the shared-
+// memory port, not the tensor pipe -- an M=128 x N=128 x K=64 MMA reads 32 KB in 256 cycles, N=64 reads 24 KB in 128 -- so sharing
+// the B tile cuts the bytes per MMA from 32 to 24 KB (BN = 128, MT = 2) and from 24 to 18 KB (BN = 64, MT = 4).
+template <int BN, int MT>
+struct ConvCfg {
+  static constexpr int A_BYTES = MT * GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (224 * 1024 / STAGE_BYTES) > 8 ? 8 : (224 * 1024 / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * MT * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM budget");
+};
+
+template <int BN, int EPI, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const ConvParams cp) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = ConvCfg<BN, MT>;
   constexpr int NS = Cfg::STAGES;
+  constexpr int TH = CONV_TH * MT;  // tile height in output pixels
   const GemmParams& p = cp.g;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -41,7 +58,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
-  const int tiles_img = cp.tiles_x * cp.tiles_y;
+  const int tiles_img = cp.tiles_x * cp.tiles_y;  // tiles_y counts TH-high tiles
   const int num_m = cp.Nimg * tiles_img;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
@@ -78,7 +95,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile % num_m, n_blk = tile / num_m;
         const int img = m_blk / tiles_img, t = m_blk - img * tiles_img;
-        const int y0 = (t / cp.tiles_x) * CONV_TH, x0 = (t % cp.tiles_x) * CONV_TW;
+        const int y0 = (t / cp.tiles_x) * TH, x0 = (t % cp.tiles_x) * CONV_TW;
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / cchunks, cc = kb - tap * cchunks;
           const int ky = tap / cp.KW, kx = tap - ky * cp.KW;
@@ -108,7 +125,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
+      const uint32_t d_tmem = tmem_base + as * (MT * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -116,15 +133,17 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         const uint64_t adesc = make_smem_desc_sw128(a_base, 16, 1024);
         const uint64_t bdesc = make_smem_desc_sw128(a_base + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k)
-          umma_ss_w(d_tmem, adesc + ((k * 32) >> 4), bdesc + ((k * 32) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_ss_w(d_tmem + mt * BN, adesc + ((mt * GEMM_BM * GEMM_BK * 2 + k * 32) >> 4), bdesc + ((k * 32) >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit_w(&empty_bar[stage]);
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
       umma_commit_w(&tfull_bar[as]);
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..5): one output pixel per thread
+    // ------------------------------------------------------------ epilogue warps (2..5): one output pixel per thread and M tile
     const int quad = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     int it = 0;
@@ -132,13 +151,16 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       const int m_blk = tile % num_m, n_blk = tile / num_m;
       const int img = m_blk / tiles_img, t = m_blk - img * tiles_img;
       const int r = quad * 32 + lane;
-      const int y = (t / cp.tiles_x) * CONV_TH + r / CONV_TW, x = (t % cp.tiles_x) * CONV_TW + r % CONV_TW;
-      const int m = (y < cp.Ho && x < cp.Wo) ? (img * cp.Ho + y) * cp.Wo + x : p.M;  // p.M = "row out of range"
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      gemm_epilogue_tile<BN, EPI>(p, tmem_base + as * BN + lane_off, m, n_blk * BN);
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int y = (t / cp.tiles_x) * TH + mt * CONV_TH + r / CONV_TW, x = (t % cp.tiles_x) * CONV_TW + r % CONV_TW;
+        const int m = (y < cp.Ho && x < cp.Wo) ? (img * cp.Ho + y) * cp.Wo + x : p.M;  // p.M = "row out of range"
+        gemm_epilogue_tile<BN, EPI>(p, tmem_base + as * (MT * BN) + mt * BN + lane_off, m, n_blk * BN);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
