@@ -29,6 +29,7 @@ HEIGHT = WIDTH = 1024
 S_TXT = 512
 PIPE_STEPS = 4  # FLUX-schnell sampling steps (README.md:93 of the reference)
 D, HEADS, FF = 3072, 24, 12288
+WORKLOAD = "FLUX-schnell MMDiT denoise step, 1024x1024 (4096 latent + 512 text tokens), 19 double + 38 single blocks"
 
 
 def step_flops(L_img=4096, S=S_TXT):
@@ -161,7 +162,7 @@ def run_reference(args):
         "impl": "reference", "metric": "denoise-steps/sec 1024px bf16", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "FLUX-schnell MMDiT denoise step 1024x1024 (4096 latent + 512 text tokens), batch 1, CPU"},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": 1, "global_batch": 1, "parallelism": "cpu (rank 0 only)"},
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -331,6 +332,25 @@ def main():
         model.use_cuda_graph = True
         del proj, opt, tb
 
+    # ---- secondary workload (SURVEY 8f N2, N=1 only): the VAE decode that follows the 4 denoise steps of an image
+    vae_info = None
+    if world == 1 and not args.no_train:
+        from x2i_b200 import vae as xvae
+        from x2i_b200.flux import init_synthetic_
+        vae = init_synthetic_(xvae.AutoencoderKL().to(dev, torch.bfloat16).eval(), seed=5, std=0.03)
+        with torch.no_grad():
+            for _ in range(2):
+                xvae.decode_latents(vae, latents, HEIGHT, WIDTH)
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for _ in range(3):
+                xvae.decode_latents(vae, latents, HEIGHT, WIDTH)
+            v1.record()
+            torch.cuda.synchronize()
+        vae_info = {"workload": "FLUX VAE decode of the step's latents -> [B,3,1024,1024] (infer/inference_qwenvl.py:209-216)",
+                    "ms_per_decode": v0.elapsed_time(v1) / 3, "algorithmic_tflop_per_image": 10.47}
+        del vae
+
     if rank == 0:
         total_steps = world * B * args.steps
         value = total_steps / t
@@ -340,14 +360,14 @@ def main():
             "metric": "denoise-steps/sec 1024px bf16", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init FLUX-schnell weights, N(0,1) embeddings/latents)",
-            "config": {"workload": "FLUX-schnell MMDiT denoise step, 1024x1024 (4096 latent + 512 text tokens), 19 double + 38 single blocks",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world} (replicas, no collective)",
                        "l2_policy": "per-step working set (24 GB weights) >> 126 MB L2; no flush needed"},
             "tflops_per_gpu": fl * B * args.steps / t_local / 1e12,
             "step_roofline_frac_bf16": fl * B * args.steps / t_local / 1e12 / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
             "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "x2i_b200.pipeline.FluxPipeline.__call__ (4-step schnell sampling per call, pinned host buffers)"},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clk, "distill_train": train_info,
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clk, "distill_train": train_info, "vae_decode": vae_info,
         }
         print(json.dumps(out))
     if world > 1:
