@@ -33,7 +33,7 @@ struct AttnParams {
 #define ATT_STAMP(slot) do { if constexpr (DBG == 1) { if (trace != nullptr && lane == 0) trace[slot] = clock64(); } } while (0)
 
 constexpr int ATT_THREADS = 320;
-constexpr int ATT_DEFAULT_POLY8 = 1;  // production instantiation (see capi.cu)
+constexpr int ATT_DEFAULT_POLY8 = 2;  // production instantiation (see capi.cu)
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 128B-swizzled boxes of [128 rows x 64 cols]
 constexpr int ATT_KV_SLOTS = 4;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + ATT_KV_SLOTS * ATT_TILE_BYTES + 1024 + 256;
@@ -49,7 +49,7 @@ __device__ __forceinline__ void exp_half(const uint32_t (&x)[32], uint64_t sc2, 
     if constexpr (DBG == 2) {  // timing experiment: no exponentials at all
       p0 = a0;
       p1 = a1;
-    } else if ((k & 3) < POLY8) {  // POLY8 of every 4 pairs: exp2 on the FMA pipe instead of MUFU
+    } else if ((k & 7) < POLY8) {  // POLY8 of every 8 pairs: exp2 on the FMA pipe instead of MUFU
       poly_exp2_x2(a0, a1, p0, p1);
     } else {
       p0 = fast_exp2(a0);
@@ -66,7 +66,12 @@ template <int POLY8, bool MASKED, int DBG>
 __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, int j, int valid,
                                              float sc, float& m_run, float& l_run, int lane, long long* trace) {
   ATT_STAMP(0);
-  mbar_wait(s_full_i, j & 1);
+  if constexpr (DBG == 4) {
+    while (!mbar_test(s_full_i, j & 1)) {
+    }
+  } else {
+    mbar_wait(s_full_i, j & 1);
+  }
   tc_fence_after();
   ATT_STAMP(1);
   uint32_t r[4][32];
@@ -157,7 +162,8 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
   l_run = l_run * alpha + (s0 + s1);
 }
 
-// POLY8: how many of every 4 element PAIRS of the softmax use the FMA-pipe poly_exp2_x2 instead of MUFU.EX2.
+// POLY8: how many of every 8 element PAIRS of the softmax use the FMA-pipe poly_exp2_x2 instead of MUFU.EX2.
+// DBG: 0 product; 1 clock64 trace; 2 / 3 timing experiments (wrong results); 4 non-suspending barrier polls (same results).
 template <int POLY8, int DBG = 0>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
@@ -252,7 +258,12 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
         const uint64_t bd = make_smem_desc_sw128(kv_base + slot * ATT_TILE_BYTES, 16384, 1024);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          mbar_wait(&p_full[i * 4 + c], ph);
+          if constexpr (DBG == 4) {
+            while (!mbar_test(&p_full[i * 4 + c], ph)) {
+            }
+          } else {
+            mbar_wait(&p_full[i * 4 + c], ph);
+          }
           tc_fence_after();
 #pragma unroll
           for (int kk = 2 * c; kk < 2 * c + 2; ++kk)

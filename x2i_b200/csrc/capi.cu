@@ -533,8 +533,8 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
   using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   KernT kern = nullptr;
 #define ATT_PICK(P, D) if (poly8 == P && dbg == D) kern = mmdit_attention_fwd_kernel<P, D>
-  ATT_PICK(0, 0); ATT_PICK(1, 0); ATT_PICK(2, 0);
-  ATT_PICK(0, 1); ATT_PICK(1, 1); ATT_PICK(0, 2); ATT_PICK(0, 3);
+  ATT_PICK(0, 0); ATT_PICK(1, 0); ATT_PICK(2, 0); ATT_PICK(3, 0); ATT_PICK(4, 0);
+  ATT_PICK(0, 1); ATT_PICK(2, 1); ATT_PICK(0, 2); ATT_PICK(0, 3); ATT_PICK(2, 4);
 #undef ATT_PICK
   if (!kern) return fail(X2I_ERR_SHAPE, "attention: no kernel instantiation for POLY8=%d DBG=%d", poly8, dbg);
   static long long* trace_dev = nullptr;
