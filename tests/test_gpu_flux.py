@@ -227,3 +227,15 @@ def test_resampler_matches_reference_golden_and_oracle(env, golden_dir):
     y = m(x.cuda(), tgt.cuda())
     assert y.shape == (3, 64, 3584)
     assert env.rel(y, ref) < TOL
+
+
+def test_mismatched_position_ids_fail_loudly(env):
+    """ids shorter than the token sequence would index the RoPE table out of bounds; the reference fails in apply_rotary_emb."""
+    from x2i_b200._lib import X2IError
+    cfg = env.tiny_config(False)
+    model, _ = env.make_pair(cfg, seed=3)
+    inp = env.to_device(env.make_inputs(cfg, B=1, hl=8, wl=8, S=16, seed=10))
+    inp["img_ids"] = inp["img_ids"][: inp["img_ids"].shape[0] // 2].contiguous()
+    with pytest.raises(X2IError):
+        with torch.no_grad():
+            model(**inp, return_dict=False)

@@ -586,6 +586,10 @@ class FluxTransformer2DModel(nn.Module):
             img_ids = img_ids[0]
         if guidance is not None and not self.config.guidance_embeds:
             guidance = None
+        if img_ids.shape[0] != hidden_states.shape[1] or txt_ids.shape[0] != encoder_hidden_states.shape[1]:
+            # the reference fails in apply_rotary_emb's broadcast; here the RoPE table would be read out of bounds
+            raise X2IError(f"FluxTransformer2DModel: img_ids / txt_ids have {img_ids.shape[0]} / {txt_ids.shape[0]} rows but the sequences "
+                           f"have {hidden_states.shape[1]} / {encoder_hidden_states.shape[1]} tokens")
         if control_nets is not None and len(control_nets) > 0:
             _no_grad_needed(hidden_states, encoder_hidden_states, pooled_projections)
             out = self._forward_eager(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
