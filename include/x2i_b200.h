@@ -287,15 +287,25 @@ int64_t x2i_proj_mix_wgrad_workspace_floats(int B, int C, int S);
  * (the injection hidden_states += out * scale of :505-507 fused into its epilogue; out may alias residual).             */
 int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
                     void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, void* stream);
+/* Same with `groups` weight sets: image n uses w[n / (Nimg / groups)] (w [groups, Cout, KH*KW*Cin], bias [groups, Cout]) -- the 19
+ * ControlNeXt nets of a LightControl step (same layer shapes, different weights) as ONE launch per layer.                   */
+int x2i_conv2d_nhwc_grouped(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
+                            void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, int groups,
+                            void* stream);
 /* ControlNeXtModel.embedding[0]: Conv2d(3 -> 64, 3x3, stride 2, pad 1) on the NCHW bf16 hint image -> NHWC bf16 [N,H/2,W/2,64];
  * w fp32 [64,3,3,3] (PyTorch layout), bias fp32 [64].                                                                  */
 int x2i_conv_first(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, void* stream);
+/* `groups` stems on the same hint: w [groups,64,3,3,3], bias [groups,64] -> out [groups, N, H/2, W/2, 64].                      */
+int x2i_conv_first_grouped(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, int groups, void* stream);
 /* nn.GroupNorm on NHWC bf16 + activation (0 none, 1 ReLU, 2 SiLU) + optional residual add: y = act(GN(x)) + residual.
  * gamma/beta bf16 [C]; C a power of two in [64, 2048], groups of 4 or a multiple of 8 channels; workspace of
  * x2i_groupnorm_workspace_floats() floats.  Deterministic.                                                                */
 int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
                        int HW, int C, int G, float eps, int act, void* stream);
 int64_t x2i_groupnorm_workspace_floats(int Nimg, int HW, int G);
+/* Same with `param_sets` (gamma, beta) pairs [param_sets, C]: image n uses set n / (Nimg / param_sets).                        */
+int x2i_groupnorm_nhwc_grouped(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
+                               int HW, int C, int G, float eps, int act, int param_sets, void* stream);
 
 /* ---- VAE decoder (reference call site infer/inference_qwenvl.py:209-216: vae.decode(latents)) ----------
  * The decoder's convolutions and GroupNorms run through x2i_conv2d_nhwc / x2i_groupnorm_nhwc (C up to 2048, groups of 4 or a

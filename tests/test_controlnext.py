@@ -198,3 +198,45 @@ def test_transformer_injection_matches_oracle(ops):
     assert rel(ref0, ref) > 1e-2
     assert rel(out, ref) < TOL
     assert rel(out_f, out) < 5e-3
+
+
+@gpu
+def test_stacked_control_nets_equal_per_net_evaluation(ops):
+    """ControlNeXtStack (one launch per layer for all nets, per-net weight sets) against the same nets evaluated one by one:
+    same kernels, same per-image arithmetic -> bit-identical; and the transformer gives the same result with stacking on/off."""
+    from x2i_b200.controlnext import ControlNeXtModel, ControlNeXtStack
+    from x2i_b200.flux import FluxTransformer2DModel, init_synthetic_
+    G, B = 3, 2
+    nets = torch.nn.ModuleList([ControlNeXtModel().eval() for _ in range(G)]).to("cuda", torch.bfloat16)
+    for i, n in enumerate(nets):
+        init_synthetic_(n, seed=70 + i, std=0.05)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    hint = (torch.rand(B, 3, 96, 64, device="cuda", generator=g) * 2 - 1).bfloat16()
+    t = torch.tensor([700.0, 123.0], device="cuda")
+    assert ControlNeXtStack.supported(nets)
+    with torch.no_grad():
+        mids = ControlNeXtStack(nets).mid_features(hint, t)
+        assert mids.shape == (G, B, 12, 8, 256)
+        for i, n in enumerate(nets):
+            x0 = torch.randn(B, 6 * 4, 3072, device="cuda", generator=g).bfloat16()
+            a, b = x0.clone(), x0.clone()
+            n.forward_tokens(hint, t, add_to=a)
+            n.finish_tokens(mids[i], add_to=b)
+            assert torch.equal(a, b), f"net {i}"
+            assert torch.equal(n.finish_tokens(mids[i]), n.forward_tokens(hint, t))
+    cfg = dict(patch_size=1, in_channels=64, num_layers=3, num_single_layers=1, attention_head_dim=128, num_attention_heads=24,
+               joint_attention_dim=64, pooled_projection_dim=32, guidance_embeds=True, axes_dims_rope=(16, 56, 56))
+    model = FluxTransformer2DModel.synthetic(cfg, device="cuda", seed=9)
+    from x2i_b200.pipeline import FluxPipeline
+    kw = dict(hidden_states=torch.randn(B, 24, 64, device="cuda", generator=g).bfloat16(),
+              encoder_hidden_states=torch.randn(B, 8, 64, device="cuda", generator=g).bfloat16(),
+              pooled_projections=torch.randn(B, 32, device="cuda", generator=g).bfloat16(), timestep=torch.tensor([0.7, 0.2], device="cuda"),
+              guidance=torch.tensor([3.5, 3.5], device="cuda"), txt_ids=torch.zeros(8, 3, device="cuda"),
+              img_ids=FluxPipeline._prepare_latent_image_ids(B, 12, 8, "cuda", torch.float32), guided_hint=hint, control_nets=nets)
+    with torch.no_grad():
+        model.stack_control_nets = True
+        y1 = model(**kw, return_dict=False)[0].clone()
+        model.stack_control_nets = False
+        y2 = model(**kw, return_dict=False)[0].clone()
+    assert torch.equal(y1, y2)
+    assert not ControlNeXtStack.supported(nets[:1])

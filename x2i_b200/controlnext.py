@@ -141,9 +141,108 @@ class ControlNeXtModel(nn.Module):
         out = self._conv(x, last)
         return out.view(B, -1, out.shape[-1])
 
+    def finish_tokens(self, x_mid, add_to=None):
+        """Last conv (2x2 / stride 2, 256 -> 3072) on this net's mid feature map [B, h, w, 256] (from ControlNeXtStack);
+        with add_to the control signal is added into the image stream by the conv's epilogue."""
+        last = self.mid_convs[1]
+        B = x_mid.shape[0]
+        if add_to is not None:
+            if add_to.dtype != BF16 or not add_to.is_contiguous() or self.scale != 1.0:
+                raise X2IError("ControlNeXtModel: add_to must be a contiguous bf16 [B, h*w, 3072] tensor and scale == 1.0")
+            Ho, Wo = x_mid.shape[1] // 2, x_mid.shape[2] // 2
+            if add_to.shape != (B, Ho * Wo, 3072):
+                raise X2IError(f"ControlNeXtModel: control grid {Ho}x{Wo} does not match the image stream {tuple(add_to.shape)}")
+            self._conv(x_mid, last, residual=add_to.view(B, Ho, Wo, 3072), out=add_to.view(B, Ho, Wo, 3072))
+            return add_to
+        out = self._conv(x_mid, last)
+        return out.view(B, -1, out.shape[-1])
+
     def forward(self, sample, timestep):
         tok = self.forward_tokens(sample, timestep)
         B, _, C = tok.shape
         hh, ww = sample.shape[2] // 16, sample.shape[3] // 16
         # NCHW *view* of the NHWC result: values and shape of the reference's control['out'] without a transposing copy
         return {"out": tok.view(B, hh, ww, C).permute(0, 3, 1, 2), "scale": self.scale}
+
+
+class ControlNeXtStack:
+    """All control nets of a LightControl step as ONE launch per layer.
+
+    The reference evaluates ``control_nets[i](guided_hint, timestep)`` inside the block loop (``lightcontrol_flux.py:504-507``),
+    but the nets depend only on the hint and the timestep, have identical layer shapes and differ only in their weights, so
+    their activations are stacked along the image dimension ([G*B, H, W, C], net-major) and every conv / GroupNorm runs once
+    with per-net weight sets (``x2i_conv2d_nhwc_grouped`` / ``x2i_groupnorm_nhwc_grouped`` / ``x2i_conv_first_grouped``): ~50
+    launches instead of ~50 per net, and the 10-60 us layers become large enough to fill the GPU.  The last conv of each net
+    stays separate (``ControlNeXtModel.finish_tokens``) so its epilogue can still add straight into the image stream at the
+    injection point.  Stacked weights are views-by-copy, rebuilt when any parameter version changes."""
+
+    def __init__(self, nets):
+        self.nets = list(nets)
+        self._cache = {}
+
+    @staticmethod
+    def supported(nets) -> bool:
+        nets = list(nets)
+        if len(nets) < 2 or not all(type(n) is ControlNeXtModel for n in nets):
+            return False
+        ref = [(k, tuple(v.shape)) for k, v in nets[0].state_dict().items()]
+        return all([(k, tuple(v.shape)) for k, v in n.state_dict().items()] == ref for n in nets[1:])
+
+    def _stacked(self, name, getter, transform):
+        params = [getter(n) for n in self.nets]
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self._cache.get(name)
+        if hit is None or hit[0] != ver:
+            hit = (ver, torch.stack([transform(p.detach()) for p in params]).contiguous())
+            self._cache[name] = hit
+        return hit[1]
+
+    def _conv(self, x, path, stride=1, **kw):
+        conv0 = path(self.nets[0])
+        w = self._stacked(("w",) + (id(conv0),), lambda n: path(n).weight, ops.pack_conv_weight)
+        b = self._stacked(("b",) + (id(conv0),), lambda n: path(n).bias, lambda t: t.to(BF16))
+        return ops.conv2d_nhwc(x, w, b, conv0.kernel_size[0], conv0.kernel_size[1], stride=conv0.stride[0], pad=conv0.padding[0],
+                               groups=len(self.nets), **kw)
+
+    def _gn(self, x, path, act, residual=None):
+        gn0 = path(self.nets[0])
+        g = self._stacked(("g",) + (id(gn0),), lambda n: path(n).weight, lambda t: t.to(BF16))
+        b = self._stacked(("be",) + (id(gn0),), lambda n: path(n).bias, lambda t: t.to(BF16))
+        return ops.groupnorm_nhwc(x, g, b, gn0.num_groups, gn0.eps, act=act, residual=residual, param_sets=len(self.nets))
+
+    def mid_features(self, sample, timestep):
+        """[G, B, h, w, 256]: every net up to (and including) the residual mid block."""
+        n0, G = self.nets[0], len(self.nets)
+        if n0.embedding[0].weight.dtype != BF16 or not sample.is_cuda:
+            raise X2IError("ControlNeXtModel runs in bf16 on a CUDA device (x2i_b200 has no CPU path): .to('cuda', torch.bfloat16)")
+        if torch.is_grad_enabled() and sample.requires_grad:
+            raise X2IError("ControlNeXtModel: forward only (LightControl inference); call under torch.no_grad()")
+        B = sample.shape[0]
+        t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=sample.device)
+        t = t.reshape(-1).to(sample.device).expand(B).float().contiguous()
+        sin = ops.timestep_sinusoid(t, 128)
+        embs = []
+        for n in self.nets:  # [B, 256] per net: tiny weight-streaming launches
+            te = n.time_embedding
+            h = ops.skinny_linear(sin, te.linear_1.weight, te.linear_1.bias)
+            embs.append(ops.skinny_linear(h, te.linear_2.weight, te.linear_2.bias, act_in=1))
+        w0 = self._stacked("stem_w", lambda n: n.embedding[0].weight, lambda t_: t_.float())
+        b0 = self._stacked("stem_b", lambda n: n.embedding[0].bias, lambda t_: t_.float())
+        x = ops.conv_first(sample.to(BF16), w0, b0)                                            # [G*B, H/2, W/2, 64]
+        x = self._gn(x, lambda n: n.embedding[1], 1)
+        x = self._gn(self._conv(x, lambda n: n.embedding[3]), lambda n: n.embedding[4], 1)
+        x = self._gn(self._conv(x, lambda n: n.embedding[6]), lambda n: n.embedding[7], 1)
+        for li in range(len(n0.down_res)):
+            tproj = torch.cat([ops.skinny_linear(e, n.down_res[li].time_emb_proj.weight, n.down_res[li].time_emb_proj.bias, act_in=1)
+                               for n, e in zip(self.nets, embs)], 0).contiguous()              # [G*B, C]: row = image
+            res0 = n0.down_res[li]
+            hcur = self._conv(self._gn(x, lambda n: n.down_res[li].norm1, 2), lambda n: n.down_res[li].conv1, rowvec=tproj)
+            hcur = self._conv(self._gn(hcur, lambda n: n.down_res[li].norm2, 2), lambda n: n.down_res[li].conv2,
+                              residual=x if res0.conv_shortcut is None else None)
+            if res0.conv_shortcut is not None:
+                hcur = self._conv(x, lambda n: n.down_res[li].conv_shortcut, residual=hcur)
+            x = self._conv(hcur, lambda n: n.down_sample[li].conv)
+        y = self._conv(x, lambda n: n.mid_convs[0][0], relu=True)
+        y = self._conv(self._gn(y, lambda n: n.mid_convs[0][2], 0), lambda n: n.mid_convs[0][3])
+        x = self._gn(y, lambda n: n.mid_convs[0][4], 0, residual=x)
+        return x.view(G, B, *x.shape[1:])

@@ -1035,12 +1035,19 @@ extern "C" {
 
 int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
                     void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, void* stream) {
+  return x2i_conv2d_nhwc_grouped(x, w, bias, rowvec, rowvec_stride, residual, out, Nimg, H, W, Cin, Cout, KH, KW, stride, pad, relu, 1, stream);
+}
+
+int x2i_conv2d_nhwc_grouped(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
+                            void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, int groups,
+                            void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   if (Nimg <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin % 64 || Cout <= 0 || Cout % 64 || KH <= 0 || KW <= 0 || KH > 3 || KW > 3 || pad < 0 ||
       pad > 1 || (stride != 1 && stride != 2))
     return fail(X2I_ERR_SHAPE, "conv2d_nhwc: need Cin %% 64 == 0, Cout %% 64 == 0, kernel <= 3x3, pad <= 1, stride 1 or 2");
   if (stride == 2 && ((H | W) & 1)) return fail(X2I_ERR_SHAPE, "conv2d_nhwc: stride 2 needs even H and W");
+  if (groups < 1 || Nimg % groups) return fail(X2I_ERR_SHAPE, "conv2d_nhwc: Nimg (%d) must be a multiple of the weight groups (%d)", Nimg, groups);
   if (!x || !w || !out) return fail(X2I_ERR_SHAPE, "conv2d_nhwc: null buffer");
   if (!aligned16(x) || !aligned16(w) || !aligned16(out) || !aligned16(bias) || !aligned16(rowvec) || !aligned16(residual) || rowvec_stride % 8)
     return fail(X2I_ERR_ALIGN, "conv2d_nhwc: alignment");
@@ -1049,6 +1056,7 @@ int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* 
   memset(&cp, 0, sizeof(cp));
   cp.Nimg = Nimg; cp.Ho = Ho; cp.Wo = Wo; cp.Cin = Cin; cp.KH = KH; cp.KW = KW; cp.stride = stride; cp.pad = pad;
   cp.tiles_x = (Wo + CONV_TW - 1) / CONV_TW; cp.tiles_y = (Ho + CONV_TH - 1) / CONV_TH;
+  cp.imgs_per_group = groups > 1 ? Nimg / groups : 0;
   GemmParams& p = cp.g;
   p.M = Nimg * Ho * Wo; p.N = Cout; p.K = KH * KW * Cin;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
@@ -1073,9 +1081,15 @@ int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* 
     uint32_t box[5] = {GEMM_BK, CONV_TW, 1, (uint32_t)(CONV_TH * mt), 1};
     if (int rc = make_map(d, &ta, x, 5, dims, str, box)) return rc;
   }
-  uint64_t db[2] = {(uint64_t)p.K, (uint64_t)Cout}, sb[2] = {1, (uint64_t)p.K};
-  uint32_t bb[2] = {GEMM_BK, (uint32_t)bn};
-  if (int rc = make_map(d, &tb, w, 2, db, sb, bb)) return rc;
+  if (groups > 1) {
+    uint64_t db[3] = {(uint64_t)p.K, (uint64_t)Cout, (uint64_t)groups}, sb[3] = {1, (uint64_t)p.K, (uint64_t)p.K * Cout};
+    uint32_t bb[3] = {GEMM_BK, (uint32_t)bn, 1};
+    if (int rc = make_map(d, &tb, w, 3, db, sb, bb)) return rc;
+  } else {
+    uint64_t db[2] = {(uint64_t)p.K, (uint64_t)Cout}, sb[2] = {1, (uint64_t)p.K};
+    uint32_t bb[2] = {GEMM_BK, (uint32_t)bn};
+    if (int rc = make_map(d, &tb, w, 2, db, sb, bb)) return rc;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (bn * 8 + mt) {
     case 256 * 8 + 1: return launch_conv_t<256, 1>(d, ta, tb, cp, st);
@@ -1088,24 +1102,34 @@ int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* 
 }
 
 int x2i_conv_first(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, void* stream) {
+  return x2i_conv_first_grouped(x, w, bias, out, Nimg, H, W, 1, stream);
+}
+
+int x2i_conv_first_grouped(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, int groups, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
-  if (Nimg <= 0 || H <= 0 || W <= 0 || ((H | W) & 1)) return fail(X2I_ERR_SHAPE, "conv_first: even H and W required");
+  if (Nimg <= 0 || H <= 0 || W <= 0 || ((H | W) & 1) || groups < 1 || groups > 65535) return fail(X2I_ERR_SHAPE, "conv_first: even H and W, 1..65535 groups required");
   if (!x || !w || !bias || !out || !aligned16(out)) return fail(X2I_ERR_SHAPE, "conv_first: null / unaligned buffer");
   const long long pix = static_cast<long long>(Nimg) * (H / 2) * (W / 2);
-  conv_first_kernel<<<static_cast<unsigned>((pix + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  conv_first_kernel<<<dim3(static_cast<unsigned>((pix + 127) / 128), groups), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), w, bias, static_cast<__nv_bfloat16*>(out), Nimg, H, W);
   return check_launch("conv_first_kernel");
 }
 
 int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
                        int HW, int C, int G, float eps, int act, void* stream) {
+  return x2i_groupnorm_nhwc_grouped(x, gamma, beta, residual, y, workspace, Nimg, HW, C, G, eps, act, 1, stream);
+}
+
+int x2i_groupnorm_nhwc_grouped(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
+                               int HW, int C, int G, float eps, int act, int param_sets, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   const bool sub2 = G > 0 && C == 4 * G;  // groups of 4 channels
   if (Nimg <= 0 || HW <= 0 || C % 64 || C <= 0 || C > 2048 || (C & (C - 1)) || G <= 0 || (!sub2 && (C / 8) % G))
     return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: C a power of two in [64, 2048] and groups of 4 or a multiple of 8 channels (C=%d G=%d)", C, G);
   if (!x || !gamma || !beta || !y || !workspace) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: null buffer");
+  if (param_sets < 1 || Nimg % param_sets) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: Nimg (%d) must be a multiple of the parameter sets (%d)", Nimg, param_sets);
   if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(residual) || !aligned16(y) || !aligned16(workspace)) return fail(X2I_ERR_ALIGN, "groupnorm_nhwc: alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int ppc = gn_pix_per_cta(HW);
@@ -1124,7 +1148,8 @@ int x2i_groupnorm_nhwc(const void* x, const void* gamma, const void* beta, const
   auto apply = sub2 ? gn_apply_kernel<2> : gn_apply_kernel<1>;
   apply<<<dim3(static_cast<unsigned>((cpi + 2047) / 2048), Nimg), 256, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), stats, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta),
-      static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), static_cast<int>(cpi), C, G, act);
+      static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), static_cast<int>(cpi), C, G, act,
+      param_sets > 1 ? Nimg / param_sets : 0);
   return check_launch("gn_apply_kernel");
 }
 int x2i_gemm_f32(const void* A, int64_t lda, const void* W, int64_t ldw, float* C32, int64_t ldc, int M, int N, int K, float alpha,

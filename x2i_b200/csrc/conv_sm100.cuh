@@ -21,6 +21,7 @@ struct ConvParams {
   GemmParams g;  // g.M = Nimg * Ho * Wo (output pixels), g.N = Cout, g.K = KH * KW * Cin; g.rows_per_batch = Ho * Wo
   int Nimg, Ho, Wo, Cin, KH, KW, stride, pad;
   int tiles_x, tiles_y;  // 16-wide / (8 * MT)-high output tiles per image
+  int imgs_per_group;    // > 0: image n uses weight set n / imgs_per_group (B tensor map is 3-D [K, Cout, groups], bias [groups, Cout])
 };
 
 constexpr int CONV_TW = 16, CONV_TH = 8;
@@ -109,7 +110,10 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             const int vx = kx - cp.pad, vy = ky - cp.pad;
             tma_load_5d(sa, &tma_a, &full_bar[stage], (vx & 1) * cp.Cin + cc * GEMM_BK, x0 + (vx >> 1), vy & 1, y0 + (vy >> 1), img);
           }
-          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+          if (cp.imgs_per_group > 0)
+            tma_load_3d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN, img / cp.imgs_per_group);
+          else
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
       }
@@ -159,7 +163,8 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       for (int mt = 0; mt < MT; ++mt) {
         const int y = (t / cp.tiles_x) * TH + mt * CONV_TH + r / CONV_TW, x = (t % cp.tiles_x) * CONV_TW + r % CONV_TW;
         const int m = (y < cp.Ho && x < cp.Wo) ? (img * cp.Ho + y) * cp.Wo + x : p.M;  // p.M = "row out of range"
-        gemm_epilogue_tile<BN, EPI>(p, tmem_base + as * (MT * BN) + mt * BN + lane_off, m, n_blk * BN);
+        gemm_epilogue_tile<BN, EPI>(p, tmem_base + as * (MT * BN) + mt * BN + lane_off, m, n_blk * BN,
+                                    cp.imgs_per_group > 0 ? static_cast<long long>(img / cp.imgs_per_group) * p.N : 0);
       }
       tc_fence_before();
       __syncwarp();
@@ -178,11 +183,15 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
 // ------------------------------------------------------------------------------------------------
 // First ControlNeXt conv: Conv2d(3 -> 64, 3x3, stride 2, pad 1) on the NCHW hint image (lightcontrol_flux.py:594),
 // output NHWC.  K = 27 is far too small for the tensor cores: direct form, one output pixel per thread, 64 channels.
+// blockIdx.y = weight set g (19 ControlNeXt nets share one hint): w [G][64][27], bias [G][64], out [G, N, H/2, W/2, 64].
 __global__ void __launch_bounds__(128) conv_first_kernel(const __nv_bfloat16* __restrict__ x /* [N,3,H,W] */,
                                                          const float* __restrict__ w /* [64][27] (co, ci, ky, kx) */,
                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out /* [N,H/2,W/2,64] */,
                                                          int Nimg, int H, int W) {
   __shared__ float ws[27 * 64 + 64];
+  w += static_cast<long long>(blockIdx.y) * 64 * 27;
+  bias += blockIdx.y * 64;
+  out += static_cast<long long>(blockIdx.y) * Nimg * (H / 2) * (W / 2) * 64;
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[(i % 27) * 64 + i / 27] = w[i];  // [tap][co]
   for (int i = threadIdx.x; i < 64; i += blockDim.x) ws[27 * 64 + i] = bias[i];
   __syncthreads();
@@ -322,7 +331,7 @@ template <int SUB>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
                                                        const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                                                        const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y, int chunks_per_img,
-                                                       int C, int G, int act) {
+                                                       int C, int G, int act, int imgs_per_set /* 0: one gamma/beta for all images */) {
   constexpr int U = 8;  // 16-byte chunks per thread, a CTA-wide stride apart (coalesced), loads issued in two batches of 4
   const int tpp = C >> 3;
   const int cg = threadIdx.x % tpp;
@@ -338,8 +347,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __nv_bfloat16* __re
       st_hi = stats[n * G + 2 * cg + 1];
     }
     float ga[8], be[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + cg), ga);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + cg), be);
+    const int pset = imgs_per_set > 0 ? (n / imgs_per_set) * tpp : 0;
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + pset + cg), ga);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + pset + cg), be);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float mean = j < 4 ? st.x : st_hi.x, rstd = j < 4 ? st.y : st_hi.y;

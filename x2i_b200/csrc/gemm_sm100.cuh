@@ -113,7 +113,8 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float (&v)
 // Fused epilogue of one 128 x BN accumulator tile: thread `m` owns output row m; t_acc is the TMEM address of the tile
 // (lane quadrant of the calling warp already applied).
 template <int BN, int EPI>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const uint32_t t_acc, const int m, const int n_tile0) {
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const uint32_t t_acc, const int m, const int n_tile0,
+                                                   const long long bias_off = 0 /* EPI_CONV with per-group weights */) {
   const bool row_ok = m < p.M;
 
   if constexpr (EPI == EPI_QKV) {
@@ -215,7 +216,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
       float x[32];
       tmem_ld32(t_acc + c * 32, r);
       if (p.bias != nullptr) {
-        load_bf16x32(p.bias + n0, x);
+        load_bf16x32(p.bias + bias_off + n0, x);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = 0.f;

@@ -574,6 +574,8 @@ class FluxTransformer2DModel(nn.Module):
 
     # -- forward --------------------------------------------------------------------------------------------
     use_cuda_graph = True  # replay one captured graph per step instead of ~410 launches (inference, default processors)
+    stack_control_nets = True  # LightControl: evaluate all ControlNeXt nets with one launch per layer (controlnext.ControlNeXtStack)
+    _cn_stack = None
 
     def forward(self, hidden_states, encoder_hidden_states=None, pooled_projections=None, timestep=None, img_ids=None,
                 txt_ids=None, guidance=None, joint_attention_kwargs=None, guided_hint=None, control_nets=None, return_dict=True):
@@ -698,6 +700,15 @@ class FluxTransformer2DModel(nn.Module):
                        out=ws["c"])
         mod = ops.skinny_linear(temb, self._w_mod, self._b_mod, act_in=1)  # every AdaLN modulation of this step
 
+        mids = None
+        if control_nets is not None and len(control_nets) > 0:
+            from .controlnext import ControlNeXtStack
+            if self.stack_control_nets and ControlNeXtStack.supported(control_nets):
+                stack = self._cn_stack if self._cn_stack is not None and self._cn_stack.nets == list(control_nets) else None
+                if stack is None:
+                    stack = self._cn_stack = ControlNeXtStack(control_nets)
+                mids = stack.mid_features(guided_hint, t1000)  # all nets, one launch per layer (they do not depend on x)
+
         off = 0
         for i, blk in enumerate(self.transformer_blocks):
             c, x = blk(hidden_states=x, encoder_hidden_states=c, temb=temb, image_rotary_emb=rope_full,
@@ -705,7 +716,9 @@ class FluxTransformer2DModel(nn.Module):
             off += 12 * D
             if control_nets is not None and i < len(control_nets):  # lightcontrol_flux.py:504-507
                 net = control_nets[i]
-                if hasattr(net, "forward_tokens"):   # x2i_b200 ControlNeXtModel: adds in the epilogue of its last conv
+                if mids is not None:
+                    net.finish_tokens(mids[i], add_to=x)
+                elif hasattr(net, "forward_tokens"):   # x2i_b200 ControlNeXtModel: adds in the epilogue of its last conv
                     net.forward_tokens(guided_hint, t1000, add_to=x)
                 else:                                # any other control net: the reference's protocol, then a fused axpy
                     control = net(guided_hint, t1000)

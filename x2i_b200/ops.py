@@ -537,22 +537,25 @@ def proj_mix_wgrad(x, g, mode):
 
 
 # ================================================================================================ ControlNeXt (LightControl)
-def conv2d_nhwc(x, w_packed, bias, kh, kw, stride=1, pad=1, rowvec=None, residual=None, relu=False, out=None):
+def conv2d_nhwc(x, w_packed, bias, kh, kw, stride=1, pad=1, rowvec=None, residual=None, relu=False, out=None, groups=1):
     """NHWC implicit-GEMM conv: x [N,H,W,Cin], w_packed [Cout, kh*kw*Cin] (from pack_conv_weight), bias [Cout];
-    out = relu?(conv + bias + rowvec[n]) + residual, [N,Ho,Wo,Cout]."""
+    out = relu?(conv + bias + rowvec[n]) + residual, [N,Ho,Wo,Cout].
+    groups > 1: w_packed [groups, Cout, kh*kw*Cin], bias [groups, Cout]; image n uses weight set n // (N // groups)."""
     for t, n in ((x, "x"), (w_packed, "w"), (bias, "bias"), (rowvec, "rowvec"), (residual, "residual"), (out, "out")):
         _chk(t, n)
     N, H, W, Cin = x.shape
-    Cout = w_packed.shape[0]
-    if w_packed.shape[1] != kh * kw * Cin or not x.is_contiguous() or not w_packed.is_contiguous():
-        raise _lib.X2IError("conv2d_nhwc: x must be contiguous NHWC and w packed [Cout, kh*kw*Cin]")
+    Cout = w_packed.shape[-2]
+    ok = w_packed.shape[-1] == kh * kw * Cin and x.is_contiguous() and w_packed.is_contiguous()
+    ok = ok and (w_packed.dim() == 2 if groups == 1 else (w_packed.dim() == 3 and w_packed.shape[0] == groups and bias.is_contiguous()))
+    if not ok:
+        raise _lib.X2IError("conv2d_nhwc: x must be contiguous NHWC and w packed [(groups,) Cout, kh*kw*Cin]")
     Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     if out is None:
         out = torch.empty(N, Ho, Wo, Cout, device=x.device, dtype=BF16)
     if residual is not None and (residual.numel() != out.numel() or not residual.is_contiguous()):
         raise _lib.X2IError("conv2d_nhwc: residual must be contiguous with the output's shape")
-    _lib.call("x2i_conv2d_nhwc", _p(x), _p(w_packed), _p(bias), _p(rowvec), rowvec.stride(0) if rowvec is not None else 0, _p(residual),
-              _p(out), N, H, W, Cin, Cout, kh, kw, stride, pad, 1 if relu else 0, _stream())
+    _lib.call("x2i_conv2d_nhwc_grouped", _p(x), _p(w_packed), _p(bias), _p(rowvec), rowvec.stride(0) if rowvec is not None else 0,
+              _p(residual), _p(out), N, H, W, Cin, Cout, kh, kw, stride, pad, 1 if relu else 0, groups, _stream())
     return out
 
 
@@ -562,26 +565,32 @@ def pack_conv_weight(w):
 
 
 def conv_first(x_nchw, w, bias):
-    """Conv2d(3->64, 3x3, s2, p1): x bf16 [N,3,H,W] -> NHWC bf16 [N,H/2,W/2,64]; w fp32 [64,3,3,3], bias fp32 [64]."""
+    """Conv2d(3->64, 3x3, s2, p1): x bf16 [N,3,H,W] -> NHWC bf16 [N,H/2,W/2,64]; w fp32 [64,3,3,3], bias fp32 [64].
+    Grouped form: w [G,64,3,3,3], bias [G,64] -> [G*N, H/2, W/2, 64] (G stems on the same input)."""
     _chk(x_nchw, "x"); _chk(w, "w", F32); _chk(bias, "bias", F32)
     N, C, H, W = x_nchw.shape
-    if C != 3 or tuple(w.shape) != (64, 3, 3, 3):
-        raise _lib.X2IError("conv_first: x [N,3,H,W], w [64,3,3,3]")
-    out = torch.empty(N, H // 2, W // 2, 64, device=x_nchw.device, dtype=BF16)
-    _lib.call("x2i_conv_first", _p(x_nchw.contiguous()), _p(w.contiguous()), _p(bias.contiguous()), _p(out), N, H, W, _stream())
+    groups = w.shape[0] if w.dim() == 5 else 1
+    if C != 3 or tuple(w.shape[-4:]) != (64, 3, 3, 3) or bias.numel() != groups * 64:
+        raise _lib.X2IError("conv_first: x [N,3,H,W], w [(G,)64,3,3,3], bias [(G,)64]")
+    out = torch.empty(groups * N, H // 2, W // 2, 64, device=x_nchw.device, dtype=BF16)
+    _lib.call("x2i_conv_first_grouped", _p(x_nchw.contiguous()), _p(w.contiguous()), _p(bias.contiguous()), _p(out), N, H, W, groups,
+              _stream())
     return out
 
 
-def groupnorm_nhwc(x, gamma, beta, groups, eps, act=0, residual=None, out=None):
-    """act(GroupNorm(x)) + residual on NHWC bf16; act 0 none, 1 relu, 2 silu."""
+def groupnorm_nhwc(x, gamma, beta, groups, eps, act=0, residual=None, out=None, param_sets=1):
+    """act(GroupNorm(x)) + residual on NHWC bf16; act 0 none, 1 relu, 2 silu.
+    param_sets > 1: gamma / beta [param_sets, C]; image n uses set n // (N // param_sets)."""
     for t, n in ((x, "x"), (gamma, "gamma"), (beta, "beta"), (residual, "residual"), (out, "out")):
         _chk(t, n)
     N, H, W, C = x.shape
+    if gamma.numel() != param_sets * C or beta.numel() != param_sets * C or not gamma.is_contiguous() or not beta.is_contiguous():
+        raise _lib.X2IError("groupnorm_nhwc: gamma / beta must be contiguous [(param_sets,) C]")
     if out is None:
         out = torch.empty_like(x)
     ws = _ws_f32("groupnorm", _lib.lib().x2i_groupnorm_workspace_floats(N, H * W, groups), x.device)
-    _lib.call("x2i_groupnorm_nhwc", _p(x), _p(gamma), _p(beta), _p(residual), _p(out), _p(ws), N, H * W, C, groups, float(eps), act,
-              _stream())
+    _lib.call("x2i_groupnorm_nhwc_grouped", _p(x), _p(gamma), _p(beta), _p(residual), _p(out), _p(ws), N, H * W, C, groups, float(eps), act,
+              param_sets, _stream())
     return out
 
 
