@@ -163,3 +163,32 @@ def test_decode_latents_and_pipeline_tail_full_size(ops):
     assert img.shape == (2, 3, 1024, 1024)
     assert torch.isfinite(img.float()).all() and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
     assert _rel(img[1:], one) < 1e-2
+
+
+@gpu
+def test_pipeline_decodes_through_vae_like_the_reference_tail(ops):
+    """FluxPipeline(vae=...)(output_type="pt") == the reference's manual tail (infer/inference_qwenvl.py:209-216) applied to the
+    output_type="latent" result of the same seed; without a vae only "latent" is allowed."""
+    from x2i_b200 import smoke, vae as xv
+    from x2i_b200._lib import X2IError
+    from x2i_b200.flux import init_synthetic_
+    from x2i_b200.pipeline import FlowMatchEulerDiscreteScheduler, FluxPipeline
+    cfg = smoke.tiny_config(False)
+    model, _ = smoke.make_pair(cfg, seed=11)
+    vae = xv.AutoencoderKL(block_out_channels=(128, 128, 256, 256)).to("cuda", torch.bfloat16).eval()
+    init_synthetic_(vae, seed=12, std=0.05)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    pe = torch.randn(1, 16, cfg["joint_attention_dim"], device="cuda", generator=g).bfloat16()
+    po = torch.randn(1, cfg["pooled_projection_dim"], device="cuda", generator=g).bfloat16()
+    kw = dict(prompt_embeds=pe, pooled_prompt_embeds=po, num_inference_steps=2, guidance_scale=3.5, height=64, width=96)
+    with torch.no_grad():
+        pipe = FluxPipeline(scheduler=FlowMatchEulerDiscreteScheduler(shift=1.0), transformer=model, vae=vae)
+        img = pipe(**kw, output_type="pt", generator=torch.Generator(device="cuda").manual_seed(7)).images
+        lat = pipe(**kw, output_type="latent", generator=torch.Generator(device="cuda").manual_seed(7)).images
+        ref = xv.decode_latents(vae, lat, 64, 96)
+        pil = pipe(**kw, output_type="pil", generator=torch.Generator(device="cuda").manual_seed(7)).images
+        bare = FluxPipeline(scheduler=FlowMatchEulerDiscreteScheduler(shift=1.0), transformer=model)
+        with pytest.raises(X2IError):
+            bare(**kw, output_type="pt")
+    assert img.shape == (1, 3, 64, 96) and float((img - ref.float()).abs().max()) < 5e-3  # fp32 vs bf16 denormalise of the same decode
+    assert len(pil) == 1 and pil[0].size == (96, 64)

@@ -526,15 +526,20 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.ld0 = ld0; p.split = split;
   p.out1 = static_cast<__nv_bfloat16*>(out1); p.ld1 = ld1;
   p.lse = lse; p.Lpad = (L + 127) / 128 * 128;
-  // Variant selection.  Production = the defaults; the env overrides exist for tools/attn_sweep.sh.  X2I_ATTN_DBG=1 prints
-  // a clock64 trace of CTA (0,0,0) to stderr after a synchronous launch; 2 / 3 are timing experiments with wrong results.
+  // Variant selection.  Production = the defaults.  X2I_ATTN_DBG=1 prints a clock64 trace of CTA (0,0,0) to stderr after a
+  // synchronous launch (same arithmetic).  Other POLY8 / DBG values (tools/attn_sweep.sh; DBG 2 / 3 are timing experiments with
+  // wrong results) exist only in a library built with -DX2I_ATTN_EXPERIMENTS.
   static const int poly8 = []() { const char* e = getenv("X2I_ATTN_POLY8"); return e ? atoi(e) : ATT_DEFAULT_POLY8; }();
   static const int dbg = []() { const char* e = getenv("X2I_ATTN_DBG"); return e ? atoi(e) : 0; }();
   using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   KernT kern = nullptr;
 #define ATT_PICK(P, D) if (poly8 == P && dbg == D) kern = mmdit_attention_fwd_kernel<P, D>
-  ATT_PICK(0, 0); ATT_PICK(1, 0); ATT_PICK(2, 0); ATT_PICK(3, 0); ATT_PICK(4, 0);
-  ATT_PICK(0, 1); ATT_PICK(2, 1); ATT_PICK(0, 2); ATT_PICK(0, 3); ATT_PICK(2, 4);
+  ATT_PICK(2, 0);  // production
+  ATT_PICK(2, 1);  // production arithmetic + clock64 trace
+#ifdef X2I_ATTN_EXPERIMENTS  // tools/attn_sweep.sh builds with X2I_BUILD_EXPERIMENTS=1; never in the shipped library
+  ATT_PICK(0, 0); ATT_PICK(1, 0); ATT_PICK(3, 0); ATT_PICK(4, 0);
+  ATT_PICK(0, 1); ATT_PICK(0, 2); ATT_PICK(0, 3); ATT_PICK(2, 4);
+#endif
 #undef ATT_PICK
   if (!kern) return fail(X2I_ERR_SHAPE, "attention: no kernel instantiation for POLY8=%d DBG=%d", poly8, dbg);
   static long long* trace_dev = nullptr;
