@@ -111,12 +111,15 @@ def test_pipeline_four_step_sampling_matches_oracle(env):
     assert FluxPipeline._unpack_latents(a, 128, 128, 16).shape == (2, 16, 16, 16)
 
 
-def test_full_width_blocks_match_oracle(env):
-    """One double + one single block at the real width (D=3072, 24 heads) and a ragged sequence (S_txt=203)."""
+@pytest.mark.parametrize("S,hl,wl,outliers", [(203, 16, 24, False), (512, 64, 64, False), (512, 64, 64, True)])
+def test_full_width_blocks_match_oracle(env, S, hl, wl, outliers):
+    """One double + one single block at the real width (D=3072, 24 heads): a ragged sequence (S_txt=203, MiniCPM's unpadded
+    prompts) and BASELINE's FULL size (512 text + 4096 latent tokens, 1024 px), the latter also with outlier channels
+    (4 channels of both streams x40, SURVEY.md 8(d): real FLUX activations carry such channels).  fp32 oracle on the GPU."""
     from oracle import flux_oracle as fo
     from x2i_b200 import flux as xf
     torch.manual_seed(0)
-    D, H, B, S, hl, wl = 3072, 24, 1, 203, 16, 24
+    D, H, B = 3072, 24, 1
     L_img = hl * wl
     od = fo.FluxTransformerBlock(D, H, 128).eval()
     os_ = fo.FluxSingleTransformerBlock(D, H, 128).eval()
@@ -129,7 +132,12 @@ def test_full_width_blocks_match_oracle(env):
     ms = xf.FluxSingleTransformerBlock(D, H, 128); ms.load_state_dict(os_.state_dict()); ms = ms.to("cuda", torch.bfloat16)
     g = torch.Generator().manual_seed(22)
     bf = lambda t: t.bfloat16().float()  # noqa: E731
-    x, c, temb = bf(torch.randn(B, L_img, D, generator=g)), bf(torch.randn(B, S, D, generator=g)), bf(torch.randn(B, D, generator=g))
+    x, c, temb = torch.randn(B, L_img, D, generator=g), torch.randn(B, S, D, generator=g), bf(torch.randn(B, D, generator=g))
+    if outliers:
+        ch = torch.randperm(D, generator=g)[:4]
+        x[..., ch] *= 40.0
+        c[..., ch] *= 40.0
+    x, c = bf(x), bf(c)
     ids = torch.cat([torch.zeros(S, 3), fo.prepare_latent_image_ids(2 * hl, 2 * wl)])
     rope = fo.rope_table(ids)
     dev = lambda t: t.to("cuda", torch.bfloat16)  # noqa: E731
