@@ -14,6 +14,12 @@
 // as the A operand from TMEM (TS form) with the streamed tile as an MN-major B operand.  The MMAs of stream tile y+2
 // and the accumulation of tile y overlap the soft-max math of tile y+1.
 //
+// Measured and rejected (tools/attn_bwd_sweep.sh, X2I_ATTN_EXPERIMENTS build): removing ALL soft-max math changes the run time by
+// < 13 % (dK/dV launch) / 0 % (dQ launch), so the kernel is bound by its MMA stream, not by MUFU or the hand-off; moving the owner
+// tiles into TMEM (TS-form T products, three single-accumulator launches) made it SLOWER (0.69 -> 0.86 ms): the 128 x 64 x 16 T
+// products take as long as 128 x 128 x 16 ones whether A comes from shared memory or TMEM, i.e. N = 64 runs the tensor pipe at
+// half rate.  The next step is a 128-wide streamed tile (needs a TMEM plan with single-buffered T2), not more soft-max tuning.
+//
 // 320 threads: warp 0 TMA producer, warp 1 MMA issuer (one lane), warps 2..5 / 6..9 two soft-max + epilogue
 // warpgroups (one owner row per thread; warpgroup g owns T buffer g).  lse / delta are [B*H, Lpad] fp32 (log2 domain, +inf / 0 in the padding) written by the forward kernel and
 // by attn_bwd_prep_kernel.  All tensors are head-major [B*H, L, 128] bf16.
@@ -30,6 +36,7 @@ struct AttnBwdParams {
   const float* delta;
   __nv_bfloat16* out0;  // KV: dK, else dQ
   __nv_bfloat16* out1;  // KV: dV
+  int dbg;  // X2I_ATTN_EXPERIMENTS builds only: 1 = soft-max warps skip all math (timing floor of the MMA / TMA pipeline, wrong results)
 };
 
 constexpr int ABW_THREADS = 320;
@@ -54,9 +61,9 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
   uint64_t* y_full = bars + 1;     // 4
   uint64_t* y_empty = bars + 5;    // 4
   uint64_t* t_full = bars + 9;     // 2
-  uint64_t* pd_full = bars + 11;   // 2
-  uint64_t* acc_full = bars + 13;  // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* pd_full = bars + 11;   // 2 buffers x 2 halves (32 streamed rows each): the accumulating MMAs start per half
+  uint64_t* acc_full = bars + 15;  // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
@@ -76,7 +83,8 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&pd_full[i], 4);
+      mbar_init(&pd_full[2 * i], 4);
+      mbar_init(&pd_full[2 * i + 1], 4);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -141,11 +149,11 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
             umma_ss_w(tmem_base + buf * 128 + op * 64, xdesc + (ox >> 4), ydesc + (oy >> 4), idesc_t, kk != 0);
           }
       };
-      auto issue_acc = [&](int y, int buf) {  // acc0 += dS~ Y0 ; KV: acc1 += P~ Y1   (A from TMEM, K = 64 streamed rows)
+      auto issue_acc = [&](int y, int buf, int half) {  // acc0 += dS~ Y0 ; KV: acc1 += P~ Y1   (A from TMEM, 32 streamed rows per half)
         const uint64_t ydesc = make_smem_desc_sw128(y_base + (y & (ABW_STAGES - 1)) * ABW_STAGE_BYTES, 8192, 1024);
         const uint32_t acc = y > 0 ? 1u : 0u;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 2 * half; kk < 2 * half + 2; ++kk) {
           umma_ts_w(tmem_base + 256, tmem_base + buf * 128 + 64 + kk * 8, ydesc + ((kk * 2048) >> 4), idesc_acc, kk > 0 ? 1u : acc);
           if constexpr (KV)
             umma_ts_w(tmem_base + 384, tmem_base + buf * 128 + kk * 8, ydesc + ((16384 + kk * 2048) >> 4), idesc_acc, kk > 0 ? 1u : acc);
@@ -166,9 +174,12 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
       }
       for (int y = 0; y < n_y; ++y) {
         const int buf = y & 1;
-        mbar_wait(&pd_full[buf], (y >> 1) & 1);
-        tc_fence_after();
-        issue_acc(y, buf);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&pd_full[2 * buf + half], (y >> 1) & 1);
+          tc_fence_after();
+          issue_acc(y, buf, half);
+        }
         umma_commit_w(&y_empty[y & (ABW_STAGES - 1)]);
         if (y + 2 < n_y) {
           y_wait(y + 2);
@@ -200,48 +211,70 @@ mmdit_attention_bwd_kernel(const __grid_constant__ CUtensorMap tma_x0, const __g
       const float* st = sstat + (y & (ABW_STAGES - 1)) * (ABW_STATS_BYTES / 4);
       if constexpr (KV) mbar_wait(&y_full[y & (ABW_STAGES - 1)], (y / ABW_STAGES) & 1);  // lse / delta of this tile landed
       const int valid = p.L - y * 64;  // streamed rows beyond L: zero-filled by TMA
+#ifdef X2I_ATTN_EXPERIMENTS
+      if (p.dbg == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&pd_full[2 * wg]); mbar_arrive(&pd_full[2 * wg + 1]); }
+        continue;
+      }
+#endif
+      // All four TMEM loads are issued up front (one round trip); each 32-row half is handed to the accumulating MMAs as soon as
+      // its P~ / dS~ stores have landed, and the completion wait of half 0 is deferred behind the math of half 1.
+      uint32_t a[2][32], d[2][32];
+      tmem_ld32(t1, a[0]);
+      tmem_ld32(t2, d[0]);
+      tmem_ld32(t1 + 32, a[1]);
+      tmem_ld32(t2 + 32, d[1]);
+      tmem_ld_wait();
+      const uint64_t sc2 = pack_f32x2(sc, sc);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t a[32], d[32];
-        tmem_ld32(t1 + c * 32, a);
-        tmem_ld32(t2 + c * 32, d);
-        tmem_ld_wait();
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
-          float l4[4], dl4[4];
+          uint64_t nl2[2], ndl2[2];  // (-lse, -lse), (-delta, -delta) pairs of the 4 streamed rows k..k+3
           if constexpr (KV) {
             const float4 lv = *reinterpret_cast<const float4*>(st + c * 32 + k);
             const float4 dv = *reinterpret_cast<const float4*>(st + 64 + c * 32 + k);
-            l4[0] = lv.x; l4[1] = lv.y; l4[2] = lv.z; l4[3] = lv.w;
-            dl4[0] = dv.x; dl4[1] = dv.y; dl4[2] = dv.z; dl4[3] = dv.w;
+            nl2[0] = pack_f32x2(-lv.x, -lv.y); nl2[1] = pack_f32x2(-lv.z, -lv.w);
+            ndl2[0] = pack_f32x2(-dv.x, -dv.y); ndl2[1] = pack_f32x2(-dv.z, -dv.w);
           } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { l4[e] = my_lse; dl4[e] = my_delta; }
+            nl2[0] = nl2[1] = pack_f32x2(-my_lse, -my_lse);
+            ndl2[0] = ndl2[1] = pack_f32x2(-my_delta, -my_delta);
           }
-          float pv[4], dsv[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            pv[e] = fast_exp2(fmaf(__uint_as_float(a[k + e]), sc, -l4[e]));
+          for (int e = 0; e < 2; ++e) {
+            const int kk = k + 2 * e;
+            float x0, x1;
+            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(a[c][kk]), __uint_as_float(a[c][kk + 1])), sc2, nl2[e]), x0, x1);
+            float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
             if constexpr (!KV) {
-              if (c * 32 + k + e >= valid) pv[e] = 0.f;  // padded keys
+              if (c * 32 + kk >= valid) p0 = 0.f;  // padded keys
+              if (c * 32 + kk + 1 >= valid) p1 = 0.f;
             }
-            dsv[e] = pv[e] * (__uint_as_float(d[k + e]) - dl4[e]);
+            const uint64_t dd = add_f32x2(pack_f32x2(__uint_as_float(d[c][kk]), __uint_as_float(d[c][kk + 1])), ndl2[e]);
+            float s0, s1;
+            unpack_f32x2(mul_f32x2(pack_f32x2(p0, p1), dd), s0, s1);
+            pk[kk >> 1] = pack_bf16x2(p0, p1);
+            dk[kk >> 1] = pack_bf16x2(s0, s1);
           }
-          pk[k >> 1] = pack_bf16x2(pv[0], pv[1]);
-          pk[(k >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-          dk[k >> 1] = pack_bf16x2(dsv[0], dsv[1]);
-          dk[(k >> 1) + 1] = pack_bf16x2(dsv[2], dsv[3]);
         }
-        // P~ / dS~ alias the first 32 columns of T1 / T2: half c lands in columns [16c, 16c+16), which this thread has
-        // already consumed (c = 0: columns 0..15 were loaded above; c = 1: columns 16..31 were loaded in the first half)
+        if (c == 1) {  // hand-off of half 0: its stores were issued before the math of half 1
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pd_full[2 * wg]);
+        }
+        // P~ / dS~ alias the first 32 columns of T1 / T2: half c lands in columns [16c, 16c+16); all 64 columns of this row
+        // were loaded above, so nothing unread is overwritten
         if constexpr (KV) tmem_st16(t1 + c * 16, pk);
         tmem_st16(t2 + c * 16, dk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pd_full[wg]);
+      if (lane == 0) mbar_arrive(&pd_full[2 * wg + 1]);
     }
     // ---- epilogue: accumulators -> bf16, head-major.  KV: warpgroup 0 drains dK, warpgroup 1 dV; else each takes 64 columns of dQ
     mbar_wait(acc_full, 0);

@@ -848,6 +848,14 @@ int x2i_mmdit_attention_bwd(const void* q, const void* k, const void* v, const v
   p.scale = 1.0f / sqrtf(128.0f);
   p.scale_log2 = 1.4426950408889634f * p.scale;
   p.lse = lse; p.delta = delta;
+  p.dbg = 0;
+#ifdef X2I_ATTN_EXPERIMENTS
+  static const int bwd_dbg = []() { const char* e = getenv("X2I_ATTN_BWD_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = bwd_dbg;
+  static const int bwd_only = []() { const char* e = getenv("X2I_ATTN_BWD_ONLY"); return e ? atoi(e) : 0; }();  // 1: KV launch only, 2: Q launch only
+#else
+  const int bwd_only = 0;
+#endif
   static std::atomic<bool> configured[16];
   if (!configured[d->index].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(mmdit_attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
@@ -858,10 +866,10 @@ int x2i_mmdit_attention_bwd(const void* q, const void* k, const void* v, const v
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid((L + 127) / 128, heads, B);
   p.out0 = static_cast<__nv_bfloat16*>(dk); p.out1 = static_cast<__nv_bfloat16*>(dv);
-  mmdit_attention_bwd_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
+  if (bwd_only != 2) mmdit_attention_bwd_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
   if (int rc = check_launch("mmdit_attention_bwd_kernel<kv>")) return rc;
   p.out0 = static_cast<__nv_bfloat16*>(dq); p.out1 = nullptr;
-  mmdit_attention_bwd_kernel<false><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tq, tdo, tk, tv, p);
+  if (bwd_only != 1) mmdit_attention_bwd_kernel<false><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tq, tdo, tk, tv, p);
   return check_launch("mmdit_attention_bwd_kernel<q>");
 }
 
