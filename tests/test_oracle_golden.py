@@ -2,6 +2,7 @@
 import json
 import os
 
+import pytest
 import torch
 
 from oracle import flux_oracle as fo
@@ -124,3 +125,27 @@ def test_resampler_oracle_matches_reference(golden_dir):
     with torch.no_grad():
         y = m(g["x"], g["tgt_sizes"])
     torch.testing.assert_close(y, g["out"], rtol=1e-5, atol=1e-6)
+
+
+def test_adaln_leaves_match_an_independent_in_image_copy():
+    """Second anchor for the un-vendored diffusers AdaLN leaves (parity is unpinned by the reference itself): the
+    F5-TTS-derived DiT inside transformers' Qwen2.5-Omni carries the same two modules (chunk order shift/scale/gate x2, and the
+    scale-FIRST order of the final AdaLayerNormContinuous).  Same weights -> identical outputs."""
+    omni = pytest.importorskip("transformers.models.qwen2_5_omni.modeling_qwen2_5_omni")
+    if not hasattr(omni, "Qwen2_5_OmniAdaLayerNormZero"):
+        pytest.skip("this transformers build has no Qwen2_5_OmniAdaLayerNormZero")
+    from oracle import flux_oracle as fo
+    torch.manual_seed(0)
+    dim = 64
+    mine, theirs = fo.AdaLayerNormZero(dim).eval(), omni.Qwen2_5_OmniAdaLayerNormZero(dim).eval()
+    theirs.load_state_dict({k: v for k, v in mine.state_dict().items() if k.startswith("linear.")}, strict=False)
+    x, emb = torch.randn(2, 7, dim), torch.randn(2, dim)
+    with torch.no_grad():
+        a, b = mine(x, emb), theirs(x, emb)
+    assert len(a) == len(b) == 5
+    for u, v in zip(a, b):
+        assert torch.allclose(u, v, atol=1e-6)
+    fin, fin_t = fo.AdaLayerNormContinuous(dim, dim).eval(), omni.Qwen2_5_OmniAdaLayerNormZero_Final(dim).eval()
+    fin_t.load_state_dict({k: v for k, v in fin.state_dict().items() if k.startswith("linear.")}, strict=False)
+    with torch.no_grad():
+        assert torch.allclose(fin(x, emb), fin_t(x, emb), atol=1e-6)
