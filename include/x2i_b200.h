@@ -288,10 +288,12 @@ int64_t x2i_proj_mix_wgrad_workspace_floats(int B, int C, int S);
 int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
                     void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, void* stream);
 /* Same with `groups` weight sets: image n uses w[n / (Nimg / groups)] (w [groups, Cout, KH*KW*Cin], bias [groups, Cout]) -- the 19
- * ControlNeXt nets of a LightControl step (same layer shapes, different weights) as ONE launch per layer.                   */
+ * ControlNeXt nets of a LightControl step (same layer shapes, different weights) as ONE launch per layer -- and with separate
+ * leading (top/left: `pad`) and trailing (bottom/right: `pad_end`) zero padding: the VAE encoder's Downsample2D pads (0,1,0,1)
+ * before its stride-2 conv.                                                                                               */
 int x2i_conv2d_nhwc_grouped(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
-                            void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, int groups,
-                            void* stream);
+                            void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int pad_end, int relu,
+                            int groups, void* stream);
 /* ControlNeXtModel.embedding[0]: Conv2d(3 -> 64, 3x3, stride 2, pad 1) on the NCHW bf16 hint image -> NHWC bf16 [N,H/2,W/2,64];
  * w fp32 [64,3,3,3] (PyTorch layout), bias fp32 [64].                                                                  */
 int x2i_conv_first(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, void* stream);

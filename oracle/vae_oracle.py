@@ -9,8 +9,8 @@ Reference call site: ``infer/inference_qwenvl.py:75`` (``AutoencoderKL.from_pret
     image = image_processor.postprocess(image, output_type="pil")                        # (x / 2 + 0.5).clamp(0, 1)
 
 ``AutoencoderKL`` lives in ``diffusers==0.31.0`` (``models/autoencoders/autoencoder_kl.py``, ``vae.py``, ``unets/unet_2d_blocks.py``,
-``resnet.py``, ``upsampling.py``, ``attention_processor.py``; un-vendored, requirements.txt:3).  This file restates the DECODER
-from the published architecture for the FLUX configuration (latent_channels 16, block_out_channels (128, 256, 512, 512),
+``resnet.py``, ``upsampling.py``, ``attention_processor.py``; un-vendored, requirements.txt:3).  This file restates the DECODER (and, for
+``vae.encode`` of ``lightcontrol/train_lightcontrol.py:678``, the ENCODER) from the published architecture for the FLUX configuration (latent_channels 16, block_out_channels (128, 256, 512, 512),
 layers_per_block 2, norm_num_groups 32, SiLU, mid-block attention with one 512-wide head, no post_quant_conv,
 scaling_factor 0.3611, shift_factor 0.1159) with diffusers' state-dict key names.
 
@@ -124,6 +124,72 @@ class Decoder(nn.Module):
         return self.conv_out(F.silu(self.conv_norm_out(x)))
 
 
+class Downsample2D(nn.Module):
+    """diffusers Downsample2D(use_conv=True, padding=0) of the VAE encoder: F.pad(x, (0, 1, 0, 1)) then Conv2d(k3, s2, p0) [D031]."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        return self.conv(F.pad(x, (0, 1, 0, 1), mode="constant", value=0))
+
+
+class DownEncoderBlock2D(nn.Module):
+    def __init__(self, in_channels, out_channels, num_layers, add_downsample, groups=32):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(in_channels if i == 0 else out_channels, out_channels, groups) for i in range(num_layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(out_channels)]) if add_downsample else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](x)
+        return x
+
+
+class Encoder(nn.Module):
+    """diffusers Encoder(double_z=True): conv_in, 4 DownEncoderBlock2D (2 resnets each, down-sampling on all but the last),
+    the same mid block as the decoder, GroupNorm + SiLU + conv_out to 2 * latent_channels (mean | logvar) [D031]."""
+
+    def __init__(self, in_channels=3, latent_channels=16, block_out_channels=(128, 256, 512, 512), layers_per_block=2, norm_num_groups=32):
+        super().__init__()
+        self.conv_in = nn.Conv2d(in_channels, block_out_channels[0], 3, padding=1)
+        self.down_blocks = nn.ModuleList()
+        prev = block_out_channels[0]
+        for i, ch in enumerate(block_out_channels):
+            self.down_blocks.append(DownEncoderBlock2D(prev, ch, layers_per_block, i != len(block_out_channels) - 1, norm_num_groups))
+            prev = ch
+        self.mid_block = UNetMidBlock2D(prev, norm_num_groups)
+        self.conv_norm_out = nn.GroupNorm(norm_num_groups, prev, eps=1e-6)
+        self.conv_out = nn.Conv2d(prev, 2 * latent_channels, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv_in(x)
+        for b in self.down_blocks:
+            x = b(x)
+        x = self.mid_block(x)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
+
+
+class DiagonalGaussianDistribution:
+    """diffusers DiagonalGaussianDistribution: mean | logvar = chunk(2, dim=1), logvar clamped to [-30, 20] [D031]."""
+
+    def __init__(self, parameters):
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def sample(self, generator=None, noise=None):
+        if noise is None:
+            noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self):
+        return self.mean
+
+
 class AutoencoderKLDecoder(nn.Module):
     """``vae.decode(z, return_dict=False)[0]`` of the FLUX AutoencoderKL (use_post_quant_conv=False: the decoder is applied
     to z directly).  Keys: ``decoder.*`` as in the diffusers checkpoint."""
@@ -140,6 +206,21 @@ class AutoencoderKLDecoder(nn.Module):
         return (self.decoder(z),)
 
 
+class AutoencoderKL(AutoencoderKLDecoder):
+    """Encoder + decoder: ``vae.encode(pixel_values).latent_dist.sample()`` of lightcontrol/train_lightcontrol.py:678 (no
+    quant_conv in the FLUX configuration) and ``vae.decode``.  Keys ``encoder.*`` / ``decoder.*`` as in the checkpoint."""
+
+    def __init__(self, **config):
+        super().__init__(**config)
+        cfg = self.cfg
+        self.encoder = Encoder(cfg["in_channels"], cfg["latent_channels"], tuple(cfg["block_out_channels"]), cfg["layers_per_block"],
+                               cfg["norm_num_groups"])
+
+    def encode(self, x):
+        from types import SimpleNamespace
+        return SimpleNamespace(latent_dist=DiagonalGaussianDistribution(self.encoder(x)))
+
+
 def decode_latents(vae, packed_latents, height, width):
     """infer/inference_qwenvl.py:209-216 up to (and including) the [0, 1] image tensor of postprocess()."""
     from .flux_oracle import unpack_latents
@@ -148,6 +229,21 @@ def decode_latents(vae, packed_latents, height, width):
     z = z / vae.cfg["scaling_factor"] + vae.cfg["shift_factor"]
     img = vae.decode(z)[0]
     return (img / 2 + 0.5).clamp(0, 1)
+
+
+def bfl_encoder_key_map(cfg=FLUX_VAE_CONFIG):
+    """diffusers encoder key prefix -> BFL (torchtitan ... autoencoder.Encoder) key prefix."""
+    n = len(cfg["block_out_channels"])
+    m = {"conv_in": "conv_in", "conv_norm_out": "norm_out", "conv_out": "conv_out",
+         "mid_block.resnets.0": "mid.block_1", "mid_block.resnets.1": "mid.block_2",
+         "mid_block.attentions.0.group_norm": "mid.attn_1.norm", "mid_block.attentions.0.to_q": "mid.attn_1.q",
+         "mid_block.attentions.0.to_k": "mid.attn_1.k", "mid_block.attentions.0.to_v": "mid.attn_1.v",
+         "mid_block.attentions.0.to_out.0": "mid.attn_1.proj_out"}
+    for i in range(n):
+        for j in range(cfg["layers_per_block"]):
+            m[f"down_blocks.{i}.resnets.{j}"] = f"down.{i}.block.{j}"
+        m[f"down_blocks.{i}.downsamplers.0.conv"] = f"down.{i}.downsample.conv"
+    return m
 
 
 def bfl_key_map(cfg=FLUX_VAE_CONFIG):

@@ -23,6 +23,26 @@ def _remap_to_bfl(vo, dec_sd, bfl_sd, cfg):
     return out
 
 
+def test_vae_oracle_encoder_matches_bfl_encoder():
+    bfl = pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
+    from oracle import vae_oracle as vo
+    torch.manual_seed(1)
+    cfg = dict(vo.FLUX_VAE_CONFIG, block_out_channels=(32, 64, 64, 64))
+    v = vo.AutoencoderKL(**cfg).eval()
+    b = bfl.Encoder(resolution=64, in_channels=3, ch=32, ch_mult=[1, 2, 2, 2], num_res_blocks=2, z_channels=16).eval()
+    m, bsd, new = vo.bfl_encoder_key_map(cfg), b.state_dict(), {}
+    for k, t in v.encoder.state_dict().items():
+        pref = max((p for p in m if k.startswith(p + ".")), key=len)
+        bk = m[pref] + "." + k[len(pref) + 1:].replace("conv_shortcut", "nin_shortcut")
+        new[bk] = t[:, :, None, None] if (bsd[bk].dim() == 4 and t.dim() == 2) else t
+    b.load_state_dict(new, strict=True)
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        assert float((v.encoder(x) - b(x)).abs().max()) < 1e-4
+        d = v.encode(x).latent_dist
+        assert d.mode().shape == (2, 16, 8, 8) and torch.equal(d.mode(), v.encoder(x)[:, :16])
+
+
 def test_vae_oracle_matches_bfl_decoder():
     """Independent sanity anchor of the unpinned diffusers leaf: same weights, BFL key layout, fp32."""
     bfl = pytest.importorskip("torchtitan.experiments.flux.model.autoencoder")
@@ -42,8 +62,10 @@ def test_vae_dropin_surface_and_keys():
     from x2i_b200 import vae as xv
     from x2i_b200._lib import X2IError
     m = xv.AutoencoderKL()
-    o = vo.AutoencoderKLDecoder()
+    o = vo.AutoencoderKL()
     assert list(m.state_dict().keys()) == list(o.state_dict().keys())
+    assert "encoder.down_blocks.0.downsamplers.0.conv.weight" in m.state_dict() and "encoder.down_blocks.3.downsamplers.0.conv.weight" not in m.state_dict()
+    assert m.state_dict()["encoder.conv_out.weight"].shape == (32, 512, 3, 3)
     assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in o.state_dict().items()}
     assert "decoder.mid_block.attentions.0.to_out.0.weight" in m.state_dict()
     assert "decoder.up_blocks.2.resnets.0.conv_shortcut.weight" in m.state_dict()
@@ -108,7 +130,7 @@ def _pair(cfg, seed):
     from oracle import vae_oracle as vo
     from x2i_b200 import vae as xv
     torch.manual_seed(seed)
-    o = vo.AutoencoderKLDecoder(**cfg).eval()
+    o = vo.AutoencoderKL(**cfg).eval()
     with torch.no_grad():
         for n, p in o.named_parameters():  # non-trivial GroupNorm affine parameters (the default init is weight 1, bias 0)
             if "norm" in n:
@@ -192,3 +214,27 @@ def test_pipeline_decodes_through_vae_like_the_reference_tail(ops):
             bare(**kw, output_type="pt")
     assert img.shape == (1, 3, 64, 96) and float((img - ref.float()).abs().max()) < 5e-3  # fp32 vs bf16 denormalise of the same decode
     assert len(pil) == 1 and pil[0].size == (96, 64)
+
+
+@gpu
+@pytest.mark.parametrize("blocks,hw", [((128, 128, 256, 256), (64, 96)), ((64, 128, 256, 512), (32, 64))])
+def test_vae_encode_matches_oracle(ops, blocks, hw):
+    """vae.encode(x).latent_dist (train_lightcontrol.py:678): moments against the fp32 oracle, sample() = mean + std * noise."""
+    cfg = dict(block_out_channels=blocks, norm_num_groups=32 if blocks[0] >= 128 else 16)
+    o, m = _pair(cfg, 13)
+    g = torch.Generator().manual_seed(14)
+    x = (torch.rand(2, 3, *hw, generator=g) * 2 - 1).bfloat16()
+    with torch.no_grad():
+        ref = o.encoder(x.float())
+        dist = m.encode(x.cuda()).latent_dist
+        got = dist.parameters
+        eager = _rel(o.to("cuda", torch.bfloat16).encoder(x.cuda()), ref)
+    assert got.shape == ref.shape == (2, 32, hw[0] // 8, hw[1] // 8)
+    err = _rel(got, ref)
+    print(f"vae encode rel err vs fp32 oracle: x2i_b200 {err:.4f}, eager bf16 {eager:.4f}")
+    assert err < max(1e-2, eager)
+    assert torch.equal(dist.mode(), got[:, :16])
+    s1 = dist.sample(generator=torch.Generator(device="cuda").manual_seed(3))
+    s2 = dist.sample(generator=torch.Generator(device="cuda").manual_seed(3))
+    assert torch.equal(s1, s2) and s1.shape == (2, 16, hw[0] // 8, hw[1] // 8)
+    assert torch.isfinite(s1.float()).all()

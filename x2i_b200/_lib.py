@@ -73,7 +73,7 @@ SIZE_FUNCS = {
     "x2i_skinny_linear_t_workspace_floats": [_i, _i],
     "x2i_proj_mix_wgrad_workspace_floats": [_i, _i, _i],
     "x2i_groupnorm_workspace_floats": [_i, _i, _i],
-    "x2i_conv2d_nhwc_grouped": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "x2i_conv2d_nhwc_grouped": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "x2i_conv_first_grouped": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "x2i_groupnorm_nhwc_grouped": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
     # ---- VAE decoder

@@ -1048,23 +1048,23 @@ extern "C" {
 
 int x2i_conv2d_nhwc(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
                     void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, void* stream) {
-  return x2i_conv2d_nhwc_grouped(x, w, bias, rowvec, rowvec_stride, residual, out, Nimg, H, W, Cin, Cout, KH, KW, stride, pad, relu, 1, stream);
+  return x2i_conv2d_nhwc_grouped(x, w, bias, rowvec, rowvec_stride, residual, out, Nimg, H, W, Cin, Cout, KH, KW, stride, pad, pad, relu, 1, stream);
 }
 
 int x2i_conv2d_nhwc_grouped(const void* x, const void* w, const void* bias, const void* rowvec, int64_t rowvec_stride, const void* residual,
-                            void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int relu, int groups,
-                            void* stream) {
+                            void* out, int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int pad_end, int relu,
+                            int groups, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   if (Nimg <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin % 64 || Cout <= 0 || Cout % 64 || KH <= 0 || KW <= 0 || KH > 3 || KW > 3 || pad < 0 ||
-      pad > 1 || (stride != 1 && stride != 2))
-    return fail(X2I_ERR_SHAPE, "conv2d_nhwc: need Cin %% 64 == 0, Cout %% 64 == 0, kernel <= 3x3, pad <= 1, stride 1 or 2");
+      pad > 1 || pad_end < 0 || pad_end > 1 || (stride != 1 && stride != 2))
+    return fail(X2I_ERR_SHAPE, "conv2d_nhwc: need Cin %% 64 == 0, Cout %% 64 == 0, kernel <= 3x3, pad / pad_end <= 1, stride 1 or 2");
   if (stride == 2 && ((H | W) & 1)) return fail(X2I_ERR_SHAPE, "conv2d_nhwc: stride 2 needs even H and W");
   if (groups < 1 || Nimg % groups) return fail(X2I_ERR_SHAPE, "conv2d_nhwc: Nimg (%d) must be a multiple of the weight groups (%d)", Nimg, groups);
   if (!x || !w || !out) return fail(X2I_ERR_SHAPE, "conv2d_nhwc: null buffer");
   if (!aligned16(x) || !aligned16(w) || !aligned16(out) || !aligned16(bias) || !aligned16(rowvec) || !aligned16(residual) || rowvec_stride % 8)
     return fail(X2I_ERR_ALIGN, "conv2d_nhwc: alignment");
-  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const int Ho = (H + pad + pad_end - KH) / stride + 1, Wo = (W + pad + pad_end - KW) / stride + 1;  // pad: top/left, pad_end: bottom/right
   ConvParams cp;
   memset(&cp, 0, sizeof(cp));
   cp.Nimg = Nimg; cp.Ho = Ho; cp.Wo = Wo; cp.Cin = Cin; cp.KH = KH; cp.KW = KW; cp.stride = stride; cp.pad = pad;

@@ -537,10 +537,11 @@ def proj_mix_wgrad(x, g, mode):
 
 
 # ================================================================================================ ControlNeXt (LightControl)
-def conv2d_nhwc(x, w_packed, bias, kh, kw, stride=1, pad=1, rowvec=None, residual=None, relu=False, out=None, groups=1):
+def conv2d_nhwc(x, w_packed, bias, kh, kw, stride=1, pad=1, rowvec=None, residual=None, relu=False, out=None, groups=1, pad_end=None):
     """NHWC implicit-GEMM conv: x [N,H,W,Cin], w_packed [Cout, kh*kw*Cin] (from pack_conv_weight), bias [Cout];
     out = relu?(conv + bias + rowvec[n]) + residual, [N,Ho,Wo,Cout].
-    groups > 1: w_packed [groups, Cout, kh*kw*Cin], bias [groups, Cout]; image n uses weight set n // (N // groups)."""
+    groups > 1: w_packed [groups, Cout, kh*kw*Cin], bias [groups, Cout]; image n uses weight set n // (N // groups).
+    pad_end: bottom/right zero padding when it differs from the top/left `pad` (VAE encoder down-sampling: pad=0, pad_end=1)."""
     for t, n in ((x, "x"), (w_packed, "w"), (bias, "bias"), (rowvec, "rowvec"), (residual, "residual"), (out, "out")):
         _chk(t, n)
     N, H, W, Cin = x.shape
@@ -549,13 +550,14 @@ def conv2d_nhwc(x, w_packed, bias, kh, kw, stride=1, pad=1, rowvec=None, residua
     ok = ok and (w_packed.dim() == 2 if groups == 1 else (w_packed.dim() == 3 and w_packed.shape[0] == groups and bias.is_contiguous()))
     if not ok:
         raise _lib.X2IError("conv2d_nhwc: x must be contiguous NHWC and w packed [(groups,) Cout, kh*kw*Cin]")
-    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    pad_end = pad if pad_end is None else pad_end
+    Ho, Wo = (H + pad + pad_end - kh) // stride + 1, (W + pad + pad_end - kw) // stride + 1
     if out is None:
         out = torch.empty(N, Ho, Wo, Cout, device=x.device, dtype=BF16)
     if residual is not None and (residual.numel() != out.numel() or not residual.is_contiguous()):
         raise _lib.X2IError("conv2d_nhwc: residual must be contiguous with the output's shape")
     _lib.call("x2i_conv2d_nhwc_grouped", _p(x), _p(w_packed), _p(bias), _p(rowvec), rowvec.stride(0) if rowvec is not None else 0,
-              _p(residual), _p(out), N, H, W, Cin, Cout, kh, kw, stride, pad, 1 if relu else 0, groups, _stream())
+              _p(residual), _p(out), N, H, W, Cin, Cout, kh, kw, stride, pad, pad_end, 1 if relu else 0, groups, _stream())
     return out
 
 

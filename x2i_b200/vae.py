@@ -1,4 +1,4 @@
-"""Drop-in ``AutoencoderKL`` DECODER for the step right after the denoise loop on sm_100a kernels.
+"""Drop-in ``AutoencoderKL`` (decoder for the step right after the denoise loop; plus the encoder) on sm_100a kernels.
 
 Reference call sites: ``infer/inference_qwenvl.py:75`` (``AutoencoderKL.from_pretrained(flux_path, subfolder="vae",
 torch_dtype=dtype).to(device)``) and ``:209-216`` (``vae.config.block_out_channels / scaling_factor / shift_factor``,
@@ -12,8 +12,9 @@ Inside, activations are NHWC bf16.  Every convolution is the implicit-GEMM tcgen
 ResnetBlock2D is fused into its second conv's epilogue), GroupNorm(32) + SiLU is the fused deterministic kernel pair,
 nearest 2x upsampling is one copy kernel, and the single-head d=512 mid-block attention over the 128x128 latent pixels is
 three tcgen05 GEMMs around a row soft-max with fp32 scores (``x2i_gemm_f32`` -> ``x2i_softmax_rows`` -> ``x2i_gemm_kn``).
-Decode only, inference only; the encoder (LightControl training, ``train_lightcontrol.py:678``) is out of scope.
-No CPU / eager fallback.
+``encode`` (``vae.encode(pixel_values).latent_dist.sample()``, ``lightcontrol/train_lightcontrol.py:678``) runs the encoder half on
+the same kernels; its down-sampling convs (``F.pad(x, (0, 1, 0, 1))`` + stride-2 conv) use the conv kernel's separate trailing
+padding.  Inference only (the VAE is frozen everywhere in the reference).  No CPU / eager fallback.
 """
 from __future__ import annotations
 
@@ -78,6 +79,53 @@ class UpDecoderBlock2D(_Holder):
         self.upsamplers = nn.ModuleList([Upsample2D(out_channels)]) if add_upsample else None
 
 
+class Downsample2D(_Holder):
+    """Conv2d(k3, s2, p0) applied after F.pad(x, (0, 1, 0, 1)) -- the padding is the conv kernel's pad_end."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=0)
+
+
+class DownEncoderBlock2D(_Holder):
+    def __init__(self, in_channels, out_channels, num_layers, add_downsample, groups):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(in_channels if i == 0 else out_channels, out_channels, groups) for i in range(num_layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(out_channels)]) if add_downsample else None
+
+
+class Encoder(_Holder):
+    def __init__(self, in_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups):
+        super().__init__()
+        self.conv_in = nn.Conv2d(in_channels, block_out_channels[0], 3, padding=1)
+        self.down_blocks = nn.ModuleList()
+        prev = block_out_channels[0]
+        for i, ch in enumerate(block_out_channels):
+            self.down_blocks.append(DownEncoderBlock2D(prev, ch, layers_per_block, i != len(block_out_channels) - 1, norm_num_groups))
+            prev = ch
+        self.mid_block = UNetMidBlock2D(prev, norm_num_groups)
+        self.conv_norm_out = nn.GroupNorm(norm_num_groups, prev, eps=1e-6)
+        self.conv_out = nn.Conv2d(prev, 2 * latent_channels, 3, padding=1)
+
+
+class DiagonalGaussianDistribution:
+    """``vae.encode(x).latent_dist`` (diffusers [D031]): mean | logvar = chunk(2, dim=1), logvar clamped to [-30, 20]."""
+
+    def __init__(self, parameters):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self):
+        return self.mean
+
+
 class Decoder(_Holder):
     def __init__(self, in_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups):
         super().__init__()
@@ -94,7 +142,7 @@ class Decoder(_Holder):
 
 
 class AutoencoderKL(nn.Module):
-    """``vae.decode(z, return_dict=False)[0]`` + ``vae.config`` of the reference's VAE (decoder half)."""
+    """``vae.decode(z, return_dict=False)[0]``, ``vae.encode(x).latent_dist`` and ``vae.config`` of the reference's VAE."""
 
     def __init__(self, **config):
         super().__init__()
@@ -107,6 +155,8 @@ class AutoencoderKL(nn.Module):
             raise X2IError("AutoencoderKL: block_out_channels must be multiples of 64")
         self.config = SimpleNamespace(**cfg)
         self.decoder = Decoder(cfg["latent_channels"], cfg["out_channels"], cfg["block_out_channels"], cfg["layers_per_block"],
+                               cfg["norm_num_groups"])
+        self.encoder = Encoder(cfg["in_channels"], cfg["latent_channels"], cfg["block_out_channels"], cfg["layers_per_block"],
                                cfg["norm_num_groups"])
         self._packed = {}
 
@@ -121,8 +171,8 @@ class AutoencoderKL(nn.Module):
     # ------------------------------------------------------------------------------------------------ loading
     @classmethod
     def from_pretrained(cls, path, subfolder=None, torch_dtype=None, **_kw):
-        """Load a diffusers VAE directory (config.json + diffusion_pytorch_model.safetensors / .bin); encoder and quant-conv
-        weights in the file are ignored (decode-only)."""
+        """Load a diffusers VAE directory (config.json + diffusion_pytorch_model.safetensors / .bin); quant-conv weights, if the
+        file has any, are ignored (the FLUX configuration has none)."""
         import glob
         import json
         import os
@@ -139,7 +189,7 @@ class AutoencoderKL(nn.Module):
         else:
             for fn in sorted(glob.glob(os.path.join(d, "*.bin"))):
                 sd.update(torch.load(fn, map_location="cpu"))
-        sd = {k: v for k, v in sd.items() if k.startswith("decoder.")}
+        sd = {k: v for k, v in sd.items() if k.startswith(("decoder.", "encoder."))}
         m.load_state_dict(sd, strict=True)
         return m.to(torch_dtype) if torch_dtype is not None else m
 
@@ -160,9 +210,10 @@ class AutoencoderKL(nn.Module):
             self._packed[key] = hit
         return hit[1], hit[2]
 
-    def _conv(self, x, conv: nn.Conv2d, residual=None, pad_in=0, pad_out=0):
+    def _conv(self, x, conv: nn.Conv2d, residual=None, pad_in=0, pad_out=0, pad_end=None):
         w, b = self._w(conv, pad_in, pad_out)
-        return ops.conv2d_nhwc(x, w, b, conv.kernel_size[0], conv.kernel_size[1], stride=1, pad=conv.padding[0], residual=residual)
+        return ops.conv2d_nhwc(x, w, b, conv.kernel_size[0], conv.kernel_size[1], stride=conv.stride[0], pad=conv.padding[0],
+                               residual=residual, pad_end=pad_end)
 
     @staticmethod
     def _gn(x, gn: nn.GroupNorm, act):
@@ -223,6 +274,40 @@ class AutoencoderKL(nn.Module):
         if return_dict:
             return SimpleNamespace(sample=img)
         return (img,)
+
+    # ------------------------------------------------------------------------------------------------ encode
+    def encode(self, x, return_dict=True):
+        """``vae.encode(pixel_values).latent_dist.sample()`` (lightcontrol/train_lightcontrol.py:678): x [B, 3, H, W] in [-1, 1]
+        -> DiagonalGaussianDistribution over [B, latent_channels, H/8, W/8]."""
+        e = self.encoder
+        if e.conv_in.weight.dtype != BF16 or not x.is_cuda:
+            raise X2IError("AutoencoderKL runs in bf16 on a CUDA device (x2i_b200 has no CPU path): .to('cuda', torch.bfloat16)")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise X2IError("AutoencoderKL.encode: inference only (the VAE is frozen in the reference); call under torch.no_grad()")
+        B, C, H, W = x.shape
+        nd = len(e.down_blocks) - 1
+        if C != self.config.in_channels or H % (1 << nd) or W % (1 << nd):
+            raise X2IError(f"AutoencoderKL.encode: expected [B, {self.config.in_channels}, H, W] with H, W multiples of {1 << nd}")
+        cin_pad = (-C) % 64
+        h = x.to(BF16).permute(0, 2, 3, 1)
+        h = torch.cat([h, h.new_zeros(B, H, W, cin_pad)], -1).contiguous() if cin_pad else h.contiguous()
+        h = self._conv(h, e.conv_in, pad_in=cin_pad)
+        for blk in e.down_blocks:
+            for r in blk.resnets:
+                h = self._resnet(h, r)
+            if blk.downsamplers is not None:
+                h = self._conv(h, blk.downsamplers[0].conv, pad_end=1)       # F.pad(x, (0, 1, 0, 1)) + Conv2d(k3, s2, p0)
+        mid = e.mid_block
+        h = self._resnet(h, mid.resnets[0])
+        h = self._attention(h, mid.attentions[0])
+        h = self._resnet(h, mid.resnets[1])
+        h = self._gn(h, e.conv_norm_out, 2)
+        cout = 2 * self.config.latent_channels
+        y = self._conv(h, e.conv_out, pad_out=(-cout) % 64)
+        dist = DiagonalGaussianDistribution(y[..., :cout].permute(0, 3, 1, 2).contiguous())
+        if return_dict:
+            return SimpleNamespace(latent_dist=dist)
+        return (dist,)
 
     def forward(self, z):
         return self.decode(z)[0]
