@@ -85,3 +85,25 @@ def test_error_paths_fail_loudly():
     with pytest.raises(X2IError):
         ops.attention(torch.randn(1, 1, 8, 64, device="cuda").bfloat16(), torch.randn(1, 1, 8, 64, device="cuda").bfloat16(),
                       torch.randn(1, 1, 8, 64, device="cuda").bfloat16())
+
+
+def test_grouped_and_vae_entry_points_reject_bad_shapes():
+    """The entry points added for the ControlNeXt stack / VAE fail loudly instead of reading out of bounds."""
+    from x2i_b200 import ops
+    from x2i_b200._lib import X2IError
+    x = torch.randn(3, 16, 16, 64, device="cuda").bfloat16()
+    w = torch.randn(2, 64, 9 * 64, device="cuda").bfloat16()
+    b = torch.zeros(2, 64, device="cuda").bfloat16()
+    with pytest.raises(X2IError):          # 3 images cannot be split over 2 weight sets
+        ops.conv2d_nhwc(x, w, b, 3, 3, groups=2)
+    with pytest.raises(X2IError):          # weight tensor does not match `groups`
+        ops.conv2d_nhwc(x, w[0], b[0], 3, 3, groups=2)
+    g = torch.ones(2, 64, device="cuda").bfloat16()
+    with pytest.raises(X2IError):
+        ops.groupnorm_nhwc(x, g, g, 8, 1e-6, param_sets=2)
+    with pytest.raises(X2IError):          # 96 channels: not a power of two
+        ops.groupnorm_nhwc(torch.randn(1, 8, 8, 96, device="cuda").bfloat16(), g[0, :64].repeat(2)[:96].contiguous(), g[0, :64].repeat(2)[:96].contiguous(), 4, 1e-6)
+    with pytest.raises(X2IError):          # soft-max rows longer than the register-resident limit
+        ops.softmax_rows(torch.zeros(2, 16388, device="cuda"))
+    with pytest.raises(X2IError):          # fp32 GEMM needs N % 32 == 0
+        ops.linear_f32(torch.randn(8, 64, device="cuda").bfloat16(), torch.randn(24, 64, device="cuda").bfloat16())
