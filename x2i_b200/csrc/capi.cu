@@ -1154,7 +1154,7 @@ int x2i_groupnorm_nhwc_grouped(const void* x, const void* gamma, const void* bet
   else
     gn_stats_partial_kernel<1><<<dim3(nsplit, Nimg), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), part, HW, C, G, nsplit);
   if (int rc = check_launch("gn_stats_partial_kernel")) return rc;
-  gn_stats_final_kernel<<<(Nimg * G + 3) / 4, 128, 0, st>>>(part, stats, G, nsplit, static_cast<double>(HW) * (C / G), eps, Nimg * G);
+  gn_stats_final_kernel<<<Nimg * G, 128, 0, st>>>(part, stats, G, nsplit, static_cast<double>(HW) * (C / G), eps, Nimg * G);
   if (int rc = check_launch("gn_stats_final_kernel")) return rc;
   const long long cpi = static_cast<long long>(HW) * (C / 8);  // 16-byte chunks per image
   if (cpi > 0x7fffffffLL - 4096) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc: image too large");

@@ -290,30 +290,31 @@ __global__ void __launch_bounds__(256) gn_stats_partial_kernel(const __nv_bfloat
     o[0] = a; o[1] = b;
   }
 }
-// one warp per (image, group): fp64 accumulation of the per-slab partials, fixed order within a lane + shuffle tree
+// one 128-thread CTA per (image, group): fp64 accumulation of the per-slab partials in a fixed order (strided per thread, shuffle
+// tree per warp, 4 warp sums added in order) -- deterministic, and short enough (<= 8 partials per thread) not to show up
+// between the two streaming passes
 __global__ void __launch_bounds__(128) gn_stats_final_kernel(const float* __restrict__ part, float2* __restrict__ stats /* [N, G] (mean, rstd) */,
                                                              int G, int nsplit, double count, float eps, int total) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // n * G + g
-  const int lane = threadIdx.x & 31;
+  __shared__ double red[2][4];
+  const int i = blockIdx.x;  // n * G + g
   if (i >= total) return;
   const int n = i / G, g = i - n * G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double a = 0.0, b = 0.0;
-  for (int s0 = lane; s0 < nsplit; s0 += 128) {  // 4 independent loads in flight; fixed summation order
-    float2 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int sidx = s0 + 32 * u;
-      v[u] = sidx < nsplit ? *reinterpret_cast<const float2*>(part + ((static_cast<long long>(n) * nsplit + sidx) * G + g) * 2) : make_float2(0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { a += v[u].x; b += v[u].y; }
+  for (int sidx = threadIdx.x; sidx < nsplit; sidx += 128) {
+    const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<long long>(n) * nsplit + sidx) * G + g) * 2);
+    a += v.x; b += v.y;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, off);
     b += __shfl_xor_sync(0xffffffffu, b, off);
   }
-  if (lane == 0) {
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    b = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
     const double mean = a / count;
     const double var = fmax(b / count - mean * mean, 0.0);
     stats[i] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
