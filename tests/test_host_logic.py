@@ -152,3 +152,25 @@ def test_projector_bundle_and_checkpoint_formats(tmp_path):
         assert torch.equal(a, b)
     d = torch.load(bundle, weights_only=True)
     assert set(d) == {"config", "state_dict"} and d["config"]["in_channels"] == 5 and d["config"]["input_dim"] == 896
+
+
+def test_bench_reference_arm_json_contract(monkeypatch, capsys):
+    """bench.py --impl reference prints ONE JSON line with the driver's keys (the CPU sample itself is mocked: it takes minutes)."""
+    import argparse
+    import json
+    import bench
+    monkeypatch.setattr(bench, "cpu_sample", lambda threads, nd=1, ns=2, repeat=1: (12.5, "mocked sample"))
+    monkeypatch.delenv("RANK", raising=False)
+    bench.run_reference(argparse.Namespace(gpus=1, steps=2, warmup=1))
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in j, k
+    assert j["impl"] == "reference" and j["unit"] == "steps/s" and abs(j["value"] - 1 / 12.5) < 1e-9 and j["higher_is_better"] is True
+    assert j["config"]["workload"] == bench.WORKLOAD and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == {"value": j["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    monkeypatch.setenv("RANK", "1")  # under torchrun only rank 0 prints
+    bench.run_reference(argparse.Namespace(gpus=2, steps=1, warmup=1))
+    assert capsys.readouterr().out.strip() == ""
