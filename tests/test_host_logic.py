@@ -174,3 +174,20 @@ def test_bench_reference_arm_json_contract(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "1")  # under torchrun only rank 0 prints
     bench.run_reference(argparse.Namespace(gpus=2, steps=1, warmup=1))
     assert capsys.readouterr().out.strip() == ""
+
+
+def test_control_net_stack_eligibility():
+    """ControlNeXtStack only takes over for >= 2 x2i_b200 ControlNeXtModels of identical layout; anything else keeps the per-net
+    protocol of lightcontrol_flux.py:504-507."""
+    import torch.nn as nn
+    from x2i_b200.controlnext import ControlNeXtModel, ControlNeXtStack
+    a, b = ControlNeXtModel(), ControlNeXtModel()
+    assert ControlNeXtStack.supported([a, b]) and ControlNeXtStack.supported(nn.ModuleList([a, b]))
+    assert not ControlNeXtStack.supported([a])
+    assert not ControlNeXtStack.supported([a, nn.Identity()])
+    assert not ControlNeXtStack.supported([a, ControlNeXtModel(out_channels=(128, 128))])
+
+    class Sub(ControlNeXtModel):  # a subclass may override forward: not stacked
+        pass
+
+    assert not ControlNeXtStack.supported([a, Sub()])

@@ -238,3 +238,32 @@ def test_vae_encode_matches_oracle(ops, blocks, hw):
     s2 = dist.sample(generator=torch.Generator(device="cuda").manual_seed(3))
     assert torch.equal(s1, s2) and s1.shape == (2, 16, hw[0] // 8, hw[1] // 8)
     assert torch.isfinite(s1.float()).all()
+
+
+def test_vae_from_pretrained_directory_layout(tmp_path):
+    """AutoencoderKL.from_pretrained(path, subfolder="vae", torch_dtype=...) as infer/inference_qwenvl.py:75 calls it: config.json +
+    diffusion_pytorch_model.{safetensors,bin}; keys outside encoder./decoder. (a checkpoint with quant convs) are ignored."""
+    import json
+    from oracle import vae_oracle as vo
+    from x2i_b200 import vae as xv
+    cfg = dict(block_out_channels=[64, 64, 128, 128], norm_num_groups=16, latent_channels=16, layers_per_block=2,
+               scaling_factor=0.3611, shift_factor=0.1159, _class_name="AutoencoderKL", _diffusers_version="0.31.0")
+    o = vo.AutoencoderKL(**{k: v for k, v in cfg.items() if not k.startswith("_")})
+    sd = dict(o.state_dict())
+    sd["quant_conv.weight"] = torch.zeros(32, 32, 1, 1)  # must be ignored
+    d = tmp_path / "flux" / "vae"
+    d.mkdir(parents=True)
+    (d / "config.json").write_text(json.dumps(cfg))
+    torch.save(sd, d / "diffusion_pytorch_model.bin")
+    m = xv.AutoencoderKL.from_pretrained(str(tmp_path / "flux"), subfolder="vae", torch_dtype=torch.bfloat16)
+    assert m.dtype == torch.bfloat16 and m.config.block_out_channels == (64, 64, 128, 128)
+    for k, v in o.state_dict().items():
+        assert torch.equal(m.state_dict()[k].float(), v.bfloat16().float()), k
+    try:
+        from safetensors.torch import save_file
+    except ImportError:
+        return
+    (d / "diffusion_pytorch_model.bin").unlink()
+    save_file({k: v.contiguous() for k, v in o.state_dict().items()}, str(d / "diffusion_pytorch_model.safetensors"))
+    m2 = xv.AutoencoderKL.from_pretrained(str(tmp_path / "flux"), subfolder="vae")
+    assert torch.equal(m2.state_dict()["decoder.conv_out.bias"], o.state_dict()["decoder.conv_out.bias"])
