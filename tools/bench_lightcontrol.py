@@ -69,11 +69,27 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         t_nets = e0.elapsed_time(e1)
+        # the same 19 nets through ControlNeXtStack (one launch per layer) + the per-net last conv with the fused injection
+        from x2i_b200.controlnext import ControlNeXtStack
+        stack = ControlNeXtStack(nets)
+        for _ in range(2):
+            mids = stack.mid_features(hint, t * 1000)
+            for i, n in enumerate(nets):
+                n.finish_tokens(mids[i], add_to=x)
+        torch.cuda.synchronize()
+        e0.record()
+        mids = stack.mid_features(hint, t * 1000)
+        for i, n in enumerate(nets):
+            n.finish_tokens(mids[i], add_to=x)
+        e1.record()
+        torch.cuda.synchronize()
+        t_stack = e0.elapsed_time(e1)
     conv_flops = 19 * 436.8e9 * B
     print(json.dumps({"workload": "LightControl editing denoise step: FLUX-dev 1024px + 19 ControlNeXt nets on a 1024x1024 hint",
                       "batch": B, "ms_per_step_with_control": res["with_control"][0], "ms_per_step_plain": res["plain"][0],
                       "steps_per_s_with_control": B * 1e3 / res["with_control"][0], "launches_per_step": res["with_control"][1],
-                      "controlnext_19_nets_ms": t_nets, "controlnext_tflops": conv_flops / (t_nets * 1e-3) / 1e12,
+                      "controlnext_19_nets_per_net_ms": t_nets, "controlnext_19_nets_stacked_ms": t_stack,
+                      "controlnext_stacked_tflops": conv_flops / (t_stack * 1e-3) / 1e12,
                       "step_tflops_with_control": (step_flops() * B + conv_flops) / (res["with_control"][0] * 1e-3) / 1e12}))
 
 
