@@ -309,6 +309,14 @@ int64_t x2i_groupnorm_workspace_floats(int Nimg, int HW, int G);
 int x2i_groupnorm_nhwc_grouped(const void* x, const void* gamma, const void* beta, const void* residual, void* y, float* workspace, int Nimg,
                                int HW, int C, int G, float eps, int act, int param_sets, void* stream);
 
+/* ---- LightControl trainer building blocks (lightcontrol/train_lightcontrol.py:672-775: the ControlNeXt nets are
+ * the trainable part; the trainer itself is not assembled yet) --------------------------------------------------------------
+ * Backward of y = act(GroupNorm(x)): dx (bf16), dgamma / dbeta (fp32 [C], overwritten or accumulated); statistics are recomputed
+ * from x.  Groups of a multiple of 8 channels.  Deterministic.  workspace: x2i_groupnorm_bwd_workspace_floats() floats.        */
+int x2i_groupnorm_nhwc_bwd(const void* x, const void* dy, const void* gamma, const void* beta, void* dx, float* dgamma, float* dbeta,
+                           float* workspace, int Nimg, int HW, int C, int G, float eps, int act, int accumulate, void* stream);
+int64_t x2i_groupnorm_bwd_workspace_floats(int Nimg, int HW, int C, int G);
+
 /* ---- VAE decoder (reference call site infer/inference_qwenvl.py:209-216: vae.decode(latents)) ----------
  * The decoder's convolutions and GroupNorms run through x2i_conv2d_nhwc / x2i_groupnorm_nhwc (C up to 2048, groups of 4 or a
  * multiple of 8 channels); these three cover what is left of diffusers' AutoencoderKL decoder [D031].

@@ -8,14 +8,15 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared():
+def _declared(with_types=False):
     src = open(os.path.join(ROOT, "include", "x2i_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    decls = {}
-    for m in re.finditer(r"\b(?:int|int64_t|long long|const char\*)\s+(x2i_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
-        args = m.group(2).strip()
-        decls[m.group(1)] = 0 if args == "void" else len([a for a in args.split(",") if a.strip()])
-    return decls
+    decls, rets = {}, {}
+    for m in re.finditer(r"\b(int|int64_t|long long|const char\*)\s+(x2i_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(3).strip()
+        decls[m.group(2)] = 0 if args == "void" else len([a for a in args.split(",") if a.strip()])
+        rets[m.group(2)] = m.group(1)
+    return (decls, rets) if with_types else decls
 
 
 @pytest.fixture(scope="module")
@@ -43,6 +44,13 @@ def test_bindings_match_header(built):
         assert name in decls and len(argtypes) == decls[name]
     unbound = set(decls) - set(built.SIGNATURES) - set(built.SIZE_FUNCS) - {"x2i_version", "x2i_last_error", "x2i_launch_count"}
     assert not unbound, f"declared but unbound: {unbound}"
+    # return types: `int` status codes are bound with restype c_int (SIGNATURES), `int64_t` sizes with c_int64 (SIZE_FUNCS);
+    # a status function bound as int64 would read the undefined upper half of RAX
+    _, rets = _declared(with_types=True)
+    for name in built.SIGNATURES:
+        assert rets[name] == "int", f"{name} returns {rets[name]} but is bound as a status (int) function"
+    for name in built.SIZE_FUNCS:
+        assert rets[name] == "int64_t", f"{name} returns {rets[name]} but is bound as a size (int64) function"
 
 
 def test_version_and_no_gpu_error_path(built):

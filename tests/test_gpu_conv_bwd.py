@@ -1,0 +1,58 @@
+"""-m gpu: building blocks of the LightControl trainer (the trainer itself is not assembled yet): GroupNorm
+backward and convolution input gradients on the sm_100a kernels against torch autograd in fp32 on the same bf16 inputs.
+Tolerance: one bf16 rounding of the output (4e-3 relative) for dx, 1e-2 for the parameter sums."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import __graft_entry__ as g
+    g.build()
+    from x2i_b200 import ops
+    return ops
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+@pytest.mark.parametrize("C,G,act,hw", [(64, 2, 1, (40, 24)), (128, 4, 2, (33, 20)), (256, 8, 0, (16, 16)), (256, 8, 2, (64, 48))])
+def test_groupnorm_backward(ops, C, G, act, hw):
+    g = torch.Generator(device="cuda").manual_seed(C + act)
+    x = (torch.randn(2, *hw, C, device="cuda", generator=g) * 1.5 + 0.3).bfloat16()
+    dy = torch.randn(2, *hw, C, device="cuda", generator=g).bfloat16()
+    ga = (torch.randn(C, device="cuda", generator=g) * 0.5 + 1).bfloat16()
+    be = (torch.randn(C, device="cuda", generator=g) * 0.5).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = ga.float().requires_grad_(True), be.float().requires_grad_(True)
+    y = F.group_norm(xr, G, gr, br, 1e-6)
+    y = {0: y, 1: torch.relu(y), 2: F.silu(y)}[act]
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    dx, dgamma, dbeta = ops.groupnorm_nhwc_bwd(x, dy, ga, be, G, 1e-6, act=act)
+    assert _rel(dx, xr.grad.permute(0, 2, 3, 1)) < 4e-3
+    assert _rel(dgamma, gr.grad) < 1e-2 and _rel(dbeta, br.grad) < 1e-2
+    dx2, dg2, db2 = ops.groupnorm_nhwc_bwd(x, dy, ga, be, G, 1e-6, act=act, dgamma=dgamma.clone(), dbeta=dbeta.clone(), accumulate=True)
+    assert torch.equal(dx, dx2)                                   # deterministic
+    assert torch.allclose(dg2, 2 * dgamma, rtol=1e-6, atol=1e-6) and torch.allclose(db2, 2 * dbeta, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,hw", [(64, 64, 3, 1, 1, (24, 40)), (128, 256, 3, 1, 1, (16, 16)), (128, 256, 1, 1, 0, (16, 32)),
+                                                        (128, 128, 3, 2, 1, (32, 48)), (256, 3072, 2, 2, 0, (16, 24))])
+def test_conv_input_gradient(ops, cin, cout, k, stride, pad, hw):
+    g = torch.Generator(device="cuda").manual_seed(cin + cout + k)
+    x = torch.randn(2, cin, *hw, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.05).bfloat16()
+    xr = x.float().requires_grad_(True)
+    y = F.conv2d(xr, w.float(), None, stride=stride, padding=pad)
+    dy = torch.randn(y.shape, device="cuda", generator=g).bfloat16()
+    y.backward(dy.float())
+    dx = ops.conv2d_nhwc_dgrad(dy.permute(0, 2, 3, 1).contiguous(), w, stride=stride, pad=pad)
+    assert dx.shape == (2, *hw, cin)
+    assert _rel(dx, xr.grad.permute(0, 2, 3, 1)) < 4e-3

@@ -66,6 +66,14 @@ SIGNATURES = {
     "x2i_conv2d_nhwc": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "x2i_conv_first": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "x2i_groupnorm_nhwc": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
+    "x2i_conv2d_nhwc_grouped": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "x2i_conv_first_grouped": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "x2i_groupnorm_nhwc_grouped": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
+    "x2i_groupnorm_nhwc_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
+    # ---- VAE decoder
+    "x2i_gemm_f32": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp],
+    "x2i_softmax_rows": [_vp, _i64, _vp, _i64, _i, _i, _vp],
+    "x2i_upsample2x_nhwc": [_vp, _vp, _i, _i, _i, _i, _vp],
 }
 # helpers that return a size instead of a status code
 SIZE_FUNCS = {
@@ -73,13 +81,7 @@ SIZE_FUNCS = {
     "x2i_skinny_linear_t_workspace_floats": [_i, _i],
     "x2i_proj_mix_wgrad_workspace_floats": [_i, _i, _i],
     "x2i_groupnorm_workspace_floats": [_i, _i, _i],
-    "x2i_conv2d_nhwc_grouped": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "x2i_conv_first_grouped": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "x2i_groupnorm_nhwc_grouped": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
-    # ---- VAE decoder
-    "x2i_gemm_f32": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp],
-    "x2i_softmax_rows": [_vp, _i64, _vp, _i64, _i, _i, _vp],
-    "x2i_upsample2x_nhwc": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "x2i_groupnorm_bwd_workspace_floats": [_i, _i, _i, _i],
 }
 
 

@@ -1197,6 +1197,52 @@ int x2i_upsample2x_nhwc(const void* x, void* out, int Nimg, int H, int W, int C,
   return check_launch("upsample2x_nhwc_kernel");
 }
 
+int x2i_groupnorm_nhwc_bwd(const void* x, const void* dy, const void* gamma, const void* beta, void* dx, float* dgamma, float* dbeta,
+                           float* workspace, int Nimg, int HW, int C, int G, float eps, int act, int accumulate, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (Nimg <= 0 || HW <= 0 || C % 64 || C <= 0 || C > 2048 || (C & (C - 1)) || G <= 0 || (C / 8) % G)
+    return fail(X2I_ERR_SHAPE, "groupnorm_nhwc_bwd: C a power of two in [64, 2048], groups of a multiple of 8 channels (C=%d G=%d)", C, G);
+  if (!x || !dy || !gamma || !beta || !dx || !dgamma || !dbeta || !workspace) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc_bwd: null buffer");
+  if (!aligned16(x) || !aligned16(dy) || !aligned16(gamma) || !aligned16(beta) || !aligned16(dx) || !aligned16(workspace))
+    return fail(X2I_ERR_ALIGN, "groupnorm_nhwc_bwd: alignment");
+  if (act < 0 || act > 2) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc_bwd: act must be 0 (none), 1 (ReLU) or 2 (SiLU)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int ppc = gn_pix_per_cta(HW);
+  const int nsplit = (HW + ppc - 1) / ppc;
+  // workspace: stats partials [N, nsplit, G, 2] | stats [N, G] | bwd partials [N, nsplit, C, 2] | chan [N, C] | gsum [N, G]
+  float* part = workspace;
+  float2* stats = reinterpret_cast<float2*>(part + static_cast<long long>(Nimg) * nsplit * G * 2);
+  float* part2 = reinterpret_cast<float*>(stats + static_cast<long long>(Nimg) * G);
+  float2* chan = reinterpret_cast<float2*>(part2 + static_cast<long long>(Nimg) * nsplit * C * 2);
+  float2* gsum = chan + static_cast<long long>(Nimg) * C;
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto DY = static_cast<const __nv_bfloat16*>(dy);
+  auto GA = static_cast<const __nv_bfloat16*>(gamma);
+  auto BE = static_cast<const __nv_bfloat16*>(beta);
+  gn_stats_partial_kernel<1><<<dim3(nsplit, Nimg), 256, 0, st>>>(X, part, HW, C, G, nsplit);
+  if (int rc = check_launch("gn_stats_partial_kernel")) return rc;
+  gn_stats_final_kernel<<<Nimg * G, 128, 0, st>>>(part, stats, G, nsplit, static_cast<double>(HW) * (C / G), eps, Nimg * G);
+  if (int rc = check_launch("gn_stats_final_kernel")) return rc;
+  gn_bwd_partial_kernel<<<dim3(nsplit, Nimg), 256, 0, st>>>(X, DY, stats, GA, BE, part2, HW, C, G, nsplit, act);
+  if (int rc = check_launch("gn_bwd_partial_kernel")) return rc;
+  gn_bwd_final_kernel<<<Nimg * G, 128, 0, st>>>(part2, GA, chan, gsum, C, G, nsplit, static_cast<double>(HW) * (C / G));
+  if (int rc = check_launch("gn_bwd_final_kernel")) return rc;
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(chan, dgamma, dbeta, Nimg, C, accumulate);
+  if (int rc = check_launch("gn_bwd_param_kernel")) return rc;
+  const long long cpi = static_cast<long long>(HW) * (C / 8);
+  if (cpi > 0x7fffffffLL - 4096) return fail(X2I_ERR_SHAPE, "groupnorm_nhwc_bwd: image too large");
+  gn_bwd_apply_kernel<<<dim3(static_cast<unsigned>((cpi + 1023) / 1024), Nimg), 256, 0, st>>>(X, DY, stats, gsum, GA, BE,
+                                                                                             static_cast<__nv_bfloat16*>(dx), static_cast<int>(cpi), C, G, act);
+  return check_launch("gn_bwd_apply_kernel");
+}
+
+int64_t x2i_groupnorm_bwd_workspace_floats(int Nimg, int HW, int C, int G) {
+  const int ppc = gn_pix_per_cta(HW);
+  const int nsplit = (HW + ppc - 1) / ppc;
+  return 2LL * Nimg * nsplit * G + 2LL * Nimg * G + 2LL * Nimg * nsplit * C + 2LL * Nimg * C + 2LL * Nimg * G + 16;
+}
+
 int64_t x2i_groupnorm_workspace_floats(int Nimg, int HW, int G) {
   const int ppc = gn_pix_per_cta(HW);
   const int nsplit = (HW + ppc - 1) / ppc;

@@ -478,4 +478,151 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// GroupNorm backward on NHWC bf16 (building block of the LightControl trainer, SURVEY.md 8(f) N4: the ControlNeXt nets are the
+// trainable part of lightcontrol/train_lightcontrol.py:672-775).  y = act(x^ * gamma + beta), x^ = (x - mean) * rstd per
+// (image, group):   g = dy * act'(x^ gamma + beta);  dgamma_c = sum g x^;  dbeta_c = sum g;
+//                   dx = rstd * (g gamma_c - S1/m - x^ S2/m),  S1 = sum_grp g gamma_c,  S2 = sum_grp g gamma_c x^,  m = |group| * HW.
+// Both group sums follow from the per-channel sums A_c = sum g, B_c = sum g x^, so the reduction pass only keeps those.
+// Deterministic: slab partials -> fixed-order fp64 reduction.  Groups of >= 8 channels (all ControlNeXt GroupNorms).
+__device__ __forceinline__ float act_grad(float z, int act) {  // act 0 none, 1 ReLU, 2 SiLU
+  if (act == 1) return z > 0.f ? 1.f : 0.f;
+  if (act == 2) return dsilu_f(z);
+  return 1.f;
+}
+__global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                             const float2* __restrict__ stats, const __nv_bfloat16* __restrict__ gamma,
+                                                             const __nv_bfloat16* __restrict__ beta, float* __restrict__ part /* [N, nsplit, C, 2] */,
+                                                             int HW, int C, int G, int nsplit, int act) {
+  __shared__ float red[16][256];
+  const int tpp = C >> 3, ppi = 256 / tpp;
+  const int cg = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const int split = blockIdx.x, n = blockIdx.y;
+  const int ppc = gn_pix_per_cta(HW);
+  const int p0 = split * ppc, p1 = min(p0 + ppc, HW);
+  const float2 st = stats[n * G + cg / (tpp / G)];
+  float ga[8], be[8], sa[8], sb[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + cg), ga);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + cg), be);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sa[j] = sb[j] = 0.f;
+  const long long base = static_cast<long long>(n) * HW * C + cg * 8;
+  for (int pp = p0 + pl; pp < p1; pp += ppi) {
+    float fx[8], fd[8];
+    unpack8(ld_stream(x + base + static_cast<long long>(pp) * C), fx);
+    unpack8(ld_stream(dy + base + static_cast<long long>(pp) * C), fd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (fx[j] - st.x) * st.y;
+      const float g = fd[j] * act_grad(fmaf(xh, ga[j], be[j]), act);
+      sa[j] += g;
+      sb[j] += g * xh;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[j][threadIdx.x] = sa[j]; red[8 + j][threadIdx.x] = sb[j]; }
+  __syncthreads();
+  for (int stride = 128; stride >= tpp; stride >>= 1) {  // fold the pixel dimension, fixed order
+    if (static_cast<int>(threadIdx.x) < stride) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + stride];
+    }
+    __syncthreads();
+  }
+  if (static_cast<int>(threadIdx.x) < tpp) {
+    float* o = part + ((static_cast<long long>(n) * nsplit + split) * C + threadIdx.x * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[2 * j] = red[j][threadIdx.x]; o[2 * j + 1] = red[8 + j][threadIdx.x]; }
+  }
+}
+// one CTA per (image, group): per-channel sums over the slabs (fp64, fixed order) -> chan[n, c] = (A_c, B_c), gsum[n, g] = (S1/m, S2/m)
+__global__ void __launch_bounds__(128) gn_bwd_final_kernel(const float* __restrict__ part, const __nv_bfloat16* __restrict__ gamma,
+                                                           float2* __restrict__ chan, float2* __restrict__ gsum, int C, int G, int nsplit, double m) {
+  __shared__ double red[2][4];
+  __shared__ double acc[2];
+  const int n = blockIdx.x / G, g = blockIdx.x - n * G;
+  const int cpg = C / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) acc[0] = acc[1] = 0.0;
+  __syncthreads();
+  for (int cc = 0; cc < cpg; ++cc) {
+    const int c = g * cpg + cc;
+    double a = 0.0, b = 0.0;
+    for (int sidx = threadIdx.x; sidx < nsplit; sidx += 128) {
+      const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<long long>(n) * nsplit + sidx) * C + c) * 2);
+      a += v.x; b += v.y;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      a = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+      b = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+      chan[static_cast<long long>(n) * C + c] = make_float2(static_cast<float>(a), static_cast<float>(b));
+      const double gm = static_cast<double>(__bfloat162float(gamma[c]));
+      acc[0] += gm * a;
+      acc[1] += gm * b;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gsum[blockIdx.x] = make_float2(static_cast<float>(acc[0] / m), static_cast<float>(acc[1] / m));
+}
+// dgamma_c (+)= sum_n B_c[n], dbeta_c (+)= sum_n A_c[n]   (fp32 outputs: parameter gradients)
+__global__ void gn_bwd_param_kernel(const float2* __restrict__ chan, float* __restrict__ dgamma, float* __restrict__ dbeta, int Nimg, int C,
+                                    int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int n = 0; n < Nimg; ++n) {
+    const float2 v = chan[static_cast<long long>(n) * C + c];
+    a += v.x; b += v.y;
+  }
+  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + static_cast<float>(a);
+  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + static_cast<float>(b);
+}
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                           const float2* __restrict__ stats, const float2* __restrict__ gsum,
+                                                           const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                                                           __nv_bfloat16* __restrict__ dx, int chunks_per_img, int C, int G, int act) {
+  constexpr int U = 4;
+  const int tpp = C >> 3;
+  const int cg = threadIdx.x % tpp;
+  const int n = blockIdx.y;
+  const float2 st = stats[n * G + cg / (tpp / G)];
+  const float2 gs = gsum[n * G + cg / (tpp / G)];
+  float ga[8], be[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(gamma) + cg), ga);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(beta) + cg), be);
+  const long long img_off = static_cast<long long>(n) * chunks_per_img;
+  const uint4* xin = reinterpret_cast<const uint4*>(x) + img_off;
+  const uint4* din = reinterpret_cast<const uint4*>(dy) + img_off;
+  uint4* out = reinterpret_cast<uint4*>(dx) + img_off;
+  const int base = blockIdx.x * (256 * U) + threadIdx.x;
+  uint4 qx[U], qd[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = base + u * 256;
+    if (i < chunks_per_img) { qx[u] = ld_stream(xin + i); qd[u] = ld_stream(din + i); }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = base + u * 256;
+    if (i >= chunks_per_img) continue;
+    float fx[8], fd[8];
+    unpack8(qx[u], fx);
+    unpack8(qd[u], fd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (fx[j] - st.x) * st.y;
+      const float g = fd[j] * act_grad(fmaf(xh, ga[j], be[j]), act);
+      fx[j] = st.y * (g * ga[j] - gs.x - xh * gs.y);
+    }
+    out[i] = pack8(fx);
+  }
+}
+
 }  // namespace x2i

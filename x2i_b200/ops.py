@@ -630,3 +630,52 @@ def upsample2x_nhwc(x, out=None):
         out = torch.empty(N, 2 * H, 2 * W, C, device=x.device, dtype=BF16)
     _lib.call("x2i_upsample2x_nhwc", _p(x), _p(out), N, H, W, C, _stream())
     return out
+
+
+# ================================================================================================ LightControl trainer building blocks
+def groupnorm_nhwc_bwd(x, dy, gamma, beta, groups, eps, act=0, dgamma=None, dbeta=None, accumulate=False):
+    """Backward of act(GroupNorm(x)) on NHWC bf16: returns (dx bf16, dgamma fp32 [C], dbeta fp32 [C]).  act 0 none, 1 relu, 2 silu.
+    With accumulate=True the parameter gradients are added into the given fp32 buffers (several images / nets per parameter)."""
+    for t, n in ((x, "x"), (dy, "dy"), (gamma, "gamma"), (beta, "beta")):
+        _chk(t, n)
+    N, H, W, C = x.shape
+    if dy.shape != x.shape or not x.is_contiguous() or not dy.is_contiguous() or gamma.numel() != C or beta.numel() != C:
+        raise _lib.X2IError("groupnorm_nhwc_bwd: x, dy contiguous NHWC of equal shape; gamma, beta [C]")
+    dx = torch.empty_like(x)
+    if dgamma is None:
+        dgamma = torch.empty(C, device=x.device, dtype=F32)
+        dbeta = torch.empty(C, device=x.device, dtype=F32)
+        accumulate = False
+    _chk(dgamma, "dgamma", F32); _chk(dbeta, "dbeta", F32)
+    ws = _ws_f32("groupnorm_bwd", _lib.lib().x2i_groupnorm_bwd_workspace_floats(N, H * W, C, groups), x.device)
+    _lib.call("x2i_groupnorm_nhwc_bwd", _p(x), _p(dy), _p(gamma.contiguous()), _p(beta.contiguous()), _p(dx), _p(dgamma), _p(dbeta), _p(ws),
+              N, H * W, C, groups, float(eps), act, 1 if accumulate else 0, _stream())
+    return dx, dgamma, dbeta
+
+
+def pack_conv_weight_dgrad(w):
+    """[Cout, Cin, KH, KW] -> the packed weight of the convolution that computes the INPUT gradient: channels swapped, taps
+    flipped, i.e. pack_conv_weight(w.transpose(0, 1).flip(2, 3)) -> bf16 [Cin, KH*KW*Cout]."""
+    return pack_conv_weight(w.detach().transpose(0, 1).flip(2, 3))
+
+
+def conv2d_nhwc_dgrad(dy, w, stride=1, pad=1):
+    """Input gradient of conv2d_nhwc for w in PyTorch layout [Cout, Cin, KH, KW]: dy [N, Ho, Wo, Cout] -> dx [N, H, W, Cin].
+      stride 1: the forward implicit-GEMM kernel on the flipped / transposed weights with padding k - 1 - pad;
+      stride 2 (3x3, pad 1, even H, W): the same on dy with zeros inserted between the pixels (Z[2o] = dy[o]);
+      2x2 / stride 2 / pad 0 (non-overlapping patches): one dgrad GEMM on the forward-packed weight + depth-to-space."""
+    _chk(dy, "dy"); _chk(w, "w")
+    Cout, Cin, kh, kw = w.shape
+    N, Ho, Wo, C = dy.shape
+    if C != Cout:
+        raise _lib.X2IError("conv2d_nhwc_dgrad: dy channels must equal w.shape[0]")
+    if stride == 1 and kh == kw and 0 <= kh - 1 - pad <= 1:
+        return conv2d_nhwc(dy.contiguous(), pack_conv_weight_dgrad(w), None, kh, kw, stride=1, pad=kh - 1 - pad)
+    if stride == 2 and kh == 3 and kw == 3 and pad == 1:
+        z = torch.zeros(N, 2 * Ho, 2 * Wo, Cout, device=dy.device, dtype=BF16)
+        z[:, ::2, ::2] = dy
+        return conv2d_nhwc(z, pack_conv_weight_dgrad(w), None, 3, 3, stride=1, pad=1)
+    if stride == 2 and kh == 2 and kw == 2 and pad == 0:
+        cols = linear_dgrad(dy.reshape(N * Ho * Wo, Cout), pack_conv_weight(w))           # [P, (ky, kx, Cin)]
+        return cols.view(N, Ho, Wo, 2, 2, Cin).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * Ho, 2 * Wo, Cin).contiguous()
+    raise _lib.X2IError("conv2d_nhwc_dgrad: supported forms are stride 1 (k - 1 - pad in {0, 1}), 3x3/s2/p1 and 2x2/s2/p0")
