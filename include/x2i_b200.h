@@ -316,6 +316,9 @@ int x2i_groupnorm_nhwc_grouped(const void* x, const void* gamma, const void* bet
 int x2i_groupnorm_nhwc_bwd(const void* x, const void* dy, const void* gamma, const void* beta, void* dx, float* dgamma, float* dbeta,
                            float* workspace, int Nimg, int HW, int C, int G, float eps, int act, int accumulate, void* stream);
 int64_t x2i_groupnorm_bwd_workspace_floats(int Nimg, int HW, int C, int G);
+/* cols[(n, yo, xo), (ky, kx, ci)] = x[n, yo*stride + ky - pad, xo*stride + kx - pad, ci] (zero outside): the explicit operand of the
+ * convolution weight gradient dW[Cout, KH*KW*Cin] = dY^T cols (x2i_gemm_wgrad).  cols: bf16 [Nimg*Ho*Wo, KH*KW*C].              */
+int x2i_im2col_nhwc(const void* x, void* cols, int Nimg, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_end, void* stream);
 
 /* ---- VAE decoder (reference call site infer/inference_qwenvl.py:209-216: vae.decode(latents)) ----------
  * The decoder's convolutions and GroupNorms run through x2i_conv2d_nhwc / x2i_groupnorm_nhwc (C up to 2048, groups of 4 or a

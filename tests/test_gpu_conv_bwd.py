@@ -56,3 +56,21 @@ def test_conv_input_gradient(ops, cin, cout, k, stride, pad, hw):
     dx = ops.conv2d_nhwc_dgrad(dy.permute(0, 2, 3, 1).contiguous(), w, stride=stride, pad=pad)
     assert dx.shape == (2, *hw, cin)
     assert _rel(dx, xr.grad.permute(0, 2, 3, 1)) < 4e-3
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,hw", [(64, 64, 3, 1, 1, (24, 40)), (128, 256, 3, 1, 1, (16, 16)), (128, 256, 1, 1, 0, (16, 32)),
+                                                        (128, 128, 3, 2, 1, (32, 48)), (256, 3072, 2, 2, 0, (16, 24))])
+def test_conv_weight_and_bias_gradient(ops, cin, cout, k, stride, pad, hw):
+    g = torch.Generator(device="cuda").manual_seed(cin + cout + k + 1)
+    x = torch.randn(2, cin, *hw, device="cuda", generator=g).bfloat16()
+    wr = (torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.05).requires_grad_(True)
+    br = torch.zeros(cout, device="cuda").requires_grad_(True)
+    y = F.conv2d(x.float(), wr, br, stride=stride, padding=pad)
+    dy = torch.randn(y.shape, device="cuda", generator=g).bfloat16()
+    y.backward(dy.float())
+    dw, db = ops.conv2d_nhwc_wgrad(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous(), k, k, stride=stride, pad=pad)
+    assert _rel(ops.unpack_conv_weight_grad(dw, cin, k, k), wr.grad) < 4e-3
+    assert _rel(db, br.grad) < 1e-3
+    dw2, db2 = ops.conv2d_nhwc_wgrad(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous(), k, k, stride=stride, pad=pad,
+                                     dw=dw.clone(), db=db.clone(), accumulate=True)
+    assert _rel(dw2, 2 * dw.float()) < 4e-3 and torch.allclose(db2, 2 * db, rtol=1e-5, atol=1e-4)

@@ -1237,6 +1237,20 @@ int x2i_groupnorm_nhwc_bwd(const void* x, const void* dy, const void* gamma, con
   return check_launch("gn_bwd_apply_kernel");
 }
 
+int x2i_im2col_nhwc(const void* x, void* cols, int Nimg, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_end, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (Nimg <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 || KH <= 0 || KW <= 0 || stride <= 0 || pad < 0 || pad_end < 0)
+    return fail(X2I_ERR_SHAPE, "im2col_nhwc: C %% 8 == 0 and positive sizes required");
+  if (!x || !cols || !aligned16(x) || !aligned16(cols)) return fail(X2I_ERR_ALIGN, "im2col_nhwc: alignment");
+  const int Ho = (H + pad + pad_end - KH) / stride + 1, Wo = (W + pad + pad_end - KW) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) return fail(X2I_ERR_SHAPE, "im2col_nhwc: empty output");
+  const long long total8 = static_cast<long long>(Nimg) * Ho * Wo * KH * KW * (C / 8);
+  im2col_nhwc_kernel<<<static_cast<unsigned>((total8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(cols), total8, H, W, Ho, Wo, C / 8, KH, KW, stride, pad);
+  return check_launch("im2col_nhwc_kernel");
+}
+
 int64_t x2i_groupnorm_bwd_workspace_floats(int Nimg, int HW, int C, int G) {
   const int ppc = gn_pix_per_cta(HW);
   const int nsplit = (HW + ppc - 1) / ppc;

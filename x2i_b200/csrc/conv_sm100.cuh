@@ -625,4 +625,26 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const __nv_bfloat16* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// im2col for the convolution WEIGHT gradient (first, explicit form: dW = dY^T cols through the MN-major wgrad GEMM; the implicit
+// split-K form is the next step): cols[(n, yo, xo), (ky, kx, ci)] = x[n, yo*s + ky - pad, xo*s + kx - pad, ci]
+// (zero outside the image).  One 16-byte chunk (8 channels) per thread, writes coalesced.
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const uint4* __restrict__ x, uint4* __restrict__ cols, long long total8, int H, int W,
+                                                          int Ho, int Wo, int c8, int KH, int KW, int stride, int pad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c = static_cast<int>(i % c8);
+  long long r = i / c8;
+  const int tap = static_cast<int>(r % (KH * KW));
+  r /= KH * KW;
+  const int xo = static_cast<int>(r % Wo);
+  r /= Wo;
+  const int yo = static_cast<int>(r % Ho);
+  const long long n = r / Ho;
+  const int yi = yo * stride + tap / KW - pad, xi = xo * stride + tap % KW - pad;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (yi >= 0 && yi < H && xi >= 0 && xi < W) v = __ldg(x + ((n * H + yi) * W + xi) * c8 + c);
+  cols[i] = v;
+}
+
 }  // namespace x2i

@@ -679,3 +679,32 @@ def conv2d_nhwc_dgrad(dy, w, stride=1, pad=1):
         cols = linear_dgrad(dy.reshape(N * Ho * Wo, Cout), pack_conv_weight(w))           # [P, (ky, kx, Cin)]
         return cols.view(N, Ho, Wo, 2, 2, Cin).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * Ho, 2 * Wo, Cin).contiguous()
     raise _lib.X2IError("conv2d_nhwc_dgrad: supported forms are stride 1 (k - 1 - pad in {0, 1}), 3x3/s2/p1 and 2x2/s2/p0")
+
+
+def conv2d_nhwc_wgrad(x, dy, kh, kw, stride=1, pad=1, pad_end=None, dw=None, db=None, accumulate=False):
+    """Weight and bias gradient of conv2d_nhwc: x [N, H, W, Cin], dy [N, Ho, Wo, Cout] -> (dW bf16 in the PACKED layout
+    [Cout, kh*kw*Cin] of pack_conv_weight, db fp32 [Cout]).  Explicit form: one image at a time, im2col (x2i_im2col_nhwc) + the
+    MN-major wgrad GEMM accumulating over the images; db = column sums of dy.  unpack_conv_weight_grad() gives PyTorch's layout."""
+    _chk(x, "x"); _chk(dy, "dy"); _chk(dw, "dw"); _chk(db, "db", F32)
+    N, H, W, Cin = x.shape
+    _, Ho, Wo, Cout = dy.shape
+    pad_end = pad if pad_end is None else pad_end
+    if (Ho, Wo) != ((H + pad + pad_end - kh) // stride + 1, (W + pad + pad_end - kw) // stride + 1) or dy.shape[0] != N:
+        raise _lib.X2IError("conv2d_nhwc_wgrad: dy does not match the convolution's output shape")
+    if not x.is_contiguous() or not dy.is_contiguous():
+        raise _lib.X2IError("conv2d_nhwc_wgrad: x and dy must be contiguous NHWC")
+    if dw is None:
+        dw = torch.empty(Cout, kh * kw * Cin, device=x.device, dtype=BF16)
+        db = torch.empty(Cout, device=x.device, dtype=F32)
+        accumulate = False
+    cols = torch.empty(Ho * Wo, kh * kw * Cin, device=x.device, dtype=BF16)
+    for n in range(N):
+        _lib.call("x2i_im2col_nhwc", _p(x[n]), _p(cols), 1, H, W, Cin, kh, kw, stride, pad, pad_end, _stream())
+        linear_wgrad(dy[n].reshape(Ho * Wo, Cout), cols, out=dw, accumulate=accumulate or n > 0)
+    colsum(dy.reshape(N * Ho * Wo, Cout), 1, N * Ho * Wo, out0=db.view(1, Cout), accumulate=accumulate)
+    return dw, db
+
+
+def unpack_conv_weight_grad(dw_packed, cin, kh, kw):
+    """[Cout, kh*kw*Cin] (tap-major, channels innermost) -> PyTorch's [Cout, Cin, kh, kw]."""
+    return dw_packed.view(dw_packed.shape[0], kh, kw, cin).permute(0, 3, 1, 2).contiguous()
