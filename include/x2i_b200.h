@@ -318,6 +318,9 @@ int x2i_groupnorm_nhwc_bwd(const void* x, const void* dy, const void* gamma, con
 int64_t x2i_groupnorm_bwd_workspace_floats(int Nimg, int HW, int C, int G);
 /* cols[(n, yo, xo), (ky, kx, ci)] = x[n, yo*stride + ky - pad, xo*stride + kx - pad, ci] (zero outside): the explicit operand of the
  * convolution weight gradient dW[Cout, KH*KW*Cin] = dY^T cols (x2i_gemm_wgrad).  cols: bf16 [Nimg*Ho*Wo, KH*KW*C].              */
+/* dx = dy where y > 0 else 0 (backward of a ReLU fused into a conv epilogue, masked by the saved output); out = silu(x).      */
+int x2i_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
+int x2i_silu(const void* x, void* out, int64_t n, void* stream);
 int x2i_im2col_nhwc(const void* x, void* cols, int Nimg, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_end, void* stream);
 
 /* ---- VAE decoder (reference call site infer/inference_qwenvl.py:209-216: vae.decode(latents)) ----------

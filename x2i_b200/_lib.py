@@ -69,6 +69,8 @@ SIGNATURES = {
     "x2i_conv2d_nhwc_grouped": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "x2i_conv_first_grouped": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "x2i_groupnorm_nhwc_grouped": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
+    "x2i_relu_bwd": [_vp, _vp, _vp, _i64, _vp],
+    "x2i_silu": [_vp, _vp, _i64, _vp],
     "x2i_im2col_nhwc": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "x2i_groupnorm_nhwc_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
     # ---- VAE decoder

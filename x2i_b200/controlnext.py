@@ -8,7 +8,9 @@ convolution except the 3-channel stem is an implicit-GEMM tcgen05 kernel (``x2i_
 the A operand, no im2col), GroupNorm + activation (+ residual) is one fused deterministic kernel pair, the time embedding uses
 the skinny-linear kernels.  The final 2x2/stride-2 conv emits [B, h*w, 3072] token-major -- exactly
 ``control['out'].flatten(2).transpose(1, 2)`` -- and, when called from the transformer, adds straight into the image
-stream in its epilogue.  Forward only (inference, BASELINE config 5); no CPU or eager fallback.
+stream in its epilogue.  With gradients enabled and trainable parameters the same kernels run under one autograd node per fused
+layer (``_forward_tokens_train``; backward = conv dgrad / wgrad, GroupNorm backward, skinny-linear backward kernels): the
+trainable part of the LightControl trainer (``lightcontrol/train_lightcontrol.py:672-775``).  No CPU or eager fallback.
 """
 from __future__ import annotations
 
@@ -58,6 +60,112 @@ class Downsample2D(_Holder):
         self.conv = nn.Conv2d(channels, out_channels or channels, 3, stride=2, padding=padding)
 
 
+
+# ------------------------------------------------------------------------------------------------ training (LightControl trainer)
+# One torch.autograd.Function per fused layer; torch only orders the graph, every forward and backward op is an x2i_b200 kernel
+# (forward: the inference kernels; backward: ops.conv2d_nhwc_dgrad / conv2d_nhwc_wgrad / groupnorm_nhwc_bwd / colsum / skinny
+# kernels).  Parameter gradients come back in the parameters' own layout and dtype.
+class _ConvFn(torch.autograd.Function):
+    """y = relu?(conv(x, w) + b + rowvec[n]) + residual on NHWC bf16 (x2i_conv2d_nhwc)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, rowvec, residual, stride, pad, relu):
+        if relu and residual is not None:
+            raise X2IError("_ConvFn: ReLU together with a residual input is not used by ControlNeXt")
+        kh, kw = weight.shape[2], weight.shape[3]
+        y = ops.conv2d_nhwc(x, ops.pack_conv_weight(weight), bias.detach().to(BF16), kh, kw, stride=stride, pad=pad, rowvec=rowvec,
+                            residual=residual, relu=relu)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.meta = (stride, pad, relu, rowvec is not None, residual is not None, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        stride, pad, relu, has_rowvec, has_res, bias_dtype = ctx.meta
+        dy = dy.contiguous()
+        g = ops.relu_bwd(dy, y) if relu else dy
+        kh, kw = weight.shape[2], weight.shape[3]
+        dx = ops.conv2d_nhwc_dgrad(g, weight, stride=stride, pad=pad) if ctx.needs_input_grad[0] else None
+        dwp, db = ops.conv2d_nhwc_wgrad(x, g, kh, kw, stride=stride, pad=pad)
+        dw = ops.unpack_conv_weight_grad(dwp, weight.shape[1], kh, kw).to(weight.dtype)
+        d_rowvec = None
+        if has_rowvec:
+            N, Ho, Wo, C = g.shape
+            d_rowvec = torch.empty(N, C, device=g.device, dtype=torch.float32)
+            ops.colsum(g.view(N * Ho * Wo, C), N, Ho * Wo, out0=d_rowvec)
+            d_rowvec = d_rowvec.to(BF16)
+        return dx, dw, db.to(bias_dtype), d_rowvec, (dy if has_res else None), None, None, None
+
+
+class _GNFn(torch.autograd.Function):
+    """y = act(GroupNorm(x)) + residual on NHWC bf16."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, groups, eps, act):
+        y = ops.groupnorm_nhwc(x, gamma, beta, groups, eps, act=act, residual=residual)
+        ctx.save_for_backward(x, gamma, beta)
+        ctx.meta = (groups, eps, act, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta = ctx.saved_tensors
+        groups, eps, act, has_res = ctx.meta
+        dy = dy.contiguous()
+        dx, dg, db = ops.groupnorm_nhwc_bwd(x, dy, gamma.detach(), beta.detach(), groups, eps, act=act)
+        return dx, dg.to(gamma.dtype), db.to(beta.dtype), (dy if has_res else None), None, None, None
+
+
+class _StemFn(torch.autograd.Function):
+    """Conv2d(3 -> 64, 3x3, s2, p1) on the NCHW hint (no gradient towards the image).  Backward = the generic weight gradient on the
+    hint re-laid out as NHWC with its 3 channels zero-padded to 64."""
+
+    @staticmethod
+    def forward(ctx, sample, weight, bias):
+        ctx.save_for_backward(sample, weight)
+        ctx.bias_dtype = bias.dtype
+        return ops.conv_first(sample, weight.detach().float(), bias.detach().float())
+
+    @staticmethod
+    def backward(ctx, dy):
+        sample, weight = ctx.saved_tensors
+        N, _, H, W = sample.shape
+        xp = torch.zeros(N, H, W, 64, device=sample.device, dtype=BF16)
+        xp[..., :3] = sample.permute(0, 2, 3, 1)
+        dwp, db = ops.conv2d_nhwc_wgrad(xp, dy.contiguous(), 3, 3, stride=2, pad=1)
+        dw = dwp.view(64, 3, 3, 64)[..., :3].permute(0, 3, 1, 2).contiguous().to(weight.dtype)
+        return None, dw, db.to(ctx.bias_dtype)
+
+
+class _SkinnyFn(torch.autograd.Function):
+    """y = silu?(x) @ W^T + b for a handful of rows (time-embedding MLPs): x2i_skinny_linear forward, x2i_skinny_linear_t for the
+    input gradient, the MN-major wgrad GEMM on zero-padded 64-row operands for dW."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act_in):
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (act_in, bias.dtype)
+        return ops.skinny_linear(x, weight, bias, act_in=act_in)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        act_in, bias_dtype = ctx.meta
+        B, N = dy.shape
+        g32 = dy.float().contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.skinny_linear_t(g32, weight.detach(), pre=x if act_in else None, dact=1 if act_in else 0).to(x.dtype)
+        a = ops.silu_rows(x) if act_in else x
+        gp = torch.zeros(64, N, device=dy.device, dtype=BF16); gp[:B] = dy
+        ap = torch.zeros(64, x.shape[1], device=dy.device, dtype=BF16); ap[:B] = a
+        dw = ops.linear_wgrad(gp, ap).to(weight.dtype)
+        db = torch.empty(1, N, device=dy.device, dtype=torch.float32)
+        ops.colsum(gp, 1, 64, out0=db)
+        return dx, dw, db.view(N).to(bias_dtype), None
+
+
 class ControlNeXtModel(nn.Module):
     _supports_gradient_checkpointing = True
 
@@ -103,8 +211,12 @@ class ControlNeXtModel(nn.Module):
         w0 = self.embedding[0]
         if w0.weight.dtype != BF16 or not sample.is_cuda:
             raise X2IError("ControlNeXtModel runs in bf16 on a CUDA device (x2i_b200 has no CPU path): .to('cuda', torch.bfloat16)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and sample.requires_grad:
-            raise X2IError("ControlNeXtModel: forward only (LightControl inference); call under torch.no_grad()")
+        if torch.is_grad_enabled() and sample.requires_grad:
+            raise X2IError("ControlNeXtModel: no gradient towards the hint image (the reference trains the nets, not the hint)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            if add_to is not None:
+                raise X2IError("ControlNeXtModel: the fused in-place injection is inference only; training returns the control tokens")
+            return self._forward_tokens_train(sample, timestep)
         B = sample.shape[0]
         t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=sample.device)
         t = t.reshape(-1).to(sample.device).expand(B).float().contiguous()
@@ -139,6 +251,36 @@ class ControlNeXtModel(nn.Module):
             self._conv(x, last, residual=add_to.view(B, Ho, Wo, 3072), out=add_to.view(B, Ho, Wo, 3072))
             return add_to
         out = self._conv(x, last)
+        return out.view(B, -1, out.shape[-1])
+
+    def _forward_tokens_train(self, sample, timestep):
+        """Differentiable forward (lightcontrol/train_lightcontrol.py:517-522,:732-743: the control nets are the trainable part of
+        the LightControl trainer): same kernels as inference, one autograd node per fused layer."""
+        B = sample.shape[0]
+        t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=sample.device)
+        t = t.reshape(-1).to(sample.device).expand(B).float().contiguous()
+        te = self.time_embedding
+        h = _SkinnyFn.apply(ops.timestep_sinusoid(t, 128), te.linear_1.weight, te.linear_1.bias, 0)
+        emb = _SkinnyFn.apply(h, te.linear_2.weight, te.linear_2.bias, 1)
+        conv = lambda x, c, rowvec=None, residual=None, relu=False: _ConvFn.apply(  # noqa: E731
+            x, c.weight, c.bias, rowvec, residual, c.stride[0], c.padding[0], relu)
+        gn = lambda x, g, act, residual=None: _GNFn.apply(x, g.weight, g.bias, residual, g.num_groups, g.eps, act)  # noqa: E731
+        e = self.embedding
+        x = gn(_StemFn.apply(sample.to(BF16), e[0].weight, e[0].bias), e[1], 1)
+        x = gn(conv(x, e[3]), e[4], 1)
+        x = gn(conv(x, e[6]), e[7], 1)
+        for res, down in zip(self.down_res, self.down_sample):
+            tproj = _SkinnyFn.apply(emb, res.time_emb_proj.weight, res.time_emb_proj.bias, 1)
+            hcur = conv(gn(x, res.norm1, 2), res.conv1, rowvec=tproj)
+            hcur = conv(gn(hcur, res.norm2, 2), res.conv2, residual=x if res.conv_shortcut is None else None)
+            if res.conv_shortcut is not None:
+                hcur = conv(x, res.conv_shortcut, residual=hcur)
+            x = conv(hcur, down.conv)
+        m = self.mid_convs[0]
+        y = conv(x, m[0], relu=True)
+        y = conv(gn(y, m[2], 0), m[3])
+        x = gn(y, m[4], 0, residual=x)
+        out = conv(x, self.mid_convs[1])
         return out.view(B, -1, out.shape[-1])
 
     def finish_tokens(self, x_mid, add_to=None):

@@ -1251,6 +1251,24 @@ int x2i_im2col_nhwc(const void* x, void* cols, int Nimg, int H, int W, int C, in
   return check_launch("im2col_nhwc_kernel");
 }
 
+int x2i_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (n <= 0 || n % 8 || !dy || !y || !dx || !aligned16(dy) || !aligned16(y) || !aligned16(dx)) return fail(X2I_ERR_SHAPE, "relu_bwd: n %% 8 == 0, aligned buffers");
+  relu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(dy), static_cast<const uint4*>(y), static_cast<uint4*>(dx), n / 8);
+  return check_launch("relu_bwd_kernel");
+}
+
+int x2i_silu(const void* x, void* out, int64_t n, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (n <= 0 || n % 8 || !x || !out || !aligned16(x) || !aligned16(out)) return fail(X2I_ERR_SHAPE, "silu: n %% 8 == 0, aligned buffers");
+  silu_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x),
+                                                                                                        static_cast<uint4*>(out), n / 8);
+  return check_launch("silu_kernel");
+}
+
 int64_t x2i_groupnorm_bwd_workspace_floats(int Nimg, int HW, int C, int G) {
   const int ppc = gn_pix_per_cta(HW);
   const int nsplit = (HW + ppc - 1) / ppc;

@@ -647,4 +647,25 @@ __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const uint4* __restric
   cols[i] = v;
 }
 
+// dx = dy where y > 0 else 0 (ReLU fused into a conv epilogue: mask by the saved output); out = silu(x) (tiny time-embedding rows)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, uint4* __restrict__ dx, long long total8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  float a[8], b[8];
+  unpack8(ld_stream(dy + i), a);
+  unpack8(ld_stream(y + i), b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] > 0.f ? a[j] : 0.f;
+  dx[i] = pack8(a);
+}
+__global__ void __launch_bounds__(256) silu_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long total8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  float a[8];
+  unpack8(__ldg(x + i), a);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = silu_f(a[j]);
+  out[i] = pack8(a);
+}
+
 }  // namespace x2i

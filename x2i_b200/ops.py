@@ -708,3 +708,22 @@ def conv2d_nhwc_wgrad(x, dy, kh, kw, stride=1, pad=1, pad_end=None, dw=None, db=
 def unpack_conv_weight_grad(dw_packed, cin, kh, kw):
     """[Cout, kh*kw*Cin] (tap-major, channels innermost) -> PyTorch's [Cout, Cin, kh, kw]."""
     return dw_packed.view(dw_packed.shape[0], kh, kw, cin).permute(0, 3, 1, 2).contiguous()
+
+
+def relu_bwd(dy, y):
+    """dy masked by y > 0 (backward of a ReLU fused into a conv epilogue)."""
+    _chk(dy, "dy"); _chk(y, "y")
+    if dy.shape != y.shape or not dy.is_contiguous() or not y.is_contiguous():
+        raise _lib.X2IError("relu_bwd: dy and y must be contiguous and of equal shape")
+    out = torch.empty_like(dy)
+    _lib.call("x2i_relu_bwd", _p(dy), _p(y), _p(out), dy.numel(), _stream())
+    return out
+
+
+def silu_rows(x):
+    """silu(x) on a small bf16 tensor (time-embedding rows)."""
+    _chk(x, "x")
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.call("x2i_silu", _p(x), _p(out), x.numel(), _stream())
+    return out
