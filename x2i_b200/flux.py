@@ -592,7 +592,12 @@ class FluxTransformer2DModel(nn.Module):
             # the reference fails in apply_rotary_emb's broadcast; here the RoPE table would be read out of bounds
             raise X2IError(f"FluxTransformer2DModel: img_ids / txt_ids have {img_ids.shape[0]} / {txt_ids.shape[0]} rows but the sequences "
                            f"have {hidden_states.shape[1]} / {encoder_hidden_states.shape[1]} tokens")
-        if control_nets is not None and len(control_nets) > 0:
+        train_ctrl = (control_nets is not None and len(control_nets) > 0 and torch.is_grad_enabled()
+                      and any(p.requires_grad for net in control_nets for p in net.parameters()))
+        if train_ctrl:  # LightControl trainer: gradients flow through the frozen transformer into the control nets
+            out = self._forward_train(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+                                      guided_hint=guided_hint, control_nets=control_nets)
+        elif control_nets is not None and len(control_nets) > 0:
             _no_grad_needed(hidden_states, encoder_hidden_states, pooled_projections)
             out = self._forward_eager(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
                                       guided_hint=guided_hint, control_nets=control_nets)
@@ -609,7 +614,8 @@ class FluxTransformer2DModel(nn.Module):
             return (out,)
         return SimpleNamespace(sample=out)
 
-    def _forward_train(self, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance):
+    def _forward_train(self, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance, guided_hint=None,
+                       control_nets=None):
         """Differentiable forward (student pass of the distillation step, train/train_qwenvl.py:578-587): one autograd node
         for the whole transformer (flux_train.FluxTrainFn); the forward hooks registered on every ``blk.attn``
         (train_qwenvl.py:206-214) are then invoked, in block order, with outputs that carry autograd history."""
@@ -618,8 +624,15 @@ class FluxTransformer2DModel(nn.Module):
             if isinstance(m, Attention) and not _default_proc(m):
                 raise X2IError("training through a plug-in attention processor is not supported (no backward for user code "
                                "inside the fused block); use the default FluxAttnProcessor2_0")
+        controls = ()
+        if control_nets is not None and len(control_nets) > 0:  # lightcontrol_flux.py:504-507 with differentiable control tokens
+            t1000 = timestep.to(BF16) * 1000
+            nets = list(control_nets)[:len(self.transformer_blocks)]
+            if not all(hasattr(n, "forward_tokens") for n in nets):
+                raise X2IError("training needs x2i_b200 ControlNeXtModel control nets (their backward runs on the x2i kernels)")
+            controls = tuple(n.forward_tokens(guided_hint, t1000) for n in nets)
         outs = flux_train.FluxTrainFn.apply(self, 0, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids,
-                                            guidance)
+                                            guidance, *controls)
         nd, ns = len(self.transformer_blocks), len(self.single_transformer_blocks)
         out, hi, ht, hs = outs[0], outs[1:1 + nd], outs[1 + nd:1 + 2 * nd], outs[1 + 2 * nd:1 + 2 * nd + ns]
         for i, blk in enumerate(self.transformer_blocks):

@@ -91,8 +91,9 @@ def _single_fwd(blk, h0, mod, rope, B, L, cat_buf):
     return h1, dict(h0=h0, qk_pre=qk_pre, mlp_pre=mlp_pre, q=q, k=k, v=v, a=a, lse=lse, y=y)
 
 
-def forward_save(model, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance):
-    """Training-mode forward.  Returns (out [B, L_img, C], hooks, tape)."""
+def forward_save(model, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance, controls=()):
+    """Training-mode forward.  Returns (out [B, L_img, C], hooks, tape).  controls: the LightControl control tokens [B, L_img, D],
+    added to the image stream after double block i (lightcontrol_flux.py:504-507)."""
     B, L_img, _ = hidden_states.shape
     S = encoder_hidden_states.shape[1]
     D = model.inner_dim
@@ -121,6 +122,9 @@ def forward_save(model, hidden_states, encoder_hidden_states, pooled, timestep, 
         hooks_img.append(sv["ya_i"].view(B, L_img, D))
         hooks_txt.append(sv["ya_t"].view(B, S, D))
         off += 12 * D
+        i_blk = len(tape["double"]) - 1
+        if i_blk < len(controls):  # hidden_states += control['out'] * scale (scale == 1.0); x is block i+1's saved input
+            ops.euler_step_(x, controls[i_blk].to(BF16).contiguous().view(B * L_img, D), 1.0)
     h = _e(B, L, D, device=dev)
     h[:, :S].copy_(c.view(B, S, D))
     h[:, S:].copy_(x.view(B, L_img, D))
@@ -220,8 +224,9 @@ def _single_bwd(blk, sv, dh1, gkd, mod, dmod, rope, B, L, dbig):
     return dh0
 
 
-def backward(model, tape, dout, dhooks_img, dhooks_txt, dhooks_single, need_hidden_grad=False):
-    """Returns (d hidden_states | None, d encoder_hidden_states [B,S,E] bf16, d pooled_projections [B,P] bf16)."""
+def backward(model, tape, dout, dhooks_img, dhooks_txt, dhooks_single, need_hidden_grad=False, n_controls=0):
+    """Returns (d hidden_states | None, d encoder_hidden_states [B,S,E] bf16, d pooled_projections [B,P] bf16, d controls list):
+    the gradient of control i is the image-stream gradient at the output of double block i."""
     B, S, L_img = tape["B"], tape["S"], tape["L_img"]
     D = model.inner_dim
     L = S + L_img
@@ -250,8 +255,11 @@ def backward(model, tape, dout, dhooks_img, dhooks_txt, dhooks_single, need_hidd
     dh3 = dh.view(B, L, D)
     dc = dh3[:, :S].contiguous().view(B * S, D)
     dx = dh3[:, S:].contiguous().view(B * L_img, D)
+    dctrl = [None] * n_controls
     for i in range(len(model.transformer_blocks) - 1, -1, -1):
         off -= 12 * D
+        if i < n_controls:
+            dctrl[i] = dx.view(B, L_img, D).clone()
         dx, dc = _double_bwd(model.transformer_blocks[i], tape["double"][i], dx, dc, _g2(dhooks_img[i], B * L_img, D),
                              _g2(dhooks_txt[i], B * S, D), mod[:, off:off + 12 * D], dmod[:, off:off + 12 * D], rope, B, L_img, S)
         tape["double"][i] = None
@@ -262,16 +270,17 @@ def backward(model, tape, dout, dhooks_img, dhooks_txt, dhooks_single, need_hidd
     dtemb = ops.skinny_linear_t(dmod, model._w_mod, pre=tape["temb"], dact=1)
     dz1 = ops.skinny_linear_t(dtemb, tte.linear_2.weight, pre=tape["z1"], dact=1)
     d_pooled = ops.f32_to_bf16(ops.skinny_linear_t(dz1, tte.linear_1.weight))
-    return d_hidden, d_enc, d_pooled
+    return d_hidden, d_enc, d_pooled, dctrl
 
 
 class FluxTrainFn(torch.autograd.Function):
     """(hidden_states, encoder_hidden_states, pooled_projections) -> (out, *hook tensors)."""
 
     @staticmethod
-    def forward(ctx, model, n_hooks, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance):
+    def forward(ctx, model, n_hooks, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance, *controls):
         out, (hi, ht, hs), tape = forward_save(model, hidden_states.detach(), encoder_hidden_states.detach(), pooled.detach(),
-                                               timestep, img_ids, txt_ids, guidance)
+                                               timestep, img_ids, txt_ids, guidance, tuple(c.detach() for c in controls))
+        ctx.ctrl_dtypes = tuple(c.dtype for c in controls)
         ctx.set_materialize_grads(False)  # hook tensors nobody used arrive as None, not as 28 MB of zeros
         ctx.model, ctx.tape = model, tape
         ctx.n = (len(hi), len(ht), len(hs))
@@ -284,7 +293,9 @@ class FluxTrainFn(torch.autograd.Function):
         if ctx.tape is None:
             raise X2IError("FluxTrainFn: backward called twice (activations are released during the first backward)")
         ni, nt, ns = ctx.n
-        d_hidden, d_enc, d_pooled = backward(ctx.model, ctx.tape, dout, dh[:ni], dh[ni:ni + nt], dh[ni + nt:], ctx.need_hidden)
+        d_hidden, d_enc, d_pooled, dctrl = backward(ctx.model, ctx.tape, dout, dh[:ni], dh[ni:ni + nt], dh[ni + nt:], ctx.need_hidden,
+                                                    len(ctx.ctrl_dtypes))
         ctx.tape = None
         t0, t1, t2 = ctx.dtypes
-        return (None, None, d_hidden.to(t0) if d_hidden is not None else None, d_enc.to(t1), d_pooled.to(t2), None, None, None, None)
+        return (None, None, d_hidden.to(t0) if d_hidden is not None else None, d_enc.to(t1), d_pooled.to(t2), None, None, None, None,
+                *[g.to(dt) for g, dt in zip(dctrl, ctx.ctrl_dtypes)])
