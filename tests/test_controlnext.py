@@ -355,3 +355,41 @@ def test_lightcontrol_gradients_through_frozen_transformer(ops):
     print(f"LightControl gradients: total rel err {tot:.4f} (eager bf16 {tot_e:.4f}); loss {float(loss):.5f} vs {float(lo):.5f}")
     assert tot < max(1e-2, 1.2 * tot_e)
     assert all(p.grad is None for p in model.parameters())  # the transformer stays frozen
+
+
+@gpu
+def test_lightcontrol_train_step_end_to_end(ops):
+    """x2i_b200.train_lightcontrol.lightcontrol_step (train_lightcontrol.py:672-775): VAE encode -> flow-matching inputs -> frozen FLUX
+    + trainable control nets -> MSE -> backward -> clip -> AdamW.  Repeating one batch with fixed noise / timesteps must reduce the
+    loss; only the control nets change."""
+    from x2i_b200 import train_lightcontrol as tl, vae as xv
+    from x2i_b200.controlnext import ControlNeXtModel
+    from x2i_b200.flux import FluxTransformer2DModel, init_synthetic_
+    cfg = dict(patch_size=1, in_channels=64, num_layers=2, num_single_layers=1, attention_head_dim=128, num_attention_heads=24,
+               joint_attention_dim=64, pooled_projection_dim=32, guidance_embeds=True, axes_dims_rope=(16, 56, 56))
+    model = FluxTransformer2DModel.synthetic(cfg, device="cuda", seed=101).requires_grad_(False)
+    vae = init_synthetic_(xv.AutoencoderKL(block_out_channels=(64, 64, 128, 128), norm_num_groups=16).to("cuda", torch.bfloat16).eval(),
+                          seed=102, std=0.05).requires_grad_(False)
+    nets = torch.nn.ModuleList([ControlNeXtModel() for _ in range(2)]).to("cuda", torch.bfloat16).train()
+    for i, n in enumerate(nets):
+        init_synthetic_(n, seed=103 + i, std=0.05)
+    before = [p.detach().clone() for p in nets.parameters()]
+    frozen = [p.detach().clone() for p in list(model.parameters())[:4] + list(vae.parameters())[:4]]
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B = 2
+    batch = dict(pixel_values=(torch.rand(B, 3, 64, 96, device="cuda", generator=g) * 2 - 1).bfloat16(),
+                 prompt_embeds=torch.randn(B, 8, 64, device="cuda", generator=g).bfloat16(),
+                 pooled_prompt_embeds=torch.randn(B, 32, device="cuda", generator=g).bfloat16())
+    opt = torch.optim.AdamW(nets.parameters(), lr=1e-4, weight_decay=0.0)  # Adam moves every weight by ~lr per step (std 0.05)
+    losses = []
+    for _ in range(8):
+        gen = torch.Generator(device="cuda").manual_seed(11)  # same latent sample, noise and timesteps every step
+        losses.append(float(tl.lightcontrol_step(nets, model, vae, batch, optimizer=opt, generator=gen,
+                                                 sigmas=torch.tensor([0.8, 0.3]))))
+    print("LightControl train losses:", [round(l, 4) for l in losses])
+    assert all(l == l and l < 1e4 for l in losses) and losses[-1] < losses[0]
+    assert any(not torch.equal(a, p.detach()) for a, p in zip(before, nets.parameters()))
+    assert all(torch.equal(a, p.detach()) for a, p in zip(frozen, list(model.parameters())[:4] + list(vae.parameters())[:4]))
+    assert all(p.grad is None for p in model.parameters()) and all(p.grad is None for p in vae.parameters())
+    packed, ts, target, h, w = tl.flow_matching_inputs(vae, batch["pixel_values"], generator=torch.Generator(device="cuda").manual_seed(11))
+    assert packed.shape == (B, 24, 64) and target.shape == (B, 16, 8, 12) and (h, w) == (8, 12) and float(ts.min()) >= 0 and float(ts.max()) <= 1000
