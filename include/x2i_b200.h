@@ -120,6 +120,12 @@ int x2i_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, con
  * as MN-major tcgen05 operands).  Projector linears: utils/proj.py:22-25 trained at train_qwenvl.py:453-459.            */
 int x2i_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw, int M, int N, int K,
                    int accumulate, void* stream);
+/* Same, with split-K when the output has only a handful of tiles (the convolution weight gradients of the LightControl trainer:
+ * N = Cout, K = KH*KW*Cin, M = pixels): the k-blocks are dealt to several tile groups whose fp32 partials (workspace) are then
+ * added in a fixed order -- deterministic.  workspace: x2i_gemm_wgrad_workspace_floats(M, N, K) floats (0 = no split needed).   */
+int x2i_gemm_wgrad_splitk(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw, int M, int N, int K,
+                          int accumulate, float* workspace, int64_t workspace_floats, void* stream);
+int64_t x2i_gemm_wgrad_workspace_floats(int M, int N, int K);
 
 /* Forward Linear + GELU that keeps the pre-activation for the backward: C_pre = A W^T + bias, C_act = act(C_pre);
  * act 1 GELU(tanh), 2 GELU(erf).                                                                                    */

@@ -69,6 +69,7 @@ SIGNATURES = {
     "x2i_conv2d_nhwc_grouped": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "x2i_conv_first_grouped": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "x2i_groupnorm_nhwc_grouped": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
+    "x2i_gemm_wgrad_splitk": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp],
     "x2i_relu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "x2i_silu": [_vp, _vp, _i64, _vp],
     "x2i_im2col_nhwc": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -85,6 +86,7 @@ SIZE_FUNCS = {
     "x2i_proj_mix_wgrad_workspace_floats": [_i, _i, _i],
     "x2i_groupnorm_workspace_floats": [_i, _i, _i],
     "x2i_groupnorm_bwd_workspace_floats": [_i, _i, _i, _i],
+    "x2i_gemm_wgrad_workspace_floats": [_i, _i, _i],
 }
 
 

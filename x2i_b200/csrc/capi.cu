@@ -115,7 +115,7 @@ int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, c
     if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     configured[d->index].store(true, std::memory_order_release);
   }
-  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN) * (p.ksplit > 1 ? p.ksplit : 1);
   const int grid = tiles < d->sms ? tiles : d->sms;
   kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
   return check_launch("gemm_tcgen05_kernel");
@@ -447,6 +447,46 @@ int x2i_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, voi
   p.C = static_cast<__nv_bfloat16*>(dW); p.ldc = lddw;
   if (accumulate) { p.residual = p.C; p.ldr = lddw; }
   return launch_gemm_mn<EPI_DACT, true>(d, dY, lddy, X, ldx, p, static_cast<cudaStream_t>(stream));
+}
+
+// number of k-groups for a weight-gradient GEMM dW[N, K] = dY[M, N]^T X[M, K] (output tiles: ceil(N / 128) x ceil(K / bn))
+static int wgrad_ksplit(DeviceInfo* d, int M, int N, int K) {
+  const int bn = (K % 256 == 0 && static_cast<long long>((N + 127) / 128) * (K / 256) >= 120) ? 256 : (K % 128 == 0 ? 128 : 64);
+  const long long tiles = static_cast<long long>((N + 127) / 128) * ((K + bn - 1) / bn);
+  const int num_kb = (M + GEMM_BK - 1) / GEMM_BK;
+  if (tiles * 2 > d->sms || num_kb < 16) return 1;
+  int s = static_cast<int>((d->sms + tiles - 1) / tiles);
+  if (s > num_kb / 4) s = num_kb / 4;  // at least 4 k-blocks per group
+  const int per = (num_kb + s - 1) / s;
+  s = (num_kb + per - 1) / per;        // no empty group
+  return s < 2 ? 1 : s;
+}
+
+int64_t x2i_gemm_wgrad_workspace_floats(int M, int N, int K) {
+  DeviceInfo* d;
+  if (device_info(&d)) return 0;
+  const int s = wgrad_ksplit(d, M, N, K);
+  return s > 1 ? static_cast<int64_t>(s) * N * K : 0;
+}
+
+int x2i_gemm_wgrad_splitk(const void* dY, int64_t lddy, const void* X, int64_t ldx, void* dW, int64_t lddw, int M, int N, int K,
+                          int accumulate, float* workspace, int64_t workspace_floats, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  const int s = wgrad_ksplit(d, M, N, K);
+  if (s <= 1) return x2i_gemm_wgrad(dY, lddy, X, ldx, dW, lddw, M, N, K, accumulate, stream);
+  if (!dW || !aligned16(dW) || lddw % 8 || K % 8) return fail(X2I_ERR_ALIGN, "gemm_wgrad_splitk: alignment");
+  if (!workspace || !aligned16(workspace) || workspace_floats < static_cast<int64_t>(s) * N * K)
+    return fail(X2I_ERR_SHAPE, "gemm_wgrad_splitk: workspace of x2i_gemm_wgrad_workspace_floats() floats required");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = N; p.N = K; p.K = M;
+  p.c32 = workspace; p.ldc32 = K; p.ksplit = s;
+  if (int rc = launch_gemm_mn<EPI_DACT, true>(d, dY, lddy, X, ldx, p, static_cast<cudaStream_t>(stream))) return rc;
+  const long long n = static_cast<long long>(N) * (K / 8);
+  splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      workspace, static_cast<__nv_bfloat16*>(dW), lddw, N, K, s, accumulate);
+  return check_launch("splitk_reduce_kernel");
 }
 
 int x2i_gemm_bias_act_save(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C_pre, int64_t ldc,

@@ -62,6 +62,10 @@ struct GemmParams {
   float* c32;
   long long ldc32;
   float alpha;
+  // split-K (single-CTA kernel only; the weight-gradient GEMMs of narrow layers have a handful of output tiles and a huge K): the
+  // k-blocks are dealt to `ksplit` tile groups, group s stores its raw fp32 accumulator to c32 + s * M * ldc32 (no epilogue math);
+  // splitk_reduce_kernel adds the partials in a fixed order.  0 / 1 = off.
+  int ksplit;
   // EPI_DACT: pre-activation [M, ldpre] (column n - n_split), derivative kind dact (1 tanh-GELU, 2 erf-GELU), addend = residual
   const __nv_bfloat16* pre;
   long long ldpre;
@@ -114,8 +118,26 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float (&v)
 // (lane quadrant of the calling warp already applied).
 template <int BN, int EPI>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const uint32_t t_acc, const int m, const int n_tile0,
-                                                   const long long bias_off = 0 /* EPI_CONV with per-group weights */) {
+                                                   const long long bias_off = 0 /* EPI_CONV with per-group weights */,
+                                                   const int ks = 0 /* split-K group */) {
   const bool row_ok = m < p.M;
+  if (p.ksplit > 1) {  // raw fp32 partial of this k-group
+    float* dst = p.c32 + (static_cast<long long>(ks) * p.M + m) * p.ldc32 + n_tile0;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      if (n_tile0 + c * 32 >= p.N) break;
+      uint32_t r[32];
+      tmem_ld32(t_acc + c * 32, r);
+      tmem_ld_wait();
+      if (row_ok) {
+        float4* d4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          d4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+    }
+    return;
+  }
 
   if constexpr (EPI == EPI_QKV) {
     const int D = p.heads * 128;
@@ -319,8 +341,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;  // host guarantees every group is non-empty
+  const int num_mn = num_m * num_n;
+  const int num_tiles = num_mn * ksplit;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -350,8 +375,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % num_m, n_blk = tile / num_m;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int ks = tile / num_mn, mn = tile - ks * num_mn;
+        const int m_blk = mn % num_m, n_blk = mn / num_m;
+        const int kb0 = ks * kb_per, kb1 = min(kb0 + kb_per, num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
@@ -387,7 +414,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int ks = tile / num_mn;
+        const int kb0 = ks * kb_per, kb1 = min(kb0 + kb_per, num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -397,7 +426,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)
             umma_ss_w(d_tmem, adesc + ((A_MN ? k * 2048 : k * 32) >> 4), bdesc + ((B_MN ? k * 2048 : k * 32) >> 4), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+                      (kb != kb0 || k != 0) ? 1u : 0u);
           umma_commit_w(&empty_bar[stage]);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
@@ -410,14 +439,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % num_m, n_blk = tile / num_m;
+      const int ks = tile / num_mn, mn = tile - ks * num_mn;
+      const int m_blk = mn % num_m, n_blk = mn / num_m;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * BN + lane_off;
       const int m = m_blk * GEMM_BM + quad * 32 + lane;
-      gemm_epilogue_tile<BN, EPI>(p, t_acc, m, n_blk * BN);
+      gemm_epilogue_tile<BN, EPI>(p, t_acc, m, n_blk * BN, 0, ks);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -430,6 +460,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+}
+
+// out[m, n] (+)= sum_s part[s, m, n] in the fixed order s = 0, 1, ...; 8 columns per thread.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out, long long ldo, int M,
+                                                            int N, int S, int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n8 = N / 8;
+  if (i >= static_cast<long long>(M) * n8) return;
+  const int m = static_cast<int>(i / n8), c = static_cast<int>(i % n8) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float4* p4 = reinterpret_cast<const float4*>(part + (static_cast<long long>(s) * M + m) * N + c);
+    const float4 a = p4[0], b = p4[1];
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + static_cast<long long>(m) * ldo + c);
+  if (accumulate) {
+    const uint4 u = *o;
+    acc[0] += bf16_lo(u.x); acc[1] += bf16_hi(u.x); acc[2] += bf16_lo(u.y); acc[3] += bf16_hi(u.y);
+    acc[4] += bf16_lo(u.z); acc[5] += bf16_hi(u.z); acc[6] += bf16_lo(u.w); acc[7] += bf16_hi(u.w);
+  }
+  uint4 r;
+  r.x = pack_bf16x2(acc[0], acc[1]); r.y = pack_bf16x2(acc[2], acc[3]); r.z = pack_bf16x2(acc[4], acc[5]); r.w = pack_bf16x2(acc[6], acc[7]);
+  *o = r;
 }
 
 }  // namespace x2i

@@ -340,7 +340,13 @@ def linear_wgrad(dy, x, out=None, accumulate=False):
     if out is None:
         out = torch.empty(N, K, device=dy.device, dtype=BF16)
         accumulate = False
-    _lib.call("x2i_gemm_wgrad", _p(dy), lddy, _p(x), ldx, _p(out), out.stride(0), M, N, K, 1 if accumulate else 0, _stream())
+    nws = _lib.lib().x2i_gemm_wgrad_workspace_floats(M, N, K) if dy.is_cuda else 0
+    if nws > 0:  # few output tiles, long contraction: split-K with a deterministic reduction
+        ws = _ws_f32("wgrad_splitk", nws, dy.device)
+        _lib.call("x2i_gemm_wgrad_splitk", _p(dy), lddy, _p(x), ldx, _p(out), out.stride(0), M, N, K, 1 if accumulate else 0, _p(ws), nws,
+                  _stream())
+    else:
+        _lib.call("x2i_gemm_wgrad", _p(dy), lddy, _p(x), ldx, _p(out), out.stride(0), M, N, K, 1 if accumulate else 0, _stream())
     return out
 
 
