@@ -36,12 +36,17 @@ def main():
     torch.cuda.synchronize()
     xdist.barrier()
     n0 = _lib.launch_count()
+    profiling = os.environ.get("X2I_NCU") == "1"  # ncu --profile-from-start off: capture only the timed steps
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStart()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         loss = tl.lightcontrol_step(nets, model, vae, batch, optimizer=opt)
     e1.record()
     torch.cuda.synchronize()
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStop()
     xdist.barrier()
     ms = xdist.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
     if rank == 0:

@@ -87,5 +87,8 @@ if __name__ == "__main__":
                    "+ model init; per-step columns = totals / 2)")
     launches(tag, steps=1, src_name="cn_launches.csv", out_name="controlnext_launch_list_summary.md",
              title=f"# {tag}: one ControlNeXt net on a 1024x1024 hint (`tools/profile_controlnext.py`, profiled pass only) under ncu")
+    launches(tag, steps=1, src_name="lc_train_launches.csv", out_name="lightcontrol_train_launch_list_summary.md",
+             title=f"# {tag}: one LightControl train step (`X2I_NCU=1 python tools/bench_lightcontrol_train.py --steps 1 --warmup 1`: FLUX-dev, 19 "
+                   "trainable ControlNeXt nets, 1024px, B = 1, VAE encode included) under ncu")
     for rep in ("prof_attn", "prof_gemm", "prof_rowwise", "prof_bwd", "prof_vae"):
         raw(tag, rep)
