@@ -191,3 +191,29 @@ def test_control_net_stack_eligibility():
         pass
 
     assert not ControlNeXtStack.supported([a, Sub()])
+
+
+def test_lightcontrol_host_helpers():
+    """Host-side pieces of the LightControl train step (lightcontrol/train_lightcontrol.py:690-703): logit-normal timestep density,
+    the training sigma table (shift 3), and the no-CPU-path rule."""
+    import pytest
+    import torch
+    from x2i_b200 import train_lightcontrol as tl
+    from x2i_b200._lib import X2IError
+    s = tl.train_sigmas(1000, 3.0)
+    assert s.shape == (1000,) and abs(float(s[0]) - 1.0) < 1e-6 and bool((s[1:] < s[:-1]).all())
+    raw = torch.linspace(1.0, 1.0 / 1000, 1000)
+    assert torch.allclose(s, 3.0 * raw / (1 + 2.0 * raw))
+    assert torch.allclose(tl.train_sigmas(1000, 1.0), raw)                      # shift 1 = the schnell table
+    g1, g2 = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
+    u1 = tl.compute_density_for_timestep_sampling("logit_normal", 64, 0.0, 1.0, generator=g1)
+    u2 = tl.compute_density_for_timestep_sampling("logit_normal", 64, 0.0, 1.0, generator=g2)
+    assert torch.equal(u1, u2) and float(u1.min()) > 0 and float(u1.max()) < 1
+    g3 = torch.Generator().manual_seed(5)
+    assert torch.allclose(u1, torch.sigmoid(torch.randn(64, generator=g3)))
+    um = tl.compute_density_for_timestep_sampling("mode", 64, generator=torch.Generator().manual_seed(1))
+    assert um.shape == (64,)
+    with pytest.raises(X2IError):
+        tl.lightcontrol_step(None, None, None, {"pixel_values": torch.zeros(1, 3, 16, 16)})
+    b = tl.synthetic_batch(1, "cpu", height=32, width=48, S=4, seed=0)
+    assert b["pixel_values"].shape == (1, 3, 32, 48) and b["prompt_embeds"].shape == (1, 4, 4096) and float(b["pixel_values"].abs().max()) <= 1
