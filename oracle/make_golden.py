@@ -192,6 +192,43 @@ def golden_helpers():
     print("helper goldens written; stubbed third-party roots:", out["stubbed"])
 
 
+# ----------------------------------------------------------------------------- B2: LightControl trainer helpers
+def golden_lightcontrol_helpers():
+    """lightcontrol/train_lightcontrol.py imported with every absent third-party root stubbed; its module-level helpers
+    (_prepare_latent_image_ids :383, _pack_latents :396, _unpack_latents :403, get_sigmas :412) are called on seeded inputs."""
+    extra = ("transformers", "zhconv")
+    finder = _StubFinder()
+    finder.ROOTS = finder.ROOTS + extra
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in ("transformers", "lightcontrol", "utils")}
+    sys.meta_path.insert(0, finder)
+    sys.path.insert(0, REF)
+    try:
+        ref = importlib.import_module("lightcontrol.train_lightcontrol")
+    finally:
+        sys.meta_path.remove(finder)
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k.split(".")[0] in finder.ROOTS + ("lightcontrol", "utils")]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
+    g = torch.Generator().manual_seed(9)
+    lat = torch.randn(2, 16, 8, 12, generator=g)
+    packed = ref._pack_latents(lat, 2, 16, 8, 12)
+
+    class Sched:  # the two attributes get_sigmas reads from FlowMatchEulerDiscreteScheduler (shift 3, 1000 train steps)
+        pass
+    sch = Sched()
+    raw = torch.linspace(1.0, 1.0 / 1000, 1000)
+    sch.sigmas = 3.0 * raw / (1 + 2.0 * raw)
+    sch.timesteps = sch.sigmas * 1000
+    idx = torch.tensor([0, 17, 500, 999])
+    out = dict(lat=lat, packed=packed, unpacked=ref._unpack_latents(packed, 64, 96, 16),
+               ids=ref._prepare_latent_image_ids(2, 8, 12, "cpu", torch.float32), idx=idx,
+               sigmas=ref.get_sigmas(sch.timesteps[idx], sch, "cpu", n_dim=4, dtype=torch.float32),
+               stubbed=sorted(set(s_.split(".")[0] for s_ in finder.stubbed)))
+    torch.save(out, os.path.join(OUT, "lightcontrol_helpers.pt"))
+    print("LightControl helper goldens written; stubbed third-party roots:", out["stubbed"])
+
+
 # ----------------------------------------------------------------------------- C: block structure
 def _fake_diffusers():
     def register_to_config(init):
@@ -441,3 +478,4 @@ if __name__ == "__main__":
     crosscheck_torchtitan()
     golden_resampler()
     golden_controlnext()
+    golden_lightcontrol_helpers()

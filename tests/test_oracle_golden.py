@@ -149,3 +149,19 @@ def test_adaln_leaves_match_an_independent_in_image_copy():
     fin_t.load_state_dict({k: v for k, v in fin.state_dict().items() if k.startswith("linear.")}, strict=False)
     with torch.no_grad():
         assert torch.allclose(fin(x, emb), fin_t(x, emb), atol=1e-6)
+
+
+def test_lightcontrol_trainer_helpers_match_reference(golden_dir):
+    """The index / layout helpers of lightcontrol/train_lightcontrol.py (:383-:422), pinned by a fixture minted from the reference
+    file itself (oracle/make_golden.py::golden_lightcontrol_helpers): bit-exact pack / unpack / ids, and the trainer's sigma table
+    equals what the reference's get_sigmas() looks up in the scheduler."""
+    from x2i_b200 import train_lightcontrol as tl
+    from x2i_b200.pipeline import FluxPipeline
+    d = torch.load(os.path.join(golden_dir, "lightcontrol_helpers.pt"))
+    assert torch.equal(FluxPipeline._pack_latents(d["lat"], 2, 16, 8, 12), d["packed"])
+    assert torch.equal(FluxPipeline._unpack_latents(d["packed"], 64, 96, 16), d["unpacked"])
+    assert torch.equal(d["unpacked"], d["lat"])                                        # round trip
+    assert torch.equal(FluxPipeline._prepare_latent_image_ids(2, 8, 12, "cpu", torch.float32), d["ids"])
+    assert torch.equal(fo.unpack_latents(d["packed"], 64, 96, 16), d["unpacked"]) and torch.equal(fo.pack_latents(d["lat"]), d["packed"])
+    table = tl.train_sigmas(1000, 3.0)
+    assert torch.allclose(table[d["idx"]], d["sigmas"].flatten(), rtol=0, atol=1e-7)
