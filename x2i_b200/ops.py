@@ -474,10 +474,13 @@ _COLSUM_WS = {}
 
 
 def _ws_f32(key, n, device):
-    t = _COLSUM_WS.get((key, str(device)))
+    """Scratch buffer of an op, one per (op, device, CUDA stream): two streams (e.g. the reference's background data-loader
+    thread doing GPU work, core/data/dataloader.py:100-123) never share a workspace; on one stream the launches are ordered."""
+    k = (key, str(device), _stream())
+    t = _COLSUM_WS.get(k)
     if t is None or t.numel() < n:
         t = torch.empty(int(n), device=device, dtype=F32)
-        _COLSUM_WS[(key, str(device))] = t
+        _COLSUM_WS[k] = t
     return t
 
 
