@@ -108,37 +108,68 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(threads, n_double=1, n_single=2, repeat=1):
-    """Bounded sample of the 1024^2 step on the host: n_double double + n_single single oracle blocks at
-    L = 512 + 4096, bf16, extrapolated to the 19 + 38 blocks of a step.  Returns (seconds per full step, description)."""
+_CPU_MODEL = None
+
+
+def cpu_model():
+    """The full 19 + 38 block oracle transformer in bf16 on the host (24 GB).  Built on the meta device and filled by initialising
+    ONE double and ONE single block and copying them into the other positions (distinct storage per block, so a step streams all
+    24 GB of weights like the real model; a per-parameter random init of 11.9 B values would take minutes and times nothing)."""
+    global _CPU_MODEL
+    if _CPU_MODEL is not None:
+        return _CPU_MODEL
+    import torch
+    from oracle import flux_oracle as fo
+    with torch.device("meta"):
+        m = fo.FluxTransformer2DModel(**FLUX_SCHNELL)
+    m = m.to(torch.bfloat16).to_empty(device="cpu").eval()
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        def init(mod):
+            for name, p in mod.named_parameters():
+                if p.ndim >= 2:
+                    p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.dtype))
+                elif "norm" in name and name.endswith("weight"):
+                    p.fill_(1.0)
+                else:
+                    p.zero_()
+        for blocks in (m.transformer_blocks, m.single_transformer_blocks):
+            init(blocks[0])
+            src = dict(blocks[0].named_parameters())
+            for b in blocks[1:]:
+                for name, p in b.named_parameters():
+                    p.copy_(src[name])
+        for mod in (m.x_embedder, m.context_embedder, m.time_text_embed, m.norm_out, m.proj_out):
+            init(mod)
+    _CPU_MODEL = m
+    return m
+
+
+def cpu_full_step(threads):
+    """ONE real denoise step of the benchmarked workload on the host cores: the oracle restatement of the diffusers FLUX transformer
+    the reference calls, all 19 double + 38 single blocks at L = 512 + 4096, bf16, B = 1, plus the Euler update.  No extrapolation.
+    Returns (seconds, description)."""
     import torch
     from oracle import flux_oracle as fo
     torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(0)
-    dbl = [fo.FluxTransformerBlock(D, HEADS, 128).to(torch.bfloat16).eval() for _ in range(n_double)]
-    sgl = [fo.FluxSingleTransformerBlock(D, HEADS, 128).to(torch.bfloat16).eval() for _ in range(n_single)]
-    x = torch.randn(1, 4096, D, generator=g).bfloat16()
-    c = torch.randn(1, S_TXT, D, generator=g).bfloat16()
-    temb = torch.randn(1, D, generator=g).bfloat16()
-    ids = torch.cat([torch.zeros(S_TXT, 3), fo.prepare_latent_image_ids(128, 128)])
-    rope = fo.rope_table(ids)
-    best_d = best_s = 1e30
+    m = cpu_model()
+    g = torch.Generator().manual_seed(1)
+    bf = torch.bfloat16
+    lat = torch.randn(1, 4096, 64, generator=g).to(bf)
+    prompt = torch.randn(1, S_TXT, 4096, generator=g).to(bf)
+    pooled = torch.randn(1, 768, generator=g).to(bf)
+    img_ids = fo.prepare_latent_image_ids(128, 128).to(bf)
+    txt_ids = torch.zeros(S_TXT, 3, dtype=bf)
     with torch.no_grad():
-        for _ in range(repeat):
-            t0 = time.perf_counter()
-            for b in dbl:
-                c, x = b(x, c, temb, rope)
-            t1 = time.perf_counter()
-            h = torch.cat([c, x], 1)
-            for b in sgl:
-                h = b(h, temb, rope)
-            t2 = time.perf_counter()
-            best_d = min(best_d, (t1 - t0) / n_double)
-            best_s = min(best_s, (t2 - t1) / n_single)
-    per_step = 19 * best_d + 38 * best_s
-    desc = (f"oracle (PyTorch restatement of the diffusers FLUX blocks the reference calls) on CPU, bf16, B=1, L=512+4096: "
-            f"{n_double} double + {n_single} single block(s) timed, extrapolated x19/x38 to one denoise step")
-    return per_step, desc
+        t0 = time.perf_counter()
+        v = m(hidden_states=lat, timestep=torch.full((1,), 0.75, dtype=bf), pooled_projections=pooled, encoder_hidden_states=prompt,
+              txt_ids=txt_ids, img_ids=img_ids, return_dict=False)[0]
+        lat = fo.euler_step(lat, v, 0.75, 0.5)
+        dt = time.perf_counter() - t0
+    assert lat.shape == (1, 4096, 64)
+    desc = ("oracle (PyTorch restatement of the diffusers FLUX transformer the reference calls) on CPU, bf16, B=1, L=512+4096: "
+            "ONE REAL full denoise step, all 19 double + 38 single blocks + Euler update (74.4 TFLOP), no extrapolation")
+    return dt, desc
 
 
 def run_reference(args):
@@ -146,21 +177,17 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    times = []
-    desc = ""
-    for i in range(args.warmup + args.steps):
-        if i < args.warmup and i > 0:
-            continue  # one warm-up pass is enough for a CPU arm measured in seconds
-        t, desc = cpu_sample(threads, 1, 2)
-        if i >= args.warmup:
-            times.append(t)
-        if sum(times) > 150:  # keep the whole run within a few minutes of host time
-            break
+    budget_s = float(os.environ.get("X2I_REF_BUDGET_S", 420))  # the whole arm stays within a few minutes of host time
+    t_warm, desc = cpu_full_step(threads)                      # one warm-up step (a CPU arm measured in tens of seconds needs no more)
+    n_steps = max(1, min(args.steps, int(budget_s / max(t_warm, 1e-3))))
+    times = [cpu_full_step(threads)[0] for _ in range(n_steps)]
     t_step = sum(times) / len(times)
     v = 1.0 / t_step
+    if n_steps < args.steps:
+        desc += f"; {n_steps} of the requested {args.steps} steps timed to keep the arm within {budget_s:.0f} s"
     print(json.dumps({
         "impl": "reference", "metric": "denoise-steps/sec 1024px bf16", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "steps": len(times), "warmup": 1, "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": 1, "global_batch": 1, "parallelism": "cpu (rank 0 only)"},
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc},
@@ -178,7 +205,8 @@ def main():
     ap.add_argument("--impl", default="x2i_b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary distillation-train-step measurement")
-    ap.add_argument("--train-batch", type=int, default=1)
+    ap.add_argument("--train-batch", type=int, default=4, help="distillation samples per GPU (BASELINE config 4: 32 / 8 GPUs)")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock-PyTorch bf16 step on the same GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -201,8 +229,11 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        t_cpu, desc = cpu_sample(threads, 1, 2)
+        global _CPU_MODEL
+        cpu_full_step(threads)  # warm-up (page-in of the 24 GB host model, thread pool)
+        t_cpu, desc = cpu_full_step(threads)
         cpu_base = {"value": 1.0 / t_cpu, "unit": "steps/s", "cores": threads, "kind": "port", "sample": desc}
+        _CPU_MODEL = None  # release the host copy
 
     model = FluxTransformer2DModel.synthetic(FLUX_SCHNELL, device=dev, seed=0)
     pipe = FluxPipeline(scheduler=FlowMatchEulerDiscreteScheduler(shift=1.0), transformer=model)
@@ -295,42 +326,113 @@ def main():
             fl = 4.0 * L * L * 128 * HEADS * B
             ach = fl / t_att / 1e12
             pk_s = pk.get("bf16_sustained") or pk["bf16"]
+            # the same kernel and the library kernel it replaces (torch SDPA -> cuDNN / flash on this box), each timed ALONE on the
+            # same q, k, v (back-to-back launches, L2-warm, burst clocks): explains the in-step number, not a bench value
+            import torch.nn.functional as F_
+            ws = model._ws
+            q_, k_, v_ = ws["q"], ws["k"], ws["v"]
+            o0 = torch.empty(B, S_TXT, D, device=dev, dtype=torch.bfloat16)
+            o1 = torch.empty(B, L_img, D, device=dev, dtype=torch.bfloat16)
+
+            def timed(fn, n=30):
+                for _ in range(5):
+                    fn()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b_.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b_) * 1e-3 / n
+
+            t_iso = timed(lambda: ops.attention(q_, k_, v_, split=S_TXT, out0=o0, out1=o1))
+            t_lib = timed(lambda: F_.scaled_dot_product_attention(q_, k_, v_))
             roof = {"kernel": "mmdit_attention_fwd_kernel", "bound": "tensor", "achieved": ach, "peak": pk_s,
                     "unit": "TFLOP/s", "frac": ach / pk_s, "frac_of_burst_peak": ach / pk["bf16"],
                     "peak_source": pk["source"] + " (sustained cuBLAS bf16: the kernel is timed inside long denoise steps)",
                     "ms_per_launch": t_att * 1e3, "launches_timed": len(durs), "algorithmic_flops_per_launch": fl, "traffic": attn_traffic(),
-                    "step_share_attention": 57 * t_att / (t_local / args.steps)}
+                    "step_share_attention": 57 * t_att / (t_local / args.steps),
+                    "isolated_tflops": fl / t_iso / 1e12, "isolated_frac_of_burst_peak": fl / t_iso / 1e12 / pk["bf16"],
+                    "library_tflops": fl / t_lib / 1e12,
+                    "library": "torch.nn.functional.scaled_dot_product_attention (torch 2.11 backend choice on sm_100), same q/k/v, timed alone"}
+
+        # ---- GPU library baseline: the oracle restatement of the reference's model in bf16 with stock PyTorch ops on
+        # this same GPU (F.scaled_dot_product_attention + cuBLAS + eager elementwise): the number X2I's own code path reaches here.
+        lib_base = None
+        if rank == 0 and world == 1 and not args.no_library_baseline:
+            from oracle import flux_oracle as fo
+            with torch.device("meta"):
+                om = fo.FluxTransformer2DModel(**FLUX_SCHNELL)
+            om = om.to(torch.bfloat16).to_empty(device=dev).eval()
+            om.load_state_dict(model.state_dict())
+            lat2 = latents.clone()
+
+            def lib_step(i):
+                nonlocal lat2
+                v = om(hidden_states=lat2, timestep=ts[i % PIPE_STEPS].expand(B), pooled_projections=pooled, encoder_hidden_states=prompt,
+                       txt_ids=txt_ids, img_ids=img_ids, return_dict=False)[0]
+                lat2 = fo.euler_step(lat2, v, 0.0, -1.0 / PIPE_STEPS)
+
+            for i in range(3):
+                lib_step(i)
+            torch.cuda.synchronize()
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            n_lib = max(4, min(args.steps, 8))
+            for i in range(n_lib):
+                lib_step(i)
+            l1.record()
+            torch.cuda.synchronize()
+            t_libstep = l0.elapsed_time(l1) * 1e-3 / n_lib
+            lib_base = {"value": B / t_libstep, "unit": "steps/s", "ms_per_step": t_libstep * 1e3, "steps": n_lib,
+                        "kind": "oracle restatement of the diffusers FLUX transformer, bf16, stock PyTorch eager ops on the same B200 "
+                                "(F.scaled_dot_product_attention + cuBLAS + elementwise kernels), same weights and inputs, device-timed",
+                        "speedup_of_x2i_b200": (t_libstep) / (t_local / args.steps)}
+            del om, lat2
+            torch.cuda.empty_cache()
 
     # ---- secondary workload (BASELINE config 4, N=1 only): the attention-distillation train step on the same frozen FLUX --
     # teacher pass + projector + student pass (saving mode) + KD loss + backward through all 57 blocks + projector wgrad +
     # AdamW.  Reported as an extra object; the headline metric above is unchanged.  tools/bench_train.py runs it under torchrun.
     train_info = None
-    if world == 1 and not args.no_train:
+    if not args.no_train:
         from x2i_b200 import proj as xproj, train as xtrain
         model.use_cuda_graph = False
+        TB = args.train_batch
         proj = xproj.create_proj3_qwen3b(37, use_t5=False, use_scale=False, use_cnn=True).to(dev, torch.bfloat16)
         opt = torch.optim.AdamW(proj.parameters(), lr=1e-4, fused=True)
-        tb = xtrain.synthetic_batch(args.train_batch, dev, FLUX_SCHNELL, seed=7)
+        bucket = xdist.GradBucket(proj.parameters())  # all projector gradients in one flat buffer: ONE all-reduce, no copies
+        tb = xtrain.synthetic_batch(TB, dev, FLUX_SCHNELL, seed=7 + rank)
         for _ in range(2):
-            xtrain.distill_step(proj, model, tb, optimizer=opt)
+            xtrain.distill_step(proj, model, tb, optimizer=opt, bucket=bucket)
         torch.cuda.synchronize()
+        xdist.barrier()
         n0 = _lib.launch_count()
+        timings = []
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0e.record()
         n_train = 3
         for _ in range(n_train):
-            tl = xtrain.distill_step(proj, model, tb, optimizer=opt)
+            tl = xtrain.distill_step(proj, model, tb, optimizer=opt, bucket=bucket, timings=timings)
         t1e.record()
         torch.cuda.synchronize()
-        tt = t0e.elapsed_time(t1e) * 1e-3 / n_train
+        xdist.barrier()
+        tt = xdist.max_over_ranks(t0e.elapsed_time(t1e) * 1e-3, dev) / n_train
+        ar_ms = xdist.max_over_ranks(sum(a.elapsed_time(b) for a, b in timings) / max(1, len(timings)), dev) if timings else 0.0
         train_info = {"workload": "attention-distillation train step (train_qwenvl.py:559-651 + teacher :717-816), 1024px latents, "
-                                  "projector qwen3b [B,37,512,2048], teacher+student on the same GPU",
-                      "batch_per_gpu": args.train_batch, "ms_per_step": tt * 1e3, "samples_per_s": args.train_batch / tt,
-                      "approx_tflops": args.train_batch * step_flops() * 4.3 / tt / 1e12, "loss": float(tl),
+                                  "projector qwen3b [B,37,512,2048], teacher+student on every GPU, DP over all ranks "
+                                  "(BASELINE config 4: 4 samples per GPU)",
+                      "batch_per_gpu": TB, "global_batch": TB * world, "n_gpus": world, "ms_per_step": tt * 1e3,
+                      "samples_per_s": TB * world / tt, "scaling": "weak",
+                      "approx_tflops_per_gpu": TB * step_flops() * 4.3 / tt / 1e12, "loss": float(tl),
                       "gpu_launches_per_step": (_lib.launch_count() - n0) / n_train,
-                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+                      "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+                      "collective": {"op": "NCCL all_reduce(AVG) of the projector gradients, one per optimizer step (train_qwenvl.py:483)",
+                                     "bytes": bucket.nbytes, "ms": ar_ms,
+                                     "share_of_step": ar_ms / (tt * 1e3) if tt > 0 else None}}
         model.use_cuda_graph = True
-        del proj, opt, tb
+        del proj, opt, tb, bucket
+        torch.cuda.empty_cache()
 
     # ---- secondary workload (SURVEY 8f N2, N=1 only): the VAE decode that follows the 4 denoise steps of an image
     vae_info = None
@@ -367,7 +469,8 @@ def main():
             "step_roofline_frac_bf16": fl * B * args.steps / t_local / 1e12 / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
             "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "x2i_b200.pipeline.FluxPipeline.__call__ (4-step schnell sampling per call, pinned host buffers)"},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "clocks": clk, "distill_train": train_info, "vae_decode": vae_info,
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "gpu_library_baseline": lib_base, "clocks": clk,
+            "distill_train": train_info, "vae_decode": vae_info,
         }
         print(json.dumps(out))
     if world > 1:

@@ -10,6 +10,9 @@ TEST INFRASTRUCTURE ONLY.  What each fixture pins, and how:
   helpers.pt                   reference ``train/train_qwenvl.py`` imported with every missing third-party
                                module auto-stubbed; ``normalize``, ``_prepare_latent_image_ids``,
                                ``_pack_latents``, ``calculate_shift`` called directly.
+  kd_loop.pt                   reference ``train/train_qwenvl.py`` imported with ``x2i_b200.compat`` as its ``diffusers``: its own
+                               ``cast_hook_list`` run on the x2i_b200 transformer, and the LITERAL loss loop (:601-620, cut out of
+                               ``train()`` with inspect and exec'ed) on seeded tensors incl. the inf/nan guard.
   flux_structure.pt            reference ``lightcontrol/lightcontrol_flux.py`` block / transformer classes
                                imported unmodified, with a fake ``diffusers`` package whose LEAF classes are
                                this repo's oracle leaves (diffusers 0.31.0 is absent).  Pins the block
@@ -192,6 +195,92 @@ def golden_helpers():
     print("helper goldens written; stubbed third-party roots:", out["stubbed"])
 
 
+# ----------------------------------------------------------------------------- B1b: the reference's own hook registration + loss loop
+def golden_kd_loop():
+    """``train/train_qwenvl.py`` imported with ``x2i_b200.compat`` standing in for ``diffusers`` (so the file's
+    ``FluxTransformer2DModel`` IS the x2i_b200 drop-in) and every other absent third-party root stubbed.  Then
+      (1) the reference's own ``cast_hook_list`` (:206-214) is run on an x2i_b200 transformer (meta device: registration needs no
+          GPU) and the hook fan-out is recorded;
+      (2) the LITERAL loss loop -- the source lines of ``train()`` from ``loss = 0`` (:601) to the line before ``train_loss = loss``
+          (:622), cut out of the file with ``inspect`` and exec'ed unchanged -- runs on seeded tensors in fp32 and in bf16 (the
+          reference's dtype), once on clean inputs and once with a NaN planted in one teacher layer (the inf/nan guard :606-609);
+          losses and student gradients are stored.
+    Pins oracle/kd_oracle.py's restated loop AND (in the -m gpu tests) x2i_b200.kd.attention_distillation_loss to the reference's
+    own lines."""
+    import contextlib
+    import io
+    import textwrap
+    from x2i_b200 import compat
+    from x2i_b200.flux import FluxTransformer2DModel
+    finder = _StubFinder()
+    finder.ROOTS = tuple(r for r in finder.ROOTS if r != "diffusers") + ("transformers",)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] in ("transformers", "diffusers")}
+    compat.install(force=True)
+    sys.meta_path.insert(0, finder)
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(REF, "train"))
+    try:
+        ref_train = importlib.import_module("train_qwenvl")
+        assert ref_train.FluxTransformer2DModel is FluxTransformer2DModel  # the drop-in is what the reference file now names
+        with torch.device("meta"):
+            model = FluxTransformer2DModel(num_layers=3, num_single_layers=4, num_attention_heads=2, joint_attention_dim=64,
+                                           pooled_projection_dim=32)
+        lists = []
+        ref_train.cast_hook_list(model, lists)  # the reference's function, verbatim
+        n_hooks = [len(b.attn._forward_hooks) for b in list(model.transformer_blocks) + list(model.single_transformer_blocks)]
+        # fire the registered callbacks the way nn.Module.__call__ / FluxTrainFn do: (module, input, output)
+        for i, b in enumerate(model.transformer_blocks):
+            for h in b.attn._forward_hooks.values():
+                h(b.attn, (), (torch.full((1,), float(i)), torch.full((1,), 100.0 + i)))
+        for i, b in enumerate(model.single_transformer_blocks):
+            for h in b.attn._forward_hooks.values():
+                h(b.attn, (), torch.full((1,), 200.0 + i))
+        fanout = [[float(t) for t in lst] for lst in lists]
+        src = inspect.getsource(ref_train.train).splitlines()
+        a = next(i for i, l in enumerate(src) if l.strip() == "loss = 0")
+        b = next(i for i, l in enumerate(src) if l.strip() == "train_loss = loss")
+        loop_src = textwrap.dedent("\n".join(src[a:b]))
+        assert "for i in range(19):" in loop_src and "for i in range(38):" in loop_src and "batchmean" in loop_src
+        normalize = ref_train.normalize
+    finally:
+        sys.meta_path.remove(finder)
+        for p_ in (REF, os.path.join(REF, "train")):
+            sys.path.remove(p_)
+        compat.uninstall()
+        for k in [k for k in sys.modules if k.split(".")[0] in finder.ROOTS]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
+
+    g = torch.Generator().manual_seed(31)
+    B, D = 2, 64
+    shapes = ((B, 19, 6, D), (B, 19, 4, D), (B, 38, 8, D))
+    teacher = [(torch.randn(s_, generator=g) * 1.5 + 0.2).bfloat16() for s_ in shapes]
+    student = [(t.float() + 0.4 * torch.randn(t.shape, generator=g)).bfloat16() for t in teacher]
+
+    def run(ts, ss, dtype):
+        ss = [x.to(dtype).clone().requires_grad_(True) for x in ss]
+        ns = dict(torch=torch, F=torch.nn.functional, normalize=normalize,
+                  KD_teacher_tensor0=ts[0].to(dtype), KD_teacher_tensor1=ts[1].to(dtype), KD_teacher_tensor2=ts[2].to(dtype),
+                  KD_student_tensor0=ss[0], KD_student_tensor1=ss[1], KD_student_tensor2=ss[2])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            exec(loop_src, ns)  # the reference's lines, unchanged
+        loss = ns["loss"]
+        grads = torch.autograd.grad(loss, ss)
+        return dict(loss=loss.detach().float(), grads=[g_.float() for g_ in grads], printed=buf.getvalue().split())
+
+    poisoned = [t.clone() for t in teacher]
+    poisoned[2][0, 5, 3, 7] = float("nan")   # one element of single-block layer 5
+    poisoned[0][1, 2, 0, 0] = float("inf")   # one element of double-block image layer 2
+    out = dict(teacher=teacher, student=student, loop_src=loop_src, n_hooks=n_hooks, hook_fanout=fanout,
+               clean_fp32=run(teacher, student, torch.float32), clean_bf16=run(teacher, student, torch.bfloat16),
+               poisoned_teacher=poisoned, poisoned_fp32=run(poisoned, student, torch.float32),
+               stubbed=sorted(set(s_.split(".")[0] for s_ in finder.stubbed)))
+    torch.save(out, os.path.join(OUT, "kd_loop.pt"))
+    print("KD loop golden written: loss fp32", float(out["clean_fp32"]["loss"]), "bf16", float(out["clean_bf16"]["loss"]),
+          "poisoned", float(out["poisoned_fp32"]["loss"]), out["poisoned_fp32"]["printed"], "hooks", n_hooks)
+
+
 # ----------------------------------------------------------------------------- B2: LightControl trainer helpers
 def golden_lightcontrol_helpers():
     """lightcontrol/train_lightcontrol.py imported with every absent third-party root stubbed; its module-level helpers
@@ -214,16 +303,27 @@ def golden_lightcontrol_helpers():
     lat = torch.randn(2, 16, 8, 12, generator=g)
     packed = ref._pack_latents(lat, 2, 16, 8, 12)
 
-    class Sched:  # the two attributes get_sigmas reads from FlowMatchEulerDiscreteScheduler (shift 3, 1000 train steps)
-        pass
-    sch = Sched()
-    raw = torch.linspace(1.0, 1.0 / 1000, 1000)
-    sch.sigmas = 3.0 * raw / (1 + 2.0 * raw)
-    sch.timesteps = sch.sigmas * 1000
+    def make_sched(num_train_timesteps=1000, shift=3.0, use_dynamic_shifting=True):
+        """FlowMatchEulerDiscreteScheduler.__init__ [D031, recalled]: timesteps = linspace(1, N, N)[::-1]; sigmas = timesteps / N; the
+        static shift is applied ONLY when use_dynamic_shifting is False; .timesteps = sigmas * N.  The reference builds it with
+        from_pretrained(FLUX.1-dev, subfolder="scheduler") (train_lightcontrol.py:495-499), whose scheduler_config.json [recalled:
+        shift 3.0, use_dynamic_shifting true, base/max_shift 0.5/1.15] therefore yields the UNSHIFTED linear table."""
+        class Sched:
+            pass
+        sch = Sched()
+        ts = torch.from_numpy(__import__("numpy").linspace(1, num_train_timesteps, num_train_timesteps, dtype="float32")[::-1].copy())
+        sig = ts / num_train_timesteps
+        if not use_dynamic_shifting:
+            sig = shift * sig / (1 + (shift - 1) * sig)
+        sch.sigmas, sch.timesteps = sig, sig * num_train_timesteps
+        return sch
+    sch, sch_static = make_sched(), make_sched(use_dynamic_shifting=False)
     idx = torch.tensor([0, 17, 500, 999])
     out = dict(lat=lat, packed=packed, unpacked=ref._unpack_latents(packed, 64, 96, 16),
                ids=ref._prepare_latent_image_ids(2, 8, 12, "cpu", torch.float32), idx=idx,
                sigmas=ref.get_sigmas(sch.timesteps[idx], sch, "cpu", n_dim=4, dtype=torch.float32),
+               sigmas_static_shift3=ref.get_sigmas(sch_static.timesteps[idx], sch_static, "cpu", n_dim=4, dtype=torch.float32),
+               scheduler_config=dict(num_train_timesteps=1000, shift=3.0, use_dynamic_shifting=True),
                stubbed=sorted(set(s_.split(".")[0] for s_ in finder.stubbed)))
     torch.save(out, os.path.join(OUT, "lightcontrol_helpers.pt"))
     print("LightControl helper goldens written; stubbed third-party roots:", out["stubbed"])
@@ -474,6 +574,7 @@ if __name__ == "__main__":
         sys.exit(0)
     golden_projector()
     golden_helpers()
+    golden_kd_loop()
     golden_flux_structure()
     crosscheck_torchtitan()
     golden_resampler()

@@ -109,6 +109,12 @@ def test_pipeline_four_step_sampling_matches_oracle(env):
              output_type="latent", generator=torch.Generator("cpu").manual_seed(3)).images
     assert torch.equal(a, b)
     assert FluxPipeline._unpack_latents(a, 128, 128, 16).shape == (2, 16, 16, 16)
+    # caller-supplied latents already in bf16 on the device are NOT overwritten by the in-place Euler updates
+    mine = packed.cuda()
+    keep = mine.clone()
+    o1 = pipe(prompt_embeds=prompt.cuda(), pooled_prompt_embeds=pooled.cuda(), num_inference_steps=4, height=128, width=128,
+              output_type="latent", latents=mine).images
+    assert torch.equal(mine, keep) and torch.equal(o1, out)
 
 
 @pytest.mark.parametrize("S,hl,wl,outliers", [(203, 16, 24, False), (512, 64, 64, False), (512, 64, 64, True)])
@@ -247,3 +253,31 @@ def test_mismatched_position_ids_fail_loudly(env):
     with pytest.raises(X2IError):
         with torch.no_grad():
             model(**inp, return_dict=False)
+
+
+def test_kd_loss_matches_the_reference_loss_loop_fixture(env, golden_dir):
+    """x2i_b200.kd.attention_distillation_loss against tests/golden/kd_loop.pt: the outputs of the reference's LITERAL loss loop
+    (train/train_qwenvl.py:601-620, exec'ed unchanged by oracle/make_golden.py::golden_kd_loop) in fp32; yardstick = the same lines
+    in the reference's own dtype (bf16).  Also the inf/nan guard: the poisoned layers are skipped and named like the reference."""
+    import contextlib
+    import io
+    from parity import check
+    from x2i_b200 import kd
+    d = torch.load(os.path.join(golden_dir, "kd_loop.pt"))
+    t = [x.cuda() for x in d["teacher"]]
+    s = [x.cuda().clone().requires_grad_(True) for x in d["student"]]
+    loss = kd.attention_distillation_loss(t, s, temperature=3.0, verbose=False)
+    grads = torch.autograd.grad(loss, s)
+    ref, eag = d["clean_fp32"], d["clean_bf16"]
+    check("KD loss vs the reference's literal loop (kd_loop.pt): loss", abs(float(loss) - float(ref["loss"])) / float(ref["loss"]),
+          abs(float(eag["loss"]) - float(ref["loss"])) / float(ref["loss"]))
+    for i, (a, b, e) in enumerate(zip(grads, ref["grads"], eag["grads"])):
+        check(f"KD loss vs the reference's literal loop (kd_loop.pt): d student group {i}", env.rel(a, b), env.rel(e, b))
+    # hook LISTS instead of stacked tensors: same value
+    l2 = kd.attention_distillation_loss([list(x.unbind(1)) for x in t], [list(x.detach().unbind(1)) for x in s], verbose=False)
+    assert abs(float(l2) - float(loss)) <= 1e-5 * abs(float(loss))
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        lp = kd.attention_distillation_loss([x.cuda() for x in d["poisoned_teacher"]], [x.cuda() for x in d["student"]], verbose=True)
+    assert buf.getvalue().split() == d["poisoned_fp32"]["printed"] == ["down_feature:2", "down_feature2:5"]
+    assert abs(float(lp) - float(d["poisoned_fp32"]["loss"])) / float(d["poisoned_fp32"]["loss"]) < 1e-2

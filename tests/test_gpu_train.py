@@ -4,6 +4,8 @@ eager-bf16 path (oracle modules in bf16 on the GPU, PyTorch autograd) measured a
 import pytest
 import torch
 
+from parity import check
+
 pytestmark = pytest.mark.gpu
 TOL = 1e-2
 
@@ -61,10 +63,26 @@ def test_student_backward_matches_oracle_autograd(env, guidance, B, hl, wl, S):
     for a, b in zip(h_mine, h_ref):
         assert env.rel(a, b) < TOL
     for name, a, b, e in zip(("d encoder_hidden_states", "d pooled_projections"), g_mine, g_ref, g_eager):
-        err, yard = env.rel(a, b), env.rel(e, b)
-        print(f"{name}: x2i_b200 {err:.4f}  eager-bf16 reference path {yard:.4f}")
         assert a.shape == b.shape and a.dtype == torch.bfloat16
-        assert err < max(TOL, 1.5 * yard)
+        check(f"tiny student backward (guidance={guidance}, B={B}): {name}", env.rel(a, b), env.rel(e, b))
+
+
+def test_gradient_checkpointing_recomputes_to_identical_gradients(env):
+    """enable_gradient_checkpointing() (train_lightcontrol.py:666; lightcontrol_flux.py:475-494,:513-531): the differentiable forward
+    keeps only block inputs and the backward re-runs each block's forward kernels -- same kernels on the same data, so outputs,
+    hooks and gradients are bit-identical to the saving mode, with less memory held between forward and backward."""
+    cfg = env.tiny_config(True)
+    model, _ = env.make_pair(cfg, seed=61)
+    inp = env.to_device(env.make_inputs(cfg, B=2, hl=8, wl=12, S=24, seed=62))
+    o0, h0, g0 = _run(model, inp, "cuda", 9)
+    model.enable_gradient_checkpointing()
+    assert model.gradient_checkpointing
+    torch.cuda.reset_peak_memory_stats()
+    o1, h1, g1 = _run(model, inp, "cuda", 9)
+    model.disable_gradient_checkpointing()
+    assert torch.equal(o0, o1)
+    assert all(torch.equal(a, b) for a, b in zip(h0, h1))
+    assert all(torch.equal(a, b) for a, b in zip(g0, g1))
 
 
 def test_hidden_states_gradient_and_no_hooks(env):
@@ -83,8 +101,9 @@ def test_hidden_states_gradient_and_no_hooks(env):
 
     g_ref = run(oracle, env.oracle_inputs(inp), "cpu")
     g_mine = run(model, env.to_device(inp), "cuda")
-    for a, b in zip(g_mine, g_ref):
-        assert env.rel(a, b) < 1.5 * TOL
+    g_eag = run(oracle.to("cuda", torch.bfloat16), env.to_device(inp), "cuda")
+    for k, a, b, e in zip(keys, g_mine, g_ref, g_eag):
+        check(f"tiny student backward without hooks: d {k}", env.rel(a, b), env.rel(e, b))
 
 
 def test_kd_training_step_matches_oracle(env):
@@ -120,10 +139,14 @@ def test_kd_training_step_matches_oracle(env):
                         lambda t, s: kd_oracle.kd_loss_stacked(*t, *s))
     l_mine, g_mine = step(model, env.to_device(t_inp), env.to_device(s_inp),
                           lambda t, s: kd.attention_distillation_loss(t, s, verbose=False))
-    print(f"KD loss: x2i_b200 {l_mine:.6f}  fp32 oracle {l_ref:.6f}")
-    assert abs(l_mine - l_ref) / abs(l_ref) < 3e-2  # the loss is a small difference of near-equal distributions
-    for a, b in zip(g_mine, g_ref):
-        assert env.rel(a, b) < 3e-2
+    # yardstick: the reference's own path -- the oracle modules in bf16 with torch eager ops and the reference's literal loss
+    l_eag, g_eag = step(oracle.to("cuda", torch.bfloat16), env.to_device(t_inp), env.to_device(s_inp),
+                        lambda t, s: kd_oracle.kd_loss_stacked(*t, *s))
+    print(f"KD loss: x2i_b200 {l_mine:.6f}  fp32 oracle {l_ref:.6f}  eager bf16 {l_eag:.6f}")
+    # the loss is a small difference of near-equal distributions: bf16 paths deviate by more than 1e-2 from fp32
+    check("tiny KD train step: loss", abs(l_mine - l_ref) / abs(l_ref), abs(l_eag - l_ref) / abs(l_ref))
+    for name, a, b, e in zip(("d encoder_hidden_states", "d pooled_projections"), g_mine, g_ref, g_eag):
+        check(f"tiny KD train step: {name}", env.rel(a, b), env.rel(e, b))
 
 
 @pytest.mark.parametrize("kind,use_scale,use_cnn,C,S,H", [("qwen3b", False, True, 5, 24, 256), ("qwen7b", True, False, 4, 20, 256),
@@ -149,15 +172,21 @@ def test_projector_backward_matches_reference_autograd(env, kind, use_scale, use
     assert env.rel(q1, p1) < TOL and env.rel(q2, p2) < TOL
     ((q1.float() * w1.cuda()).sum() + (q2.float() * w2.cuda()).sum()).backward()
     ref = dict(o.named_parameters())
+    # yardstick: the reference projector itself in bf16 under torch autograd (what train_qwenvl.py:399,:576,:625 runs)
+    import copy
+    ob = copy.deepcopy(o).to("cuda", torch.bfloat16)
+    ob.zero_grad()
+    e1, e2 = ob(x.cuda())
+    ((e1.float() * w1.cuda()).sum() + (e2.float() * w2.cuda()).sum()).backward()
+    eag = dict(ob.named_parameters())
     for name, p_ in m.named_parameters():
         assert p_.grad is not None, name
         if name == "conv.bias":
             # a constant added in front of a LayerNorm has an exactly-zero gradient; both sides hold rounding noise only
             assert float(p_.grad.float().abs().max()) < 1e-2 * float(ref["conv.weight"].grad.norm())
             continue
-        err = env.rel(p_.grad, ref[name].grad)
-        print(f"{name}: rel err {err:.4f}")
-        assert err < 1.5 * TOL, name
+        check(f"projector backward {kind} C={C} S={S} H={H}: {name}", env.rel(p_.grad, ref[name].grad),
+              env.rel(eag[name].grad, ref[name].grad))
 
 
 def test_distill_step_end_to_end(env):
@@ -208,14 +237,33 @@ def test_distill_step_end_to_end(env):
         mod._forward_hooks.clear()
     loss_o = kd_oracle.kd_loss_stacked(*[torch.stack(x, 1) for x in th], *[torch.stack(x, 1) for x in sh])
     loss_o.backward()
-    print(f"distill loss: x2i_b200 {float(loss_a):.6f}  oracle {float(loss_o):.6f}")
-    assert abs(float(loss_a) - float(loss_o)) / float(loss_o) < 3e-2
+    # yardstick: the same pipeline on the reference's own path (projector + FLUX oracle in bf16, torch eager autograd)
+    import copy
+    pb, ob = copy.deepcopy(po).to("cuda", torch.bfloat16), oracle.to("cuda", torch.bfloat16)
+    pb.zero_grad()
+    cbf = {k: (v.cuda() if k in ("txt_ids", "img_ids") else v.to("cuda", torch.bfloat16)) for k, v in common.items()}
+    cbf["timestep"], cbf["guidance"] = torch.full((B,), 1.0, device="cuda"), torch.full((B,), 3.5, device="cuda")
+    th2 = []
+    cast_hook_list(ob, th2)
+    with torch.no_grad():
+        ob(encoder_hidden_states=cb["prompt_embeds_t5"], pooled_projections=cb["pooled_clip"], return_dict=False, **cbf)
+    for mod in ob.modules():
+        mod._forward_hooks.clear()
+    sh2 = []
+    cast_hook_list(ob, sh2)
+    a2, e2 = pb(cb["text_embeddings"])
+    ob(encoder_hidden_states=e2, pooled_projections=a2, return_dict=False, **cbf)
+    for mod in ob.modules():
+        mod._forward_hooks.clear()
+    loss_e = kd_oracle.kd_loss_stacked(*[torch.stack(x, 1) for x in th2], *[torch.stack(x, 1) for x in sh2])
+    loss_e.backward()
+    eag = dict(pb.named_parameters())
+    print(f"distill loss: x2i_b200 {float(loss_a):.6f}  oracle {float(loss_o):.6f}  eager bf16 {float(loss_e):.6f}")
+    check("tiny distill step: loss", abs(float(loss_a) - float(loss_o)) / float(loss_o), abs(float(loss_e) - float(loss_o)) / float(loss_o))
     for n, p_ in po.named_parameters():
         if n == "conv.bias":
             continue  # exactly zero in exact arithmetic (constant in front of a LayerNorm)
-        err = env.rel(grads_a[n], p_.grad)
-        print(f"grad {n}: rel err {err:.4f}")
-        assert err < 4e-2, n
+        check(f"tiny distill step: grad {n}", env.rel(grads_a[n], p_.grad), env.rel(eag[n].grad, p_.grad))
     # optimizer path: parameters move, loss stays finite
     opt = torch.optim.AdamW(pm.parameters(), lr=1e-4, fused=True)
     before = pm.mlp.projector[0].weight.detach().clone()

@@ -159,7 +159,7 @@ def test_bench_reference_arm_json_contract(monkeypatch, capsys):
     import argparse
     import json
     import bench
-    monkeypatch.setattr(bench, "cpu_sample", lambda threads, nd=1, ns=2, repeat=1: (12.5, "mocked sample"))
+    monkeypatch.setattr(bench, "cpu_full_step", lambda threads: (12.5, "mocked full step"))
     monkeypatch.delenv("RANK", raising=False)
     bench.run_reference(argparse.Namespace(gpus=1, steps=2, warmup=1))
     lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
@@ -169,6 +169,7 @@ def test_bench_reference_arm_json_contract(monkeypatch, capsys):
               "data", "config", "cpu_baseline", "e2e"):
         assert k in j, k
     assert j["impl"] == "reference" and j["unit"] == "steps/s" and abs(j["value"] - 1 / 12.5) < 1e-9 and j["higher_is_better"] is True
+    assert j["steps"] == 2  # every requested step is a real, fully timed step while the arm fits its time budget
     assert j["config"]["workload"] == bench.WORKLOAD and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"] == {"value": j["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     monkeypatch.setenv("RANK", "1")  # under torchrun only rank 0 prints
@@ -195,16 +196,18 @@ def test_control_net_stack_eligibility():
 
 def test_lightcontrol_host_helpers():
     """Host-side pieces of the LightControl train step (lightcontrol/train_lightcontrol.py:690-703): logit-normal timestep density,
-    the training sigma table (shift 3), and the no-CPU-path rule."""
+    the training sigma table (FLUX.1-dev scheduler config: dynamic shifting on -> unshifted; static shift 3 when off), and the
+    no-CPU-path rule."""
     import pytest
     import torch
     from x2i_b200 import train_lightcontrol as tl
     from x2i_b200._lib import X2IError
-    s = tl.train_sigmas(1000, 3.0)
-    assert s.shape == (1000,) and abs(float(s[0]) - 1.0) < 1e-6 and bool((s[1:] < s[:-1]).all())
     raw = torch.linspace(1.0, 1.0 / 1000, 1000)
+    assert torch.equal(tl.train_sigmas(1000, 3.0), raw)                          # default: use_dynamic_shifting -> no static shift
+    s = tl.train_sigmas(1000, 3.0, use_dynamic_shifting=False)
+    assert s.shape == (1000,) and abs(float(s[0]) - 1.0) < 1e-6 and bool((s[1:] < s[:-1]).all())
     assert torch.allclose(s, 3.0 * raw / (1 + 2.0 * raw))
-    assert torch.allclose(tl.train_sigmas(1000, 1.0), raw)                      # shift 1 = the schnell table
+    assert torch.allclose(tl.train_sigmas(1000, 1.0, use_dynamic_shifting=False), raw)   # shift 1 = the schnell table
     g1, g2 = torch.Generator().manual_seed(5), torch.Generator().manual_seed(5)
     u1 = tl.compute_density_for_timestep_sampling("logit_normal", 64, 0.0, 1.0, generator=g1)
     u2 = tl.compute_density_for_timestep_sampling("logit_normal", 64, 0.0, 1.0, generator=g2)
@@ -217,3 +220,75 @@ def test_lightcontrol_host_helpers():
         tl.lightcontrol_step(None, None, None, {"pixel_values": torch.zeros(1, 3, 16, 16)})
     b = tl.synthetic_batch(1, "cpu", height=32, width=48, S=4, seed=0)
     assert b["pixel_values"].shape == (1, 3, 32, 48) and b["prompt_embeds"].shape == (1, 4, 4096) and float(b["pixel_values"].abs().max()) <= 1
+
+
+def test_master_weight_optimizer_keeps_small_updates():
+    """at the reference's lr = 1e-5 an Adam update is below half a bf16 ulp of a 0.02-0.05 weight; stepping bf16 parameters
+    directly loses it, fp32 masters (DeepSpeed bf16 engine, accelerate_config_debug.yaml) keep it."""
+    from x2i_b200.train_lightcontrol import MasterWeightOptimizer
+    torch.manual_seed(0)
+    w0 = (torch.randn(64, 64) * 0.04).bfloat16()
+    direct = torch.nn.Parameter(w0.clone())
+    shadow = torch.nn.Parameter(w0.clone())
+    opt_d = torch.optim.AdamW([direct], lr=1e-5, weight_decay=0.0)
+    opt_m = MasterWeightOptimizer([shadow], lr=1e-5, weight_decay=0.0)
+    g = torch.ones_like(w0)
+    for _ in range(40):  # constant gradient: Adam moves every weight by ~lr per step -> 4e-4 in total (several bf16 ulps of 0.04)
+        direct.grad = g.clone(); opt_d.step(); opt_d.zero_grad()
+        shadow.grad = g.clone(); opt_m.step(); opt_m.zero_grad()
+    moved_direct = float((direct.detach().float() - w0.float()).abs().mean())
+    moved_master = float((opt_m.master[0].detach() - w0.float()).abs().mean())
+    assert abs(moved_master - 40e-5) < 2e-5                      # the masters followed Adam exactly
+    assert moved_direct < 0.2 * moved_master                     # pure bf16 stalls (most updates round away)
+    assert abs(float((shadow.detach().float() - w0.float()).mean()) + 40e-5) < 1.5e-4  # bf16 weights track the masters to within rounding
+    sd = opt_m.state_dict()
+    opt_m.load_state_dict(sd)
+    assert torch.equal(shadow.detach(), opt_m.master[0].bfloat16())
+
+
+def test_grad_bucket_views_allreduce_and_clip():
+    torch.manual_seed(1)
+    lin = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
+    bucket = xdist.GradBucket(lin.parameters())
+    assert bucket.flat.numel() == sum(p.numel() for p in lin.parameters()) and bucket.nbytes == 4 * bucket.flat.numel()
+    x = torch.randn(5, 8)
+    lin(x).pow(2).sum().backward()
+    lin(x).pow(2).sum().backward()          # accumulation lands in the same buffer (train_qwenvl.py:561: grads add up over micro-steps)
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
+    ref.load_state_dict(lin.state_dict())
+    (2 * ref(x).pow(2).sum()).backward()
+    flat_ref = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in lin.parameters())
+    assert torch.allclose(bucket.flat, flat_ref, rtol=1e-5, atol=1e-6)
+    bucket.allreduce_mean_()                # world size 1: no-op
+    total = bucket.clip_grad_norm_(1.0)
+    want = torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+    assert abs(float(total) - float(want)) < 1e-4 * float(want)
+    assert torch.allclose(bucket.flat, torch.cat([p.grad.reshape(-1) for p in ref.parameters()]), rtol=1e-4, atol=1e-7)
+    bucket.zero_()
+    assert float(bucket.flat.abs().max()) == 0 and lin[0].weight.grad.data_ptr() == bucket.flat.data_ptr()
+
+
+def test_auto_resume_picks_highest_numbered_checkpoint(tmp_path):
+    """train_qwenvl.py:199-203,:404-410,:534-536: weights-only resume from {output_dir}/{max step}/diffusion_pytorch_model.bin."""
+    from x2i_b200 import train
+    assert train.get_max_numbered_filename(str(tmp_path)) is None and train.resume_projector(None, str(tmp_path / "missing")) is None
+    p = xproj.Proj7Exp(in_channels=3, input_dim=64, use_t5=False, use_scale=False, use_cnn=True)
+    for step, val in ((500, 0.25), (1500, 0.5), (1000, 0.75)):
+        with torch.no_grad():
+            p.conv.bias.fill_(val)
+        train.save_projector_checkpoint(p, str(tmp_path), step)
+    q = xproj.Proj7Exp(in_channels=3, input_dim=64, use_t5=False, use_scale=False, use_cnn=True)
+    assert train.resume_projector(q, str(tmp_path)) == 1500
+    assert float(q.conv.bias) == 0.5
+
+
+def test_lightcontrol_return_form_serves_both_call_sites():
+    """diffusers returns (sample,) for return_dict=False (train_qwenvl.py:587 indexes [0]); the vendored LightControl
+    transformer returns the bare tensor and train_lightcontrol.py:745-751 hands it straight to _unpack_latents."""
+    from x2i_b200.flux import _TensorTuple
+    t = torch.arange(2 * 6 * 64, dtype=torch.float32).view(2, 6, 64)
+    r = _TensorTuple((t,))
+    assert isinstance(r, tuple) and len(r) == 1 and r[0] is t
+    assert r.shape == t.shape and r.dtype == t.dtype
+    assert torch.equal(FluxPipeline._unpack_latents(r, 32, 48, 16), FluxPipeline._unpack_latents(t, 32, 48, 16))

@@ -163,5 +163,101 @@ def test_lightcontrol_trainer_helpers_match_reference(golden_dir):
     assert torch.equal(d["unpacked"], d["lat"])                                        # round trip
     assert torch.equal(FluxPipeline._prepare_latent_image_ids(2, 8, 12, "cpu", torch.float32), d["ids"])
     assert torch.equal(fo.unpack_latents(d["packed"], 64, 96, 16), d["unpacked"]) and torch.equal(fo.pack_latents(d["lat"]), d["packed"])
-    table = tl.train_sigmas(1000, 3.0)
+    # the reference's scheduler comes from FLUX.1-dev's scheduler_config.json (use_dynamic_shifting = true -> NO static shift)
+    table = tl.train_sigmas_from_config(d["scheduler_config"])
+    assert torch.equal(table, tl.train_sigmas()) and float(table[0]) == 1.0 and abs(float(table[500]) - 0.5) < 1e-6
     assert torch.allclose(table[d["idx"]], d["sigmas"].flatten(), rtol=0, atol=1e-7)
+    static = tl.train_sigmas(1000, 3.0, use_dynamic_shifting=False)
+    assert torch.allclose(static[d["idx"]], d["sigmas_static_shift3"].flatten(), rtol=0, atol=1e-7)
+
+
+def test_kd_oracle_matches_the_reference_loss_loop_verbatim(golden_dir):
+    """kd_loop.pt holds the outputs of the reference's LITERAL loss loop (train/train_qwenvl.py:601-620, cut out of train() and
+    exec'ed by oracle/make_golden.py::golden_kd_loop).  The oracle's restated loop must reproduce it: value, gradients, and the
+    inf/nan guard (layers skipped, names printed)."""
+    from oracle import kd_oracle
+    d = torch.load(os.path.join(golden_dir, "kd_loop.pt"))
+    assert "F.kl_div(F.softmax(normalize(KD_teacher_tensor0[:,i])/temperature0, dim=-1).log()" in d["loop_src"]
+    ss = [s.float().clone().requires_grad_(True) for s in d["student"]]
+    loss = kd_oracle.kd_loss_stacked(*[t.float() for t in d["teacher"]], *ss)
+    grads = torch.autograd.grad(loss, ss)
+    assert torch.allclose(loss, d["clean_fp32"]["loss"], rtol=1e-6, atol=1e-7)
+    for a, b in zip(grads, d["clean_fp32"]["grads"]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
+    # bf16, the reference's own dtype: same ops in the same order -> identical
+    lb = kd_oracle.kd_loss_stacked(*d["teacher"], *d["student"])
+    assert torch.equal(lb.float(), d["clean_bf16"]["loss"])
+    # guard: a NaN / inf in a teacher layer drops exactly that layer's term
+    lp = kd_oracle.kd_loss_stacked(*[t.float() for t in d["poisoned_teacher"]], *[s.float() for s in d["student"]])
+    assert torch.allclose(lp, d["poisoned_fp32"]["loss"], rtol=1e-6, atol=1e-7)
+    assert d["poisoned_fp32"]["printed"] == ["down_feature:2", "down_feature2:5"] and d["clean_fp32"]["printed"] == []
+    assert float(d["poisoned_fp32"]["loss"]) < float(d["clean_fp32"]["loss"])
+
+
+def test_reference_cast_hook_list_registers_on_the_drop_in(golden_dir):
+    """The reference's own cast_hook_list (train_qwenvl.py:206-214), run by make_golden on an x2i_b200 transformer through the compat
+    shim: one hook per attn module, (img, txt) fan-out for double blocks, tensor for single blocks -- and x2i_b200.kd.cast_hook_list
+    produces the same wiring on the same model."""
+    from x2i_b200.flux import FluxTransformer2DModel
+    from x2i_b200.kd import cast_hook_list
+    d = torch.load(os.path.join(golden_dir, "kd_loop.pt"))
+    assert d["n_hooks"] == [1] * 7
+    assert d["hook_fanout"] == [[0.0, 1.0, 2.0], [100.0, 101.0, 102.0], [200.0, 201.0, 202.0, 203.0]]
+    with torch.device("meta"):
+        model = FluxTransformer2DModel(num_layers=3, num_single_layers=4, num_attention_heads=2, joint_attention_dim=64, pooled_projection_dim=32)
+    lists = []
+    cast_hook_list(model, lists)
+    for i, b in enumerate(model.transformer_blocks):
+        for h in b.attn._forward_hooks.values():
+            h(b.attn, (), (torch.full((1,), float(i)), torch.full((1,), 100.0 + i)))
+    for i, b in enumerate(model.single_transformer_blocks):
+        for h in b.attn._forward_hooks.values():
+            h(b.attn, (), torch.full((1,), 200.0 + i))
+    assert [[float(t) for t in lst] for lst in lists] == d["hook_fanout"]
+
+
+def test_compat_diffusers_shim_surface():
+    """x2i_b200.compat.install(): every diffusers name the reference's hot-path files import resolves to the x2i_b200 drop-in."""
+    import importlib
+    import math
+    import sys
+    from x2i_b200 import compat, controlnext, flux, pipeline, vae
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.split(".")[0] == "diffusers"}
+    try:
+        compat.install(force=True)
+        import diffusers
+        from diffusers import AutoencoderKL, FluxPipeline                                            # infer/inference_qwenvl.py:7
+        from diffusers.image_processor import VaeImageProcessor                                      # :8
+        from diffusers.models.transformers import FluxTransformer2DModel                             # train/train_qwenvl.py:45
+        from diffusers.schedulers import FlowMatchEulerDiscreteScheduler                             # :44
+        from diffusers.optimization import get_scheduler                                             # :31
+        from diffusers.utils.torch_utils import is_compiled_module, randn_tensor                     # :32
+        from diffusers.models.attention import FeedForward                                           # lightcontrol_flux.py:24
+        from diffusers.models.attention_processor import Attention, FluxAttnProcessor2_0, FusedFluxAttnProcessor2_0  # :25-30
+        from diffusers.models.normalization import AdaLayerNormContinuous, AdaLayerNormZero, AdaLayerNormZeroSingle  # :32
+        from diffusers.models.embeddings import CombinedTimestepGuidanceTextProjEmbeddings, FluxPosEmbed               # :35
+        from diffusers.models.resnet import Downsample2D, ResnetBlock2D                              # :37
+        from diffusers.training_utils import compute_density_for_timestep_sampling, compute_loss_weighting_for_sd3  # train_lightcontrol.py:36
+        assert FluxTransformer2DModel is flux.FluxTransformer2DModel and FluxPipeline is pipeline.FluxPipeline
+        assert AutoencoderKL is vae.AutoencoderKL and VaeImageProcessor is vae.VaeImageProcessor
+        assert FlowMatchEulerDiscreteScheduler is pipeline.FlowMatchEulerDiscreteScheduler and Attention is flux.Attention
+        assert ResnetBlock2D is controlnext.ResnetBlock2D and Downsample2D is controlnext.Downsample2D
+        assert diffusers.utils.check_min_version("0.31.0") is None and not is_compiled_module(torch.nn.Linear(2, 2))
+        assert importlib.import_module("diffusers.loaders.lora_pipeline").SD3LoraLoaderMixin is not None
+        # the cosine schedule of train_qwenvl.sh (warm-up 100 of 100 000 steps, train_qwenvl.py:476-481)
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-4)
+        sch = get_scheduler("cosine", optimizer=opt, num_warmup_steps=100, num_training_steps=100000)
+        lrs = []
+        for _ in range(151):
+            lrs.append(sch.get_last_lr()[0]); opt.step(); sch.step()
+        assert lrs[0] == 0.0 and abs(lrs[50] - 0.5e-4) < 1e-12 and abs(lrs[100] - 1e-4) < 1e-12
+        assert abs(lrs[150] - 1e-4 * 0.5 * (1 + math.cos(math.pi * 50 / 99900))) < 1e-12
+        w = compute_loss_weighting_for_sd3("cosmap", torch.tensor([0.5]))
+        assert abs(float(w) - 2 / (math.pi * 0.5)) < 1e-6 and float(compute_loss_weighting_for_sd3("none", torch.tensor([0.3]))) == 1.0
+        assert randn_tensor((2, 3), generator=torch.Generator().manual_seed(0)).shape == (2, 3)
+        assert compute_density_for_timestep_sampling("logit_normal", 4, 0.0, 1.0).shape == (4,)
+    finally:
+        compat.uninstall()
+        for k in [k for k in sys.modules if k.split(".")[0] == "diffusers"]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)

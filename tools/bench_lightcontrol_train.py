@@ -28,7 +28,7 @@ def main():
     vae = init_synthetic_(xv.AutoencoderKL().to(dev, torch.bfloat16).eval(), seed=5, std=0.03).requires_grad_(False)
     nets = torch.nn.ModuleList([ControlNeXtModel() for _ in range(args.nets)]).to(dev, torch.bfloat16).train()
     init_synthetic_(nets, seed=1, std=0.05)
-    opt = torch.optim.AdamW(nets.parameters(), lr=1e-5, fused=True)
+    opt = tl.MasterWeightOptimizer(nets.parameters(), lr=1e-5, fused=True)  # fp32 masters (reference: DeepSpeed bf16 engine)
     batch = tl.synthetic_batch(args.batch, dev, seed=rank)
     torch.cuda.reset_peak_memory_stats()
     for _ in range(args.warmup):

@@ -64,6 +64,68 @@ def allreduce_mean_grads_(params: Iterable[torch.nn.Parameter], group=None) -> i
     return off
 
 
+class GradBucket:
+    """All gradients of a (small) trainable module as views of ONE flat buffer -- the shape DDP's ``gradient_as_bucket_view`` gives
+    the reference's projector (train/train_qwenvl.py:483).  autograd accumulates straight into the views (in place, which is
+    also what gradient accumulation over micro-steps needs, :561/:625), so the single exchange step of a train step is one
+    ``all_reduce`` on the buffer itself: no flatten copy before it and no scatter copies after it, and the clip norm is one
+    reduction over the same buffer.  ``timings`` (optional list) receives (start, end) CUDA events around the collective."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucket: no trainable parameters")
+        p0 = self.params[0]
+        if any(p.dtype != p0.dtype or p.device != p0.device for p in self.params):
+            raise ValueError("GradBucket: parameters must share dtype and device")
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=p0.dtype, device=p0.device)
+        self.attach_()
+
+    def attach_(self):
+        """(Re-)point every .grad at its slice of the buffer (needed again after optimizer.zero_grad(set_to_none=True))."""
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+        return self
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * self.flat.element_size()
+
+    def zero_(self):
+        self.flat.zero_()
+        if self.params[0].grad is None or self.params[0].grad.data_ptr() != self.flat.data_ptr():
+            self.attach_()
+
+    def allreduce_mean_(self, group=None, timings=None):
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return self
+        ev = None
+        if timings is not None and self.flat.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)  # mean over ranks inside the collective
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(world)
+        if ev is not None:
+            ev[1].record()
+            timings.append(ev)
+        return self
+
+    def clip_grad_norm_(self, max_norm: float):
+        """torch.nn.utils.clip_grad_norm_ semantics (2-norm over all gradients, scale by max_norm / (norm + 1e-6) when above) as
+        one reduction + one scale over the flat buffer, without a host sync."""
+        total = torch.linalg.vector_norm(self.flat.float(), 2.0)
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        self.flat.mul_(coef.to(self.flat.dtype))
+        return total
+
+
 def max_over_ranks(value: float, device) -> float:
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return value

@@ -33,9 +33,11 @@ BF16 = torch.bfloat16
 
 
 def _no_grad_needed(*tensors):
+    """Stand-alone leaves / blocks and plug-in processors are forward-only: autograd runs through the WHOLE transformer as one
+    node (flux_train.FluxTrainFn, used automatically by FluxTransformer2DModel.forward when an input requires grad)."""
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise X2IError("x2i_b200.flux: autograd through the MMDiT is not implemented yet (forward-only kernels); "
-                       "call under torch.no_grad() with inputs that do not require grad")
+        raise X2IError("x2i_b200.flux: this entry point is forward-only; gradients flow through FluxTransformer2DModel.forward "
+                       "(one autograd node for the whole transformer), not through a stand-alone block or a plug-in processor")
 
 
 # ------------------------------------------------------------------------------------------------ leaves
@@ -518,7 +520,13 @@ class FluxTransformer2DModel(nn.Module):
         return None
 
     def enable_gradient_checkpointing(self):
+        """train_lightcontrol.py:666.  The differentiable forward (flux_train.forward_save) then keeps only every block's inputs and
+        re-runs the block's forward kernels inside the backward (the reference's torch.utils.checkpoint per block,
+        lightcontrol_flux.py:475-494,:513-531): ~0.35 GB -> ~30 MB of saved activations per block and sample."""
         self.gradient_checkpointing = True
+
+    def disable_gradient_checkpointing(self):
+        self.gradient_checkpointing = False
 
     # -- packing of every AdaLN modulation linear into one [N_total, D] matrix (one GEMV launch per step) ----
     def _mod_linears(self):
@@ -564,12 +572,14 @@ class FluxTransformer2DModel(nn.Module):
         rc = self._rope_cache
         if rc is not None and rc[0] != key and rc[0][:2] == key[:2]:
             ids = torch.cat((txt_ids.float(), img_ids.float()), dim=0).to(self.device)
-            if torch.equal(ids, rc[3]):
-                self._rope_cache = rc = (key,) + rc[1:]
+            if torch.equal(ids, rc[3]):  # host sync: callers on a hot path pass stable id tensors (pipeline / trainers cache theirs)
+                self._rope_cache = rc = (key,) + rc[1:4] + ((txt_ids, img_ids),)
         if rc is None or rc[0] != key:
             ids = torch.cat((txt_ids.float(), img_ids.float()), dim=0).to(self.device)
             cos, sin, rope = ops.rope_table(ids, self.config.axes_dims_rope, 10000.0)
-            self._rope_cache = rc = (key, (cos, sin), rope, ids)
+            # the key is (lengths, addresses, versions): hold the id tensors themselves so the caching allocator cannot hand their
+            # addresses to different ids of the same length (e.g. 64x32 vs 32x64 latents) while this entry is alive
+            self._rope_cache = rc = (key, (cos, sin), rope, ids, (txt_ids, img_ids))
         return rc[1], rc[2]
 
     # -- forward --------------------------------------------------------------------------------------------
@@ -611,7 +621,10 @@ class FluxTransformer2DModel(nn.Module):
             out = self._forward_eager(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
                                       guidance)
         if not return_dict:
-            return (out,)
+            # diffusers returns a 1-tuple (callers index [0], train_qwenvl.py:587); the vendored LightControl class returns the BARE
+            # tensor (lightcontrol_flux.py:549-550, consumed as a tensor at train_lightcontrol.py:745-751).  With control nets the
+            # call is the LightControl form: hand back an object that serves both usages.
+            return _TensorTuple((out,)) if control_nets is not None else (out,)
         return SimpleNamespace(sample=out)
 
     def _forward_train(self, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance, guided_hint=None,
@@ -747,6 +760,14 @@ class FluxTransformer2DModel(nn.Module):
         n = ops.ln_modulate(h.view(B * (S + L_img), D), mod[:, off:off + D], mod[:, off + D:off + 2 * D], S + L_img,
                             out=ws["n"])
         return ops.linear(n, self.proj_out.weight, self.proj_out.bias).view(B, S + L_img, -1)[:, S:].contiguous()
+
+
+class _TensorTuple(tuple):
+    """1-tuple ``(sample,)`` that also forwards tensor attributes (``.shape``, ``.view``, ``.float()`` ...) to the sample, so both
+    ``model(...)[0]`` (diffusers) and ``_unpack_latents(model(...), ...)`` (lightcontrol/train_lightcontrol.py:732-751) work."""
+
+    def __getattr__(self, name):
+        return getattr(tuple.__getitem__(self, 0), name)
 
 
 def init_synthetic_(model: nn.Module, seed: int = 0, std: float = 0.02) -> nn.Module:

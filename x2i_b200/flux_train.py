@@ -112,13 +112,17 @@ def forward_save(model, hidden_states, encoder_hidden_states, pooled, timestep, 
     c = ops.linear(encoder_hidden_states.to(BF16).contiguous(), model.context_embedder.weight, model.context_embedder.bias).view(B * S, D)
     mod = ops.skinny_linear(temb, model._w_mod, model._b_mod, act_in=1)
 
+    # Gradient checkpointing (lightcontrol_flux.py:475-494,:513-531, enabled by train_lightcontrol.py:666): keep only each
+    # block's inputs (28-31 MB per sample instead of ~0.35 GB) and re-run the block's forward kernels in the backward.
+    ckpt = bool(getattr(model, "gradient_checkpointing", False))
     tape = dict(B=B, S=S, L_img=L_img, rope=rope, temb=temb, z1=z1, mod=mod, double=[], single=[],
                 enc_dim=encoder_hidden_states.shape[2], in_dim=hidden_states.shape[2])
     hooks_img, hooks_txt, hooks_single = [], [], []
     off = 0
     for blk in model.transformer_blocks:
+        x0, c0 = x, c
         x, c, sv = _double_fwd(blk, x, c, mod[:, off:off + 12 * D], rope, B, L_img, S)
-        tape["double"].append(sv)
+        tape["double"].append(dict(x0=x0, c0=c0, recompute=True) if ckpt else sv)
         hooks_img.append(sv["ya_i"].view(B, L_img, D))
         hooks_txt.append(sv["ya_t"].view(B, S, D))
         off += 12 * D
@@ -133,8 +137,9 @@ def forward_save(model, hidden_states, encoder_hidden_states, pooled, timestep, 
         F = model.single_transformer_blocks[0].mlp_hidden_dim
         cat_buf = _e(B * L, D + F, device=dev)
     for blk in model.single_transformer_blocks:
+        h0 = h
         h, sv = _single_fwd(blk, h, mod[:, off:off + 3 * D], rope, B, L, cat_buf)
-        tape["single"].append(sv)
+        tape["single"].append(dict(h0=h0, recompute=True) if ckpt else sv)
         hooks_single.append(sv["a"])
         off += 3 * D
     tape["h_final"] = h
@@ -247,10 +252,17 @@ def backward(model, tape, dout, dhooks_img, dhooks_txt, dhooks_single, need_hidd
     if len(model.single_transformer_blocks):
         F = model.single_transformer_blocks[0].mlp_hidden_dim
         dbig = _e(B * L, 3 * D + F, device=dev)
+    cat_buf = None
     for i in range(len(model.single_transformer_blocks) - 1, -1, -1):
         off -= 3 * D
-        dh = _single_bwd(model.single_transformer_blocks[i], tape["single"][i], dh, _g2(dhooks_single[i], B * L, D),
+        sv = tape["single"][i]
+        if sv.get("recompute"):  # checkpointed block: rebuild its saved activations from the block input
+            if cat_buf is None:
+                cat_buf = _e(B * L, D + F, device=dev)
+            _, sv = _single_fwd(model.single_transformer_blocks[i], sv["h0"], mod[:, off:off + 3 * D], rope, B, L, cat_buf)
+        dh = _single_bwd(model.single_transformer_blocks[i], sv, dh, _g2(dhooks_single[i], B * L, D),
                          mod[:, off:off + 3 * D], dmod[:, off:off + 3 * D], rope, B, L, dbig)
+        sv = None
         tape["single"][i] = None  # release this block's activations
     dh3 = dh.view(B, L, D)
     dc = dh3[:, :S].contiguous().view(B * S, D)
@@ -260,8 +272,12 @@ def backward(model, tape, dout, dhooks_img, dhooks_txt, dhooks_single, need_hidd
         off -= 12 * D
         if i < n_controls:
             dctrl[i] = dx.view(B, L_img, D).clone()
-        dx, dc = _double_bwd(model.transformer_blocks[i], tape["double"][i], dx, dc, _g2(dhooks_img[i], B * L_img, D),
+        sv = tape["double"][i]
+        if sv.get("recompute"):
+            _, _, sv = _double_fwd(model.transformer_blocks[i], sv["x0"], sv["c0"], mod[:, off:off + 12 * D], rope, B, L_img, S)
+        dx, dc = _double_bwd(model.transformer_blocks[i], sv, dx, dc, _g2(dhooks_img[i], B * L_img, D),
                              _g2(dhooks_txt[i], B * S, D), mod[:, off:off + 12 * D], dmod[:, off:off + 12 * D], rope, B, L_img, S)
+        sv = None
         tape["double"][i] = None
     d_enc = ops.linear_dgrad(dc, model.context_embedder.weight).view(B, S, tape["enc_dim"])
     d_hidden = ops.linear_dgrad(dx, model.x_embedder.weight).view(B, L_img, tape["in_dim"]) if need_hidden_grad else None

@@ -195,7 +195,8 @@ class FluxPipeline:
             self._ids_cache[ck] = self._prepare_latent_image_ids(batch_size, height, width, device, dtype)
         ids = self._ids_cache[ck]
         if latents is not None:
-            return latents.to(device=device, dtype=dtype), ids
+            # the Euler update runs in place on the latents: never on the caller's tensor (diffusers' step returns a new one)
+            return latents.to(device=device, dtype=dtype, copy=True), ids
         latents = randn_tensor((batch_size, num_channels_latents, height, width), generator, device, dtype)
         return self._pack_latents(latents, batch_size, num_channels_latents, height, width), ids
 

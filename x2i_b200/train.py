@@ -31,6 +31,18 @@ def prepare_latent_image_ids(height: int, width: int, device, dtype):
     return ids.reshape(-1, 3).to(device=device, dtype=dtype)
 
 
+_IDS_CACHE: Dict = {}
+
+
+def _cached_ids(S: int, height: int, width: int, device, dtype):
+    """Stable (txt_ids, img_ids) tensors per shape: the transformer's RoPE cache keys on their addresses, so rebuilding them every
+    step would cost a table rebuild or a host-synchronising content compare per step."""
+    key = (S, height, width, str(device), dtype)
+    if key not in _IDS_CACHE:
+        _IDS_CACHE[key] = (torch.zeros(S, 3, device=device, dtype=dtype), prepare_latent_image_ids(height, width, device, dtype))
+    return _IDS_CACHE[key]
+
+
 def _run_hooked(transformer, lists, **kw):
     handles = []
     lists.append([]); lists.append([]); lists.append([])
@@ -53,10 +65,42 @@ def _run_hooked(transformer, lists, **kw):
     return out
 
 
+def get_max_numbered_filename(directory: str):
+    """train_qwenvl.py:199-203: the largest integer found in the entry names of `directory` (None if there is none)."""
+    import os
+    import re
+    if not os.path.isdir(directory):
+        return None
+    pattern = re.compile(r"\d+")
+    numbers = [int(pattern.search(f).group()) for f in os.listdir(directory) if pattern.search(f)]
+    return max(numbers) if numbers else None
+
+
+def resume_projector(proj, output_dir: str):
+    """The reference's auto-resume (train_qwenvl.py:404-410, :534-536): load
+    ``{output_dir}/{max step}/diffusion_pytorch_model.bin`` into the projector (weights only: the reference saves neither optimizer,
+    LR-scheduler nor RNG state) and return that step as the new ``global_step``; None when there is no checkpoint."""
+    import os
+    from .proj import load_projector_state
+    step = get_max_numbered_filename(output_dir)
+    if step is None:
+        return None
+    path = os.path.join(output_dir, str(step), "diffusion_pytorch_model.bin")
+    load_projector_state(proj, torch.load(path, map_location="cpu"))
+    return step
+
+
 def distill_step(proj, transformer, batch: Dict[str, torch.Tensor], optimizer=None, lr_scheduler=None, max_grad_norm: float = 1.0,
                  temperature: float = 3.0, guidance_scale: float = 3.5, height: int = 128, width: int = 128, group=None,
-                 stacked: bool = False):
-    """One distillation step on this rank's batch shard.
+                 stacked: bool = False, micro_step: int = 0, gradient_accumulation_steps: int = 1, bucket=None, timings=None):
+    """One distillation (micro-)step on this rank's batch shard.
+
+    Gradient accumulation follows train_qwenvl.py:561,:625-632: every micro-step adds its gradients to ``.grad`` (the loss is NOT
+    divided by the number of micro-steps), and the optimizer fires when ``micro_step % gradient_accumulation_steps == 0``.  The
+    reference's DDP all-reduces on every micro-step (no ``no_sync``); the mean over ranks is linear, so here the ONE all-reduce
+    runs on the accumulated gradients right before the clip -- same update, 1/gas of the traffic.
+    bucket: an x2i_b200.dist.GradBucket over the projector parameters (gradients live in one flat buffer: all-reduce and clip
+    without flatten/scatter copies); timings: optional list receiving the (start, end) CUDA events of the all-reduce.
 
     batch: ``latents`` [B, L_img, 64] (pure noise, t = 1.0 in the reference), ``timestep`` [B] (x1000 scale, as the
     reference's scheduler emits; divided by 1000 here like ``:580``), ``text_embeddings`` [B, C, S, H] (all-layer MLLM
@@ -67,8 +111,7 @@ def distill_step(proj, transformer, batch: Dict[str, torch.Tensor], optimizer=No
     dt = transformer.dtype
     B = batch["latents"].shape[0]
     S = batch["prompt_embeds_t5"].shape[1]
-    txt_ids = torch.zeros(S, 3, device=dev, dtype=dt)
-    img_ids = prepare_latent_image_ids(height, width, dev, dt)
+    txt_ids, img_ids = _cached_ids(S, height, width, dev, dt)
     guidance = torch.full((B,), guidance_scale, device=dev, dtype=dt) if transformer.config.guidance_embeds else None
     common = dict(hidden_states=batch["latents"].to(dt), timestep=batch["timestep"] / 1000, txt_ids=txt_ids, img_ids=img_ids,
                   guidance=guidance)
@@ -86,15 +129,26 @@ def distill_step(proj, transformer, batch: Dict[str, torch.Tensor], optimizer=No
         s_all = kd_student[0] + kd_student[1] + kd_student[2]
         loss, _valid = kd.kd_loss_layers(t_all, s_all, temperature)
     loss.backward()
+    if micro_step % max(1, gradient_accumulation_steps) != 0:
+        return loss.detach()  # accumulate only (train_qwenvl.py:561)
     params = [p for p in proj.parameters() if p.requires_grad]
-    xdist.allreduce_mean_grads_(params, group=group)
+    if bucket is not None:
+        bucket.allreduce_mean_(group=group, timings=timings)
+    else:
+        xdist.allreduce_mean_grads_(params, group=group)
     if optimizer is not None:
         if max_grad_norm is not None:
-            torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+            if bucket is not None:
+                bucket.clip_grad_norm_(max_grad_norm)
+            else:
+                torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
         optimizer.step()
         if lr_scheduler is not None:
             lr_scheduler.step()
-        optimizer.zero_grad(set_to_none=True)
+        if bucket is not None:
+            bucket.zero_()
+        else:
+            optimizer.zero_grad(set_to_none=True)
     return loss.detach()
 
 

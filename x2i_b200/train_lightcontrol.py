@@ -39,14 +39,26 @@ def compute_density_for_timestep_sampling(weighting_scheme: str, batch_size: int
     return u
 
 
-def train_sigmas(num_train_timesteps: int = 1000, shift: float = 3.0) -> torch.Tensor:
-    """The sigma table of FlowMatchEulerDiscreteScheduler(num_train_timesteps, shift) as the training scripts index it
-    (``noise_scheduler_copy.sigmas`` / ``.timesteps``, train_lightcontrol.py:697-702): descending, sigma = shift s / (1 + (shift-1) s)."""
+def train_sigmas(num_train_timesteps: int = 1000, shift: float = 3.0, use_dynamic_shifting: bool = True) -> torch.Tensor:
+    """The sigma table the training script indexes (``noise_scheduler_copy.sigmas`` / ``.timesteps``, train_lightcontrol.py:697-702),
+    descending.  The reference builds the scheduler with ``from_pretrained(FLUX.1-dev, subfolder="scheduler")`` (:495-499); that
+    config [D031, recalled] has ``use_dynamic_shifting = true`` (shift 3.0), and diffusers' ``__init__`` applies the static shift
+    ``shift s / (1 + (shift - 1) s)`` ONLY when dynamic shifting is off -- so the reference trains on the UNSHIFTED linear table
+    ``s = 1, 0.999, ..., 0.001``, which is the default here.  Pass ``use_dynamic_shifting=False`` for a schnell-style scheduler."""
     s = torch.linspace(1.0, 1.0 / num_train_timesteps, num_train_timesteps, dtype=torch.float32)
+    if use_dynamic_shifting:
+        return s
     return shift * s / (1 + (shift - 1) * s)
 
 
-def flow_matching_inputs(vae, pixel_values, generator=None, num_train_timesteps: int = 1000, shift: float = 3.0, sigmas=None):
+def train_sigmas_from_config(config) -> torch.Tensor:
+    """``train_sigmas`` for a ``scheduler_config.json`` dict / namespace (what ``FlowMatchEulerDiscreteScheduler.from_pretrained`` reads)."""
+    cfg = dict(config) if isinstance(config, dict) else vars(config)
+    return train_sigmas(int(cfg.get("num_train_timesteps", 1000)), float(cfg.get("shift", 1.0)), bool(cfg.get("use_dynamic_shifting", False)))
+
+
+def flow_matching_inputs(vae, pixel_values, generator=None, num_train_timesteps: int = 1000, shift: float = 3.0, sigmas=None,
+                         use_dynamic_shifting: bool = True):
     """Steps 1 of the module docstring.  Returns (packed noisy latents [B, L, 64] bf16, timesteps [B] fp32 in [0, 1000],
     target [B, 16, h, w] fp32, latent height, latent width)."""
     with torch.no_grad():
@@ -55,7 +67,7 @@ def flow_matching_inputs(vae, pixel_values, generator=None, num_train_timesteps:
         B, C, h, w = z.shape
         noise = torch.randn(z.shape, generator=generator, device=z.device, dtype=torch.float32).to(torch.bfloat16)
         if sigmas is None:
-            table = train_sigmas(num_train_timesteps, shift).to(z.device)
+            table = train_sigmas(num_train_timesteps, shift, use_dynamic_shifting).to(z.device)
             u = compute_density_for_timestep_sampling("logit_normal", B, 0.0, 1.0, generator=generator, device=z.device)
             idx = (u * num_train_timesteps).long().clamp_(0, num_train_timesteps - 1)
             sigmas = table[idx]
@@ -67,13 +79,54 @@ def flow_matching_inputs(vae, pixel_values, generator=None, num_train_timesteps:
     return packed, sigmas * num_train_timesteps, target, h, w
 
 
+class MasterWeightOptimizer:
+    """fp32 master weights + fp32 optimizer state for bf16 model parameters -- what the reference's DeepSpeed ZeRO-2 bf16 engine
+    keeps (lightcontrol/accelerate_config_debug.yaml: ``zero_stage: 2``, ``mixed_precision: bf16``).  The x2i_b200 control nets hold
+    bf16 parameters (the kernels read them directly); an Adam update at the reference's lr = 1e-5 is below half a bf16 ulp of a
+    typical 0.02-0.05 weight, so stepping the optimizer on the bf16 tensors themselves would round most updates away.  Here the
+    wrapped optimizer owns fp32 copies: ``step()`` feeds it the bf16 gradients in fp32, updates the masters and writes them back
+    rounded to bf16.  Duck-types ``torch.optim.Optimizer`` for ``lightcontrol_step`` and LR schedulers (``.optimizer``)."""
+
+    def __init__(self, params, optimizer_cls=None, **kwargs):
+        self.model_params = [p for p in params if p.requires_grad]
+        self.master = [p.detach().float().clone().requires_grad_(True) for p in self.model_params]
+        cls = optimizer_cls if optimizer_cls is not None else torch.optim.AdamW
+        self.optimizer = cls(self.master, **kwargs)
+        self.param_groups = self.optimizer.param_groups
+
+    @torch.no_grad()
+    def step(self):
+        for m, p in zip(self.master, self.model_params):
+            m.grad = None if p.grad is None else p.grad.float()
+        self.optimizer.step()
+        torch._foreach_copy_(self.model_params, self.master)
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.model_params:
+            p.grad = None
+        for m in self.master:
+            m.grad = None
+
+    def state_dict(self):
+        return {"optimizer": self.optimizer.state_dict(), "master": [m.detach().cpu() for m in self.master]}
+
+    def load_state_dict(self, sd):
+        self.optimizer.load_state_dict(sd["optimizer"])
+        with torch.no_grad():
+            for m, v in zip(self.master, sd["master"]):
+                m.copy_(v)
+            torch._foreach_copy_(self.model_params, self.master)
+
+
 def lightcontrol_step(control_nets, transformer, vae, batch: Dict[str, torch.Tensor], optimizer=None, lr_scheduler=None,
                       max_grad_norm: float = 1.0, guidance_scale: float = 3.5, generator=None, sigmas=None, group=None):
     """One LightControl train step on this rank's batch shard.
 
     batch: ``pixel_values`` [B, 3, H, W] in [-1, 1] (the style image: VAE input AND control hint, train_lightcontrol.py:676,:740),
     ``prompt_embeds`` [B, S, 4096], ``pooled_prompt_embeds`` [B, 768] (outputs of the frozen MLLM + projector).
-    Returns the detached loss of this rank.  control_nets: nn.ModuleList of x2i_b200 ControlNeXtModel in train mode."""
+    Returns the detached loss of this rank.  control_nets: nn.ModuleList of x2i_b200 ControlNeXtModel in train mode.
+    optimizer: use ``MasterWeightOptimizer(control_nets.parameters(), lr=1e-5)`` (fp32 masters, like the reference's DeepSpeed bf16
+    engine); a plain optimizer on the bf16 parameters loses most updates at the reference's learning rate."""
     pixel_values = batch["pixel_values"]
     if not pixel_values.is_cuda:
         raise X2IError("lightcontrol_step: CUDA tensors required (x2i_b200 has no CPU path)")
@@ -81,8 +134,8 @@ def lightcontrol_step(control_nets, transformer, vae, batch: Dict[str, torch.Ten
     packed, timesteps, target, h, w = flow_matching_inputs(vae, pixel_values, generator=generator, sigmas=sigmas)
     B = packed.shape[0]
     S = batch["prompt_embeds"].shape[1]
-    img_ids = FluxPipeline._prepare_latent_image_ids(B, h, w, dev, torch.bfloat16)
-    txt_ids = torch.zeros(S, 3, device=dev, dtype=torch.bfloat16)
+    from .train import _cached_ids
+    txt_ids, img_ids = _cached_ids(S, h, w, dev, torch.bfloat16)  # stable tensors: the RoPE cache keys on their addresses
     guidance = torch.full((B,), guidance_scale, device=dev, dtype=torch.float32) if transformer.config.guidance_embeds else None
     pred = transformer(hidden_states=packed, timestep=(timesteps / 1000).to(torch.bfloat16), guidance=guidance,
                        pooled_projections=batch["pooled_prompt_embeds"].to(torch.bfloat16), encoder_hidden_states=batch["prompt_embeds"].to(torch.bfloat16),
