@@ -491,7 +491,7 @@ def denoise(model: FluxTransformer2DModel, latents, prompt_embeds, pooled, heigh
         if emulate_bf16_time:
             g = (g.to(torch.bfloat16) * 1000).float() / 1000
     for i in range(num_steps):
-        t = (sig[i] * 1000).expand(B).to(latents.dtype)
+        t = (sig[i] * 1000).expand(B).to(latents.device, latents.dtype)
         if emulate_bf16_time:
             t = (((sig[i] * 1000).expand(B).to(torch.bfloat16) / 1000) * 1000).float().to(latents.device)
         v = model(hidden_states=latents, timestep=t / 1000, guidance=g, pooled_projections=pooled,

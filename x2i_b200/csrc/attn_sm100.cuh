@@ -62,7 +62,15 @@ __device__ __forceinline__ void exp_half(const uint32_t (&x)[32], uint64_t sc2, 
 
 // One online-softmax step of one query row over a 128-key tile (executed by the 128 threads of a softmax warpgroup).
 // MASKED is instantiated only for the last, ragged key tile so the common path carries no masking instructions.
-template <int POLY8, bool MASKED, int DBG>
+// PAIR: the P hand-off barriers live in the leader CTA of a cta_group::2 pair (attn2_sm100.cuh) and are arrived on through mapa.
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar_local) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar_local))
+      : "memory");
+}
+template <int POLY8, bool MASKED, int DBG, bool PAIR = false>
 __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, int j, int valid,
                                              float sc, float& m_run, float& l_run, int lane, long long* trace) {
   ATT_STAMP(0);
@@ -145,7 +153,9 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
       tmem_st_wait();  // store of quarter c-1, issued half a quarter ago
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full_i[c - 1]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_rank0(&p_full_i[c - 1]); else mbar_arrive(&p_full_i[c - 1]);
+      }
       ATT_STAMP(3 + c);
     }
     if (c < 3) tmem_ld32(t_s + (c + 1) * 32, rq[(c + 1) & 1]);
@@ -155,11 +165,48 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
   tmem_st_wait();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&p_full_i[3]);
+  if (lane == 0) {
+    if constexpr (PAIR) mbar_arrive_rank0(&p_full_i[3]); else mbar_arrive(&p_full_i[3]);
+  }
   ATT_STAMP(7);
   float s0, s1;
   unpack_f32x2(add_f32x2(add_f32x2(sum2[0], sum2[1]), add_f32x2(sum2[2], sum2[3])), s0, s1);
   l_run = l_run * alpha + (s0 + s1);
+}
+
+// Epilogue of one soft-max thread (one query row): O_i / l -> bf16 -> global, token-major [.., H*128] so the out-projection GEMM
+// reads it as its A operand; optional log-sum-exp for the backward.
+__device__ __forceinline__ void attn_epilogue(const AttnParams& p, uint64_t* o_full_i, uint32_t t_o, int pos, int b, int h, int bh,
+                                              float m_run, float l_run) {
+  mbar_wait(o_full_i, 0);  // committed once, after the last PV MMA of this tile
+  tc_fence_after();
+  const float inv_l = 1.0f / l_run;
+  const bool ok = pos < p.L;
+  if (p.lse != nullptr && pos < p.Lpad)
+    p.lse[static_cast<long long>(bh) * p.Lpad + pos] = ok ? m_run + log2f(l_run) : INFINITY;
+  __nv_bfloat16* dst;
+  if (pos < p.split)
+    dst = p.out0 + (static_cast<long long>(b) * p.split + pos) * p.ld0 + h * 128;
+  else
+    dst = p.out1 + (static_cast<long long>(b) * (p.L - p.split) + (pos - p.split)) * p.ld1 + h * 128;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t o[32];
+    tmem_ld32(t_o + c * 32, o);
+    tmem_ld_wait();
+    if (ok) {
+      uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * inv_l, __uint_as_float(o[8 * k + 1]) * inv_l);
+        u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * inv_l, __uint_as_float(o[8 * k + 3]) * inv_l);
+        u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * inv_l, __uint_as_float(o[8 * k + 5]) * inv_l);
+        u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * inv_l, __uint_as_float(o[8 * k + 7]) * inv_l);
+        d4[k] = u;
+      }
+    }
+  }
 }
 
 // POLY8: how many of every 8 element PAIRS of the softmax use the FMA-pipe poly_exp2_x2 instead of MUFU.EX2.
@@ -332,36 +379,7 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
     if (ragged)
       softmax_step<POLY8, true, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, kv_valid - (n_kv - 1) * 128, sc, m_run, l_run, lane,
                                      nullptr);
-    // ---- epilogue: O_i / l -> bf16 -> global (token-major [.., H*128] so the out-projection GEMM reads it as A)
-    mbar_wait(&o_full[i], 0);  // committed once, after the last PV MMA of this tile
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const bool ok = pos < p.L;
-    if (p.lse != nullptr && pos < p.Lpad)
-      p.lse[static_cast<long long>(bh) * p.Lpad + pos] = ok ? m_run + log2f(l_run) : INFINITY;
-    __nv_bfloat16* dst;
-    if (pos < p.split)
-      dst = p.out0 + (static_cast<long long>(b) * p.split + pos) * p.ld0 + h * 128;
-    else
-      dst = p.out1 + (static_cast<long long>(b) * (p.L - p.split) + (pos - p.split)) * p.ld1 + h * 128;
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t o[32];
-      tmem_ld32(t_o + c * 32, o);
-      tmem_ld_wait();
-      if (ok) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * inv_l, __uint_as_float(o[8 * k + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * inv_l, __uint_as_float(o[8 * k + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * inv_l, __uint_as_float(o[8 * k + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * inv_l, __uint_as_float(o[8 * k + 7]) * inv_l);
-          d4[k] = u;
-        }
-      }
-    }
+    attn_epilogue(p, &o_full[i], t_o, pos, b, h, bh, m_run, l_run);
   }
 
   tc_fence_before();

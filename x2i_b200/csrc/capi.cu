@@ -10,6 +10,7 @@
 #include "../../include/x2i_b200.h"
 #include "attn_bwd_sm100.cuh"
 #include "attn_sm100.cuh"
+#include "attn2_sm100.cuh"
 #include "conv_sm100.cuh"
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
@@ -588,6 +589,25 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
     if (!trace_dev) cudaMalloc(&trace_dev, 1024 * sizeof(long long));
     cudaMemsetAsync(trace_dev, 0, 1024 * sizeof(long long), static_cast<cudaStream_t>(stream));
     p.trace = trace_dev;
+  }
+  // CTA-pair form (attn2_sm100.cuh): two CTAs share every K / V tile.  Bit-identical results, but MEASURED SLOWER on B200
+  // (profiles/r02_attn_probe.md: 829 vs 1174 TFLOP/s sustained -- the multicast commit and the remote P hand-off sit on the
+  // S -> soft-max -> PV chain that already bounds the kernel), so it is opt-in: X2I_ATTN_PAIR=1 (tools/attn_probe.py, tests).
+  static const int pair_mode = []() { const char* e = getenv("X2I_ATTN_PAIR"); return e ? atoi(e) : 0; }();
+  if (pair_mode && dbg == 0 && poly8 == ATT_DEFAULT_POLY8 && L > 256) {
+    CUtensorMap tk2;
+    uint32_t boxk[3] = {64, 64, 1};
+    if (int rc = make_map(d, &tk2, k, 3, dimk, strk, boxk)) return rc;
+    auto kern2 = mmdit_attention_fwd2_kernel<ATT_DEFAULT_POLY8>;
+    static std::atomic<bool> att2_configured[16];
+    if (!att2_configured[d->index].load(std::memory_order_acquire)) {
+      cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM_BYTES);
+      if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention pair): %s", cudaGetErrorString(e));
+      att2_configured[d->index].store(true, std::memory_order_release);
+    }
+    dim3 grid2(((L + 511) / 512) * 2, heads, B);  // __cluster_dims__(2,1,1): an even number of 256-row blocks
+    kern2<<<grid2, ATT_THREADS, ATT2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk2, tv, p);
+    return check_launch("mmdit_attention_fwd2_kernel");
   }
   static std::atomic<bool> att_configured[16];
   if (!att_configured[d->index].load(std::memory_order_acquire)) {
