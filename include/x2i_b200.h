@@ -340,6 +340,38 @@ int x2i_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int rows
 /* Upsample2D's F.interpolate(scale_factor=2, mode="nearest") on NHWC bf16: out [N, 2H, 2W, C].                              */
 int x2i_upsample2x_nhwc(const void* x, void* out, int Nimg, int H, int W, int C, void* stream);
 
+/* ---- MLLM prefill with all-layer hidden-state capture --------------------------------------------------
+ * The producer of the projector's input: the reference runs the MLLM's decoder stack once over the padded prompt and keeps every
+ * layer's hidden state -- `qwen_encoder.generate(**inputs, output_hidden_states=True, return_dict_in_generate=True)` then
+ * `torch.cat(output_hidden_state["hidden_states"][0]).unsqueeze(0)` (infer/inference_qwenvl.py:176-179,:121-132) /
+ * `torch.stack(generated_ids["hidden_states"][0], dim=1)` (train/train_qwenvl.py:773-775).  The model code is the third-party
+ * `transformers` Qwen2.5-VL text decoder (Qwen2_5_VLTextModel: RMSNorm, grouped-query attention with rotate-half RoPE, SwiGLU MLP).
+ * Here every layer writes its output straight into its slot of the projector's [B, C, S, H] input; the contractions run on
+ * x2i_gemm_bias_act / x2i_gemm_swiglu / x2i_gemm_gate_residual (gate = NULL: plain residual).
+ *
+ * out[b, s, :] = table[ids[b, s], :] (nn.Embedding); rows addressed as out + b * out_batch_stride + s * ldo.  ids: device int64.  */
+int x2i_gather_rows(const int64_t* ids, const void* table, int64_t ldt, int vocab, void* out, int64_t ldo, int64_t out_batch_stride,
+                    int rows, int rows_per_batch, int D, void* stream);
+/* y = weight * bf16(x * rsqrt(mean(x^2) + eps))   (Qwen2RMSNorm).  x and y rows addressed with a batch stride like above.         */
+int x2i_rmsnorm(const void* x, int64_t ldx, int64_t x_batch_stride, const void* weight, void* y, int64_t ldy, int64_t y_batch_stride,
+                int rows, int rows_per_batch, int D, float eps, void* stream);
+/* Fused QKV rows [B*S, ld] = [q (heads*128) | k (heads_kv*128) | v (heads_kv*128)] -> head-major q [B,heads,S,128],
+ * k, v [B,heads_kv,S,128] with the rotate-half RoPE of Qwen2 applied to q and k.  pos: device int32 [B*S] token positions
+ * (cumsum(attention_mask) - 1, padded tokens 1: Qwen2_5_VLModel.get_rope_index, text-only); inv_freq: device fp32 [64].          */
+int x2i_rope_half_split(const void* qkv, int64_t ld, const int* pos, const float* inv_freq, void* q, void* k, void* v, int B, int S,
+                        int heads, int heads_kv, void* stream);
+/* C[M, N/2] = silu(A Wg^T + bg) * (A Wu^T + bu): Qwen2MLP's gate / up projections and activation in one GEMM.  W [N, K] holds the
+ * gate and up rows interleaved in blocks of 128 (rows [256 t, 256 t + 128) = gate rows [128 t, +128), the next 128 = the matching
+ * up rows); bias (nullable) is laid out the same way.  N % 256 == 0.                                                            */
+int x2i_gemm_swiglu(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc, int M, int N, int K,
+                    void* stream);
+/* Causal grouped-query self-attention of a left-padded prompt: q [B,heads,L,128], k, v [B,heads_kv,L,128] -> out [B*L, ld] token-major
+ * (column h*128 + d).  Key j is visible to query i iff kv_start[b] <= j <= i (kv_start: device int32 [B], nullable = 0); a query row
+ * with no visible key (a padded position) outputs 0 -- the behaviour of transformers' sdpa / flash paths.  Same kernel as
+ * x2i_mmdit_attention (softmax(q k^T / sqrt(128)) v), key tiles right of the diagonal and left of kv_start are skipped.         */
+int x2i_causal_attention(const void* q, const void* k, const void* v, const int* kv_start, void* out, int64_t ld, int B, int heads,
+                         int heads_kv, int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

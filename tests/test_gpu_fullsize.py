@@ -87,6 +87,32 @@ def test_attention_full_size_matches_fp32_on_sampled_heads(ops):
         assert _rel(o[:, h:h + 1], ref) < 6e-3
 
 
+def test_attention_kernel_forms_are_bit_identical(ops):
+    """The one-item kernel, the persistent kernel (attn_persist_sm100.cuh: one CTA per SM loops over work items, X2I_ATTN_PERSIST) and the
+    CTA-pair kernel (attn2_sm100.cuh: cta_group::2, two CTAs share every K / V tile, X2I_ATTN_PAIR) run the same soft-max code on the same
+    tiles: bit-identical outputs at the full size, on a ragged length (odd number of query blocks, partial last key tile) and with more
+    work items than SMs can hold in one round."""
+    import os
+    modes = [dict(X2I_ATTN_PAIR="0", X2I_ATTN_PERSIST="0"), dict(X2I_ATTN_PAIR="0", X2I_ATTN_PERSIST="1"), dict(X2I_ATTN_PAIR="1", X2I_ATTN_PERSIST="0")]
+    for Bq, Hq, Lq in ((1, 4, L), (1, 4, 600), (2, 24, 1100)):
+        g = torch.Generator(device="cuda").manual_seed(17)
+        q, k, v = (torch.randn(Bq, Hq, Lq, DH, device="cuda", generator=g).bfloat16() for _ in range(3))
+        outs = []
+        for mode in modes:
+            os.environ.update(mode)
+            try:
+                o = torch.empty(Bq, Lq, Hq * DH, device="cuda", dtype=torch.bfloat16)
+                ops.attention(q, k, v, split=0, out1=o)
+                outs.append(o)
+            finally:
+                for kk in mode:
+                    os.environ.pop(kk, None)
+        assert torch.equal(outs[0], outs[1]), "persistent kernel differs"
+        assert torch.equal(outs[0], outs[2]), "CTA-pair kernel differs"
+        ref = torch.nn.functional.scaled_dot_product_attention(q[:, :1].float(), k[:, :1].float(), v[:, :1].float())
+        assert _rel(outs[1].view(Bq, Lq, Hq, DH).transpose(1, 2)[:, :1], ref) < 6e-3
+
+
 def test_attention_full_size_shift_invariance(ops):
     """softmax(s + c) == softmax(s): adding a constant vector to every key along a direction orthogonal to nothing
     changes all scores of a row by the same amount q.c -> same output (up to bf16 rounding of k)."""

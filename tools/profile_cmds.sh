@@ -5,7 +5,7 @@
 # attention report itself travels back.
 set -x
 export X2I_NCU=1
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train --no-library-baseline"
 full() {  # full <name> <kernel regex> <count> <extra ncu args...> -- <command...>
   local name=$1 regex=$2 count=$3; shift 3
   local extra=()

@@ -192,13 +192,13 @@ mmdit_attention_fwd2_kernel(const __grid_constant__ CUtensorMap tma_q, const __g
     float l_run = 0.f;
     const float sc = p.scale_log2;
 
-    const bool ragged = (kv_valid & 127) != 0;
-    const int n_full = ragged ? n_kv - 1 : n_kv;
-    for (int j = 0; j < n_full; ++j)
-      softmax_step<POLY8, false, 0, true>(t_s, t_o, &s_full[i], &p_full[i * 4], j, 128, sc, m_run, l_run, lane, nullptr);
-    if (ragged)
-      softmax_step<POLY8, true, 0, true>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, kv_valid - (n_kv - 1) * 128, sc, m_run, l_run, lane,
-                                         nullptr);
+    for (int j = 0; j < n_kv; ++j) {
+      const int hi = min(128, kv_valid - j * 128);
+      if (hi < 128)
+        softmax_step<POLY8, true, 0, true>(t_s, t_o, &s_full[i], &p_full[i * 4], j, hi, sc, m_run, l_run, lane, nullptr);
+      else
+        softmax_step<POLY8, false, 0, true>(t_s, t_o, &s_full[i], &p_full[i * 4], j, 128, sc, m_run, l_run, lane, nullptr);
+    }
     attn_epilogue(p, &o_full[i], t_o, pos, b, h, bh, m_run, l_run);
   }
 

@@ -28,6 +28,10 @@ struct AttnParams {
   long long ld1;
   float* lse;  // optional (training): lse[(b*H + h) * Lpad + pos] = log2-domain log-sum-exp of row pos (+inf for pos >= L)
   int Lpad;    // row stride of lse (L rounded up to 128)
+  // decoder-LM prefill form (MLLM text encoders, x2i_causal_attention): causal mask, grouped-query K/V heads, left padding
+  int causal;           // 1: key j is visible to query row i only if j <= i
+  int Hkv;              // number of K/V heads (0 or == H: one per query head); query head h reads K/V head h / (H / Hkv)
+  const int* kv_start;  // optional device array [B]: first valid key of batch b (left padding); rows with no visible key output 0
   long long* trace;  // diagnostics only (DBG == 1 instantiation): clock64 stamps of CTA (0,0,0)
 };
 #define ATT_STAMP(slot) do { if constexpr (DBG == 1) { if (trace != nullptr && lane == 0) trace[slot] = clock64(); } } while (0)
@@ -71,14 +75,19 @@ __device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar_local) {
       : "memory");
 }
 template <int POLY8, bool MASKED, int DBG, bool PAIR = false>
-__device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, int j, int valid,
-                                             float sc, float& m_run, float& l_run, int lane, long long* trace) {
+__device__ __forceinline__ void softmax_step_core(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, uint32_t parity,
+                                                  bool first, int valid, float sc, float& m_run, float& l_run, int lane, long long* trace,
+                                                  int lo) {
+  // MASKED: keys with tile index outside [lo, valid) are excluded (ragged tail, left padding, causal diagonal).  parity: phase of
+  // s_full (one completion per key step of the CTA); first: first key step of this query row (no running max yet).
+  constexpr int P8 = MASKED ? 0 : POLY8;  // masked tiles keep every exponential on MUFU: ex2(-inf) is exactly +0 (the polynomial
+                                          // clamps at 2^-125), so a row with no visible key ends with l == 0 and outputs 0
   ATT_STAMP(0);
   if constexpr (DBG == 4) {
-    while (!mbar_test(s_full_i, j & 1)) {
+    while (!mbar_test(s_full_i, parity)) {
     }
   } else {
-    mbar_wait(s_full_i, j & 1);
+    mbar_wait(s_full_i, parity);
   }
   tc_fence_after();
   ATT_STAMP(1);
@@ -92,7 +101,7 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int k = 0; k < 32; ++k)
-        if (c * 32 + k >= valid) r[c][k] = 0xff800000u;  // -inf
+        if (c * 32 + k >= valid || c * 32 + k < lo) r[c][k] = 0xff800000u;  // -inf
   }
   float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent FMNMX3 chains
 #pragma unroll
@@ -105,7 +114,7 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
   const float m_cand = fmaxf(m_run, mx * sc);
   float alpha = 1.0f;
   bool rescale = false;
-  if (j == 0) {
+  if (first) {
     m_run = m_cand;
   } else if (m_cand - m_run > 8.0f) {  // lazy rescaling: tolerate a stale max up to 2^8
     alpha = fast_exp2(m_run - m_cand);
@@ -114,7 +123,7 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
   }
   // O_i may be touched here without waiting on a barrier: S_i(j) was issued after PV_i(j-1) and tcgen05.commit
   // tracks completion of ALL earlier MMAs of the issuing thread, so s_full(j) implies PV_i(j-1) has retired.
-  if (j > 0 && __any_sync(0xffffffffu, rescale)) {
+  if (!first && __any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
@@ -126,7 +135,8 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
     }
   }
   ATT_STAMP(3);
-  const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_run, -m_run);
+  const float m_eff = (MASKED && m_run == -INFINITY) ? 0.f : m_run;  // no visible key so far: avoid (-inf) - (-inf)
+  const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_eff, -m_eff);
   uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};  // packed (FADD2) partial row sums, 4 independent chains
   // Second pass, quarter by quarter (32 keys each), software-pipelined by hand because the TMEM store -> wait::st -> fence ->
   // mbarrier arrive sequence costs ~120 cycles in which the MUFU pipe would idle:
@@ -145,10 +155,10 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
       if constexpr (MASKED) {
 #pragma unroll
         for (int k = 0; k < 32; ++k)
-          if (c * 32 + k >= valid) rq[c & 1][k] = 0xff800000u;
+          if (c * 32 + k >= valid || c * 32 + k < lo) rq[c & 1][k] = 0xff800000u;
       }
     }
-    exp_half<POLY8, DBG, 0>(x, sc2, nm2, sum2, pk);
+    exp_half<P8, DBG, 0>(x, sc2, nm2, sum2, pk);
     if (c > 0) {
       tmem_st_wait();  // store of quarter c-1, issued half a quarter ago
       tc_fence_before();
@@ -159,7 +169,7 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
       ATT_STAMP(3 + c);
     }
     if (c < 3) tmem_ld32(t_s + (c + 1) * 32, rq[(c + 1) & 1]);
-    exp_half<POLY8, DBG, 1>(x, sc2, nm2, sum2, pk);
+    exp_half<P8, DBG, 1>(x, sc2, nm2, sum2, pk);
     tmem_st16(t_s + c * 16, pk);  // P_i aliases S_i columns [0, 64)
   }
   tmem_st_wait();
@@ -173,14 +183,27 @@ __device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_
   unpack_f32x2(add_f32x2(add_f32x2(sum2[0], sum2[1]), add_f32x2(sum2[2], sum2[3])), s0, s1);
   l_run = l_run * alpha + (s0 + s1);
 }
+// one-item kernels: the key-step counter j of the CTA gives both the barrier parity and "first step"
+template <int POLY8, bool MASKED, int DBG, bool PAIR = false>
+__device__ __forceinline__ void softmax_step(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, int j, int valid,
+                                             float sc, float& m_run, float& l_run, int lane, long long* trace, int lo = 0) {
+  softmax_step_core<POLY8, MASKED, DBG, PAIR>(t_s, t_o, s_full_i, p_full_i, static_cast<uint32_t>(j & 1), j == 0, valid, sc, m_run, l_run, lane,
+                                              trace, lo);
+}
+// persistent kernel (attn_persist_sm100.cuh): parity from the CTA-wide step counter, `first` from the item-local one
+template <int POLY8, bool MASKED>
+__device__ __forceinline__ void softmax_step_p(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, uint32_t parity, bool first,
+                                               int valid, float sc, float& m_run, float& l_run, int lane, int lo) {
+  softmax_step_core<POLY8, MASKED, 0, false>(t_s, t_o, s_full_i, p_full_i, parity, first, valid, sc, m_run, l_run, lane, nullptr, lo);
+}
 
 // Epilogue of one soft-max thread (one query row): O_i / l -> bf16 -> global, token-major [.., H*128] so the out-projection GEMM
 // reads it as its A operand; optional log-sum-exp for the backward.
 __device__ __forceinline__ void attn_epilogue(const AttnParams& p, uint64_t* o_full_i, uint32_t t_o, int pos, int b, int h, int bh,
-                                              float m_run, float l_run) {
-  mbar_wait(o_full_i, 0);  // committed once, after the last PV MMA of this tile
+                                              float m_run, float l_run, uint32_t parity = 0) {
+  mbar_wait(o_full_i, parity);  // committed once per work item, after the last PV MMA of this tile
   tc_fence_after();
-  const float inv_l = 1.0f / l_run;
+  const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;  // no visible key (padded query row of a causal prefill): output 0
   const bool ok = pos < p.L;
   if (p.lse != nullptr && pos < p.Lpad)
     p.lse[static_cast<long long>(bh) * p.Lpad + pos] = ok ? m_run + log2f(l_run) : INFINITY;
@@ -211,7 +234,9 @@ __device__ __forceinline__ void attn_epilogue(const AttnParams& p, uint64_t* o_f
 
 // POLY8: how many of every 8 element PAIRS of the softmax use the FMA-pipe poly_exp2_x2 instead of MUFU.EX2.
 // DBG: 0 product; 1 clock64 trace; 2 / 3 timing experiments (wrong results); 4 non-suspending barrier polls (same results).
-template <int POLY8, int DBG = 0>
+// LM: decoder-LM prefill form (causal mask, left padding, grouped-query K/V heads).  A separate instantiation: the production MMDiT
+// instantiation sits at the 168-register limit of a 320-thread CTA, and the extra live state of the general mask spills it.
+template <int POLY8, int DBG = 0, bool LM = false>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                            const __grid_constant__ CUtensorMap tma_v, const AttnParams p) {
@@ -235,7 +260,14 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
   const int b = blockIdx.z;
   const int bh = b * p.H + h;
   const int kv_valid = p.kv_len != nullptr ? min(max(p.kv_len[b], 1), p.Lkv) : p.Lkv;
-  const int n_kv = (kv_valid + 127) / 128;
+  // key-tile window [j0, j0 + n_kv) of this CTA: all tiles, minus the tiles left of the first valid key (left padding) and right of
+  // the causal diagonal of its last query row.  At least one tile is always processed (a CTA of padded rows outputs zeros).
+  const int kv_lo = (LM && p.kv_start != nullptr) ? min(max(p.kv_start[b], 0), kv_valid - 1) : 0;
+  const int j0 = LM ? (kv_lo >> 7) : 0;
+  int j_end = (kv_valid + 127) / 128;
+  if (LM && p.causal) j_end = min(j_end, (min(q0 + 255, p.L - 1) >> 7) + 1);
+  const int n_kv = LM ? max(j_end - j0, 1) : j_end;
+  const int bh_kv = (LM && p.Hkv > 0 && p.Hkv != p.H) ? b * p.Hkv + h / (p.H / p.Hkv) : bh;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_q);
@@ -277,10 +309,10 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
         mbar_wait(&kv_empty[slot], ph ^ 1);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
         const CUtensorMap* map = (seq & 1) ? &tma_v : &tma_k;
-        const int j = seq >> 1;
+        const int j = j0 + (seq >> 1);
         uint8_t* dst = skv + slot * ATT_TILE_BYTES;
-        tma_load_3d(dst, map, &kv_full[slot], 0, j * 128, bh);
-        tma_load_3d(dst + 16384, map, &kv_full[slot], 64, j * 128, bh);
+        tma_load_3d(dst, map, &kv_full[slot], 0, j * 128, bh_kv);
+        tma_load_3d(dst + 16384, map, &kv_full[slot], 64, j * 128, bh_kv);
       }
     }
   } else if (warp == 1) {
@@ -370,15 +402,31 @@ mmdit_attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
     float l_run = 0.f;
     const float sc = p.scale_log2;
 
-    const bool ragged = (kv_valid & 127) != 0;
-    const int n_full = ragged ? n_kv - 1 : n_kv;
     const bool traced = DBG == 1 && quad == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && p.trace != nullptr;
-    for (int j = 0; j < n_full; ++j)
-      softmax_step<POLY8, false, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], j, 128, sc, m_run, l_run, lane,
-                                      (traced && j < 16) ? p.trace + (i * 16 + j) * 8 : nullptr);
-    if (ragged)
-      softmax_step<POLY8, true, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, kv_valid - (n_kv - 1) * 128, sc, m_run, l_run, lane,
-                                     nullptr);
+    if constexpr (!LM) {
+      // MMDiT joint attention / cross attention (the hot path): every key tile but a ragged last one is unmasked -- a tight loop over
+      // the mask-free instantiation (a per-step mask decision in this loop costs ~6 % of the kernel, profiles/r02_attn_probe.md)
+      const bool ragged = (kv_valid & 127) != 0;
+      const int n_full = ragged ? n_kv - 1 : n_kv;
+      for (int j = 0; j < n_full; ++j)
+        softmax_step<POLY8, false, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], j, 128, sc, m_run, l_run, lane,
+                                        (traced && j < 16) ? p.trace + (i * 16 + j) * 8 : nullptr);
+      if (ragged)
+        softmax_step<POLY8, true, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], n_kv - 1, kv_valid - (n_kv - 1) * 128, sc, m_run, l_run, lane,
+                                       nullptr);
+    } else {
+      // decoder-LM prefill: left padding and the causal diagonal make the mask a per-row, per-tile property
+      for (int it = 0; it < n_kv; ++it) {
+        const int j = j0 + it;
+        int hi = min(128, kv_valid - j * 128);                 // keys of this tile with index in [lo, hi) are visible to this row
+        const int lo = max(0, kv_lo - j * 128);
+        if (p.causal) hi = min(hi, pos - j * 128 + 1);
+        if (__any_sync(0xffffffffu, hi < 128 || lo > 0))
+          softmax_step<POLY8, true, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], it, hi, sc, m_run, l_run, lane, nullptr, lo);
+        else
+          softmax_step<POLY8, false, DBG>(t_s, t_o, &s_full[i], &p_full[i * 4], it, 128, sc, m_run, l_run, lane, nullptr);
+      }
+    }
     attn_epilogue(p, &o_full[i], t_o, pos, b, h, bh, m_run, l_run);
   }
 

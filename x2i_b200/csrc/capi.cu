@@ -11,9 +11,11 @@
 #include "attn_bwd_sm100.cuh"
 #include "attn_sm100.cuh"
 #include "attn2_sm100.cuh"
+#include "attn_persist_sm100.cuh"
 #include "conv_sm100.cuh"
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
+#include "mllm_sm100.cuh"
 #include "rowwise.cuh"
 #include "rowwise_bwd.cuh"
 
@@ -270,8 +272,8 @@ int x2i_gemm_gate_residual(const void* A, int64_t lda, const void* W, int64_t ld
                            int64_t ldc, void* aux, int64_t ldaux, int M, int N, int K, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
-  if (!gate || !residual || rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "gemm_gate_residual: gate/residual/rows_per_batch required");
-  if (!aligned16(C) || !aligned16(gate) || !aligned16(residual) || (aux && !aligned16(aux)) || (bias && !aligned16(bias)) ||
+  if (!residual || rows_per_batch <= 0) return fail(X2I_ERR_SHAPE, "gemm_gate_residual: residual/rows_per_batch required");
+  if (!aligned16(C) || (gate && !aligned16(gate)) || !aligned16(residual) || (aux && !aligned16(aux)) || (bias && !aligned16(bias)) ||
       ldc % 8 || ldr % 8 || gate_stride % 8 || (aux && ldaux % 8))
     return fail(X2I_ERR_ALIGN, "gemm_gate_residual: alignment");
   GemmParams p;
@@ -531,9 +533,13 @@ int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0,
   return x2i_cross_attention(q, k, v, nullptr, out0, ld0, split, out1, ld1, B, heads, L, L, stream);
 }
 
+#ifndef X2I_ATTN_PERSIST_DEFAULT
+#define X2I_ATTN_PERSIST_DEFAULT 1
+#endif
 namespace {
 int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len, void* out0, int64_t ld0, int split,
-                  void* out1, int64_t ld1, float* lse, int B, int heads, int L, int Lkv, void* stream);
+                  void* out1, int64_t ld1, float* lse, int B, int heads, int L, int Lkv, void* stream, int causal = 0, int heads_kv = 0,
+                  const int* kv_start = nullptr);
 }
 int x2i_cross_attention(const void* q, const void* k, const void* v, const int* kv_len, void* out0, int64_t ld0, int split,
                         void* out1, int64_t ld1, int B, int heads, int L, int Lkv, void* stream) {
@@ -546,7 +552,8 @@ int x2i_mmdit_attention_lse(const void* q, const void* k, const void* v, void* o
 }
 namespace {
 int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len, void* out0, int64_t ld0, int split,
-                  void* out1, int64_t ld1, float* lse, int B, int heads, int L, int Lkv, void* stream) {
+                  void* out1, int64_t ld1, float* lse, int B, int heads, int L, int Lkv, void* stream, int causal, int heads_kv,
+                  const int* kv_start) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   if (Lkv <= 0) return fail(X2I_ERR_SHAPE, "attention: Lkv must be positive");
@@ -557,7 +564,8 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
   CUtensorMap tq, tk, tv;
   uint64_t dims[3] = {128, (uint64_t)L, (uint64_t)B * heads}, str[3] = {1, 128, (uint64_t)L * 128};
   uint32_t box[3] = {64, 128, 1};
-  uint64_t dimk[3] = {128, (uint64_t)Lkv, (uint64_t)B * heads}, strk[3] = {1, 128, (uint64_t)Lkv * 128};
+  const int hkv = heads_kv > 0 ? heads_kv : heads;
+  uint64_t dimk[3] = {128, (uint64_t)Lkv, (uint64_t)B * hkv}, strk[3] = {1, 128, (uint64_t)Lkv * 128};
   if (int rc = make_map(d, &tq, q, 3, dims, str, box)) return rc;
   if (int rc = make_map(d, &tk, k, 3, dimk, strk, box)) return rc;
   if (int rc = make_map(d, &tv, v, 3, dimk, strk, box)) return rc;
@@ -567,6 +575,7 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
   p.out0 = static_cast<__nv_bfloat16*>(out0); p.ld0 = ld0; p.split = split;
   p.out1 = static_cast<__nv_bfloat16*>(out1); p.ld1 = ld1;
   p.lse = lse; p.Lpad = (L + 127) / 128 * 128;
+  p.causal = causal; p.Hkv = hkv; p.kv_start = kv_start;
   // Variant selection.  Production = the defaults.  X2I_ATTN_DBG=1 prints a clock64 trace of CTA (0,0,0) to stderr after a
   // synchronous launch (same arithmetic).  Other POLY8 / DBG values (tools/attn_sweep.sh; DBG 2 / 3 are timing experiments with
   // wrong results) exist only in a library built with -DX2I_ATTN_EXPERIMENTS.
@@ -593,8 +602,9 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
   // CTA-pair form (attn2_sm100.cuh): two CTAs share every K / V tile.  Bit-identical results, but MEASURED SLOWER on B200
   // (profiles/r02_attn_probe.md: 829 vs 1174 TFLOP/s sustained -- the multicast commit and the remote P hand-off sit on the
   // S -> soft-max -> PV chain that already bounds the kernel), so it is opt-in: X2I_ATTN_PAIR=1 (tools/attn_probe.py, tests).
-  static const int pair_mode = []() { const char* e = getenv("X2I_ATTN_PAIR"); return e ? atoi(e) : 0; }();
-  if (pair_mode && dbg == 0 && poly8 == ATT_DEFAULT_POLY8 && L > 256) {
+  const char* pair_env = getenv("X2I_ATTN_PAIR");  // read per call so one process can run both forms (tests)
+  const int pair_mode = pair_env ? atoi(pair_env) : 0;
+  if (pair_mode && dbg == 0 && poly8 == ATT_DEFAULT_POLY8 && L > 256 && !causal && hkv == heads && !kv_start) {
     CUtensorMap tk2;
     uint32_t boxk[3] = {64, 64, 1};
     if (int rc = make_map(d, &tk2, k, 3, dimk, strk, boxk)) return rc;
@@ -609,11 +619,35 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
     kern2<<<grid2, ATT_THREADS, ATT2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk2, tv, p);
     return check_launch("mmdit_attention_fwd2_kernel");
   }
-  static std::atomic<bool> att_configured[16];
-  if (!att_configured[d->index].load(std::memory_order_acquire)) {
+  // Persistent form (attn_persist_sm100.cuh): one CTA per SM loops over the work items.  X2I_ATTN_PERSIST=0/1 selects (read per call).
+  const char* pers_env = getenv("X2I_ATTN_PERSIST");
+  const int persist = pers_env ? atoi(pers_env) : X2I_ATTN_PERSIST_DEFAULT;
+  const bool lm = causal || kv_start != nullptr || hkv != heads;  // decoder-LM prefill form: its own instantiations
+  if (persist && dbg == 0 && poly8 == ATT_DEFAULT_POLY8) {
+    auto kernp = lm ? mmdit_attention_fwd_persistent_kernel<ATT_DEFAULT_POLY8, true> : mmdit_attention_fwd_persistent_kernel<ATT_DEFAULT_POLY8, false>;
+    static std::atomic<bool> attp_configured[16][2];
+    if (!attp_configured[d->index][lm].load(std::memory_order_acquire)) {
+      cudaError_t e = cudaFuncSetAttribute(kernp, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+      if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention persistent): %s", cudaGetErrorString(e));
+      attp_configured[d->index][lm].store(true, std::memory_order_release);
+    }
+    const int n_qblk = (L + 255) / 256;
+    const long long n_items_ll = static_cast<long long>(n_qblk) * heads * B;
+    if (n_items_ll > 0x7fffffffLL) return fail(X2I_ERR_SHAPE, "attention: too many work items");
+    const int n_items = static_cast<int>(n_items_ll);
+    const int gridp = n_items < d->sms ? n_items : d->sms;
+    kernp<<<gridp, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p, n_qblk, n_items);
+    return check_launch("mmdit_attention_fwd_persistent_kernel");
+  }
+  if (lm) {
+    if (dbg != 0 || poly8 != ATT_DEFAULT_POLY8) return fail(X2I_ERR_SHAPE, "attention: the decoder-LM form has no debug / experiment instantiations");
+    kern = mmdit_attention_fwd_kernel<ATT_DEFAULT_POLY8, 0, true>;
+  }
+  static std::atomic<bool> att_configured[16][2];
+  if (!att_configured[d->index][lm].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
     if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
-    att_configured[d->index].store(true, std::memory_order_release);
+    att_configured[d->index][lm].store(true, std::memory_order_release);
   }
   dim3 grid((L + 255) / 256, heads, B);
   kern<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
@@ -887,6 +921,73 @@ int x2i_mean_over_s(const void* y, void* out, int B, int S, int N, void* stream)
 }
 
 // ================================================================================================ backward (training)
+// ================================================================================================ MLLM prefill
+int x2i_gather_rows(const int64_t* ids, const void* table, int64_t ldt, int vocab, void* out, int64_t ldo, int64_t out_batch_stride,
+                    int rows, int rows_per_batch, int D, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || rows_per_batch <= 0 || D <= 0 || D % 8 || vocab <= 0) return fail(X2I_ERR_SHAPE, "gather_rows: bad rows/D/vocab");
+  if (!ids || !aligned16(table) || !aligned16(out) || ldt % 8 || ldo % 8 || out_batch_stride % 8) return fail(X2I_ERR_ALIGN, "gather_rows: alignment");
+  gather_rows_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), static_cast<const __nv_bfloat16*>(table), ldt, vocab, static_cast<__nv_bfloat16*>(out), ldo,
+      out_batch_stride, rows, rows_per_batch, D);
+  return check_launch("gather_rows_kernel");
+}
+
+int x2i_rmsnorm(const void* x, int64_t ldx, int64_t x_batch_stride, const void* weight, void* y, int64_t ldy, int64_t y_batch_stride,
+                int rows, int rows_per_batch, int D, float eps, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || rows_per_batch <= 0 || D <= 0 || D % 8 || D > 32 * 8 * 16) return fail(X2I_ERR_SHAPE, "rmsnorm: D=%d must be a multiple of 8 and <= 4096", D);
+  if (!aligned16(x) || !aligned16(y) || !aligned16(weight) || ldx % 8 || ldy % 8 || x_batch_stride % 8 || y_batch_stride % 8)
+    return fail(X2I_ERR_ALIGN, "rmsnorm: alignment");
+  dim3 grid((rows + 7) / 8);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto W = static_cast<const __nv_bfloat16*>(weight);
+  auto Y = static_cast<__nv_bfloat16*>(y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int nchunk = D / 8;
+  if (nchunk <= 32 * 4) rmsnorm_kernel<4><<<grid, 256, 0, st>>>(X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
+  else if (nchunk <= 32 * 8) rmsnorm_kernel<8><<<grid, 256, 0, st>>>(X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
+  else rmsnorm_kernel<16><<<grid, 256, 0, st>>>(X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
+  return check_launch("rmsnorm_kernel");
+}
+
+int x2i_rope_half_split(const void* qkv, int64_t ld, const int* pos, const float* inv_freq, void* q, void* k, void* v, int B, int S,
+                        int heads, int heads_kv, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (B <= 0 || S <= 0 || heads <= 0 || heads_kv <= 0 || heads % heads_kv) return fail(X2I_ERR_SHAPE, "rope_half_split: bad B/S/heads");
+  if (!pos || !inv_freq || !aligned16(qkv) || !aligned16(q) || !aligned16(k) || !aligned16(v) || ld % 8 || ld < (heads + 2 * heads_kv) * 128)
+    return fail(X2I_ERR_ALIGN, "rope_half_split: alignment / row stride");
+  const int rows = B * S;
+  rope_half_split_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), ld, pos, inv_freq, static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k),
+      static_cast<__nv_bfloat16*>(v), rows, S, heads, heads_kv);
+  return check_launch("rope_half_split_kernel");
+}
+
+int x2i_gemm_swiglu(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc, int M, int N, int K,
+                    void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (N % 256) return fail(X2I_ERR_SHAPE, "gemm_swiglu: N=%d (gate and up rows interleaved in blocks of 128) must be a multiple of 256", N);
+  if (!aligned16(C) || (bias && !aligned16(bias)) || ldc % 8) return fail(X2I_ERR_ALIGN, "gemm_swiglu: alignment");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.C = static_cast<__nv_bfloat16*>(C); p.ldc = ldc;
+  const bool pair = use_pair_kernel() && M > 128;  // both forms use 256-column tiles
+  return launch_gemm<EPI_SWIGLU>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream), pair ? 0 : 256);
+}
+
+int x2i_causal_attention(const void* q, const void* k, const void* v, const int* kv_start, void* out, int64_t ld, int B, int heads,
+                         int heads_kv, int L, void* stream) {
+  if (heads_kv <= 0 || heads % heads_kv) return fail(X2I_ERR_SHAPE, "causal_attention: heads must be a multiple of heads_kv");
+  return attention_fwd(q, k, v, nullptr, nullptr, 0, 0, out, ld, nullptr, B, heads, L, L, stream, 1, heads_kv, kv_start);
+}
+
 int x2i_mmdit_attention_bwd(const void* q, const void* k, const void* v, const void* dout, const float* lse, const float* delta,
                             void* dq, void* dk, void* dv, int B, int heads, int L, void* stream) {
   DeviceInfo* d;

@@ -18,6 +18,9 @@
 //   EPI_DACT            backward of a Linear followed by GELU: C = addend + acc * act'(pre) for columns >= n_split,
 //                       C = addend + acc below it (dgrad GEMMs of the distillation step)
 //
+//   EPI_SWIGLU          gated MLP of a decoder LM (Qwen2MLP: down(silu(gate(x)) * up(x))): W holds gate and up rows interleaved in
+//                       blocks of 128, so every 256-column accumulator tile is [gate(128) | up(128)] of the same 128 outputs:
+//                       C[:, n/2 ..] = silu(acc_gate + b) * (acc_up + b)           (BN = 256 only)
 //   EPI_CONV            implicit-GEMM convolution (conv_sm100.cuh): C = relu?(acc + bias + rowvec[b, :]) + residual
 //
 // Operand forms: B_MN takes B as [K, N] (N contiguous) and A_MN takes A as [K, M] (M contiguous) -- the "MN-major"
@@ -28,7 +31,7 @@
 
 namespace x2i {
 
-enum { EPI_BIAS = 0, EPI_BIAS_GELU_TANH = 1, EPI_BIAS_GELU_ERF = 2, EPI_GATE_RESIDUAL = 3, EPI_QKV = 4, EPI_DACT = 5, EPI_CONV = 6 };
+enum { EPI_BIAS = 0, EPI_BIAS_GELU_TANH = 1, EPI_BIAS_GELU_ERF = 2, EPI_GATE_RESIDUAL = 3, EPI_QKV = 4, EPI_DACT = 5, EPI_CONV = 6, EPI_SWIGLU = 7 };
 
 struct GemmParams {
   int M, N, K;
@@ -224,11 +227,31 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
         }
       }
     }
+  } else if constexpr (EPI == EPI_SWIGLU) {
+#pragma unroll 1
+    for (int c = 0; c < (BN == 256 ? 4 : 0); ++c) {  // only launched with 256-column tiles: [gate(128) | up(128)]
+      if (n_tile0 >= p.N) break;
+      uint32_t rg[32], ru[32];
+      float g[32], u[32];
+      tmem_ld32(t_acc + c * 32, rg);
+      tmem_ld32(t_acc + (BN == 256 ? 128 : 0) + c * 32, ru);
+      if (p.bias != nullptr) {
+        load_bf16x32(p.bias + n_tile0 + c * 32, g);
+        load_bf16x32(p.bias + n_tile0 + 128 + c * 32, u);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = u[j] = 0.f;
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] = silu_f(g[j] + __uint_as_float(rg[j])) * (u[j] + __uint_as_float(ru[j]));
+      if (row_ok) store_bf16x32(p.C + static_cast<long long>(m) * p.ldc + (n_tile0 >> 1) + c * 32, g);
+    }
   } else {
     const __nv_bfloat16* gate_row = nullptr;
     if constexpr (EPI == EPI_GATE_RESIDUAL) {
       const int b = row_ok ? m / p.rows_per_batch : 0;
-      gate_row = p.gate + static_cast<long long>(b) * p.gate_stride;
+      if (p.gate != nullptr) gate_row = p.gate + static_cast<long long>(b) * p.gate_stride;
     }
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -313,7 +336,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
         if constexpr (EPI == EPI_GATE_RESIDUAL) {
           if (p.aux != nullptr) store_bf16x32(p.aux + static_cast<long long>(m) * p.ldaux + n0, x);
           float g[32], res[32];
-          load_bf16x32(gate_row + n0, g);
+          if (gate_row != nullptr) {
+            load_bf16x32(gate_row + n0, g);
+          } else {  // plain residual connection (decoder LM layers): gate == 1
+#pragma unroll
+            for (int j = 0; j < 32; ++j) g[j] = 1.0f;
+          }
           load_bf16x32(p.residual + static_cast<long long>(m) * p.ldr + n0, res);
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = res[j] + g[j] * x[j];

@@ -736,3 +736,97 @@ def silu_rows(x):
     out = torch.empty_like(x)
     _lib.call("x2i_silu", _p(x), _p(out), x.numel(), _stream())
     return out
+
+
+# ================================================================================================ MLLM prefill (SURVEY 8f N3)
+def _bstrided(t, name):
+    """[B, S, D] view with unit last stride and one row stride inside a batch -> (ld, batch_stride)."""
+    _chk(t, name)
+    if t.dim() != 3:
+        raise _lib.X2IError(f"{name} must be a [B, S, D] view")
+    return t.stride(1), t.stride(0)
+
+
+def gather_rows(ids, table, out):
+    """out[b, s, :] = table[ids[b, s], :] (nn.Embedding).  ids int64 [B, S]; out: [B, S, D] view (e.g. layer slot 0 of [B, C, S, D])."""
+    _chk(ids, "ids", torch.int64); _chk(table, "table")
+    B, S = ids.shape
+    ldo, bso = _bstrided(out, "out")
+    _lib.call("x2i_gather_rows", _p(ids.contiguous()), _p(table), table.stride(0), table.shape[0], _p(out), ldo, bso, B * S, S,
+              table.shape[1], _stream())
+    return out
+
+
+def rmsnorm(x, weight, eps=1e-6, out=None):
+    """Qwen2RMSNorm on a [B, S, D] view -> [B, S, D] (dense unless `out` is given)."""
+    _chk(weight, "weight")
+    B, S, D = x.shape
+    ldx, bsx = _bstrided(x, "x")
+    if out is None:
+        out = torch.empty(B, S, D, device=x.device, dtype=BF16)
+    ldy, bsy = _bstrided(out, "out")
+    _lib.call("x2i_rmsnorm", _p(x), ldx, bsx, _p(weight), _p(out), ldy, bsy, B * S, S, D, float(eps), _stream())
+    return out
+
+
+def rope_half_split(qkv, pos, inv_freq, heads, heads_kv, q=None, k=None, v=None):
+    """Fused QKV rows [B, S, (heads + 2 heads_kv) * 128] -> rotate-half RoPE'd head-major q [B,heads,S,128], k, v [B,heads_kv,S,128]."""
+    _chk(qkv, "qkv"); _chk(pos, "pos", torch.int32); _chk(inv_freq, "inv_freq", torch.float32)
+    B, S, W = qkv.shape
+    if not qkv.is_contiguous() or W != (heads + 2 * heads_kv) * 128 or pos.numel() != B * S or inv_freq.numel() != 64:
+        raise _lib.X2IError("rope_half_split: qkv [B,S,(H+2Hkv)*128] contiguous, pos int32 [B,S], inv_freq fp32 [64]")
+    dev = qkv.device
+    q = q if q is not None else torch.empty(B, heads, S, 128, device=dev, dtype=BF16)
+    k = k if k is not None else torch.empty(B, heads_kv, S, 128, device=dev, dtype=BF16)
+    v = v if v is not None else torch.empty(B, heads_kv, S, 128, device=dev, dtype=BF16)
+    _lib.call("x2i_rope_half_split", _p(qkv), W, _p(pos.contiguous()), _p(inv_freq.contiguous()), _p(q), _p(k), _p(v), B, S, heads, heads_kv,
+              _stream())
+    return q, k, v
+
+
+def pack_swiglu_weight(gate_w, up_w):
+    """[gate; up] rows interleaved in blocks of 128 (the layout x2i_gemm_swiglu reads): [2F, K] with F % 128 == 0."""
+    F, K = gate_w.shape
+    if up_w.shape != gate_w.shape or F % 128:
+        raise _lib.X2IError("pack_swiglu_weight: gate / up must be [F, K] with F % 128 == 0")
+    return torch.stack([gate_w.view(F // 128, 128, K), up_w.view(F // 128, 128, K)], dim=1).reshape(2 * F, K).contiguous()
+
+
+def linear_swiglu(x, w_packed, out=None):
+    """silu(x @ Wg.T) * (x @ Wu.T) with w_packed = pack_swiglu_weight(Wg, Wu).  x [..., K] -> [..., F]."""
+    _chk(x, "x"); _chk(w_packed, "w_packed")
+    M, lda = _rows(x)
+    N, K = w_packed.shape
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N // 2, device=x.device, dtype=BF16)
+    _, ldc = _rows(out)
+    _lib.call("x2i_gemm_swiglu", _p(x), lda, _p(w_packed), w_packed.stride(0), 0, _p(out), ldc, M, N, K, _stream())
+    return out
+
+
+def linear_residual(x, weight, residual, out, bias=None):
+    """out = residual + x @ weight.T (+ bias): the residual connections of a decoder layer (x2i_gemm_gate_residual with gate = NULL).
+    x [M, K]; residual / out: [M, N] row-strided views (e.g. one batch element of a layer slot of the [B, C, S, H] capture buffer)."""
+    _chk(x, "x"); _chk(weight, "weight"); _chk(residual, "residual"); _chk(out, "out"); _chk(bias, "bias")
+    M, lda = _rows(x)
+    N, K = weight.shape
+    _, ldr = _rows(residual)
+    _, ldc = _rows(out)
+    _lib.call("x2i_gemm_gate_residual", _p(x), lda, _p(weight), weight.stride(0), _p(bias), 0, 0, M, _p(residual), ldr, _p(out), ldc, 0, 0,
+              M, N, K, _stream())
+    return out
+
+
+def causal_attention(q, k, v, kv_start=None, out=None):
+    """Causal grouped-query attention of a left-padded prompt: q [B,H,L,128], k, v [B,Hkv,L,128] -> [B, L, H*128]; kv_start int32 [B]
+    = first valid key per batch element (None: 0).  Padded query rows (no visible key) output 0."""
+    _chk(q, "q"); _chk(k, "k"); _chk(v, "v"); _chk(kv_start, "kv_start", torch.int32)
+    B, H, L, d = q.shape
+    Hkv = k.shape[1]
+    if d != 128 or not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()) or k.shape != (B, Hkv, L, 128) or v.shape != k.shape:
+        raise _lib.X2IError("causal_attention: q [B,H,L,128], k,v [B,Hkv,L,128] contiguous")
+    if out is None:
+        out = torch.empty(B, L, H * 128, device=q.device, dtype=BF16)
+    _chk(out, "out")
+    _lib.call("x2i_causal_attention", _p(q), _p(k), _p(v), _p(kv_start), _p(out), out.stride(-2), B, H, Hkv, L, _stream())
+    return out
