@@ -35,6 +35,15 @@ for it in range(2):
     ops.colsum(dn, B, L, out0=d0, b=x, out1=d1, stats=stats)
     ops.qk_norm_rope_bwd(dq, dk, dv, rn(L, 2 * D), rn(128), rn(128), None, dbig, L, 0)
     ops.skinny_linear_t(gm, wm)
+    # KD loss forward + backward on one single-block layer pair [1, 4608, 3072], and the projector front end [1, 37, 512, 2048]
+    from x2i_b200 import kd, proj as xproj
+    t_kd, s_kd = rn(1, 1, L, D), rn(1, 1, L, D).requires_grad_(True)
+    kd.kd_loss_stacked(t_kd, s_kd)[0].backward()
+    if it == 0:
+        pm = xproj.create_proj3_qwen3b(37, use_t5=False, use_scale=False, use_cnn=True).to("cuda", torch.bfloat16)
+        xin = rn(1, 37, 512, 2048)
+    with torch.no_grad():
+        pm(xin)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("done")

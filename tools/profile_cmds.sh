@@ -25,6 +25,8 @@ if [ "$1" != "no-gemm" ]; then
 full prof_gemm "gemm2?_tcgen05" 8 --profile-from-start off -- $BENCH
 full prof_rowwise "ln_modulate|skinny" 4 --profile-from-start off -- $BENCH
 fi
+fi
+if [ "$1" = "all" ]; then
 # 3) VAE decode and the ControlNeXt nets: launch lists + full captures of the conv / GroupNorm kernels
 unset X2I_NCU
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/vae_launches.csv python tools/bench_vae.py --steps 1 --warmup 1 > gpurun_out/ncu_vae.log 2>&1

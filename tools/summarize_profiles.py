@@ -90,5 +90,8 @@ if __name__ == "__main__":
     launches(tag, steps=1, src_name="lc_train_launches.csv", out_name="lightcontrol_train_launch_list_summary.md",
              title=f"# {tag}: one LightControl train step (`X2I_NCU=1 python tools/bench_lightcontrol_train.py --steps 1 --warmup 1`: FLUX-dev, 19 "
                    "trainable ControlNeXt nets, 1024px, B = 1, VAE encode included) under ncu")
-    for rep in ("prof_attn", "prof_gemm", "prof_rowwise", "prof_bwd", "prof_vae"):
+    launches(tag, steps=2, src_name="mllm_launches.csv", out_name="mllm_prefill_launch_list_summary.md",
+             title=f"# {tag}: every kernel of `python tools/bench_mllm.py --steps 1 --warmup 1` under ncu (2 prefills of one 512-token prompt through the "
+                   "Qwen2.5-VL-3B text decoder + Proj7Exp, + model init; per-step columns = totals / 2)")
+    for rep in ("prof_attn", "prof_gemm", "prof_rowwise", "prof_bwd", "prof_vae", "prof_train"):
         raw(tag, rep)

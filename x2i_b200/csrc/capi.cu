@@ -802,6 +802,23 @@ int x2i_euler_step(void* x, const void* v, float dsigma, int64_t n, void* stream
   return check_launch("euler_step_kernel");
 }
 
+namespace {
+// the persistent KD kernels stage KD_STAGES rows (teacher + student) in dynamic shared memory: up to 64 KB at D = 4096
+int kd_configure(DeviceInfo* d, size_t smem) {
+  static std::atomic<bool> done[16];
+  if (smem > 200 * 1024) return fail(X2I_ERR_SHAPE, "kd_loss: row too long for the shared-memory ring");
+  if (!done[d->index].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(kd_row_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kd_row_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kd_row_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kd_row_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(kd_row_kernel): %s", cudaGetErrorString(e));
+    done[d->index].store(true, std::memory_order_release);
+  }
+  return X2I_OK;
+}
+}  // namespace
+
 int x2i_kd_loss_fwd(const void* teacher, const void* student, int64_t rows, int D, float temperature,
                     const int64_t* seg_row_start, const int* seg_layer, int n_seg, int n_layers, int batch, float* row_kl,
                     double* seg_sum, float* layer_term, float* loss, int* valid, void* stream) {
@@ -815,8 +832,11 @@ int x2i_kd_loss_fwd(const void* teacher, const void* student, int64_t rows, int 
   auto T = static_cast<const __nv_bfloat16*>(teacher);
   auto S = static_cast<const __nv_bfloat16*>(student);
   const int nchunk = D / 8;
-  if (nchunk <= KD_THREADS * 3) kd_row_kernel<3, false><<<(unsigned)rows, KD_THREADS, 0, st>>>(T, S, D, 1.0f / temperature, row_kl, nullptr, nullptr);
-  else kd_row_kernel<4, false><<<(unsigned)rows, KD_THREADS, 0, st>>>(T, S, D, 1.0f / temperature, row_kl, nullptr, nullptr);
+  const unsigned kd_grid = static_cast<unsigned>(rows < 4LL * d->sms ? rows : 4LL * d->sms);  // persistent, 4 CTAs per SM (shared-memory ring)
+  const size_t kd_smem = static_cast<size_t>(KD_STAGES) * 2 * D * 2;
+  if (int rc = kd_configure(d, kd_smem)) return rc;
+  if (nchunk <= KD_THREADS * 3) kd_row_kernel<3, false><<<kd_grid, KD_THREADS, kd_smem, st>>>(T, S, D, 1.0f / temperature, row_kl, nullptr, nullptr, rows);
+  else kd_row_kernel<4, false><<<kd_grid, KD_THREADS, kd_smem, st>>>(T, S, D, 1.0f / temperature, row_kl, nullptr, nullptr, rows);
   if (int rc = check_launch("kd_row_kernel<fwd>")) return rc;
   kd_segment_reduce_kernel<<<n_seg, 256, 0, st>>>(row_kl, reinterpret_cast<const long long*>(seg_row_start), seg_sum);
   if (int rc = check_launch("kd_segment_reduce_kernel")) return rc;
@@ -840,8 +860,11 @@ int x2i_kd_loss_bwd(const void* teacher, const void* student, int64_t rows, int 
   auto S = static_cast<const __nv_bfloat16*>(student);
   auto G = static_cast<__nv_bfloat16*>(grad_student);
   const int nchunk = D / 8;
-  if (nchunk <= KD_THREADS * 3) kd_row_kernel<3, true><<<(unsigned)rows, KD_THREADS, 0, st>>>(T, S, D, 1.0f / temperature, nullptr, row_scale, G);
-  else kd_row_kernel<4, true><<<(unsigned)rows, KD_THREADS, 0, st>>>(T, S, D, 1.0f / temperature, nullptr, row_scale, G);
+  const unsigned kd_grid = static_cast<unsigned>(rows < 4LL * d->sms ? rows : 4LL * d->sms);
+  const size_t kd_smem = static_cast<size_t>(KD_STAGES) * 2 * D * 2;
+  if (int rc = kd_configure(d, kd_smem)) return rc;
+  if (nchunk <= KD_THREADS * 3) kd_row_kernel<3, true><<<kd_grid, KD_THREADS, kd_smem, st>>>(T, S, D, 1.0f / temperature, nullptr, row_scale, G, rows);
+  else kd_row_kernel<4, true><<<kd_grid, KD_THREADS, kd_smem, st>>>(T, S, D, 1.0f / temperature, nullptr, row_scale, G, rows);
   return check_launch("kd_row_kernel<bwd>");
 }
 
@@ -869,10 +892,15 @@ int proj_mix_ln_impl(const void* x, int mode, const float* w, float conv_bias, c
   const int threads = ((H / 8 + 31) / 32) * 32;
   const size_t smem = (((static_cast<size_t>(C) * 25 + 3) & ~size_t(3)) + 32) * sizeof(float);
   if (smem > 48 * 1024) return fail(X2I_ERR_SHAPE, "proj_mix_ln: too many channels (C=%d)", C);
-  const int tiles = (S + PROJ_R - 1) / PROJ_R;
-  proj_mix_ln_kernel<<<B * tiles, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), mode, w, conv_bias, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), B, C, S, H,
-      static_cast<__nv_bfloat16*>(xm));
+  const bool r2 = static_cast<long long>(B) * ((S + 1) / 2) >= 4LL * d->sms;  // enough CTAs at 2 output rows each?
+  if (r2)
+    proj_mix_ln_kernel<2><<<B * ((S + 1) / 2), threads, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), mode, w, conv_bias, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), B, C, S, H,
+        static_cast<__nv_bfloat16*>(xm));
+  else
+    proj_mix_ln_kernel<1><<<B * S, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), mode, w, conv_bias, gamma, beta, eps, static_cast<__nv_bfloat16*>(y), B, C, S, H,
+        static_cast<__nv_bfloat16*>(xm));
   return check_launch("proj_mix_ln_kernel");
 }
 }  // namespace

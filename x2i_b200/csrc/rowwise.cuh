@@ -277,6 +277,7 @@ __global__ void gate_residual_kernel(__nv_bfloat16* __restrict__ x, long long ld
 // Forward writes row_kl[row]; a second deterministic kernel sums rows per layer.
 // Backward recomputes the row statistics and writes d loss / d student in bf16.
 constexpr int KD_THREADS = 128;
+constexpr int KD_STAGES = 4;  // rows in flight per CTA (shared-memory ring of the persistent KD kernel)
 __device__ __forceinline__ float sum_f32x2(uint64_t v) {
   float a, b;
   unpack_f32x2(v, a, b);
@@ -286,24 +287,55 @@ __device__ __forceinline__ float sum_f32x2(uint64_t v) {
 // student) element pair instead of ~16, which is what keeps this kernel HBM-bound rather than issue-bound (2 MUFU.EX2 per
 // pair remain the next limiter: 384 clk per 3072-wide row per SM against 530 clk of HBM time).
 template <int MAXC, bool BWD>
-__global__ void __launch_bounds__(KD_THREADS) kd_row_kernel(const __nv_bfloat16* __restrict__ teacher,
+__global__ void __launch_bounds__(KD_THREADS, 4) kd_row_kernel(const __nv_bfloat16* __restrict__ teacher,
                                                             const __nv_bfloat16* __restrict__ student, int D,
                                                             float inv_T, float* __restrict__ row_kl,
                                                             const float* __restrict__ row_scale /* BWD: per-row upstream */,
-                                                            __nv_bfloat16* __restrict__ grad) {
+                                                            __nv_bfloat16* __restrict__ grad, long long rows) {
+  // Persistent over rows with a shared-memory ring filled by bulk async copies (cp.async.bulk, the 1-D TMA path): thread 0 keeps
+  // KD_STAGES rows (teacher + student, 2 x D x 2 B each) in flight per CTA, completion on an mbarrier per stage; the four warps copy a
+  // landed row into registers, and the stage is refilled right after the first block-wide reduction (whose barrier orders every
+  // thread's reads before the refill).  HBM requests no longer depend on registers or on the three dependent reduction phases of a row:
+  // one-row-per-CTA ran at 2.8 TB/s on a 4608-row layer, register prefetch of one row at 3.0 TB/s (profiles/r02_rowwise_bandwidth.md).
+  extern __shared__ __align__(16) uint8_t kd_smem[];
   __shared__ float red[3 * (KD_THREADS / 32)];
-  const long long row = blockIdx.x;
+  __shared__ __align__(8) uint64_t full_bar[KD_STAGES];
   const int nchunk = D >> 3;
-  const uint4* tr = reinterpret_cast<const uint4*>(teacher + row * D);
-  const uint4* sr = reinterpret_cast<const uint4*>(student + row * D);
+  const uint32_t row_bytes = static_cast<uint32_t>(D) * 2u;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KD_STAGES; ++i) mbar_init(&full_bar[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long r, int stage) {  // thread 0 only
+    uint8_t* dst = kd_smem + static_cast<size_t>(stage) * 2 * row_bytes;
+    mbar_expect_tx(&full_bar[stage], 2 * row_bytes);
+    bulk_load_1d(dst, teacher + r * D, row_bytes, &full_bar[stage]);
+    bulk_load_1d(dst + row_bytes, student + r * D, row_bytes, &full_bar[stage]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll 1
+    for (int i = 0; i < KD_STAGES; ++i) {
+      const long long r = static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x;
+      if (r < rows) issue(r, i);
+    }
+  }
+  int it = 0;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+  const int stage = it % KD_STAGES;
   uint64_t t[MAXC][4], s[MAXC][4];  // fp32x2 pairs
   uint4 tq[MAXC], sq[MAXC];
+  mbar_wait(&full_bar[stage], (it / KD_STAGES) & 1);
+  {
+    const uint4* st_t = reinterpret_cast<const uint4*>(kd_smem + static_cast<size_t>(stage) * 2 * row_bytes);
+    const uint4* st_s = reinterpret_cast<const uint4*>(kd_smem + static_cast<size_t>(stage) * 2 * row_bytes + row_bytes);
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {  // all loads first (2 * MAXC x 16 B in flight per thread)
-    const int c = i * KD_THREADS + threadIdx.x;
-    if (c < nchunk) {
-      tq[i] = ld_stream(tr + c);
-      sq[i] = ld_stream(sr + c);
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = i * KD_THREADS + threadIdx.x;
+      if (c < nchunk) {
+        tq[i] = st_t[c];
+        sq[i] = st_s[c];
+      }
     }
   }
   uint64_t at = 0ull, as = 0ull;
@@ -320,6 +352,10 @@ __global__ void __launch_bounds__(KD_THREADS) kd_row_kernel(const __nv_bfloat16*
   }
   float r2[2] = {sum_f32x2(at), sum_f32x2(as)};
   block_sum<2, KD_THREADS / 32>(r2, red);
+  if (threadIdx.x == 0) {  // every thread has read this stage (it passed the barriers of block_sum): refill it
+    const long long r = row + static_cast<long long>(KD_STAGES) * gridDim.x;
+    if (r < rows) issue(r, stage);
+  }
   const float mt = r2[0] / D, ms = r2[1] / D;
   const uint64_t nmt2 = pack_f32x2(-mt, -mt), nms2 = pack_f32x2(-ms, -ms);
   at = as = 0ull;
@@ -416,6 +452,7 @@ __global__ void __launch_bounds__(KD_THREADS) kd_row_kernel(const __nv_bfloat16*
       }
     }
   }
+  }  // row loop
 }
 
 // Deterministic reduction, stage 1: seg_sum[s] = sum of row_kl over the segment's rows.  A segment is a contiguous
@@ -475,7 +512,6 @@ __global__ void kd_row_scale_kernel(const long long* __restrict__ seg_row_start,
 // h.  Every input row s0-2 .. s0+R+1 of every channel is loaded ONCE per CTA (16 B + two 4 B halos per thread, no shared
 // memory, no barriers in the main loop) and feeds all output rows it overlaps: 40 FMAs per (input row, output row).
 // The op is FP32-FMA bound, not HBM bound: 25 MAC per input element = 25 FLOP/B.
-constexpr int PROJ_R = 2;
 __device__ __forceinline__ float block_sum_rt(float v, float* red, int nwarps) {
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   v = warp_sum(v);
@@ -486,6 +522,9 @@ __device__ __forceinline__ float block_sum_rt(float v, float* red, int nwarps) {
   for (int j = 0; j < nwarps; ++j) s += red[j];  // fixed order
   return s;
 }
+// PROJ_R = 2 when B * S / 2 CTAs fill the machine (training batches), 1 otherwise: a single 512-token prompt gives only 256 CTAs of 8 warps at
+// R = 2 -- 1.7 waves on 148 SMs at ~14 warps per SM, which left this FMA-bound stencil latency-bound (profiles/r02_prof_train_ncu_full.csv).
+template <int PROJ_R>
 __global__ void __launch_bounds__(512) proj_mix_ln_kernel(const __nv_bfloat16* __restrict__ x, int mode,
                                                           const float* __restrict__ w /* [C,5,5] | [C] */,
                                                           float conv_bias, const float* __restrict__ gamma,
