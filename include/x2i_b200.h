@@ -360,11 +360,16 @@ int x2i_rmsnorm(const void* x, int64_t ldx, int64_t x_batch_stride, const void* 
  * (cumsum(attention_mask) - 1, padded tokens 1: Qwen2_5_VLModel.get_rope_index, text-only); inv_freq: device fp32 [64].          */
 int x2i_rope_half_split(const void* qkv, int64_t ld, const int* pos, const float* inv_freq, void* q, void* k, void* v, int B, int S,
                         int heads, int heads_kv, void* stream);
-/* C[M, N/2] = silu(A Wg^T + bg) * (A Wu^T + bu): Qwen2MLP's gate / up projections and activation in one GEMM.  W [N, K] holds the
- * gate and up rows interleaved in blocks of 128 (rows [256 t, 256 t + 128) = gate rows [128 t, +128), the next 128 = the matching
- * up rows); bias (nullable) is laid out the same way.  N % 256 == 0.                                                            */
+/* C[M, N/2] = act(A Wg^T + bg) * (A Wu^T + bu): a gated MLP's gate / up projections and activation in one GEMM.  act 0 = SiLU
+ * (SwiGLU: Qwen2MLP), act 1 = tanh-GELU (GEGLU: T5's "gated-gelu" DenseGatedActDense with gelu_new, model_internvl/proj.py:143).
+ * W [N, K] holds the gate and up rows interleaved in blocks of 128 (rows [256 t, 256 t + 128) = gate rows [128 t, +128), the next
+ * 128 = the matching up rows); bias (nullable) is laid out the same way.  N % 256 == 0.                                        */
 int x2i_gemm_swiglu(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc, int M, int N, int K,
-                    void* stream);
+                    int act, void* stream);
+/* P[r, :] (bf16) = softmax(S[r, :] + bias[r % bias_rows, :]) over fp32 scores: T5Attention's `scores += position_bias` + softmax
+ * (the T5Stack inside model_internvl/proj.py:139-211; transformers' modeling_t5.py).                                            */
+int x2i_softmax_rows_bias(const float* S, int64_t lds, const float* bias, int64_t ldb, int bias_rows, void* P, int64_t ldp, int rows, int cols,
+                          void* stream);
 /* Causal grouped-query self-attention of a left-padded prompt: q [B,heads,L,128], k, v [B,heads_kv,L,128] -> out [B*L, ld] token-major
  * (column h*128 + d).  Key j is visible to query i iff kv_start[b] <= j <= i (kv_start: device int32 [B], nullable = 0); a query row
  * with no visible key (a padded position) outputs 0 -- the behaviour of transformers' sdpa / flash paths.  Same kernel as

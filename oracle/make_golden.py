@@ -7,6 +7,8 @@ TEST INFRASTRUCTURE ONLY.  What each fixture pins, and how:
 
   proj_small.pt / proj_c1.pt   reference ``utils/proj.py`` imported unmodified; synthetic weights are
                                written into it by state-dict key; outputs stored.
+  proj_legacy.pt               reference ``model_internvl/proj.py`` (a12) imported unmodified with the real ``transformers`` T5Stack: Proj,
+                               Proj2, Proj3, MLP, MLP2, MLP_plus outputs on seeded inputs and weights.
   helpers.pt                   reference ``train/train_qwenvl.py`` imported with every missing third-party
                                module auto-stubbed; ``normalize``, ``_prepare_latent_image_ids``,
                                ``_pack_latents``, ``calculate_shift`` called directly.
@@ -279,6 +281,54 @@ def golden_kd_loop():
     torch.save(out, os.path.join(OUT, "kd_loop.pt"))
     print("KD loop golden written: loss fp32", float(out["clean_fp32"]["loss"]), "bf16", float(out["clean_bf16"]["loss"]),
           "poisoned", float(out["poisoned_fp32"]["loss"]), out["poisoned_fp32"]["printed"], "hooks", n_hooks)
+
+
+# ----------------------------------------------------------------------------- A2: the older projector variants (a12)
+def golden_proj_legacy():
+    """``model_internvl/proj.py`` imported UNMODIFIED: its absent third-party roots are stubbed, ``transformers`` (the
+    real library: T5Stack / T5Config) is imported first so the stubs do not shadow it.  Proj, Proj2, Proj3 and the bare MLP / MLP2 /
+    MLP_plus run on CPU in fp32 with synthetic weights written by state-dict key; inputs, weights and outputs are stored."""
+    import contextlib
+    import io
+    import transformers  # noqa: F401
+    from transformers import (AutoModel, AutoModelForCausalLM, AutoTokenizer, BertModel, BertTokenizer, CLIPTextModel,  # noqa: F401
+                              CLIPTextModelWithProjection, CLIPTokenizer, MT5EncoderModel, T5Config, T5EncoderModel,
+                              T5ForConditionalGeneration, T5Tokenizer, T5TokenizerFast)
+    from transformers.models.t5.modeling_t5 import T5Stack  # noqa: F401
+    finder = _StubFinder()
+    sys.meta_path.insert(0, finder)
+    sys.path.insert(0, REF)
+    try:
+        ref = importlib.import_module("model_internvl.proj")
+    finally:
+        sys.meta_path.remove(finder)
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k.split(".")[0] in finder.ROOTS + ("model_internvl",)]:
+            sys.modules.pop(k)
+    out = dict(stubbed=sorted(set(s_.split(".")[0] for s_ in finder.stubbed)), transformers_version=transformers.__version__)
+    kw = dict(in_channels=3, input_dim=64, output_dim0=32, output_dim1=128, num_layers=2, num_heads=2, head_dim=64)
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 3, 32, 64, generator=g).bfloat16().float()
+    for name in ("Proj", "Proj2", "Proj3"):
+        with contextlib.redirect_stdout(io.StringIO()):  # the constructors print their T5Config
+            m = getattr(ref, name)(**kw).eval()
+        sd = synth_state(m, 42, std=0.08)
+        sd = {k: (v * 0 + 1 + 0.1 * torch.randn(v.shape, generator=g) if ("norm" in k and k.endswith("weight")) else v) for k, v in sd.items()}
+        sd = {k: v.bfloat16().float() for k, v in sd.items()}  # bf16-representable weights: the bf16 product loads them exactly
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            x1, x2 = m(x)
+        out[name] = dict(kwargs=kw, state={k: v for k, v in sd.items() if "embed_tokens" not in k}, x=x, x1=x1, x2=x2)
+    xs = torch.randn(2, 32, 64, generator=g).bfloat16().float()
+    for name in ("MLP", "MLP2", "MLP_plus"):
+        m = getattr(ref, name)(in_dim=64, out_dim=128, hidden_dim=128, out_dim1=32).eval()
+        sd = {k: v.bfloat16().float() for k, v in synth_state(m, 43, std=0.08).items()}
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            x1, x2 = m(xs)
+        out[name] = dict(state=sd, x=xs, x1=x1, x2=x2)
+    torch.save(out, os.path.join(OUT, "proj_legacy.pt"))
+    print("legacy projector goldens written (reference model_internvl/proj.py, transformers", transformers.__version__, "); stubbed:", out["stubbed"])
 
 
 # ----------------------------------------------------------------------------- B2: LightControl trainer helpers
@@ -573,6 +623,7 @@ if __name__ == "__main__":
             globals()["golden_" + name]()
         sys.exit(0)
     golden_projector()
+    golden_proj_legacy()
     golden_helpers()
     golden_kd_loop()
     golden_flux_structure()

@@ -82,7 +82,8 @@ SIGNATURES = {
     "x2i_gather_rows": [_vp, _vp, _i64, _i, _vp, _i64, _i64, _i, _i, _i, _vp],
     "x2i_rmsnorm": [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _i, _i, _i, _f, _vp],
     "x2i_rope_half_split": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "x2i_gemm_swiglu": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp],
+    "x2i_gemm_swiglu": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
+    "x2i_softmax_rows_bias": [_vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _i, _vp],
     "x2i_causal_attention": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp],
 }
 # helpers that return a size instead of a status code

@@ -996,7 +996,7 @@ int x2i_rope_half_split(const void* qkv, int64_t ld, const int* pos, const float
 }
 
 int x2i_gemm_swiglu(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* C, int64_t ldc, int M, int N, int K,
-                    void* stream) {
+                    int act, void* stream) {
   DeviceInfo* d;
   if (int rc = device_info(&d)) return rc;
   if (N % 256) return fail(X2I_ERR_SHAPE, "gemm_swiglu: N=%d (gate and up rows interleaved in blocks of 128) must be a multiple of 256", N);
@@ -1006,6 +1006,8 @@ int x2i_gemm_swiglu(const void* A, int64_t lda, const void* W, int64_t ldw, cons
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.C = static_cast<__nv_bfloat16*>(C); p.ldc = ldc;
+  if (act < 0 || act > 1) return fail(X2I_ERR_SHAPE, "gemm_swiglu: act must be 0 (SiLU gate) or 1 (tanh-GELU gate)");
+  p.aux_act = act;
   const bool pair = use_pair_kernel() && M > 128;  // both forms use 256-column tiles
   return launch_gemm<EPI_SWIGLU>(d, A, lda, W, ldw, p, static_cast<cudaStream_t>(stream), pair ? 0 : 256);
 }
@@ -1373,6 +1375,16 @@ int x2i_softmax_rows(const float* S, int64_t lds, void* P, int64_t ldp, int rows
   if (!S || !P || !aligned16(S) || !aligned16(P) || lds % 4 || ldp % 8) return fail(X2I_ERR_ALIGN, "softmax_rows: alignment");
   softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, static_cast<__nv_bfloat16*>(P), ldp, cols);
   return check_launch("softmax_rows_kernel");
+}
+
+int x2i_softmax_rows_bias(const float* S, int64_t lds, const float* bias, int64_t ldb, int bias_rows, void* P, int64_t ldp, int rows, int cols,
+                          void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows <= 0 || cols <= 0 || cols % 4 || cols > 256 * 4 * SM_VEC || bias_rows <= 0) return fail(X2I_ERR_SHAPE, "softmax_rows_bias: cols %% 4 == 0 and cols <= %d", 256 * 4 * SM_VEC);
+  if (!S || !P || !bias || !aligned16(S) || !aligned16(P) || !aligned16(bias) || lds % 4 || ldp % 8 || ldb % 4) return fail(X2I_ERR_ALIGN, "softmax_rows_bias: alignment");
+  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, static_cast<__nv_bfloat16*>(P), ldp, cols, bias, ldb, bias_rows);
+  return check_launch("softmax_rows_kernel<bias>");
 }
 
 int x2i_upsample2x_nhwc(const void* x, void* out, int Nimg, int H, int W, int C, void* stream) {

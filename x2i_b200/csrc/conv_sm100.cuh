@@ -421,10 +421,13 @@ __global__ void __launch_bounds__(256) upsample2x_nhwc_kernel(const uint4* __res
 // scores come from a GEMM with fp32 output): P[r, :] = softmax(S[r, :]).  One CTA per row, the row lives in registers
 // (cols <= 256 * 4 * SM_VEC).
 constexpr int SM_VEC = 16;  // float4 loads per thread -> up to 16384 columns
+// bias (nullable): fp32 [bias_rows, ldb] added to the scores before the soft-max, row r uses bias row r % bias_rows (T5's relative position
+// bias is shared by every sequence of the batch).
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long lds, __nv_bfloat16* __restrict__ P, long long ldp,
-                                                           int cols) {
+                                                           int cols, const float* __restrict__ bias = nullptr, long long ldb = 0, int bias_rows = 1) {
   __shared__ float red[8];
   const float* s = S + static_cast<long long>(blockIdx.x) * lds;
+  const float* brow = bias != nullptr ? bias + static_cast<long long>(blockIdx.x % bias_rows) * ldb : nullptr;
   __nv_bfloat16* o = P + static_cast<long long>(blockIdx.x) * ldp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 v[SM_VEC];
@@ -434,6 +437,10 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     const int c = (u * 256 + threadIdx.x) * 4;
     if (c < cols) {
       v[u] = *reinterpret_cast<const float4*>(s + c);
+      if (brow != nullptr) {
+        const float4 bb = *reinterpret_cast<const float4*>(brow + c);
+        v[u].x += bb.x; v[u].y += bb.y; v[u].z += bb.z; v[u].w += bb.w;
+      }
       mx = fmaxf(fmaxf(mx, fmaxf(v[u].x, v[u].y)), fmaxf(v[u].z, v[u].w));
     }
   }

@@ -244,7 +244,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
       }
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) g[j] = silu_f(g[j] + __uint_as_float(rg[j])) * (u[j] + __uint_as_float(ru[j]));
+      for (int j = 0; j < 32; ++j) {
+        const float gv = g[j] + __uint_as_float(rg[j]);
+        g[j] = (p.aux_act == 1 ? gelu_tanh_f(gv) : silu_f(gv)) * (u[j] + __uint_as_float(ru[j]));  // GEGLU (T5 gated-gelu) | SwiGLU
+      }
       if (row_ok) store_bf16x32(p.C + static_cast<long long>(m) * p.ldc + (n_tile0 >> 1) + c * 32, g);
     }
   } else {

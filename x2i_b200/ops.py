@@ -629,6 +629,17 @@ def softmax_rows(s, out=None):
     return out
 
 
+def softmax_rows_bias(s, bias, out=None):
+    """P (bf16) = softmax(s + bias) row-wise; s fp32 [rows, cols], bias fp32 [bias_rows, cols] (row r uses bias row r % bias_rows)."""
+    _chk(s, "s", F32); _chk(bias, "bias", F32)
+    rows, cols = s.shape
+    if out is None:
+        out = torch.empty(rows, cols, device=s.device, dtype=BF16)
+    _chk(out, "out")
+    _lib.call("x2i_softmax_rows_bias", _p(s), s.stride(0), _p(bias), bias.stride(0), bias.shape[0], _p(out), out.stride(0), rows, cols, _stream())
+    return out
+
+
 def upsample2x_nhwc(x, out=None):
     """Nearest 2x upsampling of NHWC bf16."""
     _chk(x, "x")
@@ -792,15 +803,15 @@ def pack_swiglu_weight(gate_w, up_w):
     return torch.stack([gate_w.view(F // 128, 128, K), up_w.view(F // 128, 128, K)], dim=1).reshape(2 * F, K).contiguous()
 
 
-def linear_swiglu(x, w_packed, out=None):
-    """silu(x @ Wg.T) * (x @ Wu.T) with w_packed = pack_swiglu_weight(Wg, Wu).  x [..., K] -> [..., F]."""
+def linear_swiglu(x, w_packed, out=None, act=0):
+    """act(x @ Wg.T) * (x @ Wu.T) with w_packed = pack_swiglu_weight(Wg, Wu); act 0 SiLU (SwiGLU), 1 tanh-GELU (GEGLU).  x [..., K] -> [..., F]."""
     _chk(x, "x"); _chk(w_packed, "w_packed")
     M, lda = _rows(x)
     N, K = w_packed.shape
     if out is None:
         out = torch.empty(*x.shape[:-1], N // 2, device=x.device, dtype=BF16)
     _, ldc = _rows(out)
-    _lib.call("x2i_gemm_swiglu", _p(x), lda, _p(w_packed), w_packed.stride(0), 0, _p(out), ldc, M, N, K, _stream())
+    _lib.call("x2i_gemm_swiglu", _p(x), lda, _p(w_packed), w_packed.stride(0), 0, _p(out), ldc, M, N, K, int(act), _stream())
     return out
 
 
