@@ -1149,14 +1149,16 @@ int x2i_colsum(const void* A, int64_t lda, const void* Bm, int64_t ldb, const vo
   if (nbatch <= 0 || rows_per_batch <= 0 || D <= 0 || D % 8) return fail(X2I_ERR_SHAPE, "colsum: D must be a multiple of 8");
   if (!A || (!out0 && !out1) || (out1 && !Bm) || !workspace) return fail(X2I_ERR_SHAPE, "colsum: missing buffer");
   if (!aligned16(A) || !aligned16(Bm) || lda % 8 || ldb % 8 || !aligned16(workspace)) return fail(X2I_ERR_ALIGN, "colsum: alignment");
-  const int nsplit = (rows_per_batch + COLSUM_ROWS - 1) / COLSUM_ROWS;
+  const int groups = colsum_groups(D);  // row groups per CTA for narrow matrices (1 for D >= 1024)
+  const int span = COLSUM_ROWS * groups;
+  const int nsplit = (rows_per_batch + span - 1) / span;
   const long long per = static_cast<long long>(nbatch) * nsplit * D;
   float* p0 = out0 ? workspace : nullptr;
   float* p1 = out1 ? workspace + (out0 ? per : 0) : nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 g1((D / 8 + 127) / 128, nsplit, nbatch);
+  dim3 g1(groups > 1 ? 1 : (D / 8 + 127) / 128, nsplit, nbatch);
   colsum_partial_kernel<<<g1, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(Bm), ldb,
-                                            static_cast<const float2*>(stats), p0, p1, rows_per_batch, D, nsplit);
+                                            static_cast<const float2*>(stats), p0, p1, rows_per_batch, D, nsplit, groups);
   if (int rc = check_launch("colsum_partial_kernel")) return rc;
   dim3 g2((D + 31) / 32, nbatch);
   if (out0) {

@@ -130,44 +130,86 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_mod_bwd_kernel(const __nv_bflo
 // Used for dshift / dscale of every AdaLN (A = dn, B = LN input), dgate (A = dx, B = the un-gated branch output),
 // the affine LayerNorm's dbeta / dgamma and bias gradients.
 constexpr int COLSUM_ROWS = 32;
+// Narrow matrices (D / 8 < 128 sixteen-byte chunks per row: the conv bias / GroupNorm / time-row sums of the ControlNeXt nets, C = 64-256
+// channels over up to 262 144 pixel rows) fold `groups` = 128 / chunks row groups into one CTA: thread (g, c) owns chunk c of rows
+// t0 + g, t0 + g + groups, ...; a split then covers COLSUM_ROWS * groups rows and the group sums are added in a fixed order through
+// shared memory.  With one chunk column per thread a 128-channel tensor ran 16 live threads per CTA and 8192 splits, whose serial
+// second stage took 25 us per launch (profiles/r01_lightcontrol_train_launch_list_summary.md).
+__host__ __device__ inline int colsum_groups(int D) {
+  const int chunks = D >> 3;
+  int g = 1;
+  while (g * 2 * chunks <= 128 && g < 16) g *= 2;
+  return g;
+}
 __global__ void __launch_bounds__(128) colsum_partial_kernel(const __nv_bfloat16* __restrict__ A, long long lda,
                                                              const __nv_bfloat16* __restrict__ Bm, long long ldb,
                                                              const float2* __restrict__ stats, float* __restrict__ part0,
-                                                             float* __restrict__ part1, int rows_per_batch, int D, int nsplit) {
-  const int c = blockIdx.x * 128 + threadIdx.x;  // 16-byte chunk index
-  if (c * 8 >= D) return;
+                                                             float* __restrict__ part1, int rows_per_batch, int D, int nsplit, int groups) {
+  __shared__ float red[2][128][8];
+  const int chunks = D >> 3;
+  int c, g;
+  if (groups > 1) {
+    g = threadIdx.x / chunks;
+    c = threadIdx.x - g * chunks;
+  } else {
+    g = 0;
+    c = blockIdx.x * 128 + threadIdx.x;  // 16-byte chunk index
+  }
+  const bool live = c < chunks && g < groups;
+  if (groups == 1 && !live) return;
   const int split = blockIdx.y, b = blockIdx.z;
-  const int t0 = split * COLSUM_ROWS, t1 = min(t0 + COLSUM_ROWS, rows_per_batch);
+  const int span = COLSUM_ROWS * groups;
+  const int t0 = split * span, t1 = min(t0 + span, rows_per_batch);
   const bool two = part1 != nullptr;
   float s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
   constexpr int U = 8;  // rows in flight per thread (2 x U independent 16-byte loads)
-  for (int t = t0; t < t1; t += U) {
-    uint4 ra[U], rb[U];
-    float2 st[U];
+  if (live) {
+    for (int t = t0 + g; t < t1; t += U * groups) {
+      uint4 ra[U], rb[U];
+      float2 st[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long r = static_cast<long long>(b) * rows_per_batch + min(t + u, t1 - 1);
-      ra[u] = ld_stream(A + r * lda + c * 8);
-      if (two) rb[u] = ld_stream(Bm + r * ldb + c * 8);
-      st[u] = (two && stats != nullptr) ? stats[r] : make_float2(0.f, 1.f);
-    }
+      for (int u = 0; u < U; ++u) {
+        const int tt = t + u * groups;
+        const long long r = static_cast<long long>(b) * rows_per_batch + (tt < t1 ? tt : t);
+        ra[u] = ld_stream(A + r * lda + c * 8);
+        if (two) rb[u] = ld_stream(Bm + r * ldb + c * 8);
+        st[u] = (two && stats != nullptr) ? stats[r] : make_float2(0.f, 1.f);
+      }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (t + u < t1) {
-        float a[8];
-        unpack8(ra[u], a);
+      for (int u = 0; u < U; ++u) {
+        if (t + u * groups < t1) {
+          float a[8];
+          unpack8(ra[u], a);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s0[j] += a[j];
-        if (two) {
-          float v[8];
-          unpack8(rb[u], v);
+          for (int j = 0; j < 8; ++j) s0[j] += a[j];
+          if (two) {
+            float v[8];
+            unpack8(rb[u], v);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) s1[j] += a[j] * ((v[j] - st[u].x) * st[u].y);
+            for (int j = 0; j < 8; ++j) s1[j] += a[j] * ((v[j] - st[u].x) * st[u].y);
+          }
         }
       }
     }
+  }
+  if (groups > 1) {  // add the row groups of this CTA in a fixed order
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[0][threadIdx.x][j] = s0[j];
+      red[1][threadIdx.x][j] = s1[j];
+    }
+    __syncthreads();
+    if (g != 0 || !live) return;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+    for (int gg = 0; gg < groups; ++gg)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += red[0][gg * chunks + c][j];
+        s1[j] += red[1][gg * chunks + c][j];
+      }
   }
   const long long o = (static_cast<long long>(b) * nsplit + split) * D + c * 8;
   if (part0 != nullptr) {
