@@ -104,6 +104,20 @@ def test_attention_backward(ops, B, H, L):
     assert rel(dv, dv_r) < 8e-3
     assert rel(dq, dq_r) < 1e-2
     assert rel(dk, dk_r) < 1e-2
+    # the cluster form (two CTAs share every streamed tile through TMA multicast; opt-in) and the one-CTA-per-tile form run the
+    # same MMAs on the same tiles in the same order: bit-identical, also when the tile count is odd (padding tile in the last pair)
+    import os
+    old = os.environ.get("X2I_ATTN_BWD_MC")
+    os.environ["X2I_ATTN_BWD_MC"] = "1"
+    try:
+        poison = lambda: torch.full_like(q, float("nan"))  # noqa: E731
+        dq1, dk1, dv1 = ops.attention_bwd(q, k, v, do_hm, lse, delta, dq=poison(), dk=poison(), dv=poison())
+    finally:
+        if old is None:
+            del os.environ["X2I_ATTN_BWD_MC"]
+        else:
+            os.environ["X2I_ATTN_BWD_MC"] = old
+    assert torch.equal(dq, dq1) and torch.equal(dk, dk1) and torch.equal(dv, dv1)
 
 
 def test_attention_bwd_prep_addend(ops):

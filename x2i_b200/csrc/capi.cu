@@ -1051,16 +1051,30 @@ int x2i_mmdit_attention_bwd(const void* q, const void* k, const void* v, const v
   if (!configured[d->index].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(mmdit_attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mmdit_attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mmdit_attention_bwd_mc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mmdit_attention_bwd_mc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
     if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
     configured[d->index].store(true, std::memory_order_release);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid((L + 127) / 128, heads, B);
+  // X2I_ATTN_BWD_MC=1: 2-CTA clusters sharing every streamed tile through TMA multicast (halves the L2 -> SM bytes).  Bit-identical;
+  // measured neutral on B200 (0.781 vs 0.775 ms sustained at a 2.5 % higher SM clock: the launch is not L2-bound), so opt-in.
+  const char* mc_env = getenv("X2I_ATTN_BWD_MC");  // read per call so one process can run both forms (tests)
+  const bool mc = mc_env ? atoi(mc_env) != 0 : false;
+  const int tiles = (L + 127) / 128;
+  dim3 grid(mc ? (tiles + 1) / 2 * 2 : tiles, heads, B);  // cluster pairs: an even number of owner tiles (a padding tile has no valid row)
   p.out0 = static_cast<__nv_bfloat16*>(dk); p.out1 = static_cast<__nv_bfloat16*>(dv);
-  if (bwd_only != 2) mmdit_attention_bwd_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
+  p.x0g = static_cast<const __nv_bfloat16*>(q); p.x1g = static_cast<const __nv_bfloat16*>(dout);
+  if (bwd_only != 2) {
+    if (mc) mmdit_attention_bwd_mc_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
+    else mmdit_attention_bwd_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
+  }
   if (int rc = check_launch("mmdit_attention_bwd_kernel<kv>")) return rc;
   p.out0 = static_cast<__nv_bfloat16*>(dq); p.out1 = nullptr;
-  if (bwd_only != 1) mmdit_attention_bwd_kernel<false><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tq, tdo, tk, tv, p);
+  if (bwd_only != 1) {
+    if (mc) mmdit_attention_bwd_mc_kernel<false><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tq, tdo, tk, tv, p);
+    else mmdit_attention_bwd_kernel<false><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tq, tdo, tk, tv, p);
+  }
   return check_launch("mmdit_attention_bwd_kernel<q>");
 }
 

@@ -715,16 +715,17 @@ class FluxTransformer2DModel(nn.Module):
         ws = self._workspace(B, S, L_img)
         rope_full, rope = self._rope(txt_ids, img_ids)
 
-        x = ops.linear(hidden_states.to(BF16).contiguous(), self.x_embedder.weight, self.x_embedder.bias, out=ws["x"])
-        # timestep / guidance arrive as t/1000; the reference scales them IN bf16 (lightcontrol_flux.py:447-449)
-        t1000 = timestep.to(BF16) * 1000
-        if guidance is not None:
-            temb = self.time_text_embed(t1000, guidance.to(BF16) * 1000, pooled_projections)
-        else:
-            temb = self.time_text_embed(t1000, pooled_projections)
-        c = ops.linear(encoder_hidden_states.to(BF16).contiguous(), self.context_embedder.weight, self.context_embedder.bias,
-                       out=ws["c"])
-        mod = ops.skinny_linear(temb, self._w_mod, self._b_mod, act_in=1)  # every AdaLN modulation of this step
+        with ops.nvtx("x2i.embed+modulation"):
+            x = ops.linear(hidden_states.to(BF16).contiguous(), self.x_embedder.weight, self.x_embedder.bias, out=ws["x"])
+            # timestep / guidance arrive as t/1000; the reference scales them IN bf16 (lightcontrol_flux.py:447-449)
+            t1000 = timestep.to(BF16) * 1000
+            if guidance is not None:
+                temb = self.time_text_embed(t1000, guidance.to(BF16) * 1000, pooled_projections)
+            else:
+                temb = self.time_text_embed(t1000, pooled_projections)
+            c = ops.linear(encoder_hidden_states.to(BF16).contiguous(), self.context_embedder.weight, self.context_embedder.bias,
+                           out=ws["c"])
+            mod = ops.skinny_linear(temb, self._w_mod, self._b_mod, act_in=1)  # every AdaLN modulation of this step
 
         mids = None
         if control_nets is not None and len(control_nets) > 0:
@@ -733,12 +734,14 @@ class FluxTransformer2DModel(nn.Module):
                 stack = self._cn_stack if self._cn_stack is not None and self._cn_stack.nets == list(control_nets) else None
                 if stack is None:
                     stack = self._cn_stack = ControlNeXtStack(control_nets)
-                mids = stack.mid_features(guided_hint, t1000)  # all nets, one launch per layer (they do not depend on x)
+                with ops.nvtx("x2i.control_nets(stacked)"):
+                    mids = stack.mid_features(guided_hint, t1000)  # all nets, one launch per layer (they do not depend on x)
 
         off = 0
         for i, blk in enumerate(self.transformer_blocks):
-            c, x = blk(hidden_states=x, encoder_hidden_states=c, temb=temb, image_rotary_emb=rope_full,
-                       _mod=mod[:, off:off + 12 * D], _rope=rope, _ws=ws)
+            with ops.nvtx("x2i.double_block"):
+                c, x = blk(hidden_states=x, encoder_hidden_states=c, temb=temb, image_rotary_emb=rope_full,
+                           _mod=mod[:, off:off + 12 * D], _rope=rope, _ws=ws)
             off += 12 * D
             if control_nets is not None and i < len(control_nets):  # lightcontrol_flux.py:504-507
                 net = control_nets[i]
@@ -754,12 +757,14 @@ class FluxTransformer2DModel(nn.Module):
         h[:, :S].copy_(c)
         h[:, S:].copy_(x)
         for blk in self.single_transformer_blocks:
-            h = blk(hidden_states=h, temb=temb, image_rotary_emb=rope_full, _mod=mod[:, off:off + 3 * D], _rope=rope, _ws=ws)
+            with ops.nvtx("x2i.single_block"):
+                h = blk(hidden_states=h, temb=temb, image_rotary_emb=rope_full, _mod=mod[:, off:off + 3 * D], _rope=rope, _ws=ws)
             off += 3 * D
         # norm_out (AdaLayerNormContinuous: scale first, then shift) + proj_out over all rows; text rows dropped after
-        n = ops.ln_modulate(h.view(B * (S + L_img), D), mod[:, off:off + D], mod[:, off + D:off + 2 * D], S + L_img,
-                            out=ws["n"])
-        return ops.linear(n, self.proj_out.weight, self.proj_out.bias).view(B, S + L_img, -1)[:, S:].contiguous()
+        with ops.nvtx("x2i.norm_out+proj_out"):
+            n = ops.ln_modulate(h.view(B * (S + L_img), D), mod[:, off:off + D], mod[:, off + D:off + 2 * D], S + L_img,
+                                out=ws["n"])
+            return ops.linear(n, self.proj_out.weight, self.proj_out.bias).view(B, S + L_img, -1)[:, S:].contiguous()
 
 
 class _TensorTuple(tuple):

@@ -1,5 +1,7 @@
 """Tensor-level wrappers over the C ABI.  PyTorch is plumbing here (device memory + streams): every op below
 enqueues hand-written sm_100a kernels from libx2i_b200.so on torch's current stream.  No fallbacks."""
+import os
+
 import torch
 
 from . import _lib
@@ -197,6 +199,26 @@ def add_pos2d(x, pos, tgt_sizes):
     _lib.call("x2i_add_pos2d", _p(x.contiguous()), _p(pos.contiguous()), _p(tgt_sizes.contiguous()), _p(out), B, L, D,
               pos.shape[0], pos.shape[1], _stream())
     return out
+
+
+class _NoRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NVTX_ON = os.environ.get("X2I_NVTX", "0") == "1"
+_NO_RANGE = _NoRange()
+
+
+def nvtx(name):
+    """NVTX range around a phase of the path (`X2I_NVTX=1`; shows up in nsys / ncu --nvtx).  A no-op object otherwise, so the
+    hot path pays one attribute lookup."""
+    if not _NVTX_ON:
+        return _NO_RANGE
+    return torch.cuda.nvtx.range(name)
 
 
 def ln_modulate(x, scale, shift, rows_per_batch, eps=1e-6, out=None):

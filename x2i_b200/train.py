@@ -116,26 +116,32 @@ def distill_step(proj, transformer, batch: Dict[str, torch.Tensor], optimizer=No
     common = dict(hidden_states=batch["latents"].to(dt), timestep=batch["timestep"] / 1000, txt_ids=txt_ids, img_ids=img_ids,
                   guidance=guidance)
     kd_teacher, kd_student = [], []
-    with torch.no_grad():
+    from .ops import nvtx
+    with torch.no_grad(), nvtx("x2i.distill.teacher"):
         _run_hooked(transformer, kd_teacher, encoder_hidden_states=batch["prompt_embeds_t5"].to(dt),
                     pooled_projections=batch["pooled_clip"].to(dt), **common)
-    add_text_embeds, prompt_embeds = proj(batch["text_embeddings"])
-    _run_hooked(transformer, kd_student, encoder_hidden_states=prompt_embeds.to(dt), pooled_projections=add_text_embeds.to(dt),
-                **common)
-    if stacked:
-        loss = kd.attention_distillation_loss(kd_teacher, kd_student, temperature, verbose=False)
-    else:
-        t_all = kd_teacher[0] + kd_teacher[1] + kd_teacher[2]
-        s_all = kd_student[0] + kd_student[1] + kd_student[2]
-        loss, _valid = kd.kd_loss_layers(t_all, s_all, temperature)
-    loss.backward()
+    with nvtx("x2i.distill.projector"):
+        add_text_embeds, prompt_embeds = proj(batch["text_embeddings"])
+    with nvtx("x2i.distill.student"):
+        _run_hooked(transformer, kd_student, encoder_hidden_states=prompt_embeds.to(dt), pooled_projections=add_text_embeds.to(dt),
+                    **common)
+    with nvtx("x2i.distill.kd_loss"):
+        if stacked:
+            loss = kd.attention_distillation_loss(kd_teacher, kd_student, temperature, verbose=False)
+        else:
+            t_all = kd_teacher[0] + kd_teacher[1] + kd_teacher[2]
+            s_all = kd_student[0] + kd_student[1] + kd_student[2]
+            loss, _valid = kd.kd_loss_layers(t_all, s_all, temperature)
+    with nvtx("x2i.distill.backward"):
+        loss.backward()
     if micro_step % max(1, gradient_accumulation_steps) != 0:
         return loss.detach()  # accumulate only (train_qwenvl.py:561)
     params = [p for p in proj.parameters() if p.requires_grad]
-    if bucket is not None:
-        bucket.allreduce_mean_(group=group, timings=timings)
-    else:
-        xdist.allreduce_mean_grads_(params, group=group)
+    with nvtx("x2i.distill.allreduce"):
+        if bucket is not None:
+            bucket.allreduce_mean_(group=group, timings=timings)
+        else:
+            xdist.allreduce_mean_grads_(params, group=group)
     if optimizer is not None:
         if max_grad_norm is not None:
             if bucket is not None:
