@@ -328,6 +328,17 @@ int64_t x2i_groupnorm_bwd_workspace_floats(int Nimg, int HW, int C, int G);
 int x2i_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
 int x2i_silu(const void* x, void* out, int64_t n, void* stream);
 int x2i_im2col_nhwc(const void* x, void* cols, int Nimg, int H, int W, int C, int KH, int KW, int stride, int pad, int pad_end, void* stream);
+/* Implicit convolution weight gradient (no im2col buffer): dW[Cout, KH*KW*Cin] (bf16, the packed layout above) (+)= sum over ALL images and
+ * output pixels of dY[pix, Cout] x X[pix * stride + tap - pad, Cin], one launch (+ the fixed-order split-K reduction).  The tcgen05 GEMM's B
+ * operand is loaded as 64-pixel x 64-channel boxes of x itself, shifted by the tap (stride 2: a 5-D parity view of x), zero padding = TMA
+ * out-of-bounds fill.  Replaces torch autograd's conv weight gradient behind the reference's ControlNeXt nets
+ * (lightcontrol/train_lightcontrol.py:760 `accelerator.backward(loss)`).  x [Nimg,H,W,Cin], dy [Nimg,Ho,Wo,Cout] contiguous NHWC bf16.
+ * _supported(): 1 when the output rows tile into 64-pixel blocks (Wo % 64 == 0, or 64 % Wo == 0 with Ho*Wo % 64 == 0), Cin % 64 == 0,
+ * kernel <= 3x3, stride 1 or 2; otherwise use x2i_im2col_nhwc + x2i_gemm_wgrad.  workspace: _workspace_floats() floats (may be 0).    */
+int64_t x2i_conv2d_nhwc_wgrad_supported(int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int pad_end);
+int64_t x2i_conv2d_nhwc_wgrad_workspace_floats(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int pad_end);
+int x2i_conv2d_nhwc_wgrad(const void* x, const void* dy, void* dw, float* workspace, int64_t workspace_floats, int Nimg, int H, int W, int Cin,
+                          int Cout, int KH, int KW, int stride, int pad, int pad_end, int accumulate, void* stream);
 
 /* ---- VAE decoder (reference call site infer/inference_qwenvl.py:209-216: vae.decode(latents)) ----------
  * The decoder's convolutions and GroupNorms run through x2i_conv2d_nhwc / x2i_groupnorm_nhwc (C up to 2048, groups of 4 or a

@@ -59,7 +59,10 @@ def test_conv_input_gradient(ops, cin, cout, k, stride, pad, hw):
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,pad,hw", [(64, 64, 3, 1, 1, (24, 40)), (128, 256, 3, 1, 1, (16, 16)), (128, 256, 1, 1, 0, (16, 32)),
-                                                        (128, 128, 3, 2, 1, (32, 48)), (256, 3072, 2, 2, 0, (16, 24))])
+                                                        (128, 128, 3, 2, 1, (32, 48)), (256, 3072, 2, 2, 0, (16, 24)),
+                                                        # output rows that tile into 64-pixel blocks: the implicit (im2col-free) kernel
+                                                        (64, 128, 3, 1, 1, (8, 128)), (64, 64, 3, 1, 1, (16, 16)), (128, 128, 3, 2, 1, (32, 256)),
+                                                        (128, 128, 3, 2, 1, (32, 32)), (256, 3072, 2, 2, 0, (16, 128)), (128, 64, 3, 1, 1, (4, 192))])
 def test_conv_weight_and_bias_gradient(ops, cin, cout, k, stride, pad, hw):
     g = torch.Generator(device="cuda").manual_seed(cin + cout + k + 1)
     x = torch.randn(2, cin, *hw, device="cuda", generator=g).bfloat16()
@@ -74,3 +77,26 @@ def test_conv_weight_and_bias_gradient(ops, cin, cout, k, stride, pad, hw):
     dw2, db2 = ops.conv2d_nhwc_wgrad(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous(), k, k, stride=stride, pad=pad,
                                      dw=dw.clone(), db=db.clone(), accumulate=True)
     assert _rel(dw2, 2 * dw.float()) < 4e-3 and torch.allclose(db2, 2 * db, rtol=1e-5, atol=1e-4)
+    ho, wo = y.shape[2], y.shape[3]
+    implicit = (wo % 64 == 0) or (64 % wo == 0 and (ho * wo) % 64 == 0)
+    from x2i_b200 import _lib
+    assert bool(_lib.lib().x2i_conv2d_nhwc_wgrad_supported(hw[0], hw[1], cin, cout, k, k, stride, pad, pad)) == implicit
+    if implicit:  # same result through the explicit im2col + GEMM form (one bf16 rounding per image there, one in total here)
+        ops.implicit_conv_wgrad = False
+        try:
+            dw3, _ = ops.conv2d_nhwc_wgrad(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous(), k, k, stride=stride, pad=pad)
+        finally:
+            ops.implicit_conv_wgrad = True
+        assert _rel(dw3, dw.float()) < 6e-3
+
+
+def test_conv_weight_gradient_asymmetric_padding(ops):
+    """The VAE encoder's down-sampling convs: F.pad(x, (0, 1, 0, 1)) + 3x3 / stride 2 / no padding = pad 0, pad_end 1."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(2, 128, 32, 128, device="cuda", generator=g).bfloat16()
+    wr = (torch.randn(128, 128, 3, 3, device="cuda", generator=g) * 0.05).requires_grad_(True)
+    y = F.conv2d(F.pad(x.float(), (0, 1, 0, 1)), wr, None, stride=2)
+    dy = torch.randn(y.shape, device="cuda", generator=g).bfloat16()
+    y.backward(dy.float())
+    dw, _ = ops.conv2d_nhwc_wgrad(x.permute(0, 2, 3, 1).contiguous(), dy.permute(0, 2, 3, 1).contiguous(), 3, 3, stride=2, pad=0, pad_end=1)
+    assert _rel(ops.unpack_conv_weight_grad(dw, 128, 3, 3), wr.grad) < 4e-3

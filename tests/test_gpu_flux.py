@@ -115,6 +115,23 @@ def test_pipeline_four_step_sampling_matches_oracle(env):
     o1 = pipe(prompt_embeds=prompt.cuda(), pooled_prompt_embeds=pooled.cuda(), num_inference_steps=4, height=128, width=128,
               output_type="latent", latents=mine).images
     assert torch.equal(mine, keep) and torch.equal(o1, out)
+    # every step's AdaLN modulation from ONE pass over the modulation weights (default) == the per-step GEMV, bit for bit; also on the
+    # eager path and with the guidance embedding (dev configuration)
+    for cfg2, graph in ((cfg, True), (cfg, False), (env.tiny_config(True), True)):
+        m2 = model if cfg2 is cfg else env.make_pair(cfg2, seed=13)[0]
+        p2 = FluxPipeline(scheduler=FlowMatchEulerDiscreteScheduler(shift=1.0), transformer=m2)
+        m2.use_cuda_graph = graph
+        kw = dict(prompt_embeds=prompt.cuda(), pooled_prompt_embeds=pooled.cuda(), num_inference_steps=3, height=128, width=128,
+                  output_type="latent", latents=packed.cuda(), guidance_scale=2.5)
+        try:
+            hoisted = p2(**kw).images
+            p2.hoist_modulation = False
+            plain = p2(**kw).images
+        finally:
+            m2.use_cuda_graph = True
+        assert torch.equal(hoisted, plain)
+    mods = model.precompute_modulation(torch.tensor([1.0, 0.5], device="cuda"), pooled.cuda())
+    assert mods.shape[:2] == (2, 2) and mods.dtype == torch.bfloat16
 
 
 @pytest.mark.parametrize("S,hl,wl,outliers", [(203, 16, 24, False), (512, 64, 64, False), (512, 64, 64, True)])

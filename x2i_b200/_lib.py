@@ -73,6 +73,7 @@ SIGNATURES = {
     "x2i_relu_bwd": [_vp, _vp, _vp, _i64, _vp],
     "x2i_silu": [_vp, _vp, _i64, _vp],
     "x2i_im2col_nhwc": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "x2i_conv2d_nhwc_wgrad": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "x2i_groupnorm_nhwc_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp],
     # ---- VAE decoder
     "x2i_gemm_f32": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp],
@@ -94,6 +95,8 @@ SIZE_FUNCS = {
     "x2i_groupnorm_workspace_floats": [_i, _i, _i],
     "x2i_groupnorm_bwd_workspace_floats": [_i, _i, _i, _i],
     "x2i_gemm_wgrad_workspace_floats": [_i, _i, _i],
+    "x2i_conv2d_nhwc_wgrad_supported": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
+    "x2i_conv2d_nhwc_wgrad_workspace_floats": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i],
 }
 
 

@@ -109,9 +109,9 @@ int make_map(DeviceInfo* d, CUtensorMap* m, const void* ptr, int rank, const uin
   return X2I_OK;
 }
 
-template <int BN, int EPI, bool B_MN, bool A_MN = false>
+template <int BN, int EPI, bool B_MN, bool A_MN = false, int B_CONV = 0>
 int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_tcgen05_kernel<BN, EPI, B_MN, A_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, EPI, B_MN, A_MN, B_CONV>;
   static std::atomic<bool> configured[16];  // per device, per instantiation (keeps the call out of graph captures)
   if (!configured[d->index].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
@@ -1319,6 +1319,96 @@ int x2i_conv2d_nhwc_grouped(const void* x, const void* w, const void* bias, cons
     case 64 * 8 + 2: return launch_conv_t<64, 2>(d, ta, tb, cp, st);
     default: return launch_conv_t<64, 1>(d, ta, tb, cp, st);
   }
+}
+
+// ---- implicit convolution weight gradient: dW[Cout, (ky, kx, Cin)] (packed layout of pack_conv_weight) over ALL images in one launch
+static bool conv_wgrad_geometry(int Ho, int Wo, int* box_w, int* box_h) {
+  if (Wo >= 64) {
+    if (Wo % 64) return false;
+    *box_w = 64; *box_h = 1;
+    return true;
+  }
+  if (Wo <= 0 || 64 % Wo || (static_cast<long long>(Ho) * Wo) % 64) return false;
+  *box_w = Wo; *box_h = 64 / Wo;
+  return true;
+}
+static int conv_wgrad_ksplit(DeviceInfo* d, long long pixels, int Cout, int ncol) {
+  const int bn = ncol % 128 == 0 ? 128 : 64;
+  const long long tiles = static_cast<long long>((Cout + 127) / 128) * (ncol / bn);
+  const int num_kb = static_cast<int>(pixels / GEMM_BK);
+  if (tiles * 2 > d->sms || num_kb < 16) return 1;
+  int s = static_cast<int>((d->sms + tiles - 1) / tiles);
+  if (s > num_kb / 4) s = num_kb / 4;
+  const int per = (num_kb + s - 1) / s;
+  s = (num_kb + per - 1) / per;
+  return s < 2 ? 1 : s;
+}
+int64_t x2i_conv2d_nhwc_wgrad_supported(int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int pad_end) {
+  if (Cin <= 0 || Cin % 64 || Cout <= 0 || Cout % 8 || KH <= 0 || KW <= 0 || KH > 3 || KW > 3 || pad < 0 || pad > 1 || pad_end < 0 || pad_end > 1) return 0;
+  if (stride != 1 && stride != 2) return 0;
+  if (stride == 2 && ((H | W) & 1)) return 0;
+  const int Ho = (H + pad + pad_end - KH) / stride + 1, Wo = (W + pad + pad_end - KW) / stride + 1;
+  int bw, bh;
+  return conv_wgrad_geometry(Ho, Wo, &bw, &bh) ? 1 : 0;
+}
+int64_t x2i_conv2d_nhwc_wgrad_workspace_floats(int Nimg, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int pad_end) {
+  DeviceInfo* d;
+  if (device_info(&d)) return 0;
+  const int Ho = (H + pad + pad_end - KH) / stride + 1, Wo = (W + pad + pad_end - KW) / stride + 1;
+  const int ncol = KH * KW * Cin;
+  const int s = conv_wgrad_ksplit(d, static_cast<long long>(Nimg) * Ho * Wo, Cout, ncol);
+  return s > 1 ? static_cast<int64_t>(s) * Cout * ncol : 0;
+}
+int x2i_conv2d_nhwc_wgrad(const void* x, const void* dy, void* dw, float* workspace, int64_t workspace_floats, int Nimg, int H, int W, int Cin,
+                          int Cout, int KH, int KW, int stride, int pad, int pad_end, int accumulate, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (Nimg <= 0 || !x2i_conv2d_nhwc_wgrad_supported(H, W, Cin, Cout, KH, KW, stride, pad, pad_end))
+    return fail(X2I_ERR_SHAPE, "conv2d_nhwc_wgrad: need Cin %% 64 == 0, kernel <= 3x3, stride 1 / 2, and output rows that tile into 64-pixel blocks "
+                               "(Wo %% 64 == 0, or 64 %% Wo == 0 with Ho * Wo %% 64 == 0)");
+  if (!x || !dy || !dw || !aligned16(x) || !aligned16(dy) || !aligned16(dw)) return fail(X2I_ERR_ALIGN, "conv2d_nhwc_wgrad: null / unaligned buffer");
+  const int Ho = (H + pad + pad_end - KH) / stride + 1, Wo = (W + pad + pad_end - KW) / stride + 1;
+  int bw = 0, bh = 0;
+  conv_wgrad_geometry(Ho, Wo, &bw, &bh);
+  const int ncol = KH * KW * Cin;
+  const long long pixels = static_cast<long long>(Nimg) * Ho * Wo;
+  if (pixels > 0x7fffffffLL) return fail(X2I_ERR_SHAPE, "conv2d_nhwc_wgrad: too many output pixels");
+  const int s = conv_wgrad_ksplit(d, pixels, Cout, ncol);
+  if (s > 1 && (!workspace || !aligned16(workspace) || workspace_floats < static_cast<int64_t>(s) * Cout * ncol))
+    return fail(X2I_ERR_SHAPE, "conv2d_nhwc_wgrad: workspace of x2i_conv2d_nhwc_wgrad_workspace_floats() floats required");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = Cout; p.N = ncol; p.K = static_cast<int>(pixels);
+  p.cv_cin = Cin; p.cv_kw = KW; p.cv_pad = pad; p.cv_wo = Wo; p.cv_howo = Ho * Wo;
+  if (s > 1) {
+    p.c32 = workspace; p.ldc32 = ncol; p.ksplit = s;
+  } else {
+    p.C = static_cast<__nv_bfloat16*>(dw); p.ldc = ncol;
+    if (accumulate) { p.residual = p.C; p.ldr = ncol; }
+  }
+  CUtensorMap ta, tb;
+  uint32_t b64[2] = {64, 64};
+  uint64_t da[2] = {(uint64_t)Cout, (uint64_t)pixels}, sa[2] = {1, (uint64_t)Cout};
+  if (int rc = make_map(d, &ta, dy, 2, da, sa, b64)) return rc;
+  if (stride == 1) {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)Nimg};
+    uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
+    uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+    if (int rc = make_map(d, &tb, x, 4, dims, str, box)) return rc;
+  } else {  // parity view [2C, W/2, 2, H/2, N] (see x2i_conv2d_nhwc_grouped)
+    uint64_t dims[5] = {(uint64_t)2 * Cin, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)Nimg};
+    uint64_t str[5] = {1, (uint64_t)2 * Cin, (uint64_t)W * Cin, (uint64_t)2 * W * Cin, (uint64_t)H * W * Cin};
+    uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, 1};
+    if (int rc = make_map(d, &tb, x, 5, dims, str, box)) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (ncol % 128 == 0) rc = stride == 1 ? launch_gemm_t<128, EPI_DACT, true, true, 1>(d, ta, tb, p, st) : launch_gemm_t<128, EPI_DACT, true, true, 2>(d, ta, tb, p, st);
+  else rc = stride == 1 ? launch_gemm_t<64, EPI_DACT, true, true, 1>(d, ta, tb, p, st) : launch_gemm_t<64, EPI_DACT, true, true, 2>(d, ta, tb, p, st);
+  if (rc || s <= 1) return rc;
+  const long long n = static_cast<long long>(Cout) * (ncol / 8);
+  splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(workspace, static_cast<__nv_bfloat16*>(dw), ncol, Cout, ncol, s, accumulate);
+  return check_launch("splitk_reduce_kernel");
 }
 
 int x2i_conv_first(const void* x, const float* w, const float* bias, void* out, int Nimg, int H, int W, void* stream) {

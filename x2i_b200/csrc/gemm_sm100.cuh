@@ -77,6 +77,9 @@ struct GemmParams {
   const __nv_bfloat16* rowvec;
   long long rowvec_stride;
   int relu;
+  // B_CONV (implicit convolution weight gradient): B = the im2col matrix of an NHWC tensor, never materialised -- the producer loads
+  // 64-pixel x 64-channel boxes of the tensor itself, shifted by the tap of the column block (zero padding = TMA's OOB fill)
+  int cv_cin, cv_kw, cv_pad, cv_wo, cv_howo;
 };
 
 constexpr int GEMM_BM = 128;
@@ -355,7 +358,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
   }
 }
 
-template <int BN, int EPI, bool B_MN, bool A_MN = false>
+// B_CONV = 1 (stride 1: 4-D map [C, W, H, N]) / 2 (stride 2: 5-D parity view [2C, W/2, 2, H/2, N]): with A_MN + B_MN this is the weight
+// gradient of a convolution, dW[Cout, (ky, kx, Cin)] = sum over output pixels of dY[pix, Cout] x X[pix * stride + tap - pad, Cin];
+// a k-block is 64 consecutive output pixels (whole rows of one image: the host checks Wo % 64 == 0, or 64 % Wo == 0 with
+// Ho * Wo % 64 == 0 and a box of 64 / Wo rows), the column block selects (tap, 64 input channels).
+template <int BN, int EPI, bool B_MN, bool A_MN = false, int B_CONV = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -421,7 +428,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             for (int g = 0; g < GEMM_BM / 64; ++g)  // A stored [K, M]: boxes of 64 (m) x 64 (k rows)
               tma_load_2d(sa + g * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + g * 64, kb * GEMM_BK);
           }
-          if constexpr (!B_MN) {
+          if constexpr (B_CONV != 0) {
+            const int k0 = kb * GEMM_BK;
+            const int img = k0 / p.cv_howo, rem = k0 - img * p.cv_howo;
+            const int yo = rem / p.cv_wo, xo = rem - yo * p.cv_wo;
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g) {
+              const int col = n_blk * BN + g * 64;
+              const int tap = col / p.cv_cin, c0 = col - tap * p.cv_cin;
+              const int ky = tap / p.cv_kw, kx = tap - ky * p.cv_kw;
+              if constexpr (B_CONV == 1) {
+                tma_load_4d(sb + g * 8192, &tma_b, &full_bar[stage], c0, xo + kx - p.cv_pad, yo + ky - p.cv_pad, img);
+              } else {
+                const int tx = kx - p.cv_pad, ty = ky - p.cv_pad;  // input pixel = 2 * output pixel + t, t in {-1, 0, 1}
+                const int px = tx & 1, py = ty & 1;
+                tma_load_5d(sb + g * 8192, &tma_b, &full_bar[stage], px * p.cv_cin + c0, xo + ((tx - px) >> 1), py, yo + ((ty - py) >> 1), img);
+              }
+            }
+          } else if constexpr (!B_MN) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
           } else {
 #pragma unroll

@@ -723,10 +723,15 @@ def conv2d_nhwc_dgrad(dy, w, stride=1, pad=1):
     raise _lib.X2IError("conv2d_nhwc_dgrad: supported forms are stride 1 (k - 1 - pad in {0, 1}), 3x3/s2/p1 and 2x2/s2/p0")
 
 
+implicit_conv_wgrad = True  # tests flip this to compare the implicit kernel with the explicit im2col + GEMM form
+
+
 def conv2d_nhwc_wgrad(x, dy, kh, kw, stride=1, pad=1, pad_end=None, dw=None, db=None, accumulate=False):
     """Weight and bias gradient of conv2d_nhwc: x [N, H, W, Cin], dy [N, Ho, Wo, Cout] -> (dW bf16 in the PACKED layout
-    [Cout, kh*kw*Cin] of pack_conv_weight, db fp32 [Cout]).  Explicit form: one image at a time, im2col (x2i_im2col_nhwc) + the
-    MN-major wgrad GEMM accumulating over the images; db = column sums of dy.  unpack_conv_weight_grad() gives PyTorch's layout."""
+    [Cout, kh*kw*Cin] of pack_conv_weight, db fp32 [Cout]).  Implicit form (x2i_conv2d_nhwc_wgrad: tap-shifted TMA boxes of x as the
+    GEMM's B operand, all images in one launch) when the output rows tile into 64-pixel blocks; otherwise the explicit form: one image
+    at a time, im2col (x2i_im2col_nhwc) + the MN-major wgrad GEMM accumulating over the images.  db = column sums of dy.
+    unpack_conv_weight_grad() gives PyTorch's layout."""
     _chk(x, "x"); _chk(dy, "dy"); _chk(dw, "dw"); _chk(db, "db", F32)
     N, H, W, Cin = x.shape
     _, Ho, Wo, Cout = dy.shape
@@ -739,10 +744,18 @@ def conv2d_nhwc_wgrad(x, dy, kh, kw, stride=1, pad=1, pad_end=None, dw=None, db=
         dw = torch.empty(Cout, kh * kw * Cin, device=x.device, dtype=BF16)
         db = torch.empty(Cout, device=x.device, dtype=F32)
         accumulate = False
-    cols = torch.empty(Ho * Wo, kh * kw * Cin, device=x.device, dtype=BF16)
-    for n in range(N):
-        _lib.call("x2i_im2col_nhwc", _p(x[n]), _p(cols), 1, H, W, Cin, kh, kw, stride, pad, pad_end, _stream())
-        linear_wgrad(dy[n].reshape(Ho * Wo, Cout), cols, out=dw, accumulate=accumulate or n > 0)
+    L = _lib.lib()
+    if implicit_conv_wgrad and L.x2i_conv2d_nhwc_wgrad_supported(H, W, Cin, Cout, kh, kw, stride, pad, pad_end):
+        # implicit form: the GEMM's B operand is x itself, loaded as tap-shifted boxes -- one launch for all images, no im2col buffer
+        nws = L.x2i_conv2d_nhwc_wgrad_workspace_floats(N, H, W, Cin, Cout, kh, kw, stride, pad, pad_end)
+        ws = _ws_f32("conv_wgrad_splitk", nws, x.device) if nws > 0 else None
+        _lib.call("x2i_conv2d_nhwc_wgrad", _p(x), _p(dy), _p(dw), _p(ws), nws, N, H, W, Cin, Cout, kh, kw, stride, pad, pad_end,
+                  1 if accumulate else 0, _stream())
+    else:  # explicit form (output rows that do not tile into 64-pixel blocks)
+        cols = torch.empty(Ho * Wo, kh * kw * Cin, device=x.device, dtype=BF16)
+        for n in range(N):
+            _lib.call("x2i_im2col_nhwc", _p(x[n]), _p(cols), 1, H, W, Cin, kh, kw, stride, pad, pad_end, _stream())
+            linear_wgrad(dy[n].reshape(Ho * Wo, Cout), cols, out=dw, accumulate=accumulate or n > 0)
     colsum(dy.reshape(N * Ho * Wo, Cout), 1, N * Ho * Wo, out0=db.view(1, Cout), accumulate=accumulate)
     return dw, db
 

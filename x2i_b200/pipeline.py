@@ -121,6 +121,8 @@ class FluxPipeline:
     """Latent-space FLUX sampler: ``pipeline(prompt_embeds=, pooled_prompt_embeds=, num_inference_steps=,
     guidance_scale=, height=, width=, output_type="latent", generator=).images -> [B, (h/16)(w/16), 64]``."""
 
+    hoist_modulation = True  # all steps' AdaLN modulations in one pass over the modulation weights (bit-identical; see __call__)
+
     def __init__(self, scheduler=None, vae=None, text_encoder=None, tokenizer=None, text_encoder_2=None, tokenizer_2=None,
                  transformer=None):
         self.scheduler = scheduler if scheduler is not None else FlowMatchEulerDiscreteScheduler()
@@ -236,13 +238,20 @@ class FluxPipeline:
         guidance = None
         if self.transformer.config.guidance_embeds:
             guidance = torch.full([1], guidance_scale, device=device, dtype=torch.float32).expand(B)
+        # The AdaLN modulations depend only on (timestep, guidance, pooled text): all steps' rows come out of ONE pass over the 6.5 GB of
+        # modulation weights (bit-identical to the per-step GEMV; FluxTransformer2DModel.precompute_modulation).  A foreign transformer
+        # without that method is called the plain way.
+        extra = [{} for _ in range(num_inference_steps)]
+        if self.hoist_modulation and hasattr(self.transformer, "precompute_modulation"):
+            mods = self.transformer.precompute_modulation(ts.to(latents.dtype) / 1000, pooled_prompt_embeds, guidance)
+            extra = [dict(x2i_modulation=mods[i]) for i in range(num_inference_steps)]
         for i in range(num_inference_steps):
             timestep = ts[i].expand(B).to(latents.dtype)
             noise_pred = self.transformer(hidden_states=latents, timestep=timestep / 1000, guidance=guidance,
                                           pooled_projections=pooled_prompt_embeds, encoder_hidden_states=prompt_embeds,
                                           txt_ids=text_ids, img_ids=latent_image_ids,
                                           joint_attention_kwargs=joint_attention_kwargs, guided_hint=guided_hint,
-                                          control_nets=control_nets, return_dict=False)[0]
+                                          control_nets=control_nets, return_dict=False, **extra[i])[0]
             latents = self.scheduler.step(noise_pred, ts[i], latents, return_dict=False)[0]
         if output_type != "latent":  # diffusers' tail: unpack -> un-scale -> vae.decode -> image_processor.postprocess
             from .vae import VaeImageProcessor
