@@ -458,7 +458,7 @@ static int wgrad_ksplit(DeviceInfo* d, int M, int N, int K) {
   const long long tiles = static_cast<long long>((N + 127) / 128) * ((K + bn - 1) / bn);
   const int num_kb = (M + GEMM_BK - 1) / GEMM_BK;
   if (tiles * 2 > d->sms || num_kb < 16) return 1;
-  int s = static_cast<int>((d->sms + tiles - 1) / tiles);
+  int s = static_cast<int>(d->sms / tiles);  // floor: tiles * s <= SMs, ONE wave (ceil gave e.g. 9 x 17 = 153 tiles on 148 SMs = two waves)
   if (s > num_kb / 4) s = num_kb / 4;  // at least 4 k-blocks per group
   const int per = (num_kb + s - 1) / s;
   s = (num_kb + per - 1) / per;        // no empty group
@@ -1337,7 +1337,7 @@ static int conv_wgrad_ksplit(DeviceInfo* d, long long pixels, int Cout, int ncol
   const long long tiles = static_cast<long long>((Cout + 127) / 128) * (ncol / bn);
   const int num_kb = static_cast<int>(pixels / GEMM_BK);
   if (tiles * 2 > d->sms || num_kb < 16) return 1;
-  int s = static_cast<int>((d->sms + tiles - 1) / tiles);
+  int s = static_cast<int>(d->sms / tiles);  // floor: tiles * s <= SMs, ONE wave (ceil gave e.g. 9 x 17 = 153 tiles on 148 SMs = two waves)
   if (s > num_kb / 4) s = num_kb / 4;
   const int per = (num_kb + s - 1) / s;
   s = (num_kb + per - 1) / per;
@@ -1533,7 +1533,7 @@ int x2i_groupnorm_nhwc_bwd(const void* x, const void* dy, const void* gamma, con
   if (int rc = check_launch("gn_stats_final_kernel")) return rc;
   gn_bwd_partial_kernel<<<dim3(nsplit, Nimg), 256, 0, st>>>(X, DY, stats, GA, BE, part2, HW, C, G, nsplit, act);
   if (int rc = check_launch("gn_bwd_partial_kernel")) return rc;
-  gn_bwd_final_kernel<<<Nimg * G, 128, 0, st>>>(part2, GA, chan, gsum, C, G, nsplit, static_cast<double>(HW) * (C / G));
+  gn_bwd_final_kernel<<<Nimg * G, 256, (C / G) * 2 * sizeof(double), st>>>(part2, GA, chan, gsum, C, G, nsplit, static_cast<double>(HW) * (C / G));
   if (int rc = check_launch("gn_bwd_final_kernel")) return rc;
   gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(chan, dgamma, dbeta, Nimg, C, accumulate);
   if (int rc = check_launch("gn_bwd_param_kernel")) return rc;

@@ -416,6 +416,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         const int ks = tile / num_mn, mn = tile - ks * num_mn;
         const int m_blk = mn % num_m, n_blk = mn / num_m;
         const int kb0 = ks * kb_per, kb1 = min(kb0 + kb_per, num_kb);
+        // B_CONV: per tile, the (tap, channel block) of each 64-column group and the first output pixel of the k range; the single
+        // producer thread must not divide per k-block (a k-block is only 192-256 tensor-pipe cycles)
+        [[maybe_unused]] int cv_c[BN / 64], cv_dx[BN / 64], cv_dy[BN / 64], cv_py[BN / 64];
+        [[maybe_unused]] int cv_img = 0, cv_yo = 0, cv_xo = 0, cv_rows = 1, cv_ho = 1;
+        if constexpr (B_CONV != 0) {
+#pragma unroll
+          for (int g = 0; g < BN / 64; ++g) {
+            const int col = n_blk * BN + g * 64;
+            const int tap = col / p.cv_cin, c0 = col - tap * p.cv_cin;
+            const int ky = tap / p.cv_kw, kx = tap - ky * p.cv_kw;
+            if constexpr (B_CONV == 1) {
+              cv_c[g] = c0; cv_dx[g] = kx - p.cv_pad; cv_dy[g] = ky - p.cv_pad; cv_py[g] = 0;
+            } else {  // input pixel = 2 * output pixel + t, t in {-1, 0, 1}: parity t & 1, half-resolution offset (t - parity) / 2
+              const int tx = kx - p.cv_pad, ty = ky - p.cv_pad;
+              const int px = tx & 1, py = ty & 1;
+              cv_c[g] = px * p.cv_cin + c0; cv_dx[g] = (tx - px) >> 1; cv_dy[g] = (ty - py) >> 1; cv_py[g] = py;
+            }
+          }
+          const int k0 = kb0 * GEMM_BK;
+          cv_img = k0 / p.cv_howo;
+          const int rem = k0 - cv_img * p.cv_howo;
+          cv_yo = rem / p.cv_wo;
+          cv_xo = rem - cv_yo * p.cv_wo;
+          cv_rows = p.cv_wo >= GEMM_BK ? 1 : GEMM_BK / p.cv_wo;
+          cv_ho = p.cv_howo / p.cv_wo;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -429,21 +455,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
               tma_load_2d(sa + g * 8192, &tma_a, &full_bar[stage], m_blk * GEMM_BM + g * 64, kb * GEMM_BK);
           }
           if constexpr (B_CONV != 0) {
-            const int k0 = kb * GEMM_BK;
-            const int img = k0 / p.cv_howo, rem = k0 - img * p.cv_howo;
-            const int yo = rem / p.cv_wo, xo = rem - yo * p.cv_wo;
 #pragma unroll
             for (int g = 0; g < BN / 64; ++g) {
-              const int col = n_blk * BN + g * 64;
-              const int tap = col / p.cv_cin, c0 = col - tap * p.cv_cin;
-              const int ky = tap / p.cv_kw, kx = tap - ky * p.cv_kw;
-              if constexpr (B_CONV == 1) {
-                tma_load_4d(sb + g * 8192, &tma_b, &full_bar[stage], c0, xo + kx - p.cv_pad, yo + ky - p.cv_pad, img);
-              } else {
-                const int tx = kx - p.cv_pad, ty = ky - p.cv_pad;  // input pixel = 2 * output pixel + t, t in {-1, 0, 1}
-                const int px = tx & 1, py = ty & 1;
-                tma_load_5d(sb + g * 8192, &tma_b, &full_bar[stage], px * p.cv_cin + c0, xo + ((tx - px) >> 1), py, yo + ((ty - py) >> 1), img);
-              }
+              if constexpr (B_CONV == 1) tma_load_4d(sb + g * 8192, &tma_b, &full_bar[stage], cv_c[g], cv_xo + cv_dx[g], cv_yo + cv_dy[g], cv_img);
+              else tma_load_5d(sb + g * 8192, &tma_b, &full_bar[stage], cv_c[g], cv_xo + cv_dx[g], cv_py[g], cv_yo + cv_dy[g], cv_img);
+            }
+            cv_xo += GEMM_BK;  // next 64 output pixels: whole rows of one image (host-checked geometry), no division on this path
+            if (cv_xo >= p.cv_wo) {
+              cv_xo = 0;
+              cv_yo += cv_rows;
+              if (cv_yo >= cv_ho) { cv_yo = 0; ++cv_img; }
             }
           } else if constexpr (!B_MN) {
             tma_load_2d(sb, &tma_b, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
