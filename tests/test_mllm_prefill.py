@@ -198,6 +198,18 @@ def test_tiny_prefill_matches_transformers(ops, B, S, pads):
     out = m.generate(input_ids=ids.cuda(), attention_mask=mask.cuda(), max_new_tokens=1, output_hidden_states=True, return_dict_in_generate=True)
     assert torch.equal(torch.stack(out["hidden_states"][0], dim=1), got)                    # train_qwenvl.py:775 on the drop-in's output
     assert out.text_embeddings.data_ptr() == out["hidden_states"][0][0].data_ptr()          # the tuple entries are views: no copy
+    # the default path replays one captured CUDA graph per (B, S); launch by launch it computes the same bits, and a second prompt of the
+    # same shape through the same graph is not contaminated by the first
+    m.use_cuda_graph = False
+    try:
+        assert torch.equal(m.prefill_hidden_states(ids.cuda(), mask.cuda()), got)
+        ids2 = torch.randint(0, 1000, (B, S), generator=torch.Generator().manual_seed(5))
+        eager2 = m.prefill_hidden_states(ids2.cuda(), mask.cuda())
+    finally:
+        m.use_cuda_graph = True
+    assert torch.equal(m.prefill_hidden_states(ids2.cuda(), mask.cuda()), eager2)
+    user_out = torch.empty_like(got)
+    assert m.prefill_hidden_states(ids.cuda(), mask.cuda(), out=user_out) is user_out and torch.equal(user_out, got)
 
 
 @gpu

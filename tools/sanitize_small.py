@@ -31,6 +31,11 @@ def main():
     do_hm, delta = ops.attention_bwd_prep(do[:, :44].contiguous(), do[:, 44:].contiguous(), o0, o1, B, H, L, 44)
     dq, dk, dv = ops.attention_bwd(q, k, v, do_hm, lse, delta)
     print("attn bwd finite", bool(torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all() and torch.isfinite(dv.float()).all()))
+    # the 2-CTA cluster form of the backward (TMA multicast of the streamed tiles, multicast commits; odd tile count -> padding tile)
+    os.environ["X2I_ATTN_BWD_MC"] = "1"
+    dq2, dk2, dv2 = ops.attention_bwd(q, k, v, do_hm, lse, delta)
+    del os.environ["X2I_ATTN_BWD_MC"]
+    print("attn bwd cluster form bit-identical", bool(torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)))
     # cross-attention form with key-padding lengths (resampler)
     qc, kc, vc = rn(2, 2, 64, 128, seed=5), rn(2, 2, 200, 128, seed=6), rn(2, 2, 200, 128, seed=7)
     oc = ops.cross_attention(qc, kc, vc, kv_len=torch.tensor([200, 77], device="cuda", dtype=torch.int32))
@@ -58,6 +63,12 @@ def main():
     xi, wi, bi = rn(1, 16, 24, 64, seed=16), rn(128, 64, 3, 3, seed=17, scale=0.05), rn(128, seed=18, scale=0.1)
     yc = ops.conv2d_nhwc(xi, ops.pack_conv_weight(wi), bi, 3, 3, stride=1, pad=1)
     print("conv finite", bool(torch.isfinite(yc.float()).all()))
+    # implicit conv weight gradient (tap-shifted boxes as the wgrad GEMM's B operand), stride 1 and the stride-2 parity view
+    xw, dyw = rn(2, 8, 64, 64, seed=19), rn(2, 8, 64, 128, seed=20)
+    dw1, _ = ops.conv2d_nhwc_wgrad(xw, dyw, 3, 3, stride=1, pad=1)
+    xs, dys = rn(1, 16, 128, 64, seed=21), rn(1, 8, 64, 64, seed=22)
+    dw2, _ = ops.conv2d_nhwc_wgrad(xs, dys, 3, 3, stride=2, pad=1)
+    print("implicit conv wgrad finite", bool(torch.isfinite(dw1.float()).all() and torch.isfinite(dw2.float()).all()))
     torch.cuda.synchronize()
     print("done")
 

@@ -165,6 +165,26 @@ int pick_bn(int N, int M) {
   return 64;
 }
 
+// Tile shape for a plain-epilogue GEMM from a wave model: cost = waves x tensor-pipe cycles of one k16 step of a tile
+// (tools/ubench/mma_rate.cu: M = 128 x N = 256 / 128 / 64 cost 128 / 64 / 48 cycles -- N = 64 is paced by the shared-memory port; a CTA-pair
+// 256 x 256 tile costs 128 on two SMs).  Bigger tiles win ties and near-ties (less shared-memory and L2 traffic per FLOP); small-M problems
+// (the M = 512 GEMMs of the MLLM prefill and the projector: 16-32 pair tiles on 148 SMs) move to narrow tiles that fill the machine.
+struct TileChoice { bool pair; int bn; };
+TileChoice choose_tiles(DeviceInfo* d, int M, int N, bool pair_ok) {
+  const long long m128 = (M + 127) / 128, m256 = (M + 255) / 256;
+  auto cost = [](long long tiles, int units, int cyc) { return ((tiles + units - 1) / units) * cyc; };
+  TileChoice c{false, pick_bn(N, M)};
+  long long best = -1;
+  auto consider = [&](bool pair, int bn, long long v) {
+    if (best < 0 || v * 100 < best * 95) { best = v; c = TileChoice{pair, bn}; }
+  };
+  if (pair_ok) consider(true, 256, cost(m256 * (N / 256), d->sms / 2, 128));
+  if (N % 256 == 0) consider(false, 256, cost(m128 * (N / 256), d->sms, 128));
+  if (N % 128 == 0) consider(false, 128, cost(m128 * (N / 128), d->sms, 64));
+  if (N % 64 == 0) consider(false, 64, cost(m128 * (N / 64), d->sms, 48));
+  return c;
+}
+
 template <int EPI>
 int launch_gemm(DeviceInfo* d, const void* A, int64_t lda, const void* W, int64_t ldw, GemmParams& p, cudaStream_t st,
                 int force_bn = 0) {
@@ -173,7 +193,11 @@ int launch_gemm(DeviceInfo* d, const void* A, int64_t lda, const void* W, int64_
   if (!aligned16(A) || !aligned16(W) || lda % 8 || ldw % 8) return fail(X2I_ERR_ALIGN, "gemm: A/W must be 16-byte aligned with ld %% 8 == 0");
   int bn = force_bn ? force_bn : pick_bn(p.N, p.M);
   if (EPI == EPI_QKV && bn == 64) return fail(X2I_ERR_SHAPE, "qkv gemm: N must be a multiple of 128");
-  const bool pair = !force_bn && use_pair_kernel() && p.N % 256 == 0 && p.M > 128;
+  bool pair = !force_bn && use_pair_kernel() && p.N % 256 == 0 && p.M > 128;
+  if (!force_bn && (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU_TANH || EPI == EPI_BIAS_GELU_ERF || EPI == EPI_GATE_RESIDUAL || EPI == EPI_DACT)) {
+    const TileChoice tc = choose_tiles(d, p.M, p.N, pair);
+    pair = tc.pair; bn = tc.bn;
+  }
   CUtensorMap ta, tb;
   uint64_t da[2] = {(uint64_t)p.K, (uint64_t)p.M}, sa[2] = {1, (uint64_t)lda};
   uint32_t ba[2] = {GEMM_BK, GEMM_BM};

@@ -30,7 +30,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from ._lib import X2IError
 
 BF16 = torch.bfloat16
@@ -159,18 +159,57 @@ class Qwen2_5_VLTextPrefill(nn.Module):
         """input_ids [B, S] int64, attention_mask [B, S] (1 = token, left-padded) -> text_embeddings [B, C, S, H] bf16 with
         C = num_hidden_layers + 1, exactly ``torch.stack(generate(...).hidden_states[0], dim=1)``."""
         cfg = self.config
-        pk = self._pack()
+        self._pack()
         dev = self.embed_tokens.weight.device
         input_ids = input_ids.to(dev)
         B, S = input_ids.shape
-        H, Hq, Hkv, L = cfg.hidden_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.num_hidden_layers
+        H, L = cfg.hidden_size, cfg.num_hidden_layers
         if attention_mask is None:
             attention_mask = torch.ones(B, S, dtype=torch.int64, device=dev)
         pos, start = self.text_positions(attention_mask.to(dev))
-        if out is None:
-            out = torch.empty(B, L + 1, S, H, device=dev, dtype=BF16)
-        elif out.shape != (B, L + 1, S, H) or out.dtype != BF16 or not out.is_contiguous():
+        if out is not None and (out.shape != (B, L + 1, S, H) or out.dtype != BF16 or not out.is_contiguous()):
             raise X2IError("prefill_hidden_states: out must be a contiguous bf16 [B, num_layers + 1, S, hidden] tensor")
+        if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
+            if out is None:
+                out = torch.empty(B, L + 1, S, H, device=dev, dtype=BF16)
+            return self._prefill_body(input_ids, pos, start, out)
+        # One captured graph per (B, S): ~8 launches per layer are host-bound when issued one by one (295 launches in 6.4 ms for the 3B
+        # model against ~3.5 ms of GPU time).  Inputs are copied into the graph's static buffers, the capture buffer is copied out.
+        w0 = self.layers[0].self_attn.q_proj.weight
+        key = (B, S, w0.data_ptr(), w0._version)
+        st = self._graphs.get(key)
+        if st is None:
+            sin = dict(ids=input_ids.clone(), pos=pos.clone(), start=start.clone(),
+                       out=torch.empty(B, L + 1, S, H, device=dev, dtype=BF16))
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up outside the capture: function attributes, workspaces
+                self._prefill_body(sin["ids"], sin["pos"], sin["start"], sin["out"])
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                self._prefill_body(sin["ids"], sin["pos"], sin["start"], sin["out"])
+            st = (graph, sin, _lib.launch_count() - n0)
+            self._graphs = {key: st}  # one shape resident
+        graph, sin, n_kernels = st
+        sin["ids"].copy_(input_ids, non_blocking=True)
+        sin["pos"].copy_(pos, non_blocking=True)
+        sin["start"].copy_(start, non_blocking=True)
+        graph.replay()
+        _lib.note_graph_replay(n_kernels)
+        if out is None:
+            return sin["out"].clone()
+        out.copy_(sin["out"])
+        return out
+
+    def _prefill_body(self, input_ids, pos, start, out):
+        cfg = self.config
+        pk = self._pack()
+        dev = out.device
+        B, S = input_ids.shape
+        H, Hq, Hkv, L = cfg.hidden_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.num_hidden_layers
         ops.gather_rows(input_ids, self.embed_tokens.weight, out[:, 0])
         xn = torch.empty(B, S, H, device=dev, dtype=BF16)
         qkv = torch.empty(B, S, (Hq + 2 * Hkv) * 128, device=dev, dtype=BF16)
@@ -197,6 +236,9 @@ class Qwen2_5_VLTextPrefill(nn.Module):
                 ops.linear_residual(act[b], layer.mlp.down_proj.weight, mid[b], h_out[b])
         ops.rmsnorm(last, self.norm.weight, cfg.rms_norm_eps, out=out[:, L])
         return out
+
+    use_cuda_graph = True  # replay one captured graph per (B, S) instead of ~8 launches per layer
+    _graphs = {}
 
     def generate(self, input_ids=None, attention_mask=None, max_new_tokens: int = 1, output_hidden_states: bool = True,
                  return_dict_in_generate: bool = True, **unused):
