@@ -16,6 +16,18 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
+// same as unpack8, but opaque to common-subexpression elimination: a kernel that keeps a row as packed bf16 and unpacks it once per
+// pass must not have the compiler keep the first pass's fp32 copy alive (that is the register footprint it is avoiding)
+__device__ __forceinline__ void unpack8_again(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t lo, hi;
+    asm volatile("shl.b32 %0, %2, 16;\n\tand.b32 %1, %2, 0xffff0000;" : "=r"(lo), "=r"(hi) : "r"(w[i]));
+    f[2 * i] = __uint_as_float(lo);
+    f[2 * i + 1] = __uint_as_float(hi);
+  }
+}
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 u;
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -55,8 +67,11 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red /* [NV * NW
 // y[r,:] = LayerNorm(x[r,:]) * (1 + scale[b,:]) + shift[b,:]     (no affine, eps inside sqrt), b = r / rows_per_batch
 // One warp per row, row kept in registers (D <= 32*8*MAXC).  AdaLayerNormZero / ZeroSingle / Continuous, norm2.
 // AFFINE: y = LN(x) * scale + shift (nn.LayerNorm weight / bias) instead of the AdaLN form LN(x) * (1 + scale) + shift.
+// The row stays in registers as PACKED bf16 (48 registers at D = 3072) and is unpacked in each of the three passes (sum, centred
+// squares, output): ~64 registers per thread instead of ~128, i.e. 4 CTAs per SM -- all 576 CTAs of a 4608-row call are resident at once
+// (one wave instead of 1.95), and the shared scale / shift rows are requested BEFORE the reductions so their L2 latency hides behind them.
 template <int MAXC, bool AFFINE = false>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+__global__ void __launch_bounds__(256, MAXC <= 12 ? 4 : 2) ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                           const __nv_bfloat16* __restrict__ scale,
                                                           const __nv_bfloat16* __restrict__ shift, long long mod_stride,
                                                           __nv_bfloat16* __restrict__ y, long long ldy, int rows, int D,
@@ -66,25 +81,30 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
   const int lane = threadIdx.x & 31;
   const int nchunk = D >> 3;  // 16-byte chunks per row
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
-  float v[MAXC][8];
+  uint4 raw[MAXC];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     const int c = i * 32 + lane;
-    if (c < nchunk) {
-      unpack8(xr[c], v[i]);
+    raw[i] = c < nchunk ? xr[c] : make_uint4(0, 0, 0, 0);
+  }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
-    }
+  for (int i = 0; i < MAXC; ++i) {
+    float v[8];
+    unpack8(raw[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];  // chunks beyond the row are zero
   }
   const float mean = warp_sum(s) / D;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     if (i * 32 + lane < nchunk) {
+      float v[8];
+      unpack8_again(raw[i], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
+        const float d = v[j] - mean;
         q += d * d;
       }
     }
@@ -98,13 +118,15 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __nv_bfloat16* _
   for (int i = 0; i < MAXC; ++i) {
     const int c = i * 32 + lane;
     if (c < nchunk) {
-      float a[8], h[8], o[8];
+      float v[8], a[8], h[8], o[8];
+      unpack8_again(raw[i], v);
       unpack8(__ldg(sc + c), a);
       unpack8(__ldg(sh + c), h);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * (AFFINE ? a[j] : 1.0f + a[j]) + h[j];
+      for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd * (AFFINE ? a[j] : 1.0f + a[j]) + h[j];
       yr[c] = pack8(o);
     }
+    if ((i & 1) == 1) asm volatile("" ::: "memory");  // keep at most two chunks' scale / shift loads in flight (register budget)
   }
 }
 
