@@ -274,6 +274,14 @@ int x2i_mean_over_s(const void* y, void* out, int B, int S, int N, void* stream)
  * x2i_proj_mix_ln that also stores xm bf16 [B,S,H], the mixed plane BEFORE the LayerNorm (needed by its backward).    */
 int x2i_proj_mix_ln_save(const void* x, int mode, const float* w, float conv_bias, const float* gamma, const float* beta,
                          float eps, void* y, void* xm, int B, int C, int S, int H, void* stream);
+/* Mode 0 (the 5x5 layer-mixing convolution, utils/proj.py:66-70) on the tensor pipe: the taps along H are a banded-Toeplitz B operand built
+ * in shared memory, the five row shifts re-read one TMA box through descriptor row offsets, fp32 accumulation in TMEM; then LayerNorm over H.
+ * Same results as x2i_proj_mix_ln(mode 0) up to fp32 summation order (bf16 taps: the reference's projector is bf16).  xm (nullable) receives
+ * the pre-LayerNorm plane in bf16.  workspace: _workspace_floats() floats.  _supported(): S % 128 == 0, C <= 40, 512 <= H <= 4096, H % 8 == 0. */
+int64_t x2i_proj_mix_ln_tc_supported(int B, int C, int S, int H);
+int64_t x2i_proj_mix_ln_tc_workspace_floats(int B, int C, int S, int H);
+int x2i_proj_mix_ln_tc(const void* x, const float* w, float conv_bias, const float* gamma, const float* beta, float eps, void* y, void* xm,
+                       float* workspace, int B, int C, int S, int H, void* stream);
 /* dy[b,s,:] = dpooled[b,:] / S : backward of the mean over S (utils/proj.py:32).                                    */
 int x2i_mean_over_s_bwd(const void* dpooled, void* dy, int B, int S, int N, void* stream);
 /* Weight gradient of the layer-mixing front end w.r.t. g = d loss / d mixed plane [B,S,H] (bf16):

@@ -107,3 +107,32 @@ def test_grouped_and_vae_entry_points_reject_bad_shapes():
         ops.softmax_rows(torch.zeros(2, 16388, device="cuda"))
     with pytest.raises(X2IError):          # fp32 GEMM needs N % 32 == 0
         ops.linear_f32(torch.randn(8, 64, device="cuda").bfloat16(), torch.randn(24, 64, device="cuda").bfloat16())
+
+
+@pytest.mark.parametrize("B,C,S,H", [(1, 5, 128, 512), (2, 37, 256, 2048), (1, 29, 128, 3584), (1, 3, 384, 520)])
+def test_layer_mixing_conv_on_the_tensor_pipe(chk, B, C, S, H):
+    """x2i_proj_mix_ln_tc (banded-Toeplitz tcgen05 form of utils/proj.py's Conv2d(C -> 1, 5x5) + LayerNorm) against torch's fp32
+    convolution on the same bf16 inputs and bf16 taps, and against the FP32-pipe stencil kernel it replaces for these shapes.
+    H = 520: the last 56-column tile is partial and the first starts left of the plane (zero padding = TMA out-of-bounds fill)."""
+    import torch.nn.functional as F
+    from x2i_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + C)
+    x = torch.randn(B, C, S, H, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(C, 25, device="cuda", generator=g) * 0.1).bfloat16().float()
+    gamma = (1 + 0.1 * torch.randn(H, device="cuda", generator=g)).float()
+    beta = (0.1 * torch.randn(H, device="cuda", generator=g)).float()
+    ref = F.conv2d(x.float(), w.view(1, C, 5, 5), torch.tensor([0.25], device="cuda"), padding=2)[:, 0]
+    refn = F.layer_norm(ref, (H,), gamma, beta, 1e-6)
+    from x2i_b200 import _lib
+    assert _lib.lib().x2i_proj_mix_ln_tc_supported(B, C, S, H) == 1
+    assert ops.proj_conv_tensor_cores
+    y, xm = ops.proj_mix_ln_save(x, 0, w, 0.25, gamma, beta, 1e-6)
+    ops.proj_conv_tensor_cores = False
+    try:
+        y0, xm0 = ops.proj_mix_ln_save(x, 0, w, 0.25, gamma, beta, 1e-6)
+    finally:
+        ops.proj_conv_tensor_cores = True
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())  # noqa: E731
+    assert rel(xm, ref) < 4e-3 and rel(y, refn) < 4e-3          # one bf16 rounding of the output
+    assert rel(y, y0) < 1e-3 and rel(xm, xm0) < 1e-3              # both kernels accumulate in fp32: they differ by summation order only
+    assert torch.equal(ops.proj_mix_ln(x, 0, w, 0.25, gamma, beta, 1e-6), y)

@@ -62,8 +62,13 @@ def main():
     m = pm.mlp
     ga, be, cb = m.layernorm.weight.detach().float(), m.layernorm.bias.detach().float(), float(pm.conv.bias.detach().float())
     t_pm = timed(lambda i: ops.proj_mix_ln(xin[i % 3], 0, w, cb, ga, be, m.layernorm.eps), 20)
-    out.append(dict(kernel="proj_mix_ln_kernel [1,37,512,2048] (5x5 conv over layers + LN)", ms=t_pm * 1e3, gbs=37 * 512 * 2048 * 2 / t_pm / 1e9,
+    out.append(dict(kernel="proj_conv_tc_kernel + ln_rows_f32_kernel [1,37,512,2048] (5x5 conv over layers on the tensor pipe + LN)", ms=t_pm * 1e3, gbs=37 * 512 * 2048 * 2 / t_pm / 1e9,
                     gflops=2 * 37 * 25 * 512 * 2048 / t_pm / 1e9))
+    ops.proj_conv_tensor_cores = False
+    t_st = timed(lambda i: ops.proj_mix_ln(xin[i % 3], 0, w, cb, ga, be, m.layernorm.eps), 20)
+    ops.proj_conv_tensor_cores = True
+    out.append(dict(kernel="proj_mix_ln_kernel [1,37,512,2048] (the FP32-pipe stencil it replaces: round 1)", ms=t_st * 1e3, gbs=37 * 512 * 2048 * 2 / t_st / 1e9,
+                    gflops=2 * 37 * 25 * 512 * 2048 / t_st / 1e9))
     for o in out:
         o["frac_of_measured_hbm"] = o["gbs"] / pk
         print(json.dumps(o))

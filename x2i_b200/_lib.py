@@ -59,6 +59,7 @@ SIGNATURES = {
     "x2i_colsum": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp],
     "x2i_skinny_linear_t": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
     "x2i_f32_to_bf16": [_vp, _vp, _i64, _vp],
+    "x2i_proj_mix_ln_tc": [_vp, _vp, _f, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "x2i_proj_mix_ln_save": [_vp, _i, _vp, _f, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp],
     "x2i_mean_over_s_bwd": [_vp, _vp, _i, _i, _i, _vp],
     "x2i_proj_mix_wgrad": [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -95,6 +96,8 @@ SIZE_FUNCS = {
     "x2i_groupnorm_workspace_floats": [_i, _i, _i],
     "x2i_groupnorm_bwd_workspace_floats": [_i, _i, _i, _i],
     "x2i_gemm_wgrad_workspace_floats": [_i, _i, _i],
+    "x2i_proj_mix_ln_tc_supported": [_i, _i, _i, _i],
+    "x2i_proj_mix_ln_tc_workspace_floats": [_i, _i, _i, _i],
     "x2i_conv2d_nhwc_wgrad_supported": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
     "x2i_conv2d_nhwc_wgrad_workspace_floats": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i],
 }

@@ -18,6 +18,7 @@
 #include "mllm_sm100.cuh"
 #include "rowwise.cuh"
 #include "rowwise_bwd.cuh"
+#include "projconv_sm100.cuh"
 
 using namespace x2i;
 
@@ -928,6 +929,48 @@ int proj_mix_ln_impl(const void* x, int mode, const float* w, float conv_bias, c
   return check_launch("proj_mix_ln_kernel");
 }
 }  // namespace
+
+// ---- the layer-mixing convolution on the tensor pipe (projconv_sm100.cuh): mode 0 of x2i_proj_mix_ln for S % 128 == 0, C <= 40
+int64_t x2i_proj_mix_ln_tc_supported(int B, int C, int S, int H) {
+  return (B > 0 && C > 0 && C <= 40 && S > 0 && S % 128 == 0 && H >= 512 && H % 8 == 0 && H <= 4096) ? 1 : 0;
+}
+int64_t x2i_proj_mix_ln_tc_workspace_floats(int B, int C, int S, int H) {
+  return x2i_proj_mix_ln_tc_supported(B, C, S, H) ? static_cast<int64_t>(B) * S * H : 0;
+}
+int x2i_proj_mix_ln_tc(const void* x, const float* w, float conv_bias, const float* gamma, const float* beta, float eps, void* y, void* xm,
+                       float* workspace, int B, int C, int S, int H, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (!x2i_proj_mix_ln_tc_supported(B, C, S, H)) return fail(X2I_ERR_SHAPE, "proj_mix_ln_tc: need S %% 128 == 0, C <= 40, 512 <= H <= 4096, H %% 8 == 0");
+  if (!x || !w || !gamma || !beta || !y || !workspace) return fail(X2I_ERR_SHAPE, "proj_mix_ln_tc: null buffer");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(workspace) || !aligned16(gamma) || !aligned16(beta) || (xm && !aligned16(xm)))
+    return fail(X2I_ERR_ALIGN, "proj_mix_ln_tc: alignment");
+  ProjConvParams p;
+  p.B = B; p.C = C; p.S = S; p.H = H;
+  p.n_htiles = (H + PC_HSHIFT + PC_NV - 1) / PC_NV;
+  p.bias = conv_bias; p.w = w; p.out = workspace;
+  CUtensorMap tx;
+  uint64_t dims[3] = {(uint64_t)H, (uint64_t)S, (uint64_t)B * C}, str[3] = {1, (uint64_t)H, (uint64_t)S * H};
+  uint32_t box[3] = {64, (uint32_t)PC_A_ROWS, 1};
+  if (int rc = make_map(d, &tx, x, 3, dims, str, box)) return rc;
+  static std::atomic<bool> configured[16];
+  if (!configured[d->index].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(proj_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(proj_conv_tc): %s", cudaGetErrorString(e));
+    configured[d->index].store(true, std::memory_order_release);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  proj_conv_tc_kernel<<<B * (S / 128) * p.n_htiles, PC_THREADS, PC_SMEM_BYTES, st>>>(tx, p);
+  if (int rc = check_launch("proj_conv_tc_kernel")) return rc;
+  const int rows = B * S;
+  auto Y = static_cast<__nv_bfloat16*>(y);
+  auto XM = static_cast<__nv_bfloat16*>(xm);
+  const int nq = H / 4;
+  if (nq <= 32 * 8) ln_rows_f32_kernel<8><<<(rows + 7) / 8, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
+  else if (nq <= 32 * 16) ln_rows_f32_kernel<16><<<(rows + 7) / 8, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
+  else ln_rows_f32_kernel<32><<<(rows + 7) / 8, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
+  return check_launch("ln_rows_f32_kernel");
+}
 
 int x2i_mean_over_s_bwd(const void* dpooled, void* dy, int B, int S, int N, void* stream) {
   DeviceInfo* d;

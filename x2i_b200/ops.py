@@ -284,11 +284,27 @@ def euler_step_(x, v, dsigma):
     return x
 
 
+proj_conv_tensor_cores = True  # tests flip this to compare the tcgen05 Toeplitz kernel with the FP32-pipe stencil kernel
+
+
+def _proj_mix_ln_tc(x, w, conv_bias, gamma, beta, eps, want_xm):
+    B, C, S, H = x.shape
+    y = torch.empty(B, S, H, device=x.device, dtype=BF16)
+    xm = torch.empty_like(y) if want_xm else None
+    ws = _ws_f32("proj_conv_tc", _lib.lib().x2i_proj_mix_ln_tc_workspace_floats(B, C, S, H), x.device)
+    _lib.call("x2i_proj_mix_ln_tc", _p(x), _p(w.contiguous()), float(conv_bias), _p(gamma.contiguous()), _p(beta.contiguous()), float(eps), _p(y),
+              _p(xm), _p(ws), B, C, S, H, _stream())
+    return y, xm
+
+
 def proj_mix_ln(x, mode, w, conv_bias, gamma, beta, eps):
-    """Projector front end: x bf16 [B,C,S,H] -> LayerNorm(mix(x)) bf16 [B,S,H]."""
+    """Projector front end: x bf16 [B,C,S,H] -> LayerNorm(mix(x)) bf16 [B,S,H].  Mode 0 (5x5 conv over the layers) runs on the tensor
+    pipe (x2i_proj_mix_ln_tc) when the shape allows, otherwise -- and for the two mean modes -- on the streaming stencil kernel."""
     _chk(x, "x"); _chk(w, "w", torch.float32); _chk(gamma, "gamma", torch.float32); _chk(beta, "beta", torch.float32)
     x = x.contiguous()
     B, C, S, H = x.shape
+    if mode == 0 and proj_conv_tensor_cores and _lib.lib().x2i_proj_mix_ln_tc_supported(B, C, S, H):
+        return _proj_mix_ln_tc(x, w, conv_bias, gamma, beta, eps, False)[0]
     y = torch.empty(B, S, H, device=x.device, dtype=BF16)
     _lib.call("x2i_proj_mix_ln", _p(x), mode, _p(w), float(conv_bias), _p(gamma), _p(beta), float(eps), _p(y), B, C, S, H, _stream())
     return y
@@ -542,6 +558,8 @@ def proj_mix_ln_save(x, mode, w, conv_bias, gamma, beta, eps):
     _chk(x, "x"); _chk(w, "w", F32); _chk(gamma, "gamma", F32); _chk(beta, "beta", F32)
     x = x.contiguous()
     B, C, S, H = x.shape
+    if mode == 0 and proj_conv_tensor_cores and _lib.lib().x2i_proj_mix_ln_tc_supported(B, C, S, H):
+        return _proj_mix_ln_tc(x, w, conv_bias, gamma, beta, eps, True)
     y = torch.empty(B, S, H, device=x.device, dtype=BF16)
     xm = torch.empty_like(y)
     _lib.call("x2i_proj_mix_ln_save", _p(x), mode, _p(w), float(conv_bias), _p(gamma), _p(beta), float(eps), _p(y), _p(xm), B, C, S, H,
