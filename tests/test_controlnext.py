@@ -226,6 +226,21 @@ def test_stacked_control_nets_equal_per_net_evaluation(ops):
             n.finish_tokens(mids[i], add_to=b)
             assert torch.equal(a, b), f"net {i}"
             assert torch.equal(n.finish_tokens(mids[i]), n.forward_tokens(hint, t))
+        # the hint-only part (embedding stack + first norm) is kept across the steps of a sampling run: a second timestep through the
+        # cache equals a fresh evaluation, a modified hint or parameter invalidates it
+        st = ControlNeXtStack(nets)
+        t2 = torch.tensor([40.0, 910.0], device="cuda")
+        st.mid_features(hint, t)
+        cached = st.mid_features(hint, t2)
+        assert st._hint is not None
+        assert torch.equal(cached, ControlNeXtStack(nets).mid_features(hint, t2))
+        hint2 = hint.clone()
+        hint2[:, :, :8] = 0.5
+        hint.copy_(hint2)                                                      # in-place change: same address, new version
+        assert torch.equal(st.mid_features(hint, t2), ControlNeXtStack(nets).mid_features(hint2, t2))
+        nets[1].embedding[3].weight.data.mul_(1.5)                            # .data bypasses the version counter: use a real update
+        nets[1].embedding[3].weight.mul_(1.0)
+        assert torch.equal(st.mid_features(hint, t2), ControlNeXtStack(nets).mid_features(hint, t2))
     cfg = dict(patch_size=1, in_channels=64, num_layers=3, num_single_layers=1, attention_head_dim=128, num_attention_heads=24,
                joint_attention_dim=64, pooled_projection_dim=32, guidance_embeds=True, axes_dims_rope=(16, 56, 56))
     model = FluxTransformer2DModel.synthetic(cfg, device="cuda", seed=9)

@@ -44,6 +44,18 @@ for it in range(2):
         xin = rn(1, 37, 512, 2048)
     with torch.no_grad():
         pm(xin)
+    # LightControl trainer kernels: implicit conv weight gradient (128 -> 128 and 64 -> 64 at 512 x 512, the 3x3 / stride-2 form at 256 x 256)
+    # and the GroupNorm backward of a 512 x 512 x 128 layer
+    if it == 0:
+        xc, dyc = rn(1, 512, 512, 128), rn(1, 512, 512, 128)
+        xc64, dyc64 = rn(1, 512, 512, 64), rn(1, 512, 512, 64)
+        dys = rn(1, 256, 256, 128)
+        gam, bet = rn(128), rn(128)
+    ops.conv2d_nhwc_wgrad(xc, dyc, 3, 3, stride=1, pad=1)
+    ops.conv2d_nhwc_wgrad(xc64, dyc64, 3, 3, stride=1, pad=1)
+    ops.conv2d_nhwc_wgrad(xc, dys, 3, 3, stride=2, pad=1)
+    ops.groupnorm_nhwc_bwd(xc, dyc, gam, bet, 4, 1e-6, act=1)
+    ops.ln_modulate(x, sc, sc, L)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("done")

@@ -965,10 +965,9 @@ int x2i_proj_mix_ln_tc(const void* x, const float* w, float conv_bias, const flo
   const int rows = B * S;
   auto Y = static_cast<__nv_bfloat16*>(y);
   auto XM = static_cast<__nv_bfloat16*>(xm);
-  const int nq = H / 4;
-  if (nq <= 32 * 8) ln_rows_f32_kernel<8><<<(rows + 7) / 8, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
-  else if (nq <= 32 * 16) ln_rows_f32_kernel<16><<<(rows + 7) / 8, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
-  else ln_rows_f32_kernel<32><<<(rows + 7) / 8, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
+  if (H <= 1024) ln_rows_f32_kernel<1><<<rows, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
+  else if (H <= 2048) ln_rows_f32_kernel<2><<<rows, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
+  else ln_rows_f32_kernel<4><<<rows, 256, 0, st>>>(workspace, gamma, beta, eps, Y, XM, rows, H);
   return check_launch("ln_rows_f32_kernel");
 }
 
@@ -1242,12 +1241,13 @@ int x2i_colsum(const void* A, int64_t lda, const void* Bm, int64_t ldb, const vo
                                             static_cast<const float2*>(stats), p0, p1, rows_per_batch, D, nsplit, groups);
   if (int rc = check_launch("colsum_partial_kernel")) return rc;
   dim3 g2((D + 31) / 32, nbatch);
+  const int fin_threads = (static_cast<long long>(g2.x) * g2.y < 64 && nsplit > 64) ? 1024 : 256;  // few CTAs, long loops: 32 groups per CTA
   if (out0) {
-    colsum_final_kernel<<<g2, 256, 0, st>>>(p0, out0, ldo0, D, nsplit, accumulate);
+    colsum_final_kernel<<<g2, fin_threads, 0, st>>>(p0, out0, ldo0, D, nsplit, accumulate);
     if (int rc = check_launch("colsum_final_kernel")) return rc;
   }
   if (out1) {
-    colsum_final_kernel<<<g2, 256, 0, st>>>(p1, out1, ldo1, D, nsplit, accumulate);
+    colsum_final_kernel<<<g2, fin_threads, 0, st>>>(p1, out1, ldo1, D, nsplit, accumulate);
     if (int rc = check_launch("colsum_final_kernel")) return rc;
   }
   return X2I_OK;
@@ -1600,7 +1600,7 @@ int x2i_groupnorm_nhwc_bwd(const void* x, const void* dy, const void* gamma, con
   if (int rc = check_launch("gn_stats_final_kernel")) return rc;
   gn_bwd_partial_kernel<<<dim3(nsplit, Nimg), 256, 0, st>>>(X, DY, stats, GA, BE, part2, HW, C, G, nsplit, act);
   if (int rc = check_launch("gn_bwd_partial_kernel")) return rc;
-  gn_bwd_final_kernel<<<Nimg * G, 256, (C / G) * 2 * sizeof(double), st>>>(part2, GA, chan, gsum, C, G, nsplit, static_cast<double>(HW) * (C / G));
+  gn_bwd_final_kernel<<<Nimg * G, GN_FIN_WARPS * 32, (GN_FIN_WARPS * 64 + (C / G) * 2) * sizeof(double), st>>>(part2, GA, chan, gsum, C, G, nsplit, static_cast<double>(HW) * (C / G));
   if (int rc = check_launch("gn_bwd_final_kernel")) return rc;
   gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(chan, dgamma, dbeta, Nimg, C, accumulate);
   if (int rc = check_launch("gn_bwd_param_kernel")) return rc;

@@ -542,40 +542,52 @@ __global__ void __launch_bounds__(256) gn_bwd_partial_kernel(const __nv_bfloat16
     for (int j = 0; j < 8; ++j) { o[2 * j] = red[j][threadIdx.x]; o[2 * j + 1] = red[8 + j][threadIdx.x]; }
   }
 }
-// one CTA per (image, group), one WARP per channel (8 warps, channels strided): per-channel sums over the slabs (fp64, lane-strided then
-// a fixed shuffle tree: deterministic) -> chan[n, c] = (A_c, B_c); the group sums gsum[n, g] = (S1/m, S2/m) are then added in channel order
-// by one thread.  (The first version walked the channels of a group one after the other with two block barriers each: 42 us per launch
-// on the 2-group layers, 7 ms of a LightControl train step.)
-__global__ void __launch_bounds__(256) gn_bwd_final_kernel(const float* __restrict__ part, const __nv_bfloat16* __restrict__ gamma,
-                                                           float2* __restrict__ chan, float2* __restrict__ gsum, int C, int G, int nsplit, double m) {
-  extern __shared__ double gn_fin[];  // [cpg][2]: gamma_c * A_c, gamma_c * B_c
+// one CTA per (image, group): lanes = 32 consecutive channels (a warp's load is one 256-byte row segment of the partials), warps = split
+// ranges; per-channel sums over the slabs in fp64 -- each warp adds its range in order, the warps' partials are added in warp order
+// (deterministic) -> chan[n, c] = (A_c, B_c); the group sums gsum[n, g] = (S1/m, S2/m) are then added in channel order by one thread.
+// (History: the first version walked the channels one after the other with two block barriers each, 42 us per launch on the 2-group
+// layers; a warp per channel with lane-strided 8-byte loads still took 27 us on a 1024-slab layer: 4 CTAs of latency-bound loads.)
+constexpr int GN_FIN_WARPS = 16;
+__global__ void __launch_bounds__(GN_FIN_WARPS * 32) gn_bwd_final_kernel(const float* __restrict__ part, const __nv_bfloat16* __restrict__ gamma,
+                                                                        float2* __restrict__ chan, float2* __restrict__ gsum, int C, int G, int nsplit,
+                                                                        double m) {
+  extern __shared__ double gn_fin[];  // [GN_FIN_WARPS][32][2] warp partials, then [cpg][2] = gamma_c * A_c, gamma_c * B_c
+  double* wpart = gn_fin;
+  double* gprod = gn_fin + GN_FIN_WARPS * 64;
   const int n = blockIdx.x / G, g = blockIdx.x - n * G;
   const int cpg = C / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int cc = warp; cc < cpg; cc += 8) {
+  const int per = (nsplit + GN_FIN_WARPS - 1) / GN_FIN_WARPS;
+  const int s0 = warp * per, s1 = min(s0 + per, nsplit);
+  for (int c0 = 0; c0 < cpg; c0 += 32) {
+    const int cc = c0 + lane;
     const int c = g * cpg + cc;
     double a = 0.0, b = 0.0;
-    for (int sidx = lane; sidx < nsplit; sidx += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<long long>(n) * nsplit + sidx) * C + c) * 2);
-      a += v.x; b += v.y;
+    if (cc < cpg) {
+      const float2* src = reinterpret_cast<const float2*>(part) + (static_cast<long long>(n) * nsplit + s0) * C + c;
+#pragma unroll 8
+      for (int sidx = s0; sidx < s1; ++sidx, src += C) {
+        const float2 v = *src;
+        a += v.x; b += v.y;
+      }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, off);
-      b += __shfl_xor_sync(0xffffffffu, b, off);
-    }
-    if (lane == 0) {
+    wpart[(warp * 32 + lane) * 2] = a;
+    wpart[(warp * 32 + lane) * 2 + 1] = b;
+    __syncthreads();
+    if (warp == 0 && cc < cpg) {
+      a = b = 0.0;
+      for (int w = 0; w < GN_FIN_WARPS; ++w) { a += wpart[(w * 32 + lane) * 2]; b += wpart[(w * 32 + lane) * 2 + 1]; }
       chan[static_cast<long long>(n) * C + c] = make_float2(static_cast<float>(a), static_cast<float>(b));
       const double gm = static_cast<double>(__bfloat162float(gamma[c]));
-      gn_fin[2 * cc] = gm * a;
-      gn_fin[2 * cc + 1] = gm * b;
+      gprod[2 * cc] = gm * a;
+      gprod[2 * cc + 1] = gm * b;
     }
+    __syncthreads();
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int cc = 0; cc < cpg; ++cc) { s1 += gn_fin[2 * cc]; s2 += gn_fin[2 * cc + 1]; }
-    gsum[blockIdx.x] = make_float2(static_cast<float>(s1 / m), static_cast<float>(s2 / m));
+    double s1g = 0.0, s2g = 0.0;
+    for (int cc = 0; cc < cpg; ++cc) { s1g += gprod[2 * cc]; s2g += gprod[2 * cc + 1]; }
+    gsum[blockIdx.x] = make_float2(static_cast<float>(s1g / m), static_cast<float>(s2g / m));
   }
 }
 // dgamma_c (+)= sum_n B_c[n], dbeta_c (+)= sum_n A_c[n]   (fp32 outputs: parameter gradients)

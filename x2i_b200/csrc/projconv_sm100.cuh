@@ -189,38 +189,37 @@ __global__ void __launch_bounds__(PC_THREADS, 1) proj_conv_tc_kernel(const __gri
 }
 
 // y[r, :] = LayerNorm(v[r, :]) * gamma + beta (bf16) from the fp32 plane; optionally xm = bf16(v) (the pre-LayerNorm mix the projector's
-// backward needs).  One warp per row, the row in registers (H <= 4096).
+// backward needs).  One 256-thread CTA per row (B * S rows: 512 CTAs for one prompt), MAXQ float4 per thread (H <= 1024 * MAXQ).
 template <int MAXQ>
 __global__ void __launch_bounds__(256) ln_rows_f32_kernel(const float* __restrict__ v, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float eps, __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ xm, int rows, int H) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
+  __shared__ float red[8];
+  const int row = blockIdx.x;
   const int nq = H >> 2;  // float4 chunks per row
   const float4* vr = reinterpret_cast<const float4*>(v + static_cast<long long>(row) * H);
   float4 r[MAXQ];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i) {
-    const int c = i * 32 + lane;
+    const int c = i * 256 + threadIdx.x;
     r[i] = c < nq ? vr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
     s += (r[i].x + r[i].y) + (r[i].z + r[i].w);
   }
-  const float mean = warp_sum(s) / H;
+  const float mean = block_sum_rt(s, red, 8) / H;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i) {
-    if (i * 32 + lane < nq) {
+    if (i * 256 + threadIdx.x < nq) {
       const float a = r[i].x - mean, b2 = r[i].y - mean, c2 = r[i].z - mean, d = r[i].w - mean;
       q += a * a + b2 * b2 + c2 * c2 + d * d;
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / H + eps);
+  const float rstd = rsqrtf(block_sum_rt(q, red, 8) / H + eps);
   uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(row) * H);
   uint2* xr = xm ? reinterpret_cast<uint2*>(xm + static_cast<long long>(row) * H) : nullptr;
 #pragma unroll
   for (int i = 0; i < MAXQ; ++i) {
-    const int c = i * 32 + lane;
+    const int c = i * 256 + threadIdx.x;
     if (c < nq) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c), be = __ldg(reinterpret_cast<const float4*>(beta) + c);
       uint2 o;
@@ -228,10 +227,10 @@ __global__ void __launch_bounds__(256) ln_rows_f32_kernel(const float* __restric
       o.y = pack_bf16x2((r[i].z - mean) * rstd * g.z + be.z, (r[i].w - mean) * rstd * g.w + be.w);
       yr[c] = o;
       if (xr) {
-        uint2 m;
-        m.x = pack_bf16x2(r[i].x, r[i].y);
-        m.y = pack_bf16x2(r[i].z, r[i].w);
-        xr[c] = m;
+        uint2 mm;
+        mm.x = pack_bf16x2(r[i].x, r[i].y);
+        mm.y = pack_bf16x2(r[i].z, r[i].w);
+        xr[c] = mm;
       }
     }
   }

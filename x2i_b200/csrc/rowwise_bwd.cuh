@@ -221,23 +221,23 @@ __global__ void __launch_bounds__(128) colsum_partial_kernel(const __nv_bfloat16
     *reinterpret_cast<float4*>(part1 + o + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
   }
 }
-// stage 2: out[b * ldo + col] (+)= sum over splits.  A 256-thread CTA owns 32 columns: 8 thread groups each sum every
-// 8th partial (coalesced 128-byte rows), then the 8 group sums are added in a fixed order (deterministic).
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, long long ldo,
-                                                           int D, int nsplit, int accumulate) {
-  __shared__ float red[8][32];
-  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+// stage 2: out[b * ldo + col] (+)= sum over splits.  A CTA owns 32 columns: its blockDim.x / 32 thread groups (8 for wide matrices, 32
+// for narrow ones whose grid would otherwise be 2-4 CTAs of long serial loops) each sum every G-th partial (coalesced 128-byte rows),
+// then the group sums are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, long long ldo,
+                                                            int D, int nsplit, int accumulate) {
+  __shared__ float red[32][32];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5, ngrp = blockDim.x >> 5;
   const int col = blockIdx.x * 32 + cl;
   const int b = blockIdx.y;
   float s = 0.f;
   if (col < D)
-    for (int i = grp; i < nsplit; i += 8) s += part[(static_cast<long long>(b) * nsplit + i) * D + col];
+    for (int i = grp; i < nsplit; i += ngrp) s += part[(static_cast<long long>(b) * nsplit + i) * D + col];
   red[grp][cl] = s;
   __syncthreads();
   if (grp == 0 && col < D) {
     float t = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t += red[j][cl];
+    for (int j = 0; j < ngrp; ++j) t += red[j][cl];
     float* o = out + static_cast<long long>(b) * ldo + col;
     *o = accumulate ? *o + t : t;
   }
