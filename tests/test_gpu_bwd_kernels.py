@@ -104,19 +104,30 @@ def test_attention_backward(ops, B, H, L):
     assert rel(dv, dv_r) < 8e-3
     assert rel(dq, dq_r) < 1e-2
     assert rel(dk, dk_r) < 1e-2
-    # the cluster form (two CTAs share every streamed tile through TMA multicast; opt-in) and the one-CTA-per-tile form run the
-    # same MMAs on the same tiles in the same order: bit-identical, also when the tile count is odd (padding tile in the last pair)
+    # Other forms of the same launches (env switches are read per call):
+    #   X2I_ATTN_BWD_KV32=1  dK / dV through the 32-query all-TS form (K_j / V_j in TMEM) instead of the default 64-query form with the
+    #                        owners in shared memory: same products, same summation order over the streamed rows (opt-in: measured slower)
+    #   X2I_ATTN_BWD_MC=1    2-CTA clusters sharing every streamed tile through TMA multicast (64-query form): bit-identical to it,
+    #                        also when the tile count is odd (padding tile in the last pair)
     import os
-    old = os.environ.get("X2I_ATTN_BWD_MC")
-    os.environ["X2I_ATTN_BWD_MC"] = "1"
-    try:
-        poison = lambda: torch.full_like(q, float("nan"))  # noqa: E731
-        dq1, dk1, dv1 = ops.attention_bwd(q, k, v, do_hm, lse, delta, dq=poison(), dk=poison(), dv=poison())
-    finally:
-        if old is None:
-            del os.environ["X2I_ATTN_BWD_MC"]
-        else:
-            os.environ["X2I_ATTN_BWD_MC"] = old
+    poison = lambda: torch.full_like(q, float("nan"))  # noqa: E731
+
+    def run(**env):
+        old = {k_: os.environ.get(k_) for k_ in env}
+        os.environ.update(env)
+        try:
+            return ops.attention_bwd(q, k, v, do_hm, lse, delta, dq=poison(), dk=poison(), dv=poison())
+        finally:
+            for k_, v_ in old.items():
+                if v_ is None:
+                    del os.environ[k_]
+                else:
+                    os.environ[k_] = v_
+
+    dq32, dk32, dv32 = run(X2I_ATTN_BWD_KV32="1")
+    assert rel(dv32, dv_r) < 8e-3 and rel(dk32, dk_r) < 1e-2 and torch.equal(dq32, dq)
+    assert rel(dk32, dk) < 2e-3 and rel(dv32, dv) < 2e-3
+    dq1, dk1, dv1 = run(X2I_ATTN_BWD_MC="1")
     assert torch.equal(dq, dq1) and torch.equal(dk, dk1) and torch.equal(dv, dv1)
 
 

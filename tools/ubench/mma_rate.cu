@@ -103,7 +103,7 @@ static void launch(Cfg c, int reps, int per_round, long long* cyc) {
   if (c.mixed) return go<64, 0, 0, 1>(c, reps, per_round, cyc);
 #define CASE(nn, a, b) if (c.n == nn && c.a_tmem == a && c.b_mn == b) return go<nn, a, b, 0>(c, reps, per_round, cyc);
   CASE(256, 0, 0) CASE(128, 0, 0) CASE(64, 0, 0) CASE(32, 0, 0) CASE(256, 1, 0) CASE(128, 1, 0) CASE(64, 1, 0)
-  CASE(128, 0, 1) CASE(128, 1, 1) CASE(64, 1, 1) CASE(64, 0, 1) CASE(256, 0, 1) CASE(256, 1, 1)
+  CASE(32, 1, 0) CASE(16, 1, 0) CASE(16, 0, 0) CASE(128, 0, 1) CASE(128, 1, 1) CASE(64, 1, 1) CASE(64, 0, 1) CASE(256, 0, 1) CASE(256, 1, 1)
   printf("no instantiation\n");
   exit(1);
 }
@@ -114,7 +114,7 @@ int main() {
       {"SS  N=256 B K-major", {256, 0, 0, 0, 0}},   {"SS  N=128 B K-major", {128, 0, 0, 0, 0}},
       {"SS  N=64  B K-major", {64, 0, 0, 0, 0}},    {"SS  N=32  B K-major", {32, 0, 0, 0, 0}},
       {"TS  N=256 B K-major", {256, 1, 0, 0, 0}},   {"TS  N=128 B K-major", {128, 1, 0, 0, 0}},
-      {"TS  N=64  B K-major", {64, 1, 0, 0, 0}},    {"SS  N=128 B MN-major", {128, 0, 1, 0, 0}},
+      {"TS  N=64  B K-major", {64, 1, 0, 0, 0}},    {"TS  N=32  B K-major", {32, 1, 0, 0, 0}},   {"TS  N=16  B K-major", {16, 1, 0, 0, 0}},   {"SS  N=16  B K-major", {16, 0, 0, 0, 0}},    {"SS  N=128 B MN-major", {128, 0, 1, 0, 0}},
       {"TS  N=128 B MN-major", {128, 1, 1, 0, 0}}, {"SS  N=64  B MN-major", {64, 0, 1, 0, 0}}, {"SS  N=256 B MN-major", {256, 0, 1, 0, 0}}, {"TS  N=256 B MN-major", {256, 1, 1, 0, 0}},  {"TS  N=64  B MN-major", {64, 1, 1, 0, 0}},
       {"SS  N=128 + smem stores", {128, 0, 0, 1, 0}}, {"SS  N=64  + smem stores", {64, 0, 0, 1, 0}},
       {"TS  N=128 MN + smem stores", {128, 1, 1, 1, 0}},

@@ -425,4 +425,253 @@ mmdit_attention_bwd_mc_kernel(const __grid_constant__ CUtensorMap tma_x0, const 
   attention_bwd_body<KV, true>(tma_x0, tma_x1, tma_y0, tma_y1, p);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------------
+// dK/dV launch, all products in the TS form (round 2, second design).  The 64-query form above keeps K_j / V_j in shared memory because
+// 2 x 128 accumulator + 2 x 128 T columns leave no TMEM for them, and its SS-form T products are paced by the shared-memory port (48
+// instead of 32 cycles).  With 32-query stream tiles a T buffer is 64 columns, so  [0,128) K_j | V_j as bf16 A operands, [128,256) two T
+// buffers (T1 | T2 of 32 columns each), [256,512) dK | dV  fits: T products run as TS N = 32 (18 cycles measured, tools/ubench/mma_rate.cu),
+// the accumulations as TS N = 128 with K = 32 (one k16 step per warpgroup half).  Per 64 queries: 2 x (16 x 18 + 4 x 65) = 1100 cycles
+// against 1306 for the SS form.  Same soft-max code path: warpgroup h owns the 16-column half h of T1 / T2 of EVERY tile.
+constexpr int ABK_YT = 32;
+constexpr int ABK_STAGES = 8;
+constexpr int ABK_STAGE_BYTES = 2 * ABK_YT * 256;   // Q | dO tile: 32 rows x 128 bf16 each, as two 64-column halves of 4 KB
+constexpr int ABK_STATS_BYTES = 2 * ABK_YT * 4;     // lse[32] | delta[32]
+constexpr int ABK_SMEM_BYTES = ABK_STAGES * (ABK_STAGE_BYTES + ABK_STATS_BYTES) + 256 + 1024;
+
+__global__ void __launch_bounds__(ABW_THREADS, 1)
+mmdit_attention_bwd_kv32_kernel(const __grid_constant__ CUtensorMap tma_y0 /* Q, 64 x 32 boxes */,
+                                const __grid_constant__ CUtensorMap tma_y1 /* dO */, const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NST = ABK_STAGES;
+  uint8_t* sy = smem;
+  float* sstat = reinterpret_cast<float*>(sy + NST * ABK_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sstat) + NST * ABK_STATS_BYTES);
+  uint64_t* t_full = bars;         // 2
+  uint64_t* t2_full = bars + 2;    // 2
+  uint64_t* pd_full = bars + 4;    // 2 buffers x 2 halves (16 streamed rows each)
+  uint64_t* acc_full = bars + 8;   // 1
+  uint64_t* x_tmem = bars + 9;     // 1: the 8 soft-max warps have stored K_j / V_j into TMEM
+  uint64_t* y_full = bars + 10;    // NST
+  uint64_t* y_empty = bars + 10 + NST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * NST);
+  static_assert((10 + 2 * NST) * 8 + 4 <= 256, "barrier block");
+  auto stg = [](int y) { return y % NST; };
+  auto sph = [](int y) { return static_cast<uint32_t>((y / NST) & 1); };
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 128;
+  const int bh = blockIdx.z * p.H + blockIdx.y;
+  const int n_y = (p.L + ABK_YT - 1) / ABK_YT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_y0);
+    tma_prefetch_desc(&tma_y1);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&y_full[i], 1);
+      mbar_init(&y_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t2_full[i], 1);
+      mbar_init(&pd_full[2 * i], 4);
+      mbar_init(&pd_full[2 * i + 1], 4);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(x_tmem, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t TOFF = 128u, TBUF = 2u * ABK_YT, ACC0 = 256u, ACC1 = 384u;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      for (int y = 0; y < n_y; ++y) {
+        const int stage = stg(y);
+        mbar_wait(&y_empty[stage], sph(y) ^ 1);
+        mbar_expect_tx(&y_full[stage], ABK_STAGE_BYTES + ABK_STATS_BYTES);
+        uint8_t* dst = sy + stage * ABK_STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; ++op)
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            tma_load_3d(dst + op * (ABK_YT * 256) + g * (ABK_YT * 128), op ? &tma_y1 : &tma_y0, &y_full[stage], g * 64, y * ABK_YT, bh);
+        float* st = sstat + stage * (ABK_STATS_BYTES / 4);
+        const long long off = static_cast<long long>(bh) * p.Lpad + y * ABK_YT;
+        bulk_load_1d(st, p.lse + off, ABK_YT * 4, &y_full[stage]);
+        bulk_load_1d(st + ABK_YT, p.delta + off, ABK_YT * 4, &y_full[stage]);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (whole warp, elected lane issues)
+    constexpr uint32_t idesc_t = make_idesc_bf16(128, ABK_YT, 0, 0);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(128, 128, 0, 1);
+    const uint32_t y_base = smem_u32(sy);
+    auto issue_t = [&](int y, int buf) {  // T1 = K_j Q^T, T2 = V_j dO^T  (128 x 32 each, K = 128), A from TMEM; one commit per product
+      const uint64_t ydesc = make_smem_desc_sw128(y_base + stg(y) * ABK_STAGE_BYTES, 16, 1024);
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t oy = op * (ABK_YT * 256) + (kk >> 2) * (ABK_YT * 128) + (kk & 3) * 32;
+          umma_ts_w(tmem_base + TOFF + buf * TBUF + op * ABK_YT, tmem_base + op * 64 + kk * 8, ydesc + (oy >> 4), idesc_t, kk != 0);
+        }
+        umma_commit_w(op ? &t2_full[buf] : &t_full[buf]);
+      }
+    };
+    auto issue_acc = [&](int y, int buf, int half) {  // dK_j += dS~ Q, dV_j += P~ dO over the 16 streamed rows of this half (one k16 step)
+      const uint64_t ydesc = make_smem_desc_sw128(y_base + stg(y) * ABK_STAGE_BYTES, ABK_YT * 128, 1024);
+      const uint32_t acc = (y > 0 || half > 0) ? 1u : 0u;
+      const uint32_t a_base = tmem_base + TOFF + buf * TBUF + half * (ABK_YT / 2);  // bf16 results sit in the first 8 columns of the half
+      umma_ts_w(tmem_base + ACC0, a_base + ABK_YT, ydesc + ((half * 2048) >> 4), idesc_acc, acc);
+      umma_ts_w(tmem_base + ACC1, a_base, ydesc + ((ABK_YT * 256 + half * 2048) >> 4), idesc_acc, acc);
+    };
+    auto y_wait = [&](int y) { mbar_wait(&y_full[stg(y)], sph(y)); };
+
+    mbar_wait(x_tmem, 0);
+    y_wait(0);
+    tc_fence_after();
+    issue_t(0, 0);
+    if (n_y > 1) {
+      y_wait(1);
+      tc_fence_after();
+      issue_t(1, 1);
+    }
+    for (int y = 0; y < n_y; ++y) {
+      const int buf = y & 1;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&pd_full[2 * buf + half], (y >> 1) & 1);
+        tc_fence_after();
+        issue_acc(y, buf, half);
+      }
+      umma_commit_w(&y_empty[stg(y)]);
+      if (y + 2 < n_y) {
+        y_wait(y + 2);
+        tc_fence_after();
+        issue_t(y + 2, buf);
+      }
+    }
+    umma_commit_w(acc_full);
+  } else {
+    // ---------------------------------------------------------------- two soft-max warpgroups: warpgroup h owns columns [16h, 16h + 16)
+    const int wg = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int grow = r0 + quad * 32 + lane;  // owner row = key
+    const float sc = p.scale_log2;
+    {
+      // K_j (warpgroup 0) / V_j (warpgroup 1) rows -> TMEM as the bf16 A operands of the T products
+      const uint4* src = reinterpret_cast<const uint4*>((wg == 0 ? p.x0g : p.x1g) + (static_cast<long long>(bh) * p.L + grow) * 128);
+      const bool in = grow < p.L;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 u = in ? __ldg(src + h * 8 + i) : make_uint4(0, 0, 0, 0);
+          w[4 * i] = u.x; w[4 * i + 1] = u.y; w[4 * i + 2] = u.z; w[4 * i + 3] = u.w;
+        }
+        tmem_st32(tmem_base + lane_off + wg * 64 + h * 32, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_tmem);
+    }
+    constexpr int HC = ABK_YT / 2;  // columns (streamed rows) per warpgroup and tile
+    for (int y = 0; y < n_y; ++y) {
+      const int buf = y & 1;
+      const uint32_t ph = (y >> 1) & 1;
+      const uint32_t t1 = tmem_base + TOFF + buf * TBUF + wg * HC + lane_off, t2 = t1 + ABK_YT;
+      const float* st = sstat + stg(y) * (ABK_STATS_BYTES / 4) + wg * HC;
+      mbar_wait(&t_full[buf], ph);
+      tc_fence_after();
+      uint32_t a[HC], d[HC];
+      tmem_ld16(t1, a);
+      mbar_wait(&y_full[stg(y)], sph(y));  // lse / delta of this tile landed
+      tmem_ld_wait();
+      const uint64_t sc2 = pack_f32x2(sc, sc);
+      uint32_t pk[HC / 2], dk[HC / 2];
+#pragma unroll
+      for (int k = 0; k < HC; k += 4) {
+        const float4 lv = *reinterpret_cast<const float4*>(st + k);
+        const uint64_t nl2[2] = {pack_f32x2(-lv.x, -lv.y), pack_f32x2(-lv.z, -lv.w)};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kk = k + 2 * e;
+          float x0, x1;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(a[kk]), __uint_as_float(a[kk + 1])), sc2, nl2[e]), x0, x1);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);  // streamed rows beyond L carry lse = +inf: P~ = 0
+          a[kk] = __float_as_uint(p0);
+          a[kk + 1] = __float_as_uint(p1);
+          pk[kk >> 1] = pack_bf16x2(p0, p1);
+        }
+      }
+      mbar_wait(&t2_full[buf], ph);
+      tc_fence_after();
+      tmem_ld16(t2, d);
+      tmem_ld_wait();
+      tmem_st8(t1, pk);  // P~ / dS~ alias the first 8 columns of this warpgroup's own 16 columns of T1 / T2
+#pragma unroll
+      for (int k = 0; k < HC; k += 4) {
+        const float4 dv = *reinterpret_cast<const float4*>(st + ABK_YT + k);
+        const uint64_t ndl2[2] = {pack_f32x2(-dv.x, -dv.y), pack_f32x2(-dv.z, -dv.w)};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int kk = k + 2 * e;
+          const uint64_t dd = add_f32x2(pack_f32x2(__uint_as_float(d[kk]), __uint_as_float(d[kk + 1])), ndl2[e]);
+          float s0, s1;
+          unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(a[kk]), __uint_as_float(a[kk + 1])), dd), s0, s1);
+          dk[kk >> 1] = pack_bf16x2(s0, s1);
+        }
+      }
+      tmem_st8(t2, dk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pd_full[2 * buf + wg]);
+    }
+    // ---- epilogue: warpgroup 0 drains dK (scaled), warpgroup 1 dV
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool ok = grow < p.L;
+    const float mul = wg == 0 ? p.scale : 1.0f;
+    __nv_bfloat16* dst = (wg == 0 ? p.out0 : p.out1) + (static_cast<long long>(bh) * p.L + grow) * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem_base + (wg == 0 ? ACC0 : ACC1) + lane_off + c * 32, o);
+      tmem_ld_wait();
+      if (ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * mul, __uint_as_float(o[8 * k + 1]) * mul);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * mul, __uint_as_float(o[8 * k + 3]) * mul);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul);
+          d4[k] = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace x2i

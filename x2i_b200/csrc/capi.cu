@@ -1117,6 +1117,7 @@ int x2i_mmdit_attention_bwd(const void* q, const void* k, const void* v, const v
   if (!configured[d->index].load(std::memory_order_acquire)) {
     cudaError_t e = cudaFuncSetAttribute(mmdit_attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mmdit_attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mmdit_attention_bwd_kv32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ABK_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mmdit_attention_bwd_mc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mmdit_attention_bwd_mc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABW_SMEM_BYTES);
     if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
@@ -1131,8 +1132,21 @@ int x2i_mmdit_attention_bwd(const void* q, const void* k, const void* v, const v
   dim3 grid(mc ? (tiles + 1) / 2 * 2 : tiles, heads, B);  // cluster pairs: an even number of owner tiles (a padding tile has no valid row)
   p.out0 = static_cast<__nv_bfloat16*>(dk); p.out1 = static_cast<__nv_bfloat16*>(dv);
   p.x0g = static_cast<const __nv_bfloat16*>(q); p.x1g = static_cast<const __nv_bfloat16*>(dout);
+  // dK/dV launch: X2I_ATTN_BWD_KV32=1 = 32-query stream tiles with K_j / V_j in TMEM (all products in the TS form: 1100 instead of 1306
+  // tensor-pipe cycles per 64 queries); default 0 = the 64-query form with the owners in shared memory (SS-form T products).  Measured on
+  // one box, sustained: 0.774-0.778 ms against 0.761-0.764 -- twice the hand-offs per query cost more than the faster products give.
+  const char* kv32_env = getenv("X2I_ATTN_BWD_KV32");
+  const bool kv32 = (kv32_env ? atoi(kv32_env) != 0 : false) && !mc;
   if (bwd_only != 2) {
-    if (mc) mmdit_attention_bwd_mc_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
+    if (kv32) {
+      CUtensorMap tq32, tdo32;
+      uint32_t box32[3] = {64, ABK_YT, 1};
+      if (int rc = make_map(d, &tq32, q, 3, dims, str, box32)) return rc;
+      if (int rc = make_map(d, &tdo32, dout, 3, dims, str, box32)) return rc;
+      p.x0g = static_cast<const __nv_bfloat16*>(k); p.x1g = static_cast<const __nv_bfloat16*>(v);
+      mmdit_attention_bwd_kv32_kernel<<<dim3(tiles, heads, B), ABW_THREADS, ABK_SMEM_BYTES, st>>>(tq32, tdo32, p);
+      p.x0g = static_cast<const __nv_bfloat16*>(q); p.x1g = static_cast<const __nv_bfloat16*>(dout);
+    } else if (mc) mmdit_attention_bwd_mc_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
     else mmdit_attention_bwd_kernel<true><<<grid, ABW_THREADS, ABW_SMEM_BYTES, st>>>(tk, tv, tq, tdo, p);
   }
   if (int rc = check_launch("mmdit_attention_bwd_kernel<kv>")) return rc;
