@@ -378,6 +378,21 @@ def test_lightcontrol_gradients_through_frozen_transformer(ops):
     print(f"LightControl gradients: total rel err {tot:.4f} (eager bf16 {tot_e:.4f}); loss {float(loss):.5f} vs {float(lo):.5f}")
     check("LightControl gradients through the frozen real-width transformer", tot, tot_e)
     assert all(p.grad is None for p in model.parameters())  # the transformer stays frozen
+    # the control nets run round-robin on side streams by default (forward and, through autograd's stream tracking, backward): same
+    # kernels on the same data -> the single-stream run gives bit-identical gradients
+    multi = [p_.grad.clone() for net in nets for p_ in net.parameters()]
+    assert model.control_net_streams > 1
+    for net in nets:
+        net.zero_grad()
+    model.control_net_streams = 1
+    try:
+        out1 = model(**dev, guided_hint=hint.to("cuda", torch.bfloat16), control_nets=nets, return_dict=False)[0]
+        ((out1.float() - target.cuda()) ** 2).mean().backward()
+    finally:
+        model.control_net_streams = 8
+    assert torch.equal(out1, out)
+    for a_, p_ in zip(multi, [p_ for net in nets for p_ in net.parameters()]):
+        assert torch.equal(a_, p_.grad)
 
 
 @gpu

@@ -25,6 +25,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     model = FluxTransformer2DModel.synthetic(dict(FLUX_SCHNELL, guidance_embeds=True), device=dev, seed=0).requires_grad_(False)
+    if os.environ.get("X2I_CN_STREAMS"):
+        model.control_net_streams = int(os.environ["X2I_CN_STREAMS"])
     vae = init_synthetic_(xv.AutoencoderKL().to(dev, torch.bfloat16).eval(), seed=5, std=0.03).requires_grad_(False)
     nets = torch.nn.ModuleList([ControlNeXtModel() for _ in range(args.nets)]).to(dev, torch.bfloat16).train()
     init_synthetic_(nets, seed=1, std=0.05)

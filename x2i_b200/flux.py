@@ -644,7 +644,7 @@ class FluxTransformer2DModel(nn.Module):
             nets = list(control_nets)[:len(self.transformer_blocks)]
             if not all(hasattr(n, "forward_tokens") for n in nets):
                 raise X2IError("training needs x2i_b200 ControlNeXtModel control nets (their backward runs on the x2i kernels)")
-            controls = tuple(n.forward_tokens(guided_hint, t1000) for n in nets)
+            controls = self._control_tokens_multistream(nets, guided_hint, t1000)
         outs = flux_train.FluxTrainFn.apply(self, 0, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids,
                                             guidance, *controls)
         nd, ns = len(self.transformer_blocks), len(self.single_transformer_blocks)
@@ -656,6 +656,32 @@ class FluxTransformer2DModel(nn.Module):
             for hook in list(blk.attn._forward_hooks.values()):
                 hook(blk.attn, (), hs[i])
         return out
+
+    control_net_streams = 8  # LightControl training: the independent control nets run round-robin on this many CUDA streams (1 = off)
+    _cn_streams = None
+
+    def _control_tokens_multistream(self, nets, guided_hint, t1000):
+        """Differentiable control tokens of every net.  The nets are independent of each other and of the image stream and consist of
+        ~50 short kernels each (10-60 us; forward AND backward), so they are issued round-robin on a few side streams: launch ramps,
+        tails and small grids of one net overlap with the others'.  Autograd runs each backward op on the stream of its forward op and
+        synchronises the stream boundaries itself; op workspaces are per (op, device, stream)."""
+        S = max(1, min(int(self.control_net_streams), len(nets)))
+        if S == 1:
+            return tuple(n.forward_tokens(guided_hint, t1000) for n in nets)
+        if self._cn_streams is None or len(self._cn_streams) != S:
+            self._cn_streams = [torch.cuda.Stream(device=self.device) for _ in range(S)]
+        cur = torch.cuda.current_stream()
+        for st in self._cn_streams:
+            st.wait_stream(cur)  # hint, timestep and the nets' parameters are ready
+        controls = [None] * len(nets)
+        for i, n in enumerate(nets):
+            with torch.cuda.stream(self._cn_streams[i % S]):
+                controls[i] = n.forward_tokens(guided_hint, t1000)
+        for st in self._cn_streams:
+            cur.wait_stream(st)
+        for c in controls:
+            c.record_stream(cur)  # allocated on a side stream, consumed by the transformer on this one
+        return tuple(controls)
 
     def _graphable(self):
         if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
