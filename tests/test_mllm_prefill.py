@@ -258,3 +258,47 @@ def test_qwen2_5_vl_3b_prefill_full_size_feeds_the_projector(ops):
         ep, es = po.to(torch.bfloat16)(eag)
     check("prefill -> projector: prompt_embeds [2,512,4096]", rel(gs, rs), rel(es, rs))
     check("prefill -> projector: pooled [2,768]", rel(gp, rp), rel(ep, rp))
+
+
+@gpu
+def test_qwen2_5_vl_7b_width_prefill_feeds_the_7b_projector(ops):
+    """The 7B variant of the conditioning path (infer/inference_qwenvl.py:80-81, train_qwenvl.py:401: `create_proj3_qwen7b(in_channels=29)`)
+    at its real WIDTH and reduced depth: hidden 3584, 28 query / 4 key-value heads (7 : 1 grouped-query attention), intermediate 18944,
+    28 layers in the checkpoint -- 6 here, so the projector is built for C = 7.  Covers the K = 3584 GEMM shapes, the 28 / 4 head split of the
+    RoPE kernel and the causal attention kernel, and the 3584-wide layer-mixing convolution."""
+    from oracle import mllm_oracle as mo, proj_oracle
+    from x2i_b200 import mllm, proj as xproj
+    from x2i_b200.flux import init_synthetic_
+    cfg = dict(mllm.QWEN2_5_VL_7B, vocab_size=4096, num_hidden_layers=6)
+    o = mo.build(cfg, seed=15, empty_on="cuda")
+    init_synthetic_(o, seed=16, std=0.02)
+    with torch.no_grad():
+        for p in o.parameters():
+            p.copy_(p.bfloat16().float())
+    m = mllm.Qwen2_5_VLTextPrefill(**cfg)
+    m.load_hf_state_dict(o.state_dict())
+    m = m.to("cuda", torch.bfloat16).eval()
+    B, S = 2, 512
+    ids = torch.randint(0, 4096, (B, S), device="cuda", generator=torch.Generator(device="cuda").manual_seed(17))
+    mask = torch.ones(B, S, dtype=torch.long, device="cuda")
+    mask[0, :200] = 0
+    ref = mo.prefill_hidden_states(o, ids, mask)
+    got = m.prefill_hidden_states(ids, mask)
+    eag = mo.prefill_hidden_states(o.to(torch.bfloat16), ids, mask)
+    assert got.shape == (B, 7, S, 3584)
+    valid = mask.bool()[:, None, :, None].expand_as(ref)
+    check("Qwen2.5-VL-7B width (6 layers) prefill [2,7,512,3584]: all layers, valid tokens", rel(got[valid], ref[valid]), rel(eag[valid], ref[valid]))
+    po = proj_oracle.Proj7Exp(in_channels=7, input_dim=3584, use_scale=False, use_cnn=True).cuda()
+    init_synthetic_(po, seed=18, std=0.02)
+    with torch.no_grad():
+        for p in po.parameters():
+            p.copy_(p.bfloat16().float())
+    pm = xproj.create_proj3_qwen7b(7, use_t5=False, use_scale=False, use_cnn=True)
+    pm.load_state_dict(po.state_dict())
+    pm = pm.to("cuda", torch.bfloat16)
+    with torch.no_grad():
+        rp, rs = po(ref)
+        gp, gs = pm(got)
+        ep, es = po.to(torch.bfloat16)(eag)
+    check("7B-width prefill -> projector (qwen7b): prompt_embeds [2,512,4096]", rel(gs, rs), rel(es, rs))
+    check("7B-width prefill -> projector (qwen7b): pooled [2,768]", rel(gp, rp), rel(ep, rp))
