@@ -461,6 +461,57 @@ def main():
         vae_info = {"workload": "FLUX VAE decode of the step's latents -> [B,3,1024,1024] (infer/inference_qwenvl.py:209-216)",
                     "ms_per_decode": v0.elapsed_time(v1) / 3, "algorithmic_tflop_per_image": 10.47}
         del vae
+        torch.cuda.empty_cache()
+
+    # ---- secondary workloads (SURVEY 8f N3 / N4 and BASELINE config 5, N=1 only): the step right before the path and the LightControl branch.
+    # Extra objects of the same line so the driver's record carries them; each is a few seconds.  --no-train skips them too.
+    mllm_info = lc_info = None
+    if world == 1 and not args.no_train:
+        from x2i_b200 import mllm as xmllm, proj as xproj
+        del model
+        torch.cuda.empty_cache()
+        with torch.no_grad():
+            mm = xmllm.Qwen2_5_VLTextPrefill.synthetic(xmllm.QWEN2_5_VL_3B, device=dev, seed=0)
+            pm = xproj.create_proj3_qwen3b(37, use_t5=False, use_scale=False, use_cnn=True).to(dev, torch.bfloat16)
+            gen = torch.Generator(device=dev).manual_seed(1)
+            ids = torch.randint(0, 151000, (1, S_TXT), device=dev, generator=gen)
+            mask = torch.ones(1, S_TXT, dtype=torch.long, device=dev)
+            mask[:, :300] = 0  # a 212-token prompt, left-padded to 512 like the reference's processor call
+            te = torch.empty(1, 37, S_TXT, 2048, device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                pm(mm.prefill_hidden_states(ids, mask, out=te))
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for _ in range(10):
+                pm(mm.prefill_hidden_states(ids, mask, out=te))
+            m1.record()
+            torch.cuda.synchronize()
+        mllm_info = {"workload": "Qwen2.5-VL-3B text prefill with all-layer capture [1,37,512,2048] + Proj7Exp (infer/inference_qwenvl.py:176-179)",
+                     "ms_per_prompt": m0.elapsed_time(m1) / 10}
+        del mm, pm, te
+        torch.cuda.empty_cache()
+        from x2i_b200 import train_lightcontrol as tl, vae as xvae2
+        from x2i_b200.controlnext import ControlNeXtModel
+        from x2i_b200.flux import init_synthetic_ as init_syn
+        dev_model = FluxTransformer2DModel.synthetic(dict(FLUX_SCHNELL, guidance_embeds=True), device=dev, seed=0).requires_grad_(False)
+        vae2 = init_syn(xvae2.AutoencoderKL().to(dev, torch.bfloat16).eval(), seed=5, std=0.03).requires_grad_(False)
+        nets = torch.nn.ModuleList([ControlNeXtModel() for _ in range(19)]).to(dev, torch.bfloat16).train()
+        init_syn(nets, seed=1, std=0.05)
+        opt2 = tl.MasterWeightOptimizer(nets.parameters(), lr=1e-5, fused=True)
+        lb = tl.synthetic_batch(1, dev, seed=0)
+        tl.lightcontrol_step(nets, dev_model, vae2, lb, optimizer=opt2)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(2):
+            ll = tl.lightcontrol_step(nets, dev_model, vae2, lb, optimizer=opt2)
+        l1.record()
+        torch.cuda.synchronize()
+        lc_info = {"workload": "LightControl train step (lightcontrol/train_lightcontrol.py:672-775): FLUX-dev 1024px, 19 trainable ControlNeXt nets, "
+                               "VAE encode in the step, B = 1",
+                   "ms_per_step": l0.elapsed_time(l1) / 2, "loss": float(ll)}
+        del dev_model, vae2, nets, opt2, lb
+        torch.cuda.empty_cache()
 
     if rank == 0:
         total_steps = world * B * args.steps
@@ -479,7 +530,7 @@ def main():
             "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "x2i_b200.pipeline.FluxPipeline.__call__ (4-step schnell sampling per call, pinned host buffers)"},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_base, "gpu_library_baseline": lib_base, "clocks": clk,
-            "distill_train": train_info, "vae_decode": vae_info,
+            "distill_train": train_info, "vae_decode": vae_info, "mllm_prefill": mllm_info, "lightcontrol_train": lc_info,
         }
         print(json.dumps(out))
     if world > 1:
