@@ -50,3 +50,30 @@ def prefill_hidden_states(model, input_ids, attention_mask):
     out = model(input_ids=input_ids, attention_mask=attention_mask, position_ids=text_positions(attention_mask).to(input_ids.device),
                 output_hidden_states=True, use_cache=False)
     return torch.stack(out.hidden_states, dim=1)
+
+
+def build_qwen2(config: dict, attn_implementation: str = "sdpa", seed: int = 0):
+    """Random-weight plain ``Qwen2Model`` (the language model inside InternVL2.5-4B = Qwen2.5-3B-Instruct and MiniCPM-o-2.6 = Qwen2.5-7B;
+    the reference vendors the same class as ``model_internvl/modeling_qwen2.py:778``): parameter names equal the product's."""
+    from transformers import Qwen2Config, Qwen2Model
+    cfg = Qwen2Config(vocab_size=config["vocab_size"], hidden_size=config["hidden_size"], intermediate_size=config["intermediate_size"],
+                      num_hidden_layers=config["num_hidden_layers"], num_attention_heads=config["num_attention_heads"],
+                      num_key_value_heads=config["num_key_value_heads"], rms_norm_eps=config["rms_norm_eps"], max_position_embeddings=32768,
+                      rope_theta=config["rope_theta"], tie_word_embeddings=False)
+    cfg._attn_implementation = attn_implementation
+    torch.manual_seed(seed)
+    return Qwen2Model(cfg).eval()
+
+
+@torch.no_grad()
+def prefill_hidden_states_plain(model, input_ids, attention_mask, position_mode: str = "arange"):
+    """The two ways the reference drives a plain Qwen2 language model: 'arange' = ``language_model(inputs_embeds=..., attention_mask=...,
+    output_hidden_states=True)`` without position_ids (InternVL, modeling_internvl_chat.py:357-363); 'cumsum' = HF ``generate``'s
+    ``prepare_inputs_for_generation`` rule (MiniCPM-o)."""
+    pos = None
+    if position_mode == "cumsum":
+        mask = attention_mask.to(torch.int64)
+        pos = (mask.cumsum(-1) - 1).masked_fill(mask == 0, 1)
+    out = model(inputs_embeds=model.embed_tokens(input_ids), attention_mask=attention_mask, position_ids=pos, output_hidden_states=True,
+                use_cache=False)
+    return torch.stack(out.hidden_states, dim=1)

@@ -53,6 +53,39 @@ def test_text_positions_and_left_padding_rule():
         mllm.Qwen2_5_VLTextPrefill.text_positions(bad)
 
 
+def test_other_mllm_families_share_the_decoder():
+    """InternVL2.5-4B (Qwen2.5-3B-Instruct inside) and MiniCPM-o-2.6 (Qwen2.5-7B inside) -- the MLLMs of infer/inference_internvl.py
+    and infer/inference_minicpm.py -- run the same text decoder: their configurations produce the projectors' C x H (37 x 2048,
+    29 x 3584: utils/proj.py create_proj_internvl4b / create_proj_minicpm), a plain ``Qwen2Model`` with the same weights gives the
+    same states as the Qwen2.5-VL text model, their checkpoint prefixes load, and the two position rules (a forward without
+    position_ids = arange; HF generate = cumsum(mask) - 1) differ only by rounding at the real tokens (RoPE is relative)."""
+    from oracle import mllm_oracle as mo
+    from x2i_b200 import mllm
+    assert (mllm.INTERNVL2_5_4B_LLM["num_hidden_layers"] + 1, mllm.INTERNVL2_5_4B_LLM["hidden_size"]) == (37, 2048)
+    assert (mllm.MINICPM_O_2_6_LLM["num_hidden_layers"] + 1, mllm.MINICPM_O_2_6_LLM["hidden_size"]) == (29, 3584)
+    assert mllm.INTERNVL2_5_4B_LLM["position_mode"] == "arange" and mllm.MINICPM_O_2_6_LLM["position_mode"] == "cumsum"
+    plain = mo.build_qwen2(TINY, seed=1)
+    vl = mo.build(TINY, seed=2)
+    vl.load_state_dict(plain.state_dict(), strict=False)
+    ids = torch.randint(0, 1000, (2, 40), generator=torch.Generator().manual_seed(3))
+    mask = torch.ones(2, 40, dtype=torch.long)
+    mask[1, :13] = 0
+    a = mo.prefill_hidden_states_plain(plain, ids, mask, "arange")
+    c = mo.prefill_hidden_states_plain(plain, ids, mask, "cumsum")
+    v = mask.bool()[:, None, :, None].expand_as(a)
+    assert torch.equal(c, mo.prefill_hidden_states(vl, ids, mask))                # same weights, same rule: the same model
+    assert float((a[v] - c[v]).norm() / c[v].norm()) < 1e-5                        # arange vs cumsum: rounding only
+    pos, start = mllm.Qwen2_5_VLTextPrefill.text_positions(mask, "arange")
+    assert pos[1].tolist() == list(range(40)) and start.tolist() == [0, 13]
+    m = mllm.Qwen2_5_VLTextPrefill(**dict(TINY, position_mode="arange"))
+    for prefix in ("language_model.model.", "llm.model."):                         # InternVLChatModel / MiniCPMO checkpoints
+        sd = {prefix + k: v_ for k, v_ in plain.state_dict().items()}
+        sd.update({"vision_model.embeddings.class_embedding": torch.zeros(1), "mlp1.0.weight": torch.zeros(1), "vpm.x": torch.zeros(1),
+                   "resampler.query": torch.zeros(1), "language_model.lm_head.weight": torch.zeros(1), "llm.lm_head.weight": torch.zeros(1)})
+        m.load_hf_state_dict(sd)
+        assert torch.equal(m.layers[1].self_attn.k_proj.bias, plain.layers[1].self_attn.k_proj.bias)
+
+
 def test_swiglu_weight_packing_layout():
     from x2i_b200 import ops
     g = torch.arange(256 * 8, dtype=torch.float32).view(256, 8)
@@ -210,6 +243,31 @@ def test_tiny_prefill_matches_transformers(ops, B, S, pads):
     assert torch.equal(m.prefill_hidden_states(ids2.cuda(), mask.cuda()), eager2)
     user_out = torch.empty_like(got)
     assert m.prefill_hidden_states(ids.cuda(), mask.cuda(), out=user_out) is user_out and torch.equal(user_out, got)
+
+
+@gpu
+def test_internvl_style_prefill_matches_plain_qwen2_forward(ops):
+    """The InternVL path (model_internvl/internvl/modeling_internvl_chat.py:357-363): a plain Qwen2 language model called without
+    position_ids on a left-padded prompt -> positions = arange(S)."""
+    from oracle import mllm_oracle as mo
+    from x2i_b200 import mllm
+    o = mo.build_qwen2(TINY, seed=21)
+    with torch.no_grad():
+        for p in o.parameters():
+            p.copy_(p.bfloat16().float())
+    m = mllm.Qwen2_5_VLTextPrefill(**dict(TINY, position_mode="arange"))
+    m.load_hf_state_dict({"language_model.model." + k: v for k, v in o.state_dict().items()})
+    m = m.to("cuda", torch.bfloat16).eval()
+    B, S = 2, 300
+    ids = torch.randint(0, 1000, (B, S), generator=torch.Generator().manual_seed(22))
+    mask = torch.ones(B, S, dtype=torch.long)
+    mask[1, :170] = 0
+    ref = mo.prefill_hidden_states_plain(o, ids, mask, "arange")
+    got = m.prefill_hidden_states(ids.cuda(), mask.cuda())
+    eag = mo.prefill_hidden_states_plain(o.to("cuda", torch.bfloat16), ids.cuda(), mask.cuda(), "arange")
+    valid = mask.bool()[:, None, :, None].expand_as(ref)
+    check("InternVL-style prefill (plain Qwen2, arange positions): all layers, valid tokens", rel(got.cpu().float()[valid], ref[valid]),
+          rel(eag.cpu().float()[valid], ref[valid]))
 
 
 @gpu

@@ -17,6 +17,13 @@ third-party ``transformers`` package (``Qwen2_5_VLTextModel``); this file is its
     left-padding (the fused tcgen05 attention kernel, tiles right of the diagonal skipped) -> o_proj + residual -> RMSNorm ->
     gate/up GEMM with the SwiGLU epilogue -> down_proj + residual.
 
+The language models of the reference's other two MLLM families are the same decoder: InternVL2.5-4B wraps Qwen2.5-3B-Instruct
+(``infer/inference_internvl.py:76,:178-184``: its patched ``generate`` returns ``self.language_model(inputs_embeds, attention_mask,
+output_hidden_states=True).hidden_states`` -- 37 x 2048, positions = ``arange(S)`` because no ``position_ids`` are passed,
+``model_internvl/internvl/modeling_internvl_chat.py:357-363``), MiniCPM-o-2.6 wraps Qwen2.5-7B (``infer/inference_minicpm.py:78,:174-176``:
+HF ``generate`` -> 29 x 3584, positions = cumsum(mask) - 1).  ``INTERNVL2_5_4B_LLM`` / ``MINICPM_O_2_6_LLM`` below are those configurations;
+``position_mode`` selects the position rule (RoPE is relative, so both rules give the same states for the real tokens up to rounding).
+
 Scope: text-only prompts (BASELINE config 2).  Image / video inputs need the vision tower, which stays with ``transformers``.
 Padded positions: query rows with no visible key get a zero attention output (what transformers' sdpa and flash paths produce; its
 eager path averages all values instead -- the reference's result at padded positions depends on the attention backend it runs with).
@@ -78,6 +85,12 @@ QWEN2_5_VL_3B = dict(vocab_size=151936, hidden_size=2048, intermediate_size=1100
                      num_key_value_heads=2, rms_norm_eps=1e-6, rope_theta=1000000.0)
 QWEN2_5_VL_7B = dict(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_hidden_layers=28, num_attention_heads=28,
                      num_key_value_heads=4, rms_norm_eps=1e-6, rope_theta=1000000.0)
+# The language models inside the reference's other MLLMs (vocabulary sizes as published in the model repositories' config.json, recalled:
+# no network here -- a checkpoint's own config wins).  InternVL2.5-1B's Qwen2.5-0.5B has head_dim 64 and is outside the d = 128 kernel.
+INTERNVL2_5_4B_LLM = dict(vocab_size=151674, hidden_size=2048, intermediate_size=11008, num_hidden_layers=36, num_attention_heads=16,
+                          num_key_value_heads=2, rms_norm_eps=1e-6, rope_theta=1000000.0, position_mode="arange")
+MINICPM_O_2_6_LLM = dict(vocab_size=151700, hidden_size=3584, intermediate_size=18944, num_hidden_layers=28, num_attention_heads=28,
+                         num_key_value_heads=4, rms_norm_eps=1e-6, rope_theta=1000000.0, position_mode="cumsum")
 
 
 class Qwen2_5_VLTextPrefill(nn.Module):
@@ -85,8 +98,12 @@ class Qwen2_5_VLTextPrefill(nn.Module):
     ``norm``); ``load_hf_state_dict`` accepts a ``Qwen2_5_VLForConditionalGeneration`` checkpoint (either key generation)."""
 
     def __init__(self, vocab_size=151936, hidden_size=2048, intermediate_size=11008, num_hidden_layers=36, num_attention_heads=16,
-                 num_key_value_heads=2, rms_norm_eps=1e-6, rope_theta=1000000.0, head_dim=128):
+                 num_key_value_heads=2, rms_norm_eps=1e-6, rope_theta=1000000.0, head_dim=128, position_mode="cumsum"):
         super().__init__()
+        if position_mode not in ("cumsum", "arange"):
+            raise X2IError("Qwen2_5_VLTextPrefill: position_mode is 'cumsum' (Qwen2.5-VL get_rope_index / HF generate) or 'arange' "
+                           "(a plain forward without position_ids: InternVL's patched generate)")
+        self.position_mode = position_mode
         if head_dim != 128 or hidden_size // num_attention_heads != 128:
             raise X2IError("Qwen2_5_VLTextPrefill: the attention kernel is specialised for head_dim 128 (all Qwen2.5-VL sizes)")
         if intermediate_size % 128 or hidden_size % 64 or num_attention_heads % num_key_value_heads:
@@ -114,11 +131,12 @@ class Qwen2_5_VLTextPrefill(nn.Module):
         ``model.*`` (4.49, the reference's pin) or bare; ``visual.*`` and ``lm_head.*`` are ignored."""
         sd = {}
         for k, v in state_dict.items():
-            for pre in ("model.language_model.", "language_model.model.", "language_model.", "model."):
+            for pre in ("model.language_model.", "language_model.model.", "language_model.", "llm.model.", "llm.", "model."):
                 if k.startswith(pre):
                     k = k[len(pre):]
                     break
-            if k.startswith(("visual.", "lm_head.", "model.visual.")):
+            if k.startswith(("visual.", "lm_head.", "model.visual.", "vision_model.", "mlp1.", "vpm.", "resampler.", "apm.", "tts.",
+                             "audio_projection_layer.", "audio_avg_pooler.")):
                 continue
             sd[k] = v
         self._packed = None
@@ -143,11 +161,15 @@ class Qwen2_5_VLTextPrefill(nn.Module):
 
     # ---- prefill ---------------------------------------------------------------------------------------------------------
     @staticmethod
-    def text_positions(attention_mask):
-        """Qwen2_5_VLModel.get_rope_index for text-only inputs: position = cumsum(mask) - 1, padded tokens 1 (all three M-RoPE
-        sections carry it).  Also the first valid key per row for the attention kernel (left padding)."""
+    def text_positions(attention_mask, mode: str = "cumsum"):
+        """mode 'cumsum': Qwen2_5_VLModel.get_rope_index for text-only inputs (and HF generate's rule for plain Qwen2): position =
+        cumsum(mask) - 1, padded tokens 1 (all three M-RoPE sections carry it).  mode 'arange': position = column index, what a forward
+        without position_ids uses (InternVL's patched generate).  Also the first valid key per row for the attention kernel (left padding)."""
         mask = attention_mask.to(torch.int64)
-        pos = (mask.cumsum(-1) - 1).masked_fill(mask == 0, 1)
+        if mode == "arange":
+            pos = torch.arange(mask.shape[1], device=mask.device, dtype=torch.int64)[None].expand_as(mask)
+        else:
+            pos = (mask.cumsum(-1) - 1).masked_fill(mask == 0, 1)
         if bool(((mask[:, 1:] - mask[:, :-1]) < 0).any()):
             raise X2IError("Qwen2_5_VLTextPrefill: only left padding is supported (the reference pads on the left, "
                            "train/train_qwenvl.py:397); a 1 -> 0 transition was found in attention_mask")
@@ -166,7 +188,7 @@ class Qwen2_5_VLTextPrefill(nn.Module):
         H, L = cfg.hidden_size, cfg.num_hidden_layers
         if attention_mask is None:
             attention_mask = torch.ones(B, S, dtype=torch.int64, device=dev)
-        pos, start = self.text_positions(attention_mask.to(dev))
+        pos, start = self.text_positions(attention_mask.to(dev), self.position_mode)
         if out is not None and (out.shape != (B, L + 1, S, H) or out.dtype != BF16 or not out.is_contiguous()):
             raise X2IError("prefill_hidden_states: out must be a contiguous bf16 [B, num_layers + 1, S, hidden] tensor")
         if not self.use_cuda_graph or torch.cuda.is_current_stream_capturing():
