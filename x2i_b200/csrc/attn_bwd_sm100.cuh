@@ -143,6 +143,10 @@ __device__ __forceinline__ void attention_bwd_body(const CUtensorMap& tma_x0, co
   __syncthreads();
   if constexpr (MC) abw_cluster_sync();  // the peer's barriers exist before any multicast box or commit can reach them
   tc_fence_after();
+  if constexpr (!MC) {
+    griddep_launch();  // PDL (common.cuh): the dQ launch's prologue overlaps the dK/dV launch's tail, and so on down the stream
+    griddep_wait();
+  }
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t crank = MC ? abw_cluster_ctarank() : 0u;
   // TMEM columns, dK/dV launch: [0,128) T buffer 0 (T1 | T2), [128,256) T buffer 1, [256,384) acc0, [384,512) acc1

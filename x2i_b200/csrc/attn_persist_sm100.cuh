@@ -85,6 +85,8 @@ mmdit_attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tma_q,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  griddep_launch();  // PDL (common.cuh): prologue overlaps the predecessor's tail; global memory only after griddep_wait()
+  griddep_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {

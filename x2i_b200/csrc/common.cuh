@@ -233,6 +233,14 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream is still
+// draining: griddep_wait() blocks until every earlier grid has completed and its memory is visible -- nothing before it may touch global
+// memory that an earlier kernel writes or reads; griddep_launch() lets the NEXT kernel's CTAs be scheduled as soon as this grid's CTAs
+// have all started (they then sit in their own griddep_wait() behind their prologue: barrier init, TMEM allocation, descriptor prefetch).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -154,6 +154,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
   cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();  // PDL: the next kernel's prologue may overlap this kernel's tail ...
+  griddep_wait();    // ... and this kernel touches global memory only after its predecessors are complete
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (one per CTA)

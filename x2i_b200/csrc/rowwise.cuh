@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(256, MAXC <= 12 ? 4 : 2) ln_modulate_kernel(co
                                                           const __nv_bfloat16* __restrict__ shift, long long mod_stride,
                                                           __nv_bfloat16* __restrict__ y, long long ldy, int rows, int D,
                                                           int rows_per_batch, float eps) {
+  griddep_launch();  // PDL (common.cuh)
+  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
