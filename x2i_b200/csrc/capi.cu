@@ -110,21 +110,6 @@ int make_map(DeviceInfo* d, CUtensorMap* m, const void* ptr, int rank, const uin
   return X2I_OK;
 }
 
-template <int BN, int EPI, bool B_MN, bool A_MN = false, int B_CONV = 0>
-int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_tcgen05_kernel<BN, EPI, B_MN, A_MN, B_CONV>;
-  static std::atomic<bool> configured[16];  // per device, per instantiation (keeps the call out of graph captures)
-  if (!configured[d->index].load(std::memory_order_acquire)) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
-    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
-    configured[d->index].store(true, std::memory_order_release);
-  }
-  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN) * (p.ksplit > 1 ? p.ksplit : 1);
-  const int grid = tiles < d->sms ? tiles : d->sms;
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, st>>>(ta, tb, p);
-  return check_launch("gemm_tcgen05_kernel");
-}
-
 // Launch with programmatic stream serialisation (PDL, common.cuh): only for kernels that call griddep_wait() before touching global
 // memory.  X2I_PDL=0 launches them the plain way (same kernels, the in-kernel calls are then no-ops).  Measured on the denoise step
 // (GEMM, attention and ln_modulate kernels = 98 % of its launches; A/B on two boxes): 62.4-63.8 -> 61.9-63.4 ms, +0.7-0.9 %.
@@ -155,6 +140,21 @@ void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // errors surface through check_launch()
+}
+
+template <int BN, int EPI, bool B_MN, bool A_MN = false, int B_CONV = 0>
+int launch_gemm_t(DeviceInfo* d, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_tcgen05_kernel<BN, EPI, B_MN, A_MN, B_CONV>;
+  static std::atomic<bool> configured[16];  // per device, per instantiation (keeps the call out of graph captures)
+  if (!configured[d->index].load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+    configured[d->index].store(true, std::memory_order_release);
+  }
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN) * (p.ksplit > 1 ? p.ksplit : 1);
+  const int grid = tiles < d->sms ? tiles : d->sms;
+  launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), GemmCfg<BN>::SMEM_BYTES, st, ta, tb, p);
+  return check_launch("gemm_tcgen05_kernel");
 }
 
 template <int EPI, bool B_MN = false>
@@ -1074,9 +1074,9 @@ int x2i_rmsnorm(const void* x, int64_t ldx, int64_t x_batch_stride, const void* 
   auto Y = static_cast<__nv_bfloat16*>(y);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nchunk = D / 8;
-  if (nchunk <= 32 * 4) rmsnorm_kernel<4><<<grid, 256, 0, st>>>(X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
-  else if (nchunk <= 32 * 8) rmsnorm_kernel<8><<<grid, 256, 0, st>>>(X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
-  else rmsnorm_kernel<16><<<grid, 256, 0, st>>>(X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
+  if (nchunk <= 32 * 4) launch_pdl(rmsnorm_kernel<4>, dim3(grid), dim3(256), 0, st, X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
+  else if (nchunk <= 32 * 8) launch_pdl(rmsnorm_kernel<8>, dim3(grid), dim3(256), 0, st, X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
+  else launch_pdl(rmsnorm_kernel<16>, dim3(grid), dim3(256), 0, st, X, ldx, x_batch_stride, W, Y, ldy, y_batch_stride, rows, rows_per_batch, D, eps);
   return check_launch("rmsnorm_kernel");
 }
 
@@ -1088,9 +1088,9 @@ int x2i_rope_half_split(const void* qkv, int64_t ld, const int* pos, const float
   if (!pos || !inv_freq || !aligned16(qkv) || !aligned16(q) || !aligned16(k) || !aligned16(v) || ld % 8 || ld < (heads + 2 * heads_kv) * 128)
     return fail(X2I_ERR_ALIGN, "rope_half_split: alignment / row stride");
   const int rows = B * S;
-  rope_half_split_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), ld, pos, inv_freq, static_cast<__nv_bfloat16*>(q), static_cast<__nv_bfloat16*>(k),
-      static_cast<__nv_bfloat16*>(v), rows, S, heads, heads_kv);
+  launch_pdl(rope_half_split_kernel, dim3((rows + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const __nv_bfloat16*>(qkv), static_cast<long long>(ld), pos, inv_freq, static_cast<__nv_bfloat16*>(q),
+             static_cast<__nv_bfloat16*>(k), static_cast<__nv_bfloat16*>(v), rows, S, heads, heads_kv);
   return check_launch("rope_half_split_kernel");
 }
 

@@ -406,6 +406,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();  // PDL (common.cuh): prologue above overlaps the predecessor's tail; no global access before the wait
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

@@ -31,6 +31,8 @@ template <int MAXC>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long x_batch_stride,
                                                       const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
                                                       long long y_batch_stride, int rows, int rows_per_batch, int D, float eps) {
+  griddep_launch();  // PDL (common.cuh)
+  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -74,6 +76,8 @@ __global__ void __launch_bounds__(256) rope_half_split_kernel(const __nv_bfloat1
                                                               const float* __restrict__ inv_freq, __nv_bfloat16* __restrict__ q,
                                                               __nv_bfloat16* __restrict__ k, __nv_bfloat16* __restrict__ v, int rows,
                                                               int S, int H, int Hkv) {
+  griddep_launch();  // PDL (common.cuh)
+  griddep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
