@@ -324,7 +324,7 @@ int x2i_groupnorm_nhwc_grouped(const void* x, const void* gamma, const void* bet
                                int HW, int C, int G, float eps, int act, int param_sets, void* stream);
 
 /* ---- LightControl trainer building blocks (lightcontrol/train_lightcontrol.py:672-775: the ControlNeXt nets are
- * the trainable part; the trainer itself is not assembled yet) --------------------------------------------------------------
+ * the trainable part; the trainer is x2i_b200/train_lightcontrol.py) --------------------------------------------------------------
  * Backward of y = act(GroupNorm(x)): dx (bf16), dgamma / dbeta (fp32 [C], overwritten or accumulated); statistics are recomputed
  * from x.  Groups of a multiple of 8 channels.  Deterministic.  workspace: x2i_groupnorm_bwd_workspace_floats() floats.        */
 int x2i_groupnorm_nhwc_bwd(const void* x, const void* dy, const void* gamma, const void* beta, void* dx, float* dgamma, float* dbeta,
