@@ -184,6 +184,11 @@ int x2i_cross_attention(const void* q, const void* k, const void* v, const int* 
  * ZeroSingle / Continuous [D031] and norm2 + modulate (lightcontrol_flux.py:89, :166-170, :183-184, :196-197, :542). */
 int x2i_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* shift, int64_t mod_stride, void* y,
                     int64_t ldy, int rows, int D, int rows_per_batch, float eps, void* stream);
+/* The same for TWO row segments in one launch: the image and the text stream of a double block (FluxTransformerBlock.norm1 / norm1_context
+ * and the two norm2 + modulate steps, lightcontrol_flux.py:140-146,:171-179) live in separate buffers with their own modulation rows. */
+int x2i_ln_modulate2(const void* x0, int64_t ldx0, const void* scale0, const void* shift0, int64_t mod_stride0, void* y0, int64_t ldy0, int rows0,
+                     int rows_per_batch0, const void* x1, int64_t ldx1, const void* scale1, const void* shift1, int64_t mod_stride1, void* y1,
+                     int64_t ldy1, int rows1, int rows_per_batch1, int D, float eps, void* stream);
 
 /* y = LayerNorm(x) * gamma + beta (nn.LayerNorm with affine): Resampler ln_q / ln_kv / ln_post (minicpm/resampler.py:
  * 116-119, :166-168, :184).                                                                                         */

@@ -1,0 +1,16 @@
+#!/bin/bash
+# GPU job 3J: image + text ln_modulate of a double block in one launch: parity tests, row-wise timing, bench line.
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r03j_build.log 2>&1
+timeout 1500 python -m pytest tests/test_gpu_flux.py tests/test_gpu_kernels.py tests/test_gpu_parity_full.py tests/test_gpu_fullsize.py tests/test_controlnext.py -x -q -m gpu > gpurun_out/r03j_tests.log 2>&1; echo "tests rc=$?" | tee gpurun_out/r03j_rc.log
+tail -3 gpurun_out/r03j_tests.log
+timeout 300 python tools/bench_rowwise.py 2>/dev/null | grep ln_modulate | cut -c1-200
+for rep in 1 2; do
+timeout 600 python bench.py --steps 20 --warmup 5 --no-train --no-cpu-baseline --no-library-baseline > gpurun_out/r03j_b.json 2> gpurun_out/r03j_b.err; echo "rep=$rep rc=$?"
+python - <<PY
+import json
+j = json.loads([l for l in open("gpurun_out/r03j_b.json") if l.startswith("{")][0])
+r = j["roofline"]
+print("   value", round(j["value"], 3), "ms", round(j["ms_per_step"], 3), "e2e", round(j["e2e"]["value"], 3), "attn ms", round(r["ms_per_launch"], 4), j["clocks"]["sm_mhz"], "launches", j["gpu_launches"])
+PY
+done

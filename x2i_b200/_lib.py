@@ -35,6 +35,7 @@ SIGNATURES = {
     "x2i_layernorm_affine": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _vp],
     "x2i_add_pos2d": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "x2i_ln_modulate": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp],
+    "x2i_ln_modulate2": [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp],
     "x2i_gate_residual": [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _vp],
     "x2i_skinny_linear": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "x2i_timestep_sinusoid": [_vp, _vp, _i, _i, _vp],

@@ -745,10 +745,39 @@ int x2i_ln_modulate(const void* x, int64_t ldx, const void* scale, const void* s
   auto Y = static_cast<__nv_bfloat16*>(y);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nchunk = D / 8;
-  if (nchunk <= 32 * 4) launch_pdl(ln_modulate_kernel<4, false>, dim3(grid), dim3(256), 0, st, X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps);
-  else if (nchunk <= 32 * 12) launch_pdl(ln_modulate_kernel<12, false>, dim3(grid), dim3(256), 0, st, X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps);
-  else launch_pdl(ln_modulate_kernel<16, false>, dim3(grid), dim3(256), 0, st, X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps);
+  LnSeg s1;
+  memset(&s1, 0, sizeof(s1));
+  if (nchunk <= 32 * 4) launch_pdl(ln_modulate_kernel<4, false>, dim3(grid), dim3(256), 0, st, X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps, s1);
+  else if (nchunk <= 32 * 12) launch_pdl(ln_modulate_kernel<12, false>, dim3(grid), dim3(256), 0, st, X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps, s1);
+  else launch_pdl(ln_modulate_kernel<16, false>, dim3(grid), dim3(256), 0, st, X, ldx, SC, SH, mod_stride, Y, ldy, rows, D, rows_per_batch, eps, s1);
   return check_launch("ln_modulate_kernel");
+}
+
+int x2i_ln_modulate2(const void* x0, int64_t ldx0, const void* scale0, const void* shift0, int64_t mod_stride0, void* y0, int64_t ldy0, int rows0,
+                     int rows_per_batch0, const void* x1, int64_t ldx1, const void* scale1, const void* shift1, int64_t mod_stride1, void* y1,
+                     int64_t ldy1, int rows1, int rows_per_batch1, int D, float eps, void* stream) {
+  DeviceInfo* d;
+  if (int rc = device_info(&d)) return rc;
+  if (rows0 <= 0 || rows1 <= 0 || D <= 0 || D % 8 || D > 32 * 8 * 16 || rows_per_batch0 <= 0 || rows_per_batch1 <= 0)
+    return fail(X2I_ERR_SHAPE, "ln_modulate2: D=%d must be a multiple of 8 and <= 4096, both segments non-empty", D);
+  if (!aligned16(x0) || !aligned16(y0) || !aligned16(scale0) || !aligned16(shift0) || ldx0 % 8 || ldy0 % 8 || mod_stride0 % 8 || !aligned16(x1) ||
+      !aligned16(y1) || !aligned16(scale1) || !aligned16(shift1) || ldx1 % 8 || ldy1 % 8 || mod_stride1 % 8)
+    return fail(X2I_ERR_ALIGN, "ln_modulate2: alignment");
+  LnSeg s1;
+  s1.x = static_cast<const __nv_bfloat16*>(x1); s1.scale = static_cast<const __nv_bfloat16*>(scale1); s1.shift = static_cast<const __nv_bfloat16*>(shift1);
+  s1.y = static_cast<__nv_bfloat16*>(y1); s1.ldx = ldx1; s1.ldy = ldy1; s1.mod_stride = mod_stride1; s1.rows = rows1; s1.rows_per_batch = rows_per_batch1;
+  dim3 grid((rows0 + rows1 + 7) / 8);
+  auto X = static_cast<const __nv_bfloat16*>(x0);
+  auto SC = static_cast<const __nv_bfloat16*>(scale0);
+  auto SH = static_cast<const __nv_bfloat16*>(shift0);
+  auto Y = static_cast<__nv_bfloat16*>(y0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long l0 = ldx0, l1 = mod_stride0, l2 = ldy0;
+  const int nchunk = D / 8;
+  if (nchunk <= 32 * 4) launch_pdl(ln_modulate_kernel<4, false>, grid, dim3(256), 0, st, X, l0, SC, SH, l1, Y, l2, rows0, D, rows_per_batch0, eps, s1);
+  else if (nchunk <= 32 * 12) launch_pdl(ln_modulate_kernel<12, false>, grid, dim3(256), 0, st, X, l0, SC, SH, l1, Y, l2, rows0, D, rows_per_batch0, eps, s1);
+  else launch_pdl(ln_modulate_kernel<16, false>, grid, dim3(256), 0, st, X, l0, SC, SH, l1, Y, l2, rows0, D, rows_per_batch0, eps, s1);
+  return check_launch("ln_modulate_kernel(2 segments)");
 }
 
 int x2i_layernorm_affine(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy, int rows, int D,
@@ -765,9 +794,9 @@ int x2i_layernorm_affine(const void* x, int64_t ldx, const void* gamma, const vo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int nchunk = D / 8;
   // gamma / beta are shared by all rows: one "batch" spanning every row, modulation stride 0
-  if (nchunk <= 32 * 4) ln_modulate_kernel<4, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps);
-  else if (nchunk <= 32 * 12) ln_modulate_kernel<12, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps);
-  else ln_modulate_kernel<16, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps);
+  if (nchunk <= 32 * 4) ln_modulate_kernel<4, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps, LnSeg{});
+  else if (nchunk <= 32 * 12) ln_modulate_kernel<12, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps, LnSeg{});
+  else ln_modulate_kernel<16, true><<<grid, 256, 0, st>>>(X, ldx, G, Bt, 0, Y, ldy, rows, D, rows, eps, LnSeg{});
   return check_launch("ln_modulate_kernel<affine>");
 }
 

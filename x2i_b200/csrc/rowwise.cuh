@@ -70,16 +70,31 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* red /* [NV * NW
 // The row stays in registers as PACKED bf16 (48 registers at D = 3072) and is unpacked in each of the three passes (sum, centred
 // squares, output): ~64 registers per thread instead of ~128, i.e. 4 CTAs per SM -- all 576 CTAs of a 4608-row call are resident at once
 // (one wave instead of 1.95), and the shared scale / shift rows are requested BEFORE the reductions so their L2 latency hides behind them.
+// Two row segments in one launch (the image and the text stream of a double block live in separate buffers with their own modulation
+// rows): rows [0, rows) belong to segment 0, rows [rows, rows + s1.rows) to `s1`.  s1.rows == 0: a plain single-segment call.
+struct LnSeg {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* scale;
+  const __nv_bfloat16* shift;
+  __nv_bfloat16* y;
+  long long ldx, ldy, mod_stride;
+  int rows, rows_per_batch;
+};
 template <int MAXC, bool AFFINE = false>
 __global__ void __launch_bounds__(256, MAXC <= 12 ? 4 : 2) ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                           const __nv_bfloat16* __restrict__ scale,
                                                           const __nv_bfloat16* __restrict__ shift, long long mod_stride,
                                                           __nv_bfloat16* __restrict__ y, long long ldy, int rows, int D,
-                                                          int rows_per_batch, float eps) {
+                                                          int rows_per_batch, float eps, const LnSeg s1) {
   griddep_launch();  // PDL (common.cuh)
   griddep_wait();
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows + s1.rows) return;
+  if (row >= rows) {  // warp-uniform: second segment
+    row -= rows;
+    x = s1.x; ldx = s1.ldx; scale = s1.scale; shift = s1.shift; mod_stride = s1.mod_stride; y = s1.y; ldy = s1.ldy;
+    rows_per_batch = s1.rows_per_batch;
+  }
   const int lane = threadIdx.x & 31;
   const int nchunk = D >> 3;  // 16-byte chunks per row
   const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);

@@ -348,8 +348,12 @@ class FluxTransformerBlock(nn.Module):
         if _rope is None and image_rotary_emb is not None:
             _rope = compact_rope(image_rotary_emb)
         x2, c2 = x.view(B * L_img, D), c.view(B * S, D)
-        nx = ops.ln_modulate(x2, mi[1], mi[0], L_img, out=ws.get("nx")).view(B, L_img, D)
-        nc = ops.ln_modulate(c2, mc[1], mc[0], S, out=ws.get("nc")).view(B, S, D)
+        nx_buf, nc_buf = ws.get("nx"), ws.get("nc")
+        if nx_buf is None or nc_buf is None:
+            nx_buf = torch.empty(B * L_img, D, device=x.device, dtype=BF16)
+            nc_buf = torch.empty(B * S, D, device=x.device, dtype=BF16)
+        ops.ln_modulate2(x2, mi[1], mi[0], L_img, nx_buf, c2, mc[1], mc[0], S, nc_buf)  # image + text stream in one launch
+        nx, nc = nx_buf.view(B, L_img, D), nc_buf.view(B, S, D)
         if _default_proc(self.attn):
             ctx = FusedCtx(rope=_rope, gate_img=mi[2], res_img=x2, gate_txt=mc[2], res_txt=c2,
                            want_aux=len(self.attn._forward_hooks) > 0, ws=ws)
@@ -358,8 +362,7 @@ class FluxTransformerBlock(nn.Module):
             a_img, a_txt = self.attn(hidden_states=nx, encoder_hidden_states=nc, image_rotary_emb=image_rotary_emb)
             ops.gate_residual_(x2, a_img.reshape(B * L_img, D), mi[2], L_img)
             ops.gate_residual_(c2, a_txt.reshape(B * S, D), mc[2], S)
-        nx2 = ops.ln_modulate(x2, mi[4], mi[3], L_img, out=ws.get("nx"))
-        nc2 = ops.ln_modulate(c2, mc[4], mc[3], S, out=ws.get("nc"))
+        nx2, nc2 = ops.ln_modulate2(x2, mi[4], mi[3], L_img, nx_buf, c2, mc[4], mc[3], S, nc_buf)
         F = self.ff.net[0].proj.weight.shape[0]
         hx, hc = ws.get("ffx"), ws.get("ffc")
         if hx is None or hx.shape != (B * L_img, F) or hc.shape != (B * S, F):

@@ -221,6 +221,20 @@ def nvtx(name):
     return torch.cuda.nvtx.range(name)
 
 
+def ln_modulate2(x0, scale0, shift0, rpb0, out0, x1, scale1, shift1, rpb1, out1, eps=1e-6):
+    """ln_modulate of two row segments (image + text stream of a double block) in ONE launch; outputs are written in place."""
+    for t, n in ((x0, "x0"), (scale0, "scale0"), (shift0, "shift0"), (out0, "out0"), (x1, "x1"), (scale1, "scale1"), (shift1, "shift1"), (out1, "out1")):
+        _chk(t, n)
+    r0, ldx0 = _rows(x0)
+    r1, ldx1 = _rows(x1)
+    D = x0.shape[-1]
+    if x1.shape[-1] != D or scale0.stride(0) != shift0.stride(0) or scale1.stride(0) != shift1.stride(0):
+        raise _lib.X2IError("ln_modulate2: both segments share D; scale and shift of a segment share one row stride")
+    _lib.call("x2i_ln_modulate2", _p(x0), ldx0, _p(scale0), _p(shift0), scale0.stride(0), _p(out0), _rows(out0)[1], r0, rpb0,
+              _p(x1), ldx1, _p(scale1), _p(shift1), scale1.stride(0), _p(out1), _rows(out1)[1], r1, rpb1, D, eps, _stream())
+    return out0, out1
+
+
 def ln_modulate(x, scale, shift, rows_per_batch, eps=1e-6, out=None):
     """LayerNorm(x) * (1 + scale[b]) + shift[b]; scale/shift: [B, D] views sharing one row stride."""
     _chk(x, "x"); _chk(scale, "scale"); _chk(shift, "shift")
