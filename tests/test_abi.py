@@ -74,3 +74,24 @@ def test_library_has_blackwell_sass(built):
     for op in ("UTCHMMA", "LDTM", "UTMALDG", "STTM"):
         assert op in sass, f"{op} missing from SASS"
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path found"
+
+
+def test_shape_rules_of_the_tensor_pipe_forms(built):
+    """The `_supported` helpers are pure host logic (no device needed): which shapes take the implicit convolution weight gradient and the
+    tensor-pipe layer-mixing convolution, and which fall back to the explicit / stencil kernels."""
+    from x2i_b200 import _lib
+    L = _lib.lib()
+    wg = L.x2i_conv2d_nhwc_wgrad_supported  # (H, W, Cin, Cout, KH, KW, stride, pad, pad_end)
+    assert wg(512, 512, 128, 128, 3, 3, 1, 1, 1) == 1          # ControlNeXt resnet conv at 512 x 512: Wo = 512
+    assert wg(512, 512, 128, 128, 3, 3, 2, 1, 1) == 1          # the stride-2 down-sampling conv: Wo = 256
+    assert wg(128, 128, 256, 3072, 2, 2, 2, 0, 0) == 1         # the 2x2 / stride-2 output conv: Wo = 64
+    assert wg(16, 16, 64, 64, 3, 3, 1, 1, 1) == 1              # short rows: 64 % Wo == 0 and Ho * Wo % 64 == 0 (boxes of 4 rows)
+    assert wg(24, 40, 64, 64, 3, 3, 1, 1, 1) == 0              # Wo = 40 does not tile into 64-pixel blocks -> explicit im2col form
+    assert wg(12, 16, 64, 64, 3, 3, 1, 1, 1) == 1 and wg(6, 16, 64, 64, 3, 3, 1, 1, 1) == 0   # Ho * Wo must be a multiple of 64
+    assert wg(512, 512, 3, 64, 3, 3, 2, 1, 1) == 0             # Cin % 64 (the stem pads its 3 channels before calling)
+    assert wg(33, 64, 64, 64, 3, 3, 2, 1, 1) == 0              # stride 2 needs even H and W
+    pc = L.x2i_proj_mix_ln_tc_supported  # (B, C, S, H)
+    assert pc(1, 37, 512, 2048) == 1 and pc(4, 29, 512, 3584) == 1   # the Qwen2.5-VL 3B / 7B projectors
+    assert pc(1, 37, 500, 2048) == 0                           # S % 128 != 0 -> stencil kernel
+    assert pc(1, 64, 512, 2048) == 0                           # more than 40 input channels (weights staged in 4 KB of shared memory)
+    assert pc(1, 25, 512, 896) == 1 and pc(1, 25, 512, 256) == 0    # InternVL-1B projector width is fine, tiny H is not worth it
