@@ -613,8 +613,17 @@ class FluxTransformer2DModel(nn.Module):
                                       guided_hint=guided_hint, control_nets=control_nets)
         elif control_nets is not None and len(control_nets) > 0:
             _no_grad_needed(hidden_states, encoder_hidden_states, pooled_projections)
-            out = self._forward_eager(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
-                                      guided_hint=guided_hint, control_nets=control_nets, mod=x2i_modulation)
+            stack = self._control_stack(control_nets) if self._graphable() else None
+            if stack is not None:
+                # LightControl editing step through the graph: the nets' mid features (hint-only part cached across steps) are computed
+                # launch by launch, the transformer with the 19 injection convs is ONE graph replay
+                with ops.nvtx("x2i.control_nets(stacked)"):
+                    mids = stack.mid_features(guided_hint, timestep.to(BF16) * 1000)
+                out = self._forward_graphed(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+                                            mod=x2i_modulation, mids=mids, control_nets=control_nets)
+            else:
+                out = self._forward_eager(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
+                                          guided_hint=guided_hint, control_nets=control_nets, mod=x2i_modulation)
         elif torch.is_grad_enabled() and any(t is not None and t.requires_grad
                                              for t in (hidden_states, encoder_hidden_states, pooled_projections)):
             out = self._forward_train(hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance)
@@ -694,11 +703,24 @@ class FluxTransformer2DModel(nn.Module):
                 return False  # hooks / plug-in processors run Python per block: eager path
         return True
 
-    def _forward_graphed(self, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance, mod=None):
+    def _control_stack(self, control_nets):
+        """The ControlNeXtStack of `control_nets` (cached), or None when the nets cannot be stacked."""
+        from .controlnext import ControlNeXtStack
+        if not (self.stack_control_nets and ControlNeXtStack.supported(control_nets)):
+            return None
+        if self._cn_stack is None or self._cn_stack.nets != list(control_nets):
+            self._cn_stack = ControlNeXtStack(control_nets)
+        return self._cn_stack
+
+    def _forward_graphed(self, hidden_states, encoder_hidden_states, pooled, timestep, img_ids, txt_ids, guidance, mod=None, mids=None,
+                         control_nets=None):
         B, L_img, _ = hidden_states.shape
         S = encoder_hidden_states.shape[1]
         _, rope = self._rope(txt_ids, img_ids)
         key = (B, S, L_img, guidance is not None, rope.data_ptr(), self._w_mod.data_ptr(), mod is not None)
+        if mids is not None:  # the injection convs read the nets' last-conv weights inside the graph
+            key += tuple((n.mid_convs[1].weight.data_ptr(), n.mid_convs[1].weight._version, n.mid_convs[1].bias._version) for n in control_nets)
+            key += (tuple(mids.shape),)
         st = self._graphs.get(key) if hasattr(self, "_graphs") else None
         if st is None:
             if not hasattr(self, "_graphs"):
@@ -709,28 +731,31 @@ class FluxTransformer2DModel(nn.Module):
                        p=torch.empty(B, pooled.shape[1], device=dev, dtype=BF16),
                        t=torch.empty(B, device=dev, dtype=torch.float32),
                        g=torch.empty(B, device=dev, dtype=torch.float32) if guidance is not None else None,
-                       m=torch.empty_like(mod) if mod is not None else None)
-            self._copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance, mod)
+                       m=torch.empty_like(mod) if mod is not None else None,
+                       c=torch.empty_like(mids) if mids is not None else None)
+            self._copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance, mod, mids)
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):  # warm-up outside the capture: packing, workspaces, function attributes
-                self._forward_eager(sin["h"], sin["e"], sin["p"], sin["t"], img_ids, txt_ids, sin["g"], mod=sin["m"])
+                self._forward_eager(sin["h"], sin["e"], sin["p"], sin["t"], img_ids, txt_ids, sin["g"], mod=sin["m"], mids=sin["c"],
+                                    control_nets=control_nets)
             cur.wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with torch.cuda.graph(graph):
-                out = self._forward_eager(sin["h"], sin["e"], sin["p"], sin["t"], img_ids, txt_ids, sin["g"], mod=sin["m"])
+                out = self._forward_eager(sin["h"], sin["e"], sin["p"], sin["t"], img_ids, txt_ids, sin["g"], mod=sin["m"], mids=sin["c"],
+                                          control_nets=control_nets)
             st = (graph, sin, out, _lib.launch_count() - n0)
             self._graphs = {key: st}  # keep one shape resident (24 GB of weights leave room, but workspaces are per shape)
         graph, sin, out, n_kernels = st
-        self._copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance, mod)
+        self._copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance, mod, mids)
         graph.replay()
         _lib.note_graph_replay(n_kernels)
         return out.clone()
 
     @staticmethod
-    def _copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance, mod=None):
+    def _copy_inputs(sin, hidden_states, encoder_hidden_states, pooled, timestep, guidance, mod=None, mids=None):
         sin["h"].copy_(hidden_states, non_blocking=True)
         sin["e"].copy_(encoder_hidden_states, non_blocking=True)
         sin["p"].copy_(pooled, non_blocking=True)
@@ -739,6 +764,8 @@ class FluxTransformer2DModel(nn.Module):
             sin["g"].copy_(guidance.expand(sin["g"].shape[0]) if guidance.dim() > 0 else guidance, non_blocking=True)
         if sin.get("m") is not None:
             sin["m"].copy_(mod, non_blocking=True)
+        if sin.get("c") is not None:
+            sin["c"].copy_(mids, non_blocking=True)
 
     def precompute_modulation(self, timesteps, pooled_projections, guidance=None):
         """Every AdaLN modulation of EVERY step of a sampling schedule in one pass over the modulation weights.
@@ -764,7 +791,7 @@ class FluxTransformer2DModel(nn.Module):
         return out.view(T, B, -1)
 
     def _forward_eager(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids, guidance,
-                       guided_hint=None, control_nets=None, mod=None):
+                       guided_hint=None, control_nets=None, mod=None, mids=None):
         B, L_img, _ = hidden_states.shape
         S = encoder_hidden_states.shape[1]
         D = self.inner_dim
@@ -785,13 +812,9 @@ class FluxTransformer2DModel(nn.Module):
                     temb = self.time_text_embed(t1000, pooled_projections)
                 mod = ops.skinny_linear(temb, self._w_mod, self._b_mod, act_in=1)  # every AdaLN modulation of this step
 
-        mids = None
-        if control_nets is not None and len(control_nets) > 0:
-            from .controlnext import ControlNeXtStack
-            if self.stack_control_nets and ControlNeXtStack.supported(control_nets):
-                stack = self._cn_stack if self._cn_stack is not None and self._cn_stack.nets == list(control_nets) else None
-                if stack is None:
-                    stack = self._cn_stack = ControlNeXtStack(control_nets)
+        if mids is None and control_nets is not None and len(control_nets) > 0:
+            stack = self._control_stack(control_nets)
+            if stack is not None:
                 with ops.nvtx("x2i.control_nets(stacked)"):
                     mids = stack.mid_features(guided_hint, t1000)  # all nets, one launch per layer (they do not depend on x)
 
