@@ -111,6 +111,23 @@ def test_attention_kernel_forms_are_bit_identical(ops):
         assert torch.equal(outs[0], outs[2]), "CTA-pair kernel differs"
         ref = torch.nn.functional.scaled_dot_product_attention(q[:, :1].float(), k[:, :1].float(), v[:, :1].float())
         assert _rel(outs[1].view(Bq, Lq, Hq, DH).transpose(1, 2)[:, :1], ref) < 6e-3
+        # column-split soft-max (attn_cs_sm100.cuh: both warpgroups on the same query tile, row max / row sum combined from two halves):
+        # same exponentials and the same P, the row sum is added in a different order -> equal up to the last bf16 bit of O
+        os.environ["X2I_ATTN_CS"] = "1"
+        try:
+            ocs = torch.full((Bq, Lq, Hq * DH), float("nan"), device="cuda", dtype=torch.bfloat16)
+            ops.attention(q, k, v, split=0, out1=ocs)
+        finally:
+            os.environ.pop("X2I_ATTN_CS", None)
+        assert _rel(ocs.view(Bq, Lq, Hq, DH).transpose(1, 2)[:, :1], ref) < 6e-3
+        assert _rel(ocs, outs[1]) < 2e-3 and float((ocs.float() - outs[1].float()).abs().max()) < 0.05
+        os.environ["X2I_ATTN_CS"] = "0"
+        try:
+            o0 = torch.empty_like(ocs)
+            ops.attention(q, k, v, split=0, out1=o0)
+        finally:
+            os.environ.pop("X2I_ATTN_CS", None)
+        assert torch.equal(o0, outs[1])
 
 
 def test_attention_full_size_shift_invariance(ops):

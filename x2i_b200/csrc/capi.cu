@@ -12,6 +12,7 @@
 #include "attn_sm100.cuh"
 #include "attn2_sm100.cuh"
 #include "attn_persist_sm100.cuh"
+#include "attn_cs_sm100.cuh"
 #include "conv_sm100.cuh"
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
@@ -590,6 +591,9 @@ int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0,
   return x2i_cross_attention(q, k, v, nullptr, out0, ld0, split, out1, ld1, B, heads, L, L, stream);
 }
 
+#ifndef X2I_ATTN_CS_DEFAULT
+#define X2I_ATTN_CS_DEFAULT 0
+#endif
 #ifndef X2I_ATTN_PERSIST_DEFAULT
 #define X2I_ATTN_PERSIST_DEFAULT 1
 #endif
@@ -693,6 +697,20 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
     if (n_items_ll > 0x7fffffffLL) return fail(X2I_ERR_SHAPE, "attention: too many work items");
     const int n_items = static_cast<int>(n_items_ll);
     const int gridp = n_items < d->sms ? n_items : d->sms;
+    // Column-split soft-max (attn_cs_sm100.cuh): both warpgroups on the same query tile.  X2I_ATTN_CS=0/1, read per call (tests run both).
+    const char* cs_env = getenv("X2I_ATTN_CS");
+    const int cs = cs_env ? atoi(cs_env) : X2I_ATTN_CS_DEFAULT;
+    if (cs && !lm) {
+      auto kerncs = mmdit_attention_fwd_persistent_cs_kernel<ATT_DEFAULT_POLY8>;
+      static std::atomic<bool> attcs_configured[16];
+      if (!attcs_configured[d->index].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(kerncs, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTCS_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention column-split): %s", cudaGetErrorString(e));
+        attcs_configured[d->index].store(true, std::memory_order_release);
+      }
+      launch_pdl(kerncs, dim3(gridp), dim3(ATT_THREADS), ATTCS_SMEM_BYTES, static_cast<cudaStream_t>(stream), tq, tk, tv, p, n_qblk, n_items);
+      return check_launch("mmdit_attention_fwd_persistent_cs_kernel");
+    }
     static const bool pdl_attn = []() { const char* e = getenv("X2I_PDL_ATTN"); return e ? atoi(e) != 0 : true; }();  // experiment switch
     launch_pdl_if(pdl_enabled() && pdl_attn, kernp, dim3(gridp), dim3(ATT_THREADS), ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream), tq, tk, tv, p, n_qblk, n_items);
     return check_launch("mmdit_attention_fwd_persistent_kernel");
