@@ -93,7 +93,10 @@ def test_attention_kernel_forms_are_bit_identical(ops):
     tiles: bit-identical outputs at the full size, on a ragged length (odd number of query blocks, partial last key tile) and with more
     work items than SMs can hold in one round."""
     import os
-    modes = [dict(X2I_ATTN_PAIR="0", X2I_ATTN_PERSIST="0"), dict(X2I_ATTN_PAIR="0", X2I_ATTN_PERSIST="1"), dict(X2I_ATTN_PAIR="1", X2I_ATTN_PERSIST="0")]
+    # X2I_ATTN_LAG=0: the classic soft-max step in the persistent kernel (its default, the lagged step, is not bit-identical to the other forms:
+    # test_attention_lagged_form_matches_fp32_and_default)
+    modes = [dict(X2I_ATTN_PAIR="0", X2I_ATTN_PERSIST="0"), dict(X2I_ATTN_PAIR="0", X2I_ATTN_PERSIST="1", X2I_ATTN_LAG="0"),
+             dict(X2I_ATTN_PAIR="1", X2I_ATTN_PERSIST="0")]
     for Bq, Hq, Lq in ((1, 4, L), (1, 4, 600), (2, 24, 1100)):
         g = torch.Generator(device="cuda").manual_seed(17)
         q, k, v = (torch.randn(Bq, Hq, Lq, DH, device="cuda", generator=g).bfloat16() for _ in range(3))
@@ -121,13 +124,65 @@ def test_attention_kernel_forms_are_bit_identical(ops):
             os.environ.pop("X2I_ATTN_CS", None)
         assert _rel(ocs.view(Bq, Lq, Hq, DH).transpose(1, 2)[:, :1], ref) < 6e-3
         assert _rel(ocs, outs[1]) < 2e-3 and float((ocs.float() - outs[1].float()).abs().max()) < 0.05
-        os.environ["X2I_ATTN_CS"] = "0"
+        os.environ.update(X2I_ATTN_CS="0", X2I_ATTN_LAG="0")
         try:
             o0 = torch.empty_like(ocs)
             ops.attention(q, k, v, split=0, out1=o0)
         finally:
             os.environ.pop("X2I_ATTN_CS", None)
+            os.environ.pop("X2I_ATTN_LAG", None)
         assert torch.equal(o0, outs[1])
+
+
+def test_attention_lagged_form_matches_fp32_and_default(ops):
+    """Lagged soft-max steps (softmax_step_lagged, X2I_ATTN_LAG=1): the exponentials of a key step run against the reference the row
+    already has, the next reference comes from the step's row sum (one step late); a step whose sum exceeds 2^64 -- or whose
+    polynomial-lane arguments exceed 126 -- makes the CTA re-run its items with the classic step.  Checked against torch fp32 and the
+    default form on (a) random scores, (b) scores that GROW along the keys by ~2^42 per tile (a lagged rescale at every step), (c) the
+    same with ~2^167 per tile (MUFU lanes return inf -> redo pass), (d) a few late keys that dominate single rows by ~2^25, (e) ONE late
+    key ~2^200 above everything else, once on a polynomial lane of the soft-max (its exponent insertion would wrap around silently) and
+    once on a MUFU lane, at the full size, a ragged length and more work items than SMs."""
+    import os
+
+    def run(q, k, v, lag):
+        os.environ["X2I_ATTN_LAG"] = "1" if lag else "0"
+        try:
+            Bq, Hq, Lq, _ = q.shape
+            o = torch.full((Bq, Lq, Hq * DH), float("nan"), device="cuda", dtype=torch.bfloat16)
+            ops.attention(q, k, v, split=0, out1=o)
+            return o
+        finally:
+            os.environ.pop("X2I_ATTN_LAG", None)
+
+    for Bq, Hq, Lq in ((1, 4, L), (1, 4, 600), (2, 24, 1100)):
+        g = torch.Generator(device="cuda").manual_seed(23)
+        q, k, v = (torch.randn(Bq, Hq, Lq, DH, device="cuda", generator=g) for _ in range(3))
+        cases = {"random": (q, k)}
+        # q.k_j = 4 * 128 * slope * j: slope 0.005 -> +328 per 128 keys in raw score units = +42 in the exp2 domain; 0.02 -> +167
+        for name, slope in (("ramp", 0.005), ("steep ramp", 0.02)):
+            ramp = (torch.arange(Lq, device="cuda", dtype=torch.float32) * slope).view(1, 1, Lq, 1)
+            cases[name] = (torch.full_like(q, 4.0) + 0.1 * q, ramp.expand(Bq, Hq, Lq, DH) + 0.05 * k)
+        # 16 late keys aligned with 16 query rows: a spike of ~ +25 in the exp2 domain, elsewhere random
+        k2 = k.clone()
+        rows = torch.randperm(Lq, device="cuda", generator=g)[:16]
+        keys = torch.randint(Lq // 2, Lq, (16,), device="cuda", generator=g)
+        k2[:, :, keys] = q[:, :, rows] * 1.5
+        cases["spikes"] = (q, k2)
+        # one key far above everything: q = 3 + noise, that key = 4 -> q.k ~ 1536 raw = +196 in the exp2 domain.  Lane of key index t within
+        # its 128-key tile: pair (t % 32) // 2; pairs 0, 1, 8, 9 of every quarter run on the polynomial (POLY8 = 2), the rest on MUFU.EX2
+        for name, t_in_tile in (("huge key on a polynomial lane", 32 + 2), ("huge key on a MUFU lane", 32 + 10)):
+            k3 = k.clone()
+            k3[:, :, 256 + t_in_tile] = 4.0
+            cases[name] = (torch.full_like(q, 3.0) + 0.1 * q, k3)
+        for name, (qq, kk) in cases.items():
+            qb, kb, vb = qq.bfloat16(), kk.bfloat16(), v.bfloat16()
+            o_lag, o_def = run(qb, kb, vb, True), run(qb, kb, vb, False)
+            assert torch.isfinite(o_lag.float()).all(), (name, Lq)
+            ref = torch.nn.functional.scaled_dot_product_attention(qb[:, :1].float(), kb[:, :1].float(), vb[:, :1].float())
+            e_lag = _rel(o_lag.view(Bq, Lq, Hq, DH).transpose(1, 2)[:, :1], ref)
+            e_def = _rel(o_def.view(Bq, Lq, Hq, DH).transpose(1, 2)[:, :1], ref)
+            assert e_lag < 6e-3, (name, Lq, e_lag, e_def)
+            assert _rel(o_lag, o_def) < 6e-3, (name, Lq)
 
 
 def test_attention_full_size_shift_invariance(ops):

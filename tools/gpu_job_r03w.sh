@@ -1,0 +1,13 @@
+#!/bin/bash
+# GPU job 3W: lagged-max soft-max steps of the persistent attention forward (X2I_ATTN_LAG=1): correctness (lagged rescale, overflow redo pass), then sustained A/B.
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/r03w_build.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_fullsize.py -x -q -m gpu -k "lagged_max or forms_are_bit_identical" > gpurun_out/r03w_tests.log 2>&1; echo "tests rc=$?" | tee gpurun_out/r03w_rc.log
+tail -12 gpurun_out/r03w_tests.log
+: > gpurun_out/r03w_probe.jsonl
+for rep in 1 2; do
+X2I_ATTN_LAG=0 timeout 120 python tools/attn_probe.py --tag "persistent (default)" >> gpurun_out/r03w_probe.jsonl 2>> gpurun_out/r03w_probe.err
+X2I_ATTN_LAG=1 timeout 120 python tools/attn_probe.py --tag "lagged-max" >> gpurun_out/r03w_probe.jsonl 2>> gpurun_out/r03w_probe.err
+done
+timeout 120 python tools/attn_probe.py --sdpa --tag "sdpa" >> gpurun_out/r03w_probe.jsonl 2>> gpurun_out/r03w_probe.err
+cut -c1-360 gpurun_out/r03w_probe.jsonl; tail -3 gpurun_out/r03w_probe.err

@@ -37,58 +37,20 @@ __device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int w, int n_
   return t;
 }
 
-template <int POLY8, bool LM = false>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-mmdit_attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
-                                      const __grid_constant__ CUtensorMap tma_v, const AttnParams p, const int n_qblk, const int n_items) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sq = smem;                         // Q0 | Q1
-  uint8_t* skv = smem + 2 * ATT_TILE_BYTES;   // ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(skv + ATT_KV_SLOTS * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;                       // 1
-  uint64_t* q_empty = bars + 1;                  // 1: all S products of the item have been issued and retired -> Q may be overwritten
-  uint64_t* kv_full = bars + 2;                  // ATT_KV_SLOTS
-  uint64_t* kv_empty = kv_full + ATT_KV_SLOTS;   // ATT_KV_SLOTS
-  uint64_t* s_full = kv_empty + ATT_KV_SLOTS;    // 2
-  uint64_t* p_full = s_full + 2;                 // 2 x 4
-  uint64_t* o_full = p_full + 8;                 // 2
-  uint64_t* o_empty = o_full + 2;                // 2: the soft-max warpgroup has read O_i of the previous item out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
-  static_assert(ATTP_BARRIERS * 8 + 4 <= 256, "barrier block");
-
-  const int warp = uniform_warp_id();
-  const int lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_q);
-    tma_prefetch_desc(&tma_k);
-    tma_prefetch_desc(&tma_v);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int i = 0; i < ATT_KV_SLOTS; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      for (int c = 0; c < 4; ++c) mbar_init(&p_full[i * 4 + c], 4);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 4);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  griddep_launch();  // PDL (common.cuh): prologue overlaps the predecessor's tail; global memory only after griddep_wait()
-  griddep_wait();
-  const uint32_t tmem_base = *tmem_slot;
-
+// The three warp roles over this CTA's work items.  LAGGED: lagged soft-max steps (softmax_step_lagged, attn_sm100.cuh) for every unmasked
+// key step but the first of a row.
+template <int POLY8, bool LM, bool LAGGED>
+__device__ __forceinline__ void attn_persist_roles(const CUtensorMap& tma_q, const CUtensorMap& tma_k, const CUtensorMap& tma_v, const AttnParams& p,
+                                                   const int n_qblk, const int n_items, uint8_t* sq, uint8_t* skv, uint64_t* bars,
+                                                   const uint32_t tmem_base, int* redo_flag, const int warp, const int lane) {
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;
+  uint64_t* kv_empty = kv_full + ATT_KV_SLOTS;
+  uint64_t* s_full = kv_empty + ATT_KV_SLOTS;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = p_full + 8;
+  uint64_t* o_empty = o_full + 2;
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -211,8 +173,18 @@ mmdit_attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tma_q,
       if constexpr (!LM) {  // hot path: mask-free tight loop, a ragged last tile apart (see attn_sm100.cuh)
         const bool ragged = (t.kv_valid & 127) != 0;
         const int n_full = ragged ? t.n_kv - 1 : t.n_kv;
-        for (int jj = 0; jj < n_full; ++jj, ++it)
-          softmax_step_p<POLY8, false>(t_s, t_o, &s_full[i], &p_full[i * 4], it & 1, jj == 0, 128, sc, m_run, l_run, lane, 0);
+        if constexpr (LAGGED) {
+          float m_next = -INFINITY;
+          if (n_full > 0) {
+            softmax_step_p<POLY8, false>(t_s, t_o, &s_full[i], &p_full[i * 4], it & 1, true, 128, sc, m_run, l_run, lane, 0);
+            ++it;
+          }
+          for (int jj = 1; jj < n_full; ++jj, ++it)
+            softmax_step_lagged<POLY8>(t_s, t_o, &s_full[i], &p_full[i * 4], it & 1, sc, m_run, l_run, m_next, lane, redo_flag);
+        } else {
+          for (int jj = 0; jj < n_full; ++jj, ++it)
+            softmax_step_p<POLY8, false>(t_s, t_o, &s_full[i], &p_full[i * 4], it & 1, jj == 0, 128, sc, m_run, l_run, lane, 0);
+        }
         if (ragged) {
           softmax_step_p<POLY8, true>(t_s, t_o, &s_full[i], &p_full[i * 4], it & 1, n_full == 0, t.kv_valid - n_full * 128, sc, m_run, l_run,
                                       lane, 0);
@@ -234,6 +206,104 @@ mmdit_attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tma_q,
       tc_fence_before();  // the tcgen05.ld of O are complete (wait::ld inside the epilogue): hand O_i back to the MMA warp
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[i]);
+    }
+  }
+
+}
+
+// LAG: lagged soft-max steps in the main pass.  A step whose exponentials may have overflowed sets the CTA's redo flag; the CTA then drains,
+// re-initialises its barriers and runs its items once more with the classic step (a second, straight-line copy of the role code: a loop
+// around the roles cost 13 % -- profiles/r02_attn_probe_lagged.md), overwriting the outputs of the first pass.
+template <int POLY8, bool LM = false, bool LAG = false>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+mmdit_attention_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                                      const __grid_constant__ CUtensorMap tma_v, const AttnParams p, const int n_qblk, const int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sq = smem;                         // Q0 | Q1
+  uint8_t* skv = smem + 2 * ATT_TILE_BYTES;   // ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(skv + ATT_KV_SLOTS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                       // 1
+  uint64_t* q_empty = bars + 1;                  // 1: all S products of the item have been issued and retired -> Q may be overwritten
+  uint64_t* kv_full = bars + 2;                  // ATT_KV_SLOTS
+  uint64_t* kv_empty = kv_full + ATT_KV_SLOTS;   // ATT_KV_SLOTS
+  uint64_t* s_full = kv_empty + ATT_KV_SLOTS;    // 2
+  uint64_t* p_full = s_full + 2;                 // 2 x 4
+  uint64_t* o_full = p_full + 8;                 // 2
+  uint64_t* o_empty = o_full + 2;                // 2: the soft-max warpgroup has read O_i of the previous item out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+  int* redo_flag = reinterpret_cast<int*>(tmem_slot + 1);       // LAG: some step of this CTA may have overflowed
+  uint64_t* drain_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);  // LAG: all tcgen05 work of the first pass has retired
+  static_assert(ATTP_BARRIERS * 8 + 16 <= 256, "barrier block");
+
+  const int warp = uniform_warp_id();
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_k);
+    tma_prefetch_desc(&tma_v);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < ATT_KV_SLOTS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      for (int c = 0; c < 4; ++c) mbar_init(&p_full[i * 4 + c], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 4);
+    }
+    mbar_init(drain_bar, 1);
+    *redo_flag = 0;
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  griddep_launch();  // PDL (common.cuh): prologue overlaps the predecessor's tail; global memory only after griddep_wait()
+  griddep_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  attn_persist_roles<POLY8, LM, LAG>(tma_q, tma_k, tma_v, p, n_qblk, n_items, sq, skv, bars, tmem_base, redo_flag, warp, lane);
+  if constexpr (LAG) {
+    tc_fence_before();
+    __syncthreads();  // every role is through its items: the flag is final
+    tc_fence_after();
+    if (*redo_flag != 0) {  // rare; uniform over the CTA
+      if (warp == 1) {      // no commit of the first pass may still be in flight when the barriers are re-initialised
+        umma_commit_w(drain_bar);
+        mbar_wait(drain_bar, 0);
+      }
+      __syncthreads();
+      if (warp == 0 && lane == 0) {
+        for (int i = 0; i < ATTP_BARRIERS; ++i) mbar_inval(&bars[i]);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int i = 0; i < ATT_KV_SLOTS; ++i) {
+          mbar_init(&kv_full[i], 1);
+          mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+          mbar_init(&s_full[i], 1);
+          for (int c = 0; c < 4; ++c) mbar_init(&p_full[i * 4 + c], 4);
+          mbar_init(&o_full[i], 1);
+          mbar_init(&o_empty[i], 4);
+        }
+        fence_barrier_init();
+      }
+      __syncthreads();
+      // second, straight-line copy of the role code; its inputs are re-derived here so that nothing of it extends a live range of the main pass
+      uint8_t* smem2 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+      uint64_t* bars2 = reinterpret_cast<uint64_t*>(smem2 + (2 + ATT_KV_SLOTS) * ATT_TILE_BYTES);
+      const uint32_t tmem_base2 = *reinterpret_cast<volatile uint32_t*>(bars2 + ATTP_BARRIERS);
+      attn_persist_roles<POLY8, LM, false>(tma_q, tma_k, tma_v, p, n_qblk, n_items, smem2, smem2 + 2 * ATT_TILE_BYTES, bars2, tmem_base2, redo_flag,
+                                       uniform_warp_id(), static_cast<int>(threadIdx.x & 31));
     }
   }
 

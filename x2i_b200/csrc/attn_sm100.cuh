@@ -43,8 +43,11 @@ constexpr int ATT_KV_SLOTS = 4;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + ATT_KV_SLOTS * ATT_TILE_BYTES + 1024 + 256;
 
 // exp2(x * sc - m) of one half (HALF = 0 / 1) of a 32-score quarter -> 8 of its 16 packed bf16x2 words + packed partial sums
-template <int POLY8, int DBG, int HALF>
-__device__ __forceinline__ void exp_half(const uint32_t (&x)[32], uint64_t sc2, uint64_t nm2, uint64_t (&sum2)[4], uint32_t (&pk)[16]) {
+// GUARD (lagged-max steps): pguard collects the max ARGUMENT of the polynomial lanes -- above 127 their exponent insertion wraps around
+// silently, where MUFU.EX2 returns +inf (which the row sum shows).
+template <int POLY8, int DBG, int HALF, bool GUARD = false>
+__device__ __forceinline__ void exp_half(const uint32_t (&x)[32], uint64_t sc2, uint64_t nm2, uint64_t (&sum2)[4], uint32_t (&pk)[16],
+                                         float* pguard = nullptr) {
 #pragma unroll
   for (int k = 8 * HALF; k < 8 * HALF + 8; ++k) {
     const uint64_t a2 = fma_f32x2(pack_f32x2(__uint_as_float(x[2 * k]), __uint_as_float(x[2 * k + 1])), sc2, nm2);
@@ -54,6 +57,7 @@ __device__ __forceinline__ void exp_half(const uint32_t (&x)[32], uint64_t sc2, 
       p0 = a0;
       p1 = a1;
     } else if ((k & 7) < POLY8) {  // POLY8 of every 8 pairs: exp2 on the FMA pipe instead of MUFU
+      if constexpr (GUARD) *pguard = max3f(*pguard, a0, a1);
       poly_exp2_x2(a0, a1, p0, p1);
     } else {
       p0 = fast_exp2(a0);
@@ -182,6 +186,79 @@ __device__ __forceinline__ void softmax_step_core(uint32_t t_s, uint32_t t_o, ui
   float s0, s1;
   unpack_f32x2(add_f32x2(add_f32x2(sum2[0], sum2[1]), add_f32x2(sum2[2], sum2[3])), s0, s1);
   l_run = l_run * alpha + (s0 + s1);
+}
+// Lagged form of a key step (persistent kernel, X2I_ATTN_LAG; unmasked, not the first step of a row).  The max pass over the 128
+// scores (~270-390 cycles of every ~2800-cycle step, all of it on the S -> soft-max -> PV -> S chain that bounds the kernel,
+// profiles/r02_attn_clock64_trace.txt) disappears: the exponentials of step j start right away against the reference m_run the
+// row already has, and the reference for step j + 1 comes from the step's own ROW SUM, which is computed anyway:
+//     max_k p_k <= sum_k p_k <= 128 max_k p_k,   p_k = 2^(s_k - m_run)
+// so m_run + log2(sum) bounds the tile's max from above within 7 (log2 units).  The reference need not be the true max -- O, l and
+// m_run stay consistent at every step and the final O / l does not depend on it -- it only has to keep p away from overflow:
+// when a step's sum exceeds 2^16 the next step first rescales O and l (the lazy rescale, one step late).
+// Overflow guard: a tile that exceeds the reference by more than 2^64 (44 nats above EVERY earlier key of the row) shows as a sum
+// above 2^64 or inf / nan; the polynomial lanes, whose exponent insertion would wrap silently beyond 2^127, are covered by the
+// max of their arguments (16 FMNMX3 per step).  Either sets the CTA's redo flag and the kernel re-runs that CTA's items with
+// the classic step (attn_persist_sm100.cuh).
+// What did NOT work (profiles/r02_attn_probe_lagged.md): comparing each quarter's max before its exponentials (exact p <= 2^8
+// bound, one uniform branch per quarter) was 4 % slower than the classic step -- ptxas cannot overlap a quarter's pack / store tail
+// with the next quarter's exponentials across a basic-block boundary; forming the tile's true max in the shadow of the MUFU stream
+// (64 FMNMX3 per step) kept only +2.7 % of the +6.8 % that the missing max pass is worth.
+constexpr float ATT_LAG_RESCALE = 16.0f;  // log2 of the step sum above which the next step rescales
+constexpr float ATT_LAG_LIMIT = 64.0f;    // log2 of the step sum above which the step counts as overflowed
+template <int POLY8>
+__device__ __forceinline__ void softmax_step_lagged(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, uint32_t parity,
+                                                    float sc, float& m_run, float& l_run, float& m_next, int lane, int* redo_flag) {
+  // lazy rescale against the reference the PREVIOUS step proposed (m_next); alpha does not depend on this step's scores
+  const bool rescale = m_next - m_run > ATT_LAG_RESCALE;
+  const float alpha = rescale ? fast_exp2(m_run - m_next) : 1.0f;
+  if (rescale) m_run = m_next;
+  mbar_wait(s_full_i, parity);
+  tc_fence_after();
+  uint32_t rq[2][32];
+  uint32_t pk[16];
+  tmem_ld32(t_s, rq[0]);
+  // O_i may be touched without a barrier: s_full(j) implies P.V_i(j-1) has retired (see softmax_step_core)
+  if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t o[32];
+      tmem_ld32(t_o + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+      tmem_st32(t_o + c * 32, o);
+    }
+  }
+  const uint64_t sc2 = pack_f32x2(sc, sc), nm2 = pack_f32x2(-m_run, -m_run);
+  uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
+  float pguard = -INFINITY;
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t(&x)[32] = rq[c & 1];
+    if (c < 3) tmem_ld32(t_s + (c + 1) * 32, rq[(c + 1) & 1]);
+    exp_half<POLY8, 0, 0, true>(x, sc2, nm2, sum2, pk, &pguard);
+    if (c > 0) {
+      tmem_st_wait();  // store of quarter c-1, issued half a quarter ago
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full_i[c - 1]);
+    }
+    if (c < 3) tmem_ld_wait();
+    exp_half<POLY8, 0, 1, true>(x, sc2, nm2, sum2, pk, &pguard);
+    tmem_st16(t_s + c * 16, pk);  // P_i aliases S_i columns [0, 64)
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&p_full_i[3]);
+  float s0, s1;
+  unpack_f32x2(add_f32x2(add_f32x2(sum2[0], sum2[1]), add_f32x2(sum2[2], sum2[3])), s0, s1);
+  const float step_sum = s0 + s1;
+  l_run = l_run * alpha + step_sum;
+  const float lg = __log2f(step_sum);  // -inf for an all-underflow step: no rescale
+  m_next = m_run + lg;
+  if (!(lg <= ATT_LAG_LIMIT) || pguard > 126.0f) *redo_flag = 1;  // p may have overflowed: this CTA's items are re-run with the classic step
 }
 // one-item kernels: the key-step counter j of the CTA gives both the barrier parity and "first step"
 template <int POLY8, bool MASKED, int DBG, bool PAIR = false>

@@ -594,6 +594,9 @@ int x2i_mmdit_attention(const void* q, const void* k, const void* v, void* out0,
 #ifndef X2I_ATTN_CS_DEFAULT
 #define X2I_ATTN_CS_DEFAULT 0
 #endif
+#ifndef X2I_ATTN_LAG_DEFAULT
+#define X2I_ATTN_LAG_DEFAULT 1
+#endif
 #ifndef X2I_ATTN_PERSIST_DEFAULT
 #define X2I_ATTN_PERSIST_DEFAULT 1
 #endif
@@ -712,6 +715,20 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
       return check_launch("mmdit_attention_fwd_persistent_cs_kernel");
     }
     static const bool pdl_attn = []() { const char* e = getenv("X2I_PDL_ATTN"); return e ? atoi(e) != 0 : true; }();  // experiment switch
+    // Lagged soft-max steps (softmax_step_lagged, attn_sm100.cuh).  X2I_ATTN_LAG=0/1, read per call (tests run both).
+    const char* lag_env = getenv("X2I_ATTN_LAG");
+    const int lag = lag_env ? atoi(lag_env) : X2I_ATTN_LAG_DEFAULT;
+    if (lag && !lm) {
+      auto kernlg = mmdit_attention_fwd_persistent_kernel<ATT_DEFAULT_POLY8, false, true>;
+      static std::atomic<bool> attlg_configured[16];
+      if (!attlg_configured[d->index].load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(kernlg, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(X2I_ERR_LAUNCH, "cudaFuncSetAttribute(attention lagged): %s", cudaGetErrorString(e));
+        attlg_configured[d->index].store(true, std::memory_order_release);
+      }
+      launch_pdl_if(pdl_enabled() && pdl_attn, kernlg, dim3(gridp), dim3(ATT_THREADS), ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream), tq, tk, tv, p, n_qblk, n_items);
+      return check_launch("mmdit_attention_fwd_persistent_kernel<lagged>");
+    }
     launch_pdl_if(pdl_enabled() && pdl_attn, kernp, dim3(gridp), dim3(ATT_THREADS), ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream), tq, tk, tv, p, n_qblk, n_items);
     return check_launch("mmdit_attention_fwd_persistent_kernel");
   }
