@@ -355,7 +355,7 @@ def main():
 
             t_iso = timed(lambda: ops.attention(q_, k_, v_, split=S_TXT, out0=o0, out1=o1))
             t_lib = timed(lambda: F_.scaled_dot_product_attention(q_, k_, v_))
-            roof = {"kernel": "mmdit_attention_fwd_persistent_kernel<2, 0>" if os.environ.get("X2I_ATTN_PERSIST", "1") == "1" else "mmdit_attention_fwd_kernel<2, 0, 0>", "bound": "tensor", "achieved": ach, "peak": pk_s,
+            roof = {"kernel": ("mmdit_attention_fwd_persistent_kernel<2, 0, %d>" % int(os.environ.get("X2I_ATTN_LAG", "1") != "0")) if os.environ.get("X2I_ATTN_PERSIST", "1") == "1" else "mmdit_attention_fwd_kernel<2, 0, 0>", "bound": "tensor", "achieved": ach, "peak": pk_s,
                     "unit": "TFLOP/s", "frac": ach / pk_s, "frac_of_burst_peak": ach / pk["bf16"],
                     "peak_source": pk["source"] + " (sustained cuBLAS bf16: the kernel is timed inside long denoise steps)",
                     "ms_per_launch": t_att * 1e3, "launches_timed": len(durs), "algorithmic_flops_per_launch": fl, "traffic": attn_traffic(),

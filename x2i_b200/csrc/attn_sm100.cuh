@@ -37,7 +37,10 @@ struct AttnParams {
 #define ATT_STAMP(slot) do { if constexpr (DBG == 1) { if (trace != nullptr && lane == 0) trace[slot] = clock64(); } } while (0)
 
 constexpr int ATT_THREADS = 320;
-constexpr int ATT_DEFAULT_POLY8 = 2;  // production instantiation (see capi.cu)
+#ifndef X2I_ATT_POLY8  // tools/gpu_job_r04i.sh builds alternative libraries with 1 / 3 (sweep of the lagged form)
+#define X2I_ATT_POLY8 2
+#endif
+constexpr int ATT_DEFAULT_POLY8 = X2I_ATT_POLY8;  // production instantiation (see capi.cu)
 constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 128B-swizzled boxes of [128 rows x 64 cols]
 constexpr int ATT_KV_SLOTS = 4;
 constexpr int ATT_SMEM_BYTES = 2 * ATT_TILE_BYTES + ATT_KV_SLOTS * ATT_TILE_BYTES + 1024 + 256;

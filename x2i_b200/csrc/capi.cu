@@ -648,7 +648,7 @@ int attention_fwd(const void* q, const void* k, const void* v, const int* kv_len
   using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
   KernT kern = nullptr;
 #define ATT_PICK(P, D) if (poly8 == P && dbg == D) kern = mmdit_attention_fwd_kernel<P, D>
-  ATT_PICK(2, 0);  // production
+  ATT_PICK(ATT_DEFAULT_POLY8, 0);  // production (2 unless the library was built with -DX2I_ATT_POLY8=n for a sweep)
   ATT_PICK(2, 1);  // production arithmetic + clock64 trace
 #ifdef X2I_ATTN_EXPERIMENTS  // tools/attn_sweep.sh builds with X2I_BUILD_EXPERIMENTS=1; never in the shipped library
   ATT_PICK(0, 0); ATT_PICK(1, 0); ATT_PICK(3, 0); ATT_PICK(4, 0);
