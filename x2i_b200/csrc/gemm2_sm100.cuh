@@ -225,7 +225,36 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * BN + lane_off;
       const int m = t.m2 * 256 + rank * 128 + quad * 32 + lane;
+#if defined(X2I_GEMM_EPI_TMEM_ONLY)  // timing experiment (tools/gpu_job_r04m.sh): the epilogue only READS the accumulator tile
+      {
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_acc + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc ^= r[j];
+        }
+        if (acc == 0x12345678u && m < g.p[t.prob].M) g.p[t.prob].C[m] = __float2bfloat16(1.0f);
+      }
+#elif defined(X2I_GEMM_EPI_STORE_ONLY)  // timing experiment: the epilogue only WRITES (zeros), no TMEM read
+      {
+        const GemmParams& gp = g.p[t.prob];
+        if (m < gp.M && gp.C != nullptr) {
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            const int n0 = t.n_blk * BN + c * 32;
+            if (n0 >= gp.N) break;
+            uint4* d4 = reinterpret_cast<uint4*>(gp.C + static_cast<long long>(m) * gp.ldc + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d4[j] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+#elif !defined(X2I_GEMM_SKIP_EPI)  // X2I_GEMM_SKIP_EPI: timing experiment (tools/gpu_job_r04l.sh): mainloop only, no results
       gemm_epilogue_tile<BN, EPI>(g.p[t.prob], t_acc, m, t.n_blk * BN);
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);

@@ -96,7 +96,21 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// 64 B of one input row per thread (read-only data): two 256-bit loads when 32-byte aligned (full-sector requests, see store_bf16x32)
 __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float (&out)[32]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint32_t w[8];
+      ld_global_nc_256(p + 16 * i, w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        out[16 * i + 2 * j] = bf16_lo(w[j]);
+        out[16 * i + 2 * j + 1] = bf16_hi(w[j]);
+      }
+    }
+    return;
+  }
   const uint4* p4 = reinterpret_cast<const uint4*>(p);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -107,16 +121,21 @@ __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* p, float (&out
     out[8 * i + 6] = bf16_lo(u.w); out[8 * i + 7] = bf16_hi(u.w);
   }
 }
+// 64 B of one output row per thread.  Two 256-bit stores (sm_100: STG.E.256) when the row segment is 32-byte aligned, so that every request is
+// a FULL 32-byte sector: with four 128-bit stores each warp instruction carries 32 half-sector writes to 32 different rows, and that
+// request stream competes with the TMA loads of the shared-memory-bound mainloop (tools/gemm_probe.py: an epilogue that only reads TMEM costs
+// nothing, one that only stores costs the plain epilogue's 8 %; profiles/r02_gemm_epilogue_probe.md).
 __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float (&v)[32]) {
-  uint4* p4 = reinterpret_cast<uint4*>(p);
+  uint32_t w[16];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-    p4[i] = u;
+  for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    st_global_256(p, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+    st_global_256(p + 16, w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]);
+  } else {
+    uint4* p4 = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p4[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
   }
 }
 
