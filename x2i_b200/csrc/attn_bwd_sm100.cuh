@@ -390,18 +390,7 @@ __device__ __forceinline__ void attention_bwd_body(const CUtensorMap& tma_x0, co
       uint32_t o[32];
       tmem_ld32(tmem_base + ACC0 + which * 128 + lane_off + c * 32, o);
       tmem_ld_wait();
-      if (ok) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * mul, __uint_as_float(o[8 * k + 1]) * mul);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * mul, __uint_as_float(o[8 * k + 3]) * mul);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul);
-          d4[k] = u;
-        }
-      }
+      if (ok) st_bf16x32_scaled(dst + c * 32, o, mul);
     }
   }
 
@@ -656,18 +645,7 @@ mmdit_attention_bwd_kv32_kernel(const __grid_constant__ CUtensorMap tma_y0 /* Q,
       uint32_t o[32];
       tmem_ld32(tmem_base + (wg == 0 ? ACC0 : ACC1) + lane_off + c * 32, o);
       tmem_ld_wait();
-      if (ok) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * k + 0]) * mul, __uint_as_float(o[8 * k + 1]) * mul);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * mul, __uint_as_float(o[8 * k + 3]) * mul);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul);
-          d4[k] = u;
-        }
-      }
+      if (ok) st_bf16x32_scaled(dst + c * 32, o, mul);
     }
   }
   tc_fence_before();

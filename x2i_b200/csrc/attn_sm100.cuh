@@ -297,20 +297,7 @@ __device__ __forceinline__ void attn_epilogue(const AttnParams& p, uint64_t* o_f
     uint32_t o[32];
     tmem_ld32(t_o + c * 32, o);
     tmem_ld_wait();
-    if (ok) {
-      uint32_t w[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) w[k] = pack_bf16x2(__uint_as_float(o[2 * k]) * inv_l, __uint_as_float(o[2 * k + 1]) * inv_l);
-      __nv_bfloat16* d = dst + c * 32;
-      if ((reinterpret_cast<uintptr_t>(d) & 31) == 0) {  // full-sector requests (see store_bf16x32, gemm_sm100.cuh)
-        st_global_256(d, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
-        st_global_256(d + 16, w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]);
-      } else {
-        uint4* d4 = reinterpret_cast<uint4*>(d);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) d4[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
-      }
-    }
+    if (ok) st_bf16x32_scaled(dst + c * 32, o, inv_l);
   }
 }
 

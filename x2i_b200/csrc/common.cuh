@@ -261,6 +261,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 32 fp32 accumulator values (raw bits) of one output row x scale -> 64 B of bf16: two 256-bit stores when 32-byte aligned (full-sector
+// requests, see store_bf16x32 in gemm_sm100.cuh), else four 128-bit ones
+__device__ __forceinline__ void st_bf16x32_scaled(__nv_bfloat16* d, const uint32_t (&o)[32], float mul) {
+  uint32_t w[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w[k] = pack_bf16x2(__uint_as_float(o[2 * k]) * mul, __uint_as_float(o[2 * k + 1]) * mul);
+  if ((reinterpret_cast<uintptr_t>(d) & 31) == 0) {
+    st_global_256(d, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+    st_global_256(d + 16, w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]);
+  } else {
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d4[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+  }
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

@@ -207,9 +207,22 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
           for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(r[j]) + bb[j]) * rinv * ww[j];
           if (p.rope != nullptr && row_ok) {
             const float4* rp = reinterpret_cast<const float4*>(p.rope + static_cast<long long>(pos) * 64 + c * 16);
+            float4 csv[8];  // 128 B of this row's table: four 256-bit loads when the table is 32-byte aligned
+            if ((reinterpret_cast<uintptr_t>(rp) & 31) == 0) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t w[8];
+                ld_global_nc_256(rp + 2 * j, w);
+                csv[2 * j] = make_float4(__uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]), __uint_as_float(w[3]));
+                csv[2 * j + 1] = make_float4(__uint_as_float(w[4]), __uint_as_float(w[5]), __uint_as_float(w[6]), __uint_as_float(w[7]));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) csv[j] = __ldg(rp + j);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 cs = __ldg(rp + j);  // (cos0, sin0, cos1, sin1)
+              const float4 cs = csv[j];  // (cos0, sin0, cos1, sin1)
               const float a0 = x[4 * j + 0], a1 = x[4 * j + 1], a2 = x[4 * j + 2], a3 = x[4 * j + 3];
               x[4 * j + 0] = a0 * cs.x - a1 * cs.y;
               x[4 * j + 1] = a1 * cs.x + a0 * cs.y;
