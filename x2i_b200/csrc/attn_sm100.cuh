@@ -37,7 +37,7 @@ struct AttnParams {
 #define ATT_STAMP(slot) do { if constexpr (DBG == 1) { if (trace != nullptr && lane == 0) trace[slot] = clock64(); } } while (0)
 
 constexpr int ATT_THREADS = 320;
-#ifndef X2I_ATT_POLY8  // tools/gpu_job_r04i.sh builds alternative libraries with 1 / 3 (sweep of the lagged form)
+#ifndef X2I_ATT_POLY8  // tools/jobs/gpu_job_r04i.sh builds alternative libraries with 1 / 3 (sweep of the lagged form)
 #define X2I_ATT_POLY8 2
 #endif
 constexpr int ATT_DEFAULT_POLY8 = X2I_ATT_POLY8;  // production instantiation (see capi.cu)

@@ -225,7 +225,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
       tc_fence_after();
       const uint32_t t_acc = tmem_base + as * BN + lane_off;
       const int m = t.m2 * 256 + rank * 128 + quad * 32 + lane;
-#if defined(X2I_GEMM_EPI_TMEM_ONLY)  // timing experiment (tools/gpu_job_r04m.sh): the epilogue only READS the accumulator tile
+#if defined(X2I_GEMM_EPI_TMEM_ONLY)  // timing experiment (tools/jobs/gpu_job_r04m.sh): the epilogue only READS the accumulator tile
       {
         uint32_t acc = 0;
 #pragma unroll 1
@@ -252,7 +252,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
           }
         }
       }
-#elif !defined(X2I_GEMM_SKIP_EPI)  // X2I_GEMM_SKIP_EPI: timing experiment (tools/gpu_job_r04l.sh): mainloop only, no results
+#elif !defined(X2I_GEMM_SKIP_EPI)  // X2I_GEMM_SKIP_EPI: timing experiment (tools/jobs/gpu_job_r04l.sh): mainloop only, no results
       gemm_epilogue_tile<BN, EPI>(g.p[t.prob], t_acc, m, t.n_blk * BN);
 #endif
       tc_fence_before();
