@@ -18,7 +18,11 @@ namespace x2i {
 
 constexpr int GEMM2_STAGES = 6;
 constexpr int GEMM2_STAGE_BYTES = 2 * 128 * GEMM_BK * 2;  // A half (16 KB) + W half (16 KB) per CTA
+#ifdef X2I_EPI_STAGE  // experiment build: + 4 KB per epilogue warp for the store transpose (gemm_epilogue_tile)
+constexpr int GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256 + 4 * 4096;
+#else
 constexpr int GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256;
+#endif
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared-window address -> the pair's even CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -253,7 +257,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_co
         }
       }
 #elif !defined(X2I_GEMM_SKIP_EPI)  // X2I_GEMM_SKIP_EPI: timing experiment (tools/jobs/gpu_job_r04l.sh): mainloop only, no results
+#ifdef X2I_EPI_STAGE
+      {
+        const GemmParams& gp = g.p[t.prob];  // staged stores need 32-byte aligned rows and whole 64-column pairs
+        const bool ok = (reinterpret_cast<uintptr_t>(gp.C) & 31) == 0 && (gp.ldc & 15) == 0 && gp.C != nullptr;
+        gemm_epilogue_tile<BN, EPI>(gp, t_acc, m, t.n_blk * BN, 0, 0, ok ? smem + NS * GEMM2_STAGE_BYTES + 256 + (warp - 2) * 4096 : nullptr);
+      }
+#else
       gemm_epilogue_tile<BN, EPI>(g.p[t.prob], t_acc, m, t.n_blk * BN);
+#endif
 #endif
       tc_fence_before();
       __syncwarp();

@@ -144,7 +144,11 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* p, const float (&v)
 template <int BN, int EPI>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const uint32_t t_acc, const int m, const int n_tile0,
                                                    const long long bias_off = 0 /* EPI_CONV with per-group weights */,
-                                                   const int ks = 0 /* split-K group */) {
+                                                   const int ks = 0 /* split-K group */
+#ifdef X2I_EPI_STAGE
+                                                   , uint8_t* stage = nullptr /* experiment builds: 4 KB of shared memory per epilogue warp */
+#endif
+                                                   ) {
   const bool row_ok = m < p.M;
   if (p.ksplit > 1) {  // raw fp32 partial of this k-group
     float* dst = p.c32 + (static_cast<long long>(ks) * p.M + m) * p.ldc32 + n_tile0;
@@ -384,8 +388,44 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const ui
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = res[j] + g[j] * x[j];
         }
+#ifdef X2I_EPI_STAGE
+        if (stage == nullptr) store_bf16x32(p.C + static_cast<long long>(m) * p.ldc + n0, x);
+#else
         store_bf16x32(p.C + static_cast<long long>(m) * p.ldc + n0, x);
+#endif
       }
+#ifdef X2I_EPI_STAGE
+      // Experiment (opt-in build, profiles/r02_gemm_epilogue_probe.md): the warp's 32 rows x 64 columns go through a 4 KB shared-memory
+      // transpose (16-byte units, unit' = unit ^ (row & 7): conflict-free both ways) so that each 256-bit store instruction writes 8 rows x
+      // one full 128-byte line instead of 32 rows x one 32-byte sector -- 4x fewer requests for the same bytes.
+      if (stage != nullptr) {
+        const int lane = threadIdx.x & 31;
+        const uint32_t sbase = smem_u32(stage);
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sbase + (lane * 8 + (((c & 1) * 4 + u) ^ (lane & 7))) * 16), "r"(w[4 * u]),
+                       "r"(w[4 * u + 1]), "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
+                       : "memory");
+        if (c & 1) {
+          __syncwarp();
+          const int m0 = m - lane;                 // first row of this warp
+          const int ncol = n0 - 32;                // first column of the 64-column pair
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + (lane >> 2), q = lane & 3;
+            uint4 a, b;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(sbase + (r * 8 + ((2 * q) ^ (r & 7))) * 16) : "memory");
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(sbase + (r * 8 + ((2 * q + 1) ^ (r & 7))) * 16) : "memory");
+            if (m0 + r < p.M)
+              st_global_256(p.C + static_cast<long long>(m0 + r) * p.ldc + ncol + q * 16, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
+          }
+          __syncwarp();
+        }
+      }
+#endif
     }
   }
 }
