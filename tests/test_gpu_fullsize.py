@@ -136,7 +136,7 @@ def test_attention_kernel_forms_are_bit_identical(ops):
 
 def test_attention_lagged_form_matches_fp32_and_default(ops):
     """Lagged soft-max steps (softmax_step_lagged, X2I_ATTN_LAG=1): the exponentials of a key step run against the reference the row
-    already has, the next reference comes from the step's row sum (one step late); a step whose sum exceeds 2^64 -- or whose
+    already has, the next reference comes from the step's row sum (one step late); a step whose sum exceeds 2^96 -- or whose
     polynomial-lane arguments exceed 126 -- makes the CTA re-run its items with the classic step.  Checked against torch fp32 and the
     default form on (a) random scores, (b) scores that GROW along the keys by ~2^42 per tile (a lagged rescale at every step), (c) the
     same with ~2^167 per tile (MUFU lanes return inf -> redo pass), (d) a few late keys that dominate single rows by ~2^25, (e) ONE late

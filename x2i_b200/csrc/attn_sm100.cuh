@@ -198,8 +198,8 @@ __device__ __forceinline__ void softmax_step_core(uint32_t t_s, uint32_t t_o, ui
 // so m_run + log2(sum) bounds the tile's max from above within 7 (log2 units).  The reference need not be the true max -- O, l and
 // m_run stay consistent at every step and the final O / l does not depend on it -- it only has to keep p away from overflow:
 // when a step's sum exceeds 2^16 the next step first rescales O and l (the lazy rescale, one step late).
-// Overflow guard: a tile that exceeds the reference by more than 2^64 (44 nats above EVERY earlier key of the row) shows as a sum
-// above 2^64 or inf / nan; the polynomial lanes, whose exponent insertion would wrap silently beyond 2^127, are covered by the
+// Overflow guard: a tile that exceeds the reference by more than 2^96 (66 nats above EVERY earlier key of the row) shows as a sum
+// above 2^96 or inf / nan; the polynomial lanes, whose exponent insertion would wrap silently beyond 2^127, are covered by the
 // max of their arguments (16 FMNMX3 per step).  Either sets the CTA's redo flag and the kernel re-runs that CTA's items with
 // the classic step (attn_persist_sm100.cuh).
 // What did NOT work (profiles/r02_attn_probe_lagged.md): comparing each quarter's max before its exponentials (exact p <= 2^8
@@ -207,7 +207,8 @@ __device__ __forceinline__ void softmax_step_core(uint32_t t_s, uint32_t t_o, ui
 // with the next quarter's exponentials across a basic-block boundary; forming the tile's true max in the shadow of the MUFU stream
 // (64 FMNMX3 per step) kept only +2.7 % of the +6.8 % that the missing max pass is worth.
 constexpr float ATT_LAG_RESCALE = 16.0f;  // log2 of the step sum above which the next step rescales
-constexpr float ATT_LAG_LIMIT = 64.0f;    // log2 of the step sum above which the step counts as overflowed
+constexpr float ATT_LAG_LIMIT = 96.0f;    // log2 of the step sum above which the step counts as overflowed (p <= 2^96: P.V partial sums stay below
+                                          // 2^96 x 128 keys x |v| -- far from the fp32 range for any bf16 V a network produces)
 template <int POLY8>
 __device__ __forceinline__ void softmax_step_lagged(uint32_t t_s, uint32_t t_o, uint64_t* s_full_i, uint64_t* p_full_i, uint32_t parity,
                                                     float sc, float& m_run, float& l_run, float& m_next, int lane, int* redo_flag) {
